@@ -1,0 +1,152 @@
+"""ctypes binding of libcalm_b200.so — the C-ABI kernel library declared in include/calm_b200.h.
+
+Only plumbing lives here: locate/load the shared library, declare every prototype, translate torch tensors into raw
+device pointers and raise on a non-zero return code. There is NO fallback: if the library is missing (or there is no
+CUDA device) every call raises, so a silent PyTorch/CPU path can never stand in for the kernels.
+"""
+import ctypes as C
+import os
+import threading
+
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libcalm_b200.so")
+
+BF16, F32 = 0, 1
+MAJOR_K, MAJOR_MN = 0, 1
+EPI_NONE, EPI_GELU, EPI_DGELU = 0, 1, 2
+CNN_NPARAM = 547
+
+i32, i64, f32, vp = C.c_int32, C.c_int64, C.c_float, C.c_void_p
+
+
+class GemmArgs(C.Structure):
+    """Mirror of calm_gemm_args (include/calm_b200.h)."""
+    _fields_ = [
+        ("a", vp), ("b", vp), ("c", vp),
+        ("M", i32), ("N", i32), ("K", i32), ("batch", i32),
+        ("lda", i64), ("ldb", i64), ("ldc", i64),
+        ("stride_a", i64), ("stride_b", i64), ("stride_c", i64),
+        ("a_major", i32), ("b_major", i32), ("c_dtype", i32), ("epilogue", i32),
+        ("bias", vp),
+        ("addend", vp), ("addend_dtype", i32), ("_pad0", i32), ("ld_addend", i64), ("stride_addend", i64),
+        ("aux", vp), ("ld_aux", i64), ("stride_aux", i64),
+        ("reduce_batch", i32), ("splits", i32), ("stride_split", i64),
+        ("alpha", f32), ("_pad1", i32),
+    ]
+
+
+class SnLayer(C.Structure):
+    """Mirror of calm_sn_layer (include/calm_b200.h)."""
+    _fields_ = [
+        ("w", vp), ("u", vp), ("v", vp), ("rowscale", vp), ("w_eff", vp), ("w_eff_t", vp),
+        ("grad_w", vp), ("grad_rowscale", vp), ("g_eff", vp),
+        ("rows", i32), ("cols", i32), ("g_splits", i32), ("eff_f32", i32),
+        ("tmp", vp), ("sigma", vp),
+        ("g_split_stride", i64), ("ld_t", i32), ("_pad", i32),
+    ]
+
+
+# name -> (restype, argtypes); every symbol include/calm_b200.h declares
+PROTOTYPES = {
+    "calm_abi_version": (i32, []),
+    "calm_last_error": (C.c_char_p, []),
+    "calm_set_debug_flags": (None, [i32]),
+    "calm_get_debug_flags": (i32, []),
+    "calm_set_error_flag_buffer": (i32, [vp]),
+    "calm_gemm": (i32, [C.POINTER(GemmArgs), vp]),
+    "calm_gemm_default_splits": (i32, [i32, i32, i32, i32, i32]),
+    "calm_sn_forward": (i32, [vp, i32, i32, i32, i32, f32, vp]),
+    "calm_sn_backward": (i32, [vp, i32, i32, i32, vp]),
+    "calm_layernorm_fwd": (i32, [vp, vp, vp, i32, vp, vp, i64, i32, f32, vp]),
+    "calm_layernorm_bwd": (i32, [vp, i32, vp, vp, vp, vp, vp, vp, vp, i32, vp, i64, i32, vp]),
+    "calm_layernorm_bwd_parts": (i32, [i64, i32]),
+    "calm_rope_table": (i32, [vp, vp, i32, i32, vp]),
+    "calm_rope_fwd": (i32, [vp, i64, vp, i64, vp, i64, vp, i64, i32, i32, i32, i32, vp]),
+    "calm_rope_bwd_scratch_floats": (i32, [i32, i32]),
+    "calm_rope_bwd": (i32, [vp, i64, vp, i64, vp, i64, vp, i64, vp, vp, vp, i64, i32, i32, i32, i32, vp]),
+    "calm_attention_fwd": (i32, [vp, vp, vp, vp, vp, vp, i64, i64, i64, i64, i32, i32, i32, i32, vp]),
+    "calm_attention_bwd": (i32, [vp] * 12 + [i64] * 8 + [i32] * 4 + [vp]),
+    "calm_latent_fwd": (i32, [vp, vp, vp, vp, vp, vp, i32, i64, i32, vp]),
+    "calm_latent_bwd": (i32, [vp, vp, vp, f32, vp, vp, i64, i32, vp]),
+    "calm_latent_blocks": (i32, [i64, i32]),
+    "calm_cnn_fwd": (i32, [vp] * 8 + [i32, i32, vp]),
+    "calm_cnn_bwd": (i32, [vp] * 10 + [i32, vp, i32, i32, vp]),
+    "calm_cnn_bwd_blocks": (i32, [i32, i32]),
+    "calm_token_transpose": (i32, [vp, vp, i32, i32, vp]),
+    "calm_nchw_to_tokens": (i32, [vp, vp, i32, i32, vp]),
+    "calm_colsum": (i32, [vp, i64, vp, i32, vp, i64, i32, vp]),
+    "calm_colsum_parts": (i32, [i64, i32]),
+    "calm_add3": (i32, [vp, vp, vp, vp, i64, vp]),
+    "calm_cast_bf16": (i32, [vp, vp, i64, vp]),
+    "calm_seq_mean_fwd": (i32, [vp, vp, i32, i32, i32, vp]),
+    "calm_seq_mean_bwd": (i32, [vp, vp, i32, i32, i32, vp]),
+}
+
+_lib = None
+_lock = threading.Lock()
+launch_count = 0  # kernels-launching C-ABI calls made through this binding (bench.py reports it)
+
+
+class CalmError(RuntimeError):
+    pass
+
+
+def load(build_if_missing=True):
+    """Load libcalm_b200.so (building it in-tree with nvcc if it is absent and nvcc exists). Raises if impossible."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH) and build_if_missing:
+            import importlib.util
+            spec = importlib.util.spec_from_file_location("calm_build_ext", os.path.join(HERE, "build_ext.py"))
+            mod = importlib.util.module_from_spec(spec)
+            spec.loader.exec_module(mod)
+            mod.build()
+        if not os.path.exists(LIB_PATH):
+            raise CalmError("libcalm_b200.so not found at %s — run `python __graft_entry__.py` (build) first" % LIB_PATH)
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in PROTOTYPES.items():
+            fn = getattr(lib, name)  # AttributeError = the library does not export what the header declares
+            fn.restype = res
+            fn.argtypes = args
+        if lib.calm_abi_version() != 1:
+            raise CalmError("libcalm_b200.so ABI version %d, expected 1" % lib.calm_abi_version())
+        _lib = lib
+    return _lib
+
+
+def last_error():
+    return load().calm_last_error().decode("utf-8", "replace")
+
+
+def check(rc, what):
+    if rc != 0:
+        raise CalmError("%s failed (rc=%d): %s" % (what, rc, last_error()))
+
+
+def ptr(t):
+    """Raw device pointer of a tensor (None -> NULL). The tensor must live on a CUDA device."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise CalmError("calm_b200 kernels need CUDA tensors (got %s); there is no CPU fallback" % t.device)
+    return t.data_ptr()
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def call(name, *args):
+    """Invoke an int32-returning entry point on the current torch stream (appended as last argument)."""
+    global launch_count
+    lib = load()
+    rc = getattr(lib, name)(*args, stream())
+    launch_count += 1
+    if rc != 0:
+        raise CalmError("%s failed (rc=%d): %s" % (name, rc, last_error()))

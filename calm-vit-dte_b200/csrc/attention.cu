@@ -1,0 +1,520 @@
+// Fused axial attention with a learned additive bias shared by all heads (forward + backward).
+//   O = softmax(Q K^T / sqrt(hd) + bias[b]) V          replaces F.scaled_dot_product_attention(q,k,v,attn_mask=...)
+//   (Vi_Tools_CNN_less_V2.py:293-298), the bias being linear_mask(q_mask @ k_mask^T).unsqueeze(1) (:288-291).
+// Each image is one sequence of S row- (or column-) tokens per head (S = 80..224 at 224^2, <= 512 at 512^2); scores never
+// touch HBM. Backward: dV = P^T dO, dP = dO V^T, dS = P (.) (dP - rowsum(dO (.) O)),
+// dQ = dS K / sqrt(hd), dK = dS^T Q / sqrt(hd), dbias[b] = sum_h dS_h  — split into a query-major kernel (dQ) and a
+// key-major kernel (dK, dV, dbias accumulated over heads in shared memory) so that nothing needs atomics and the result
+// is deterministic.
+// Round-1 implementation: warp-level mma.sync.m16n8k16 (bf16 in, fp32 accumulate), 64x64 tiles, online softmax in
+// registers with warp shuffles. Q/K/V are read straight from the token-major GEMM outputs (B*S, heads*hd) — head dims
+// that are not multiples of 16 (56, 44, 20, ...) are zero-padded in shared memory only.
+#include "common.cuh"
+#include "../../include/calm_b200.h"
+#include <math.h>
+
+namespace {
+
+constexpr int TILE = 64;            // query rows / keys per tile
+constexpr int ATT_THREADS = 128;    // 4 warps x 16 rows
+constexpr float LOG2E = 1.4426950408889634f;
+constexpr float LN2 = 0.6931471805599453f;
+
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void mma16816(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t sm_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// Load a TILE x hd slab (rows row0.. of a token-major matrix, head offset already applied) into smem [TILE][P],
+// zero-filling rows >= nvalid and columns >= hd.
+template <int HDP>
+__device__ __forceinline__ void load_tile(bf16* dst, const bf16* __restrict__ src, long long ld, int nvalid, int hd) {
+  constexpr int P = HDP + 8;
+  constexpr int WPR = HDP / 2;  // 32-bit words per padded row
+  uint32_t* d32 = reinterpret_cast<uint32_t*>(dst);
+  for (int idx = threadIdx.x; idx < TILE * WPR; idx += ATT_THREADS) {
+    const int r = idx / WPR, w = idx - r * WPR;
+    uint32_t val = 0u;
+    if (r < nvalid && 2 * w < hd) val = *reinterpret_cast<const uint32_t*>(src + (long long)r * ld + 2 * w);
+    d32[r * (P / 2) + w] = val;
+  }
+}
+
+// A-operand fragments (16 rows x HDP) of this warp's 16-row slab
+template <int HDP>
+__device__ __forceinline__ void load_a_frags(uint32_t (*f)[4], const bf16* tile, int row0, int lane) {
+  constexpr int P = HDP + 8;
+#pragma unroll
+  for (int ks = 0; ks < HDP / 16; ++ks)
+    ldsm_x4(sm_addr(tile + (row0 + (lane & 15)) * P + ks * 16 + (lane >> 4) * 8), f[ks][0], f[ks][1], f[ks][2], f[ks][3]);
+}
+
+// C[16 x 64] += A(16 x HDP) . T^T where T is a [64][P] smem tile (rows = output columns), i.e. "A . T^T"
+template <int HDP>
+__device__ __forceinline__ void mma_a_tT(float (*c)[4], const uint32_t (*af)[4], const bf16* tile, int lane) {
+  constexpr int P = HDP + 8;
+#pragma unroll
+  for (int ks = 0; ks < HDP / 16; ++ks) {
+#pragma unroll
+    for (int np = 0; np < 4; ++np) {
+      uint32_t b0, b1, b2, b3;
+      ldsm_x4(sm_addr(tile + (np * 16 + (lane & 7) + ((lane >> 4) << 3)) * P + ks * 16 + ((lane >> 3) & 1) * 8), b0, b1, b2, b3);
+      mma16816(c[2 * np], af[ks], b0, b1);
+      mma16816(c[2 * np + 1], af[ks], b2, b3);
+    }
+  }
+}
+
+// C[16 x HDP] += Pm(16 x 64, from accumulator registers) . T where T is a [64][P] smem tile (rows = contraction index)
+template <int HDP>
+__device__ __forceinline__ void mma_p_t(float (*c)[4], const float (*pm)[4], const bf16* tile, int lane) {
+  constexpr int P = HDP + 8;
+#pragma unroll
+  for (int kk = 0; kk < 4; ++kk) {
+    uint32_t a[4];
+    a[0] = pack_bf16x2(pm[2 * kk][0], pm[2 * kk][1]);
+    a[1] = pack_bf16x2(pm[2 * kk][2], pm[2 * kk][3]);
+    a[2] = pack_bf16x2(pm[2 * kk + 1][0], pm[2 * kk + 1][1]);
+    a[3] = pack_bf16x2(pm[2 * kk + 1][2], pm[2 * kk + 1][3]);
+#pragma unroll
+    for (int np = 0; np < HDP / 16; ++np) {
+      uint32_t b0, b1, b2, b3;
+      ldsm_x4_t(sm_addr(tile + (kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * P + np * 16 + (lane >> 4) * 8), b0, b1, b2, b3);
+      mma16816(c[2 * np], a, b0, b1);
+      mma16816(c[2 * np + 1], a, b2, b3);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// forward: grid (ceil(S/64), heads, B)
+// ---------------------------------------------------------------------------------------------------------------
+template <int HDP>
+__global__ void __launch_bounds__(ATT_THREADS)
+attn_fwd_kernel(const bf16* __restrict__ q, const bf16* __restrict__ k, const bf16* __restrict__ v, const bf16* __restrict__ bias,
+                bf16* __restrict__ o, float* __restrict__ lse, long long ld_q, long long ld_k, long long ld_v, long long ld_o,
+                int S, int heads, int hd, float scale_log2) {
+  constexpr int P = HDP + 8, NT = HDP / 8;
+  extern __shared__ __align__(16) uint8_t att_smem[];
+  bf16* Qs = reinterpret_cast<bf16*>(att_smem);
+  bf16* Ks = Qs + TILE * P;
+  bf16* Vs = Ks + TILE * P;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int q0 = blockIdx.x * TILE, h = blockIdx.y, b = blockIdx.z;
+  const long long tok0 = (long long)b * S;
+
+  load_tile<HDP>(Qs, q + (tok0 + q0) * ld_q + (long long)h * hd, ld_q, S - q0, hd);
+  __syncthreads();
+  uint32_t qf[HDP / 16][4];
+  load_a_frags<HDP>(qf, Qs, warp * 16, lane);
+
+  float oacc[NT][4];
+#pragma unroll
+  for (int i = 0; i < NT; ++i) { oacc[i][0] = oacc[i][1] = oacc[i][2] = oacc[i][3] = 0.f; }
+  float m[2] = {-INFINITY, -INFINITY}, l[2] = {0.f, 0.f};
+  const int row_lo = q0 + warp * 16 + (lane >> 2);  // this thread's rows: row_lo and row_lo + 8
+  const bf16* bias_b = bias + (long long)b * S * S;
+
+  for (int kb0 = 0; kb0 < S; kb0 += TILE) {
+    __syncthreads();
+    load_tile<HDP>(Ks, k + (tok0 + kb0) * ld_k + (long long)h * hd, ld_k, S - kb0, hd);
+    load_tile<HDP>(Vs, v + (tok0 + kb0) * ld_v + (long long)h * hd, ld_v, S - kb0, hd);
+    __syncthreads();
+    float s[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f; }
+    mma_a_tT<HDP>(s, qf, Ks, lane);
+    // scale, bias, key mask
+    float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      const int key = kb0 + nt * 8 + (lane & 3) * 2;
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        const int row = row_lo + hh * 8;
+        float b0 = 0.f, b1 = 0.f;
+        if (row < S && key < S) {
+          const float2 bb = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(bias_b + (long long)row * S + key));
+          b0 = bb.x; b1 = bb.y;
+        }
+        float v0 = s[nt][2 * hh] * scale_log2 + b0 * LOG2E;
+        float v1 = s[nt][2 * hh + 1] * scale_log2 + b1 * LOG2E;
+        if (key >= S) v0 = -INFINITY;
+        if (key + 1 >= S) v1 = -INFINITY;
+        s[nt][2 * hh] = v0; s[nt][2 * hh + 1] = v1;
+        mx[hh] = fmaxf(mx[hh], fmaxf(v0, v1));
+      }
+    }
+    float alpha[2];
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
+      mx[hh] = fmaxf(mx[hh], __shfl_xor_sync(0xffffffffu, mx[hh], 1));
+      mx[hh] = fmaxf(mx[hh], __shfl_xor_sync(0xffffffffu, mx[hh], 2));
+      const float mnew = fmaxf(m[hh], mx[hh]);
+      alpha[hh] = exp2f(m[hh] - mnew);
+      m[hh] = mnew;
+    }
+    float rs[2] = {0.f, 0.f};
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        const float p0 = exp2f(s[nt][2 * hh] - m[hh]), p1 = exp2f(s[nt][2 * hh + 1] - m[hh]);
+        s[nt][2 * hh] = p0; s[nt][2 * hh + 1] = p1;
+        rs[hh] += p0 + p1;
+      }
+    }
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
+      rs[hh] += __shfl_xor_sync(0xffffffffu, rs[hh], 1);
+      rs[hh] += __shfl_xor_sync(0xffffffffu, rs[hh], 2);
+      l[hh] = l[hh] * alpha[hh] + rs[hh];
+    }
+#pragma unroll
+    for (int i = 0; i < NT; ++i) {
+      oacc[i][0] *= alpha[0]; oacc[i][1] *= alpha[0]; oacc[i][2] *= alpha[1]; oacc[i][3] *= alpha[1];
+    }
+    mma_p_t<HDP>(oacc, s, Vs, lane);
+  }
+
+#pragma unroll
+  for (int hh = 0; hh < 2; ++hh) {
+    const int row = row_lo + hh * 8;
+    if (row < S) {
+      const float inv = 1.0f / l[hh];
+      bf16* op = o + (tok0 + row) * ld_o + (long long)h * hd;
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {
+        const int c = nt * 8 + (lane & 3) * 2;
+        if (c < hd) *reinterpret_cast<uint32_t*>(op + c) = pack_bf16x2(oacc[nt][2 * hh] * inv, oacc[nt][2 * hh + 1] * inv);
+      }
+      if ((lane & 3) == 0) lse[((long long)b * heads + h) * S + row] = (m[hh] + log2f(l[hh])) * LN2;
+    }
+  }
+}
+
+// delta[b,h,s] = sum_c dO[t, h*hd + c] * O[t, h*hd + c]   (one warp per (token, head))
+__global__ void attn_delta_kernel(const bf16* __restrict__ o, const bf16* __restrict__ d_o, float* __restrict__ delta, long long ld_o,
+                                  long long ld_do, long long tokens, int S, int heads, int hd) {
+  const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (w >= tokens * heads) return;
+  const long long t = w / heads;
+  const int h = (int)(w - t * heads);
+  const bf16* op = o + t * ld_o + (long long)h * hd;
+  const bf16* dp = d_o + t * ld_do + (long long)h * hd;
+  float acc = 0.f;
+  for (int c = lane * 2; c < hd; c += 64) {
+    const float2 a = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(op + c));
+    const float2 g = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(dp + c));
+    acc += a.x * g.x + a.y * g.y;
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) delta[((t / S) * heads + h) * S + (t % S)] = acc;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// backward, query-major: dQ.  grid (ceil(S/64), heads, B)
+// ---------------------------------------------------------------------------------------------------------------
+template <int HDP>
+__global__ void __launch_bounds__(ATT_THREADS)
+attn_bwd_dq_kernel(const bf16* __restrict__ q, const bf16* __restrict__ k, const bf16* __restrict__ v, const bf16* __restrict__ bias,
+                   const bf16* __restrict__ d_o, const float* __restrict__ lse, const float* __restrict__ delta, bf16* __restrict__ dq,
+                   long long ld_q, long long ld_k, long long ld_v, long long ld_do, long long ld_dq, int S, int heads, int hd,
+                   float scale, float scale_log2) {
+  constexpr int P = HDP + 8, NT = HDP / 8;
+  extern __shared__ __align__(16) uint8_t att_smem[];
+  bf16* Qs = reinterpret_cast<bf16*>(att_smem);
+  bf16* dOs = Qs + TILE * P;
+  bf16* Ks = dOs + TILE * P;
+  bf16* Vs = Ks + TILE * P;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int q0 = blockIdx.x * TILE, h = blockIdx.y, b = blockIdx.z;
+  const long long tok0 = (long long)b * S;
+
+  load_tile<HDP>(Qs, q + (tok0 + q0) * ld_q + (long long)h * hd, ld_q, S - q0, hd);
+  load_tile<HDP>(dOs, d_o + (tok0 + q0) * ld_do + (long long)h * hd, ld_do, S - q0, hd);
+  __syncthreads();
+  uint32_t qf[HDP / 16][4], dof[HDP / 16][4];
+  load_a_frags<HDP>(qf, Qs, warp * 16, lane);
+  load_a_frags<HDP>(dof, dOs, warp * 16, lane);
+
+  const int row_lo = q0 + warp * 16 + (lane >> 2);
+  float lse2[2], dlt[2];
+#pragma unroll
+  for (int hh = 0; hh < 2; ++hh) {
+    const int row = row_lo + hh * 8;
+    const long long idx = ((long long)b * heads + h) * S + row;
+    lse2[hh] = row < S ? lse[idx] * LOG2E : 0.f;
+    dlt[hh] = row < S ? delta[idx] : 0.f;
+  }
+  float dqacc[NT][4];
+#pragma unroll
+  for (int i = 0; i < NT; ++i) { dqacc[i][0] = dqacc[i][1] = dqacc[i][2] = dqacc[i][3] = 0.f; }
+  const bf16* bias_b = bias + (long long)b * S * S;
+
+  for (int kb0 = 0; kb0 < S; kb0 += TILE) {
+    __syncthreads();
+    load_tile<HDP>(Ks, k + (tok0 + kb0) * ld_k + (long long)h * hd, ld_k, S - kb0, hd);
+    load_tile<HDP>(Vs, v + (tok0 + kb0) * ld_v + (long long)h * hd, ld_v, S - kb0, hd);
+    __syncthreads();
+    float s[8][4], dp[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f; dp[i][0] = dp[i][1] = dp[i][2] = dp[i][3] = 0.f; }
+    mma_a_tT<HDP>(s, qf, Ks, lane);
+    mma_a_tT<HDP>(dp, dof, Vs, lane);
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      const int key = kb0 + nt * 8 + (lane & 3) * 2;
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        const int row = row_lo + hh * 8;
+        float b0 = 0.f, b1 = 0.f;
+        const bool ok = row < S && key < S;
+        if (ok) {
+          const float2 bb = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(bias_b + (long long)row * S + key));
+          b0 = bb.x; b1 = bb.y;
+        }
+        const float p0 = ok ? exp2f(s[nt][2 * hh] * scale_log2 + b0 * LOG2E - lse2[hh]) : 0.f;
+        const float p1 = (ok && key + 1 < S) ? exp2f(s[nt][2 * hh + 1] * scale_log2 + b1 * LOG2E - lse2[hh]) : 0.f;
+        s[nt][2 * hh] = p0 * (dp[nt][2 * hh] - dlt[hh]);          // dS
+        s[nt][2 * hh + 1] = p1 * (dp[nt][2 * hh + 1] - dlt[hh]);
+      }
+    }
+    mma_p_t<HDP>(dqacc, s, Ks, lane);
+  }
+#pragma unroll
+  for (int hh = 0; hh < 2; ++hh) {
+    const int row = row_lo + hh * 8;
+    if (row < S) {
+      bf16* op = dq + (tok0 + row) * ld_dq + (long long)h * hd;
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {
+        const int c = nt * 8 + (lane & 3) * 2;
+        if (c < hd) *reinterpret_cast<uint32_t*>(op + c) = pack_bf16x2(dqacc[nt][2 * hh] * scale, dqacc[nt][2 * hh + 1] * scale);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// backward, key-major: dK, dV and dbias = sum over heads of dS.  grid (ceil(S/64), B); loops heads x query tiles.
+// Works on transposed tiles (keys x queries) so that P^T / dS^T feed the next MMA straight from registers.
+// ---------------------------------------------------------------------------------------------------------------
+template <int HDP>
+__global__ void __launch_bounds__(ATT_THREADS)
+attn_bwd_dkv_kernel(const bf16* __restrict__ q, const bf16* __restrict__ k, const bf16* __restrict__ v, const bf16* __restrict__ bias,
+                    const bf16* __restrict__ d_o, const float* __restrict__ lse, const float* __restrict__ delta, bf16* __restrict__ dk,
+                    bf16* __restrict__ dv, bf16* __restrict__ dbias, long long ld_q, long long ld_k, long long ld_v, long long ld_do,
+                    long long ld_dk, long long ld_dv, int S, int heads, int hd, float scale, float scale_log2, int s_pad) {
+  constexpr int P = HDP + 8, NT = HDP / 8;
+  constexpr int DBP = TILE + 1;  // dbias smem pitch (floats)
+  extern __shared__ __align__(16) uint8_t att_smem[];
+  bf16* Ks = reinterpret_cast<bf16*>(att_smem);
+  bf16* Vs = Ks + TILE * P;
+  bf16* Qs = Vs + TILE * P;
+  bf16* dOs = Qs + TILE * P;
+  float* lse_s = reinterpret_cast<float*>(dOs + TILE * P);  // TILE
+  float* dlt_s = lse_s + TILE;                               // TILE
+  float* db_s = dlt_s + TILE;                                // s_pad x DBP   [query][key]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int k0 = blockIdx.x * TILE, b = blockIdx.y;
+  const long long tok0 = (long long)b * S;
+  const bf16* bias_b = bias + (long long)b * S * S;
+  for (int i = threadIdx.x; i < s_pad * DBP; i += ATT_THREADS) db_s[i] = 0.f;
+  const int key_lo = k0 + warp * 16 + (lane >> 2);  // this thread's keys: key_lo, key_lo + 8
+
+  for (int h = 0; h < heads; ++h) {
+    __syncthreads();
+    load_tile<HDP>(Ks, k + (tok0 + k0) * ld_k + (long long)h * hd, ld_k, S - k0, hd);
+    load_tile<HDP>(Vs, v + (tok0 + k0) * ld_v + (long long)h * hd, ld_v, S - k0, hd);
+    __syncthreads();
+    uint32_t kf[HDP / 16][4], vf[HDP / 16][4];
+    load_a_frags<HDP>(kf, Ks, warp * 16, lane);
+    load_a_frags<HDP>(vf, Vs, warp * 16, lane);
+    float dkacc[NT][4], dvacc[NT][4];
+#pragma unroll
+    for (int i = 0; i < NT; ++i) {
+      dkacc[i][0] = dkacc[i][1] = dkacc[i][2] = dkacc[i][3] = 0.f;
+      dvacc[i][0] = dvacc[i][1] = dvacc[i][2] = dvacc[i][3] = 0.f;
+    }
+    for (int q0 = 0; q0 < S; q0 += TILE) {
+      __syncthreads();
+      load_tile<HDP>(Qs, q + (tok0 + q0) * ld_q + (long long)h * hd, ld_q, S - q0, hd);
+      load_tile<HDP>(dOs, d_o + (tok0 + q0) * ld_do + (long long)h * hd, ld_do, S - q0, hd);
+      if (threadIdx.x < TILE) {
+        const int row = q0 + threadIdx.x;
+        const long long idx = ((long long)b * heads + h) * S + row;
+        lse_s[threadIdx.x] = row < S ? lse[idx] * LOG2E : 0.f;
+        dlt_s[threadIdx.x] = row < S ? delta[idx] : 0.f;
+      }
+      __syncthreads();
+      float st[8][4], dpt[8][4];  // [keys(16) x queries(64)] transposed tiles
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { st[i][0] = st[i][1] = st[i][2] = st[i][3] = 0.f; dpt[i][0] = dpt[i][1] = dpt[i][2] = dpt[i][3] = 0.f; }
+      mma_a_tT<HDP>(st, kf, Qs, lane);    // S^T = K Q^T
+      mma_a_tT<HDP>(dpt, vf, dOs, lane);  // dP^T = V dO^T
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int key = key_lo + (e >> 1) * 8;
+          const int ql = nt * 8 + (lane & 3) * 2 + (e & 1);
+          const int qrow = q0 + ql;
+          float p = 0.f;
+          if (key < S && qrow < S) {
+            const float bb = __bfloat162float(bias_b[(long long)qrow * S + key]);
+            p = exp2f(st[nt][e] * scale_log2 + bb * LOG2E - lse_s[ql]);
+          }
+          st[nt][e] = p;                                   // P^T
+          const float ds = p * (dpt[nt][e] - dlt_s[ql]);
+          dpt[nt][e] = ds;                                 // dS^T
+          if (key < S && qrow < S) db_s[qrow * DBP + (key - k0)] += ds;  // each (q,key) owned by exactly one thread
+        }
+      }
+      mma_p_t<HDP>(dvacc, st, dOs, lane);  // dV += P^T dO
+      mma_p_t<HDP>(dkacc, dpt, Qs, lane);  // dK += dS^T Q
+    }
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
+      const int key = key_lo + hh * 8;
+      if (key < S) {
+        bf16* dkp = dk + (tok0 + key) * ld_dk + (long long)h * hd;
+        bf16* dvp = dv + (tok0 + key) * ld_dv + (long long)h * hd;
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+          const int c = nt * 8 + (lane & 3) * 2;
+          if (c < hd) {
+            *reinterpret_cast<uint32_t*>(dkp + c) = pack_bf16x2(dkacc[nt][2 * hh] * scale, dkacc[nt][2 * hh + 1] * scale);
+            *reinterpret_cast<uint32_t*>(dvp + c) = pack_bf16x2(dvacc[nt][2 * hh], dvacc[nt][2 * hh + 1]);
+          }
+        }
+      }
+    }
+  }
+  __syncthreads();
+  bf16* db_b = dbias + (long long)b * S * S;
+  const int nk = min(TILE, S - k0);
+  for (int i = threadIdx.x; i < S * TILE; i += ATT_THREADS) {
+    const int qrow = i / TILE, kk = i - qrow * TILE;
+    if (kk < nk) db_b[(long long)qrow * S + k0 + kk] = __float2bfloat16(db_s[qrow * DBP + kk]);
+  }
+}
+
+template <int HDP> size_t fwd_smem() { return (size_t)3 * TILE * (HDP + 8) * sizeof(bf16); }
+template <int HDP> size_t dq_smem() { return (size_t)4 * TILE * (HDP + 8) * sizeof(bf16); }
+template <int HDP> size_t dkv_smem(int s_pad) {
+  return (size_t)4 * TILE * (HDP + 8) * sizeof(bf16) + 2 * TILE * sizeof(float) + (size_t)s_pad * (TILE + 1) * sizeof(float);
+}
+
+template <typename K>
+int ensure_smem(K kernel, size_t smem, const char* name) {
+  if (smem <= 48 * 1024) return CALM_OK;
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) { calm_set_error("%s: smem %zu: %s", name, smem, cudaGetErrorString(e)); return CALM_ERR_CUDA; }
+  return CALM_OK;
+}
+
+template <int HDP>
+int launch_fwd(const void* q, const void* k, const void* v, const void* bias, void* o, float* lse, int64_t ld_q, int64_t ld_k,
+               int64_t ld_v, int64_t ld_o, int B, int S, int heads, int hd, cudaStream_t stream) {
+  const size_t smem = fwd_smem<HDP>();
+  int rc = ensure_smem(attn_fwd_kernel<HDP>, smem, "calm_attention_fwd");
+  if (rc) return rc;
+  const float scale = 1.0f / sqrtf((float)hd);
+  dim3 grid((S + TILE - 1) / TILE, heads, B);
+  attn_fwd_kernel<HDP><<<grid, ATT_THREADS, smem, stream>>>(
+      reinterpret_cast<const bf16*>(q), reinterpret_cast<const bf16*>(k), reinterpret_cast<const bf16*>(v),
+      reinterpret_cast<const bf16*>(bias), reinterpret_cast<bf16*>(o), lse, ld_q, ld_k, ld_v, ld_o, S, heads, hd, scale * LOG2E);
+  CALM_CHECK_LAUNCH("calm_attention_fwd");
+  return CALM_OK;
+}
+
+template <int HDP>
+int launch_bwd(const void* q, const void* k, const void* v, const void* bias, const void* d_o, const float* lse, const float* delta,
+               void* dq, void* dk, void* dv, void* dbias, int64_t ld_q, int64_t ld_k, int64_t ld_v, int64_t ld_do, int64_t ld_dq,
+               int64_t ld_dk, int64_t ld_dv, int B, int S, int heads, int hd, cudaStream_t stream) {
+  const float scale = 1.0f / sqrtf((float)hd);
+  {
+    const size_t smem = dq_smem<HDP>();
+    int rc = ensure_smem(attn_bwd_dq_kernel<HDP>, smem, "calm_attention_bwd(dq)");
+    if (rc) return rc;
+    dim3 grid((S + TILE - 1) / TILE, heads, B);
+    attn_bwd_dq_kernel<HDP><<<grid, ATT_THREADS, smem, stream>>>(
+        reinterpret_cast<const bf16*>(q), reinterpret_cast<const bf16*>(k), reinterpret_cast<const bf16*>(v),
+        reinterpret_cast<const bf16*>(bias), reinterpret_cast<const bf16*>(d_o), lse, delta, reinterpret_cast<bf16*>(dq), ld_q, ld_k,
+        ld_v, ld_do, ld_dq, S, heads, hd, scale, scale * LOG2E);
+    CALM_CHECK_LAUNCH("calm_attention_bwd(dq)");
+  }
+  {
+    const int s_pad = ((S + TILE - 1) / TILE) * TILE;
+    const size_t smem = dkv_smem<HDP>(s_pad);
+    if (smem > 227 * 1024) { calm_set_error("calm_attention_bwd: S=%d hd=%d needs %zu B smem", S, hd, smem); return CALM_ERR_UNSUPPORTED; }
+    int rc = ensure_smem(attn_bwd_dkv_kernel<HDP>, smem, "calm_attention_bwd(dkv)");
+    if (rc) return rc;
+    dim3 grid((S + TILE - 1) / TILE, B);
+    attn_bwd_dkv_kernel<HDP><<<grid, ATT_THREADS, smem, stream>>>(
+        reinterpret_cast<const bf16*>(q), reinterpret_cast<const bf16*>(k), reinterpret_cast<const bf16*>(v),
+        reinterpret_cast<const bf16*>(bias), reinterpret_cast<const bf16*>(d_o), lse, delta, reinterpret_cast<bf16*>(dk),
+        reinterpret_cast<bf16*>(dv), reinterpret_cast<bf16*>(dbias), ld_q, ld_k, ld_v, ld_do, ld_dk, ld_dv, S, heads, hd, scale,
+        scale * LOG2E, s_pad);
+    CALM_CHECK_LAUNCH("calm_attention_bwd(dkv)");
+  }
+  return CALM_OK;
+}
+
+int check_common(const char* name, int B, int S, int heads, int hd) {
+  CALM_CHECK_ARG(B > 0 && S > 0 && heads > 0 && hd > 0, "%s: empty problem", name);
+  CALM_CHECK_ARG(hd % 2 == 0 && hd <= 128, "%s: head_dim=%d must be even and <= 128", name, hd);
+  CALM_CHECK_ARG(S % 2 == 0, "%s: S=%d must be even", name, S);
+  return CALM_OK;
+}
+
+}  // namespace
+
+#define DISPATCH_HDP(hd, CALL)                         \
+  do {                                                 \
+    if ((hd) <= 16) { constexpr int HDP = 16; CALL; }  \
+    else if ((hd) <= 32) { constexpr int HDP = 32; CALL; }  \
+    else if ((hd) <= 48) { constexpr int HDP = 48; CALL; }  \
+    else if ((hd) <= 64) { constexpr int HDP = 64; CALL; }  \
+    else if ((hd) <= 96) { constexpr int HDP = 96; CALL; }  \
+    else { constexpr int HDP = 128; CALL; }            \
+  } while (0)
+
+extern "C" int32_t calm_attention_fwd(const void* q, const void* k, const void* v, const void* bias, void* o, float* lse,
+                                      int64_t ld_q, int64_t ld_k, int64_t ld_v, int64_t ld_o, int32_t B, int32_t S,
+                                      int32_t heads, int32_t hd, cudaStream_t stream) {
+  int rc = check_common("calm_attention_fwd", B, S, heads, hd);
+  if (rc) return rc;
+  CALM_CHECK_ARG(ld_q % 2 == 0 && ld_k % 2 == 0 && ld_v % 2 == 0 && ld_o % 2 == 0, "calm_attention_fwd: leading dims must be even");
+  DISPATCH_HDP(hd, return launch_fwd<HDP>(q, k, v, bias, o, lse, ld_q, ld_k, ld_v, ld_o, B, S, heads, hd, stream));
+  return CALM_OK;
+}
+
+extern "C" int32_t calm_attention_bwd(const void* q, const void* k, const void* v, const void* bias, const void* o, const void* d_o,
+                                      const float* lse, float* delta, void* dq, void* dk, void* dv, void* dbias, int64_t ld_q,
+                                      int64_t ld_k, int64_t ld_v, int64_t ld_o, int64_t ld_do, int64_t ld_dq, int64_t ld_dk,
+                                      int64_t ld_dv, int32_t B, int32_t S, int32_t heads, int32_t hd, cudaStream_t stream) {
+  int rc = check_common("calm_attention_bwd", B, S, heads, hd);
+  if (rc) return rc;
+  CALM_CHECK_ARG(ld_q % 2 == 0 && ld_k % 2 == 0 && ld_v % 2 == 0 && ld_o % 2 == 0 && ld_do % 2 == 0 && ld_dq % 2 == 0 &&
+                 ld_dk % 2 == 0 && ld_dv % 2 == 0, "calm_attention_bwd: leading dims must be even");
+  const long long tokens = (long long)B * S;
+  const long long warps = tokens * heads;
+  attn_delta_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, stream>>>(
+      reinterpret_cast<const bf16*>(o), reinterpret_cast<const bf16*>(d_o), delta, ld_o, ld_do, tokens, S, heads, hd);
+  CALM_CHECK_LAUNCH("calm_attention_bwd(delta)");
+  DISPATCH_HDP(hd, return launch_bwd<HDP>(q, k, v, bias, d_o, lse, delta, dq, dk, dv, dbias, ld_q, ld_k, ld_v, ld_do, ld_dq, ld_dk,
+                                          ld_dv, B, S, heads, hd, stream));
+  return CALM_OK;
+}

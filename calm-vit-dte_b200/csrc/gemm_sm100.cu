@@ -1,0 +1,582 @@
+// calm_gemm: bf16 x bf16 -> fp32-accumulate GEMM family for the CALM-ViT hot path on sm_100a.
+//
+//   C[b] (M x N) = epilogue( alpha * A[b] (M x K) . B[b]^T (N x K) )
+//
+// One persistent, warp-specialised kernel:  TMA (cp.async.bulk.tensor, 128B swizzle) -> 4-stage smem ring
+// -> tcgen05.mma (cta_group::1, M=128, runtime N<=256, K=16 per instruction) -> double-buffered TMEM
+// accumulators -> tcgen05.ld epilogue (bias / addend / GELU / dGELU / bf16|fp32 store).
+// Both operands may be K-major (row = m|n, K contiguous) or MN-major (row = k, m|n contiguous), which covers
+// every contraction of the path without materialising a transpose:
+//   Linear fwd            X(M,K) . W(N,K)^T                       A:K  B:K      (Vi_Tools_CNN_less_V2.py:265-267,300,312)
+//   Linear dgrad          dY(M,N) . Wt(K,N)^T                     A:K  B:K
+//   Linear wgrad          dY^T . X  (contraction over tokens)     A:MN B:MN  + split-K partials
+//   mask logits           Q_b(S,D) . K_b(S,D)^T   batched         A:K  B:K      (:288-290)
+//   mask logits bwd       dL_b . K_b ,  dL_b^T . Q_b              A:K|MN B:MN
+//   seq-axis Linear       W(S2,S1) . X_b(S1,D)    batched         A:K(bcast) B:MN   (:224-229,250-264,304-306)
+//   seq-axis wgrad        sum_b dY_b(S2,D) . X_b(S1,D)^T          A:K  B:K   reduce over batch
+#include "common.cuh"
+#include <cuda.h>
+#include <stdlib.h>
+#include <string.h>
+#include "../../include/calm_b200.h"
+
+namespace {
+
+constexpr int BM = 128;        // rows per CTA tile == UMMA M
+constexpr int BK = 64;         // K elements per pipeline stage (one 128B swizzle row of bf16)
+constexpr int BN_MAX = 256;    // max UMMA N
+constexpr int STAGES = 4;
+constexpr int A_STAGE_BYTES = BM * BK * 2;       // 16 KB
+constexpr int B_STAGE_BYTES = BN_MAX * BK * 2;   // 32 KB
+constexpr int SMEM_BYTES = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int NUM_THREADS = 256;  // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warp3 idle, warps4-7 epilogue
+constexpr int TMEM_COLS = 512;
+
+struct GemmParams {
+  int M, N, K, batch;
+  int BN, tiles_m, tiles_n, kblocks;
+  int reduce_batch, splits, kb_per_split, total_kb;
+  int total_tiles;
+  int a_bcast, b_bcast;
+  long long stride_split;
+  void* c; int c_f32; long long ldc, stride_c;
+  const float* bias;
+  const void* addend; int addend_f32; long long ld_add, stride_add;
+  void* aux; long long ld_aux, stride_aux;
+  int epi;
+  float alpha;
+  int* err_flag;
+};
+
+// ---------------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug becomes a trap (visible CUDA error) instead of a hung GPU box.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* err_flag, int code) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > (1LL << 32)) {  // ~2 s at 2 GHz
+      if (err_flag) atomicExch(err_flag, code);
+      __threadfence_system();
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// Shared-memory matrix descriptor for tcgen05.mma, 128B swizzle (layout_type 2), descriptor version 1.
+//   K-major : rows of 128 B (64 bf16 along K), 8-row groups 1024 B apart (SBO); LBO unused.
+//   MN-major: k-rows of 128 B (64 bf16 along M|N), 8-k groups 1024 B apart (SBO), next 64-wide M|N slab LBO bytes on.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;  // version = 1 (Blackwell)
+  d |= (uint64_t)2 << 61;  // SWIZZLE_128B
+  return d;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Epilogue math on one 16-column chunk owned by one thread (one output row)
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void epilogue_chunk16(const GemmParams& p, float* v, long long row, int col0, int b) {
+  // row: row index within the batch element's matrix; col0: first column (multiple of 16); cols < N valid in groups of 8
+  const int nvalid = min(16, p.N - col0);  // N is a multiple of 8 -> nvalid in {8,16}
+#pragma unroll
+  for (int j = 0; j < 16; ++j) v[j] *= p.alpha;
+  if (p.bias) {
+#pragma unroll
+    for (int j = 0; j < 16; j += 4) {
+      if (j < nvalid) {
+        const float4 bb = *reinterpret_cast<const float4*>(p.bias + col0 + j);
+        v[j] += bb.x; v[j + 1] += bb.y; v[j + 2] += bb.z; v[j + 3] += bb.w;
+      }
+    }
+  }
+  if (p.addend) {
+    if (p.addend_f32) {
+      const float* ap = reinterpret_cast<const float*>(p.addend) + (long long)b * p.stride_add + row * p.ld_add + col0;
+#pragma unroll
+      for (int j = 0; j < 16; j += 4) {
+        if (j < nvalid) {
+          const float4 a = *reinterpret_cast<const float4*>(ap + j);
+          v[j] += a.x; v[j + 1] += a.y; v[j + 2] += a.z; v[j + 3] += a.w;
+        }
+      }
+    } else {
+      const bf16* ap = reinterpret_cast<const bf16*>(p.addend) + (long long)b * p.stride_add + row * p.ld_add + col0;
+#pragma unroll
+      for (int j = 0; j < 16; j += 8) {
+        if (j < nvalid) {
+          const uint4 a = *reinterpret_cast<const uint4*>(ap + j);
+          float2 f;
+          f = unpack_bf16x2(a.x); v[j] += f.x; v[j + 1] += f.y;
+          f = unpack_bf16x2(a.y); v[j + 2] += f.x; v[j + 3] += f.y;
+          f = unpack_bf16x2(a.z); v[j + 4] += f.x; v[j + 5] += f.y;
+          f = unpack_bf16x2(a.w); v[j + 6] += f.x; v[j + 7] += f.y;
+        }
+      }
+    }
+  }
+  if (p.epi == CALM_EPI_GELU) {
+    bf16* up = reinterpret_cast<bf16*>(p.aux) + (long long)b * p.stride_aux + row * p.ld_aux + col0;
+#pragma unroll
+    for (int j = 0; j < 16; j += 8) {
+      if (j < nvalid) {
+        uint4 u;
+        u.x = pack_bf16x2(v[j], v[j + 1]); u.y = pack_bf16x2(v[j + 2], v[j + 3]);
+        u.z = pack_bf16x2(v[j + 4], v[j + 5]); u.w = pack_bf16x2(v[j + 6], v[j + 7]);
+        *reinterpret_cast<uint4*>(up + j) = u;
+      }
+    }
+    // GELU is applied to the bf16-rounded pre-activation so that backward (which only sees aux) is consistent.
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = gelu_erf(__bfloat162float(__float2bfloat16(v[j])));
+  } else if (p.epi == CALM_EPI_DGELU) {
+    const bf16* up = reinterpret_cast<const bf16*>(p.aux) + (long long)b * p.stride_aux + row * p.ld_aux + col0;
+#pragma unroll
+    for (int j = 0; j < 16; j += 8) {
+      if (j < nvalid) {
+        const uint4 u = *reinterpret_cast<const uint4*>(up + j);
+        float2 f;
+        f = unpack_bf16x2(u.x); v[j] *= dgelu_erf(f.x); v[j + 1] *= dgelu_erf(f.y);
+        f = unpack_bf16x2(u.y); v[j + 2] *= dgelu_erf(f.x); v[j + 3] *= dgelu_erf(f.y);
+        f = unpack_bf16x2(u.z); v[j + 4] *= dgelu_erf(f.x); v[j + 5] *= dgelu_erf(f.y);
+        f = unpack_bf16x2(u.w); v[j + 6] *= dgelu_erf(f.x); v[j + 7] *= dgelu_erf(f.y);
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ void store_chunk16(const GemmParams& p, const float* v, long long row, int col0, int b, int split) {
+  const int nvalid = min(16, p.N - col0);
+  if (p.c_f32) {
+    float* cp = reinterpret_cast<float*>(p.c) + (long long)split * p.stride_split + (long long)b * p.stride_c + row * p.ldc + col0;
+#pragma unroll
+    for (int j = 0; j < 16; j += 4)
+      if (j < nvalid) *reinterpret_cast<float4*>(cp + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+  } else {
+    bf16* cp = reinterpret_cast<bf16*>(p.c) + (long long)b * p.stride_c + row * p.ldc + col0;
+#pragma unroll
+    for (int j = 0; j < 16; j += 8) {
+      if (j < nvalid) {
+        uint4 u;
+        u.x = pack_bf16x2(v[j], v[j + 1]); u.y = pack_bf16x2(v[j + 2], v[j + 3]);
+        u.z = pack_bf16x2(v[j + 4], v[j + 5]); u.w = pack_bf16x2(v[j + 6], v[j + 7]);
+        *reinterpret_cast<uint4*>(cp + j) = u;
+      }
+    }
+  }
+}
+
+struct TileCoord { int m_t, n_t, b, split; };
+__device__ __forceinline__ TileCoord decode_tile(const GemmParams& p, int t) {
+  TileCoord c;
+  c.n_t = t % p.tiles_n; t /= p.tiles_n;
+  c.m_t = t % p.tiles_m; t /= p.tiles_m;
+  if (p.reduce_batch) { c.b = 0; c.split = t; }
+  else { c.b = t % p.batch; c.split = t / p.batch; }
+  return c;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// The tcgen05 kernel
+// ---------------------------------------------------------------------------------------------------------
+template <int A_MN, int B_MN>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + STAGES * A_STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * (A_STAGE_BYTES + B_STAGE_BYTES));
+  // bars[0..S) full, [S..2S) empty, [2S..2S+2) tmem_full, [2S+2..2S+4) tmem_empty
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(smem_u32(&bars[i]), 1);
+      mbar_init(smem_u32(&bars[STAGES + i]), 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(smem_u32(&bars[2 * STAGES + i]), 1);
+      mbar_init(smem_u32(&bars[2 * STAGES + 2 + i]), 4);  // one arrive per epilogue warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int nb_boxes = (p.BN + 63) / 64;
+  const uint32_t b_bytes = B_MN ? (uint32_t)nb_boxes * (BK * 128) : (uint32_t)p.BN * (BK * 2);
+  const uint32_t stage_tx = A_STAGE_BYTES + b_bytes;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+        const TileCoord tc = decode_tile(p, t);
+        const int m0 = tc.m_t * BM, n0 = tc.n_t * p.BN;
+        const int kb_begin = tc.split * p.kb_per_split;
+        const int kb_end = min(kb_begin + p.kb_per_split, p.total_kb);
+        for (int ci = kb_begin; ci < kb_end; ++ci) {
+          int b = tc.b, kb = ci;
+          if (p.reduce_batch) { b = ci / p.kblocks; kb = ci - b * p.kblocks; }
+          const int k0 = kb * BK;
+          const int ba = p.a_bcast ? 0 : b, bb = p.b_bcast ? 0 : b;
+          mbar_wait(smem_u32(&bars[STAGES + stage]), phase ^ 1, p.err_flag, 1);
+          const uint32_t full = smem_u32(&bars[stage]);
+          mbar_expect_tx(full, stage_tx);
+          const uint32_t sa = smem_u32(smem_a + stage * A_STAGE_BYTES);
+          const uint32_t sb = smem_u32(smem_b + stage * B_STAGE_BYTES);
+          if (A_MN) {
+            tma_load_3d(sa, &tmA, full, m0, k0, ba);
+            tma_load_3d(sa + BK * 128, &tmA, full, m0 + 64, k0, ba);
+          } else {
+            tma_load_3d(sa, &tmA, full, k0, m0, ba);
+          }
+          if (B_MN) {
+            for (int i = 0; i < nb_boxes; ++i) tma_load_3d(sb + i * (BK * 128), &tmB, full, n0 + 64 * i, k0, bb);
+          } else {
+            tma_load_3d(sb, &tmB, full, k0, n0, bb);
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)A_MN << 15) | ((uint32_t)B_MN << 16) |
+                             ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+        const TileCoord tc = decode_tile(p, t);
+        const int kb_begin = tc.split * p.kb_per_split;
+        const int kb_end = min(kb_begin + p.kb_per_split, p.total_kb);
+        mbar_wait(smem_u32(&bars[2 * STAGES + 2 + acc]), acc_phase ^ 1, p.err_flag, 2);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)acc * BN_MAX;
+        for (int ci = kb_begin; ci < kb_end; ++ci) {
+          mbar_wait(smem_u32(&bars[stage]), phase, p.err_flag, 3);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem_a + stage * A_STAGE_BYTES);
+          const uint32_t sb = smem_u32(smem_b + stage * B_STAGE_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t adesc = A_MN ? make_smem_desc(sa + k * 2048, BK * 128, 1024) : make_smem_desc(sa + k * 32, 16, 1024);
+            const uint64_t bdesc = B_MN ? make_smem_desc(sb + k * 2048, BK * 128, 1024) : make_smem_desc(sb + k * 32, 16, 1024);
+            tc_mma_bf16(tmem_d, adesc, bdesc, idesc, (ci > kb_begin || k > 0) ? 1u : 0u);
+          }
+          tc_commit(smem_u32(&bars[STAGES + stage]));  // frees this smem stage when the MMAs above retire
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        tc_commit(smem_u32(&bars[2 * STAGES + acc]));  // accumulator ready for the epilogue
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue (TMEM -> registers -> global) =====================
+    const int q = warp & 3;  // TMEM lane quadrant this warp may access
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+      const TileCoord tc = decode_tile(p, t);
+      const int m0 = tc.m_t * BM, n0 = tc.n_t * p.BN;
+      mbar_wait(smem_u32(&bars[2 * STAGES + acc]), acc_phase, p.err_flag, 4);
+      tc_fence_after();
+      const long long row = m0 + q * 32 + lane;
+      const bool row_ok = row < p.M;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * BN_MAX;
+      const int ncols = min(p.BN, p.N - n0);
+      for (int c = 0; c < ncols; c += 16) {
+        uint32_t r[16];
+        tmem_ld16(taddr + c, r);
+        tmem_ld_wait();
+        if (row_ok) {
+          float v[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+          epilogue_chunk16(p, v, row, n0 + c, tc.b);
+          store_chunk16(p, v, row, n0 + c, tc.b, tc.split);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&bars[2 * STAGES + 2 + acc]));
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Bring-up / debug path: plain CUDA-core tiled GEMM with the same argument semantics. Never used unless
+// calm_set_debug_flags(CALM_DEBUG_SIMT_GEMM) was called (kernel bring-up on a new driver / bisecting a fault).
+// ---------------------------------------------------------------------------------------------------------
+__global__ void gemm_simt_debug_kernel(const bf16* A, const bf16* B, GemmParams p, long long lda, long long ldb,
+                                       long long stride_a, long long stride_b, int a_mn, int b_mn) {
+  __shared__ float As[16][17], Bs[16][17];
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int bz = blockIdx.z;
+  const int split = p.reduce_batch ? bz : bz / p.batch;
+  const int bidx = p.reduce_batch ? 0 : bz % p.batch;
+  const int m = blockIdx.y * 16 + ty, n = blockIdx.x * 16 + tx;
+  const int kb_begin = split * p.kb_per_split, kb_end = min(kb_begin + p.kb_per_split, p.total_kb);
+  float acc = 0.f;
+  for (int ci = kb_begin; ci < kb_end; ++ci) {
+    int b = bidx, kb = ci;
+    if (p.reduce_batch) { b = ci / p.kblocks; kb = ci - b * p.kblocks; }
+    const bf16* Ab = A + (p.a_bcast ? 0 : (long long)b * stride_a);
+    const bf16* Bb = B + (p.b_bcast ? 0 : (long long)b * stride_b);
+    for (int k0 = kb * BK; k0 < min((kb + 1) * BK, p.K); k0 += 16) {
+      const int ka = k0 + tx, kbb = k0 + ty;
+      As[ty][tx] = (m < p.M && ka < p.K) ? __bfloat162float(a_mn ? Ab[(long long)ka * lda + m] : Ab[(long long)m * lda + ka]) : 0.f;
+      const int nn = blockIdx.x * 16 + tx;
+      Bs[ty][tx] = (nn < p.N && kbb < p.K) ? __bfloat162float(b_mn ? Bb[(long long)kbb * ldb + nn] : Bb[(long long)nn * ldb + kbb]) : 0.f;
+      __syncthreads();
+#pragma unroll
+      for (int kk = 0; kk < 16; ++kk) acc += As[ty][kk] * Bs[kk][tx];
+      __syncthreads();
+    }
+  }
+  if (m >= p.M || n >= p.N) return;
+  float v = acc * p.alpha;
+  if (p.bias) v += p.bias[n];
+  if (p.addend) {
+    const long long off = (long long)bidx * p.stride_add + (long long)m * p.ld_add + n;
+    v += p.addend_f32 ? reinterpret_cast<const float*>(p.addend)[off] : __bfloat162float(reinterpret_cast<const bf16*>(p.addend)[off]);
+  }
+  if (p.epi == CALM_EPI_GELU) {
+    bf16 u = __float2bfloat16(v);
+    reinterpret_cast<bf16*>(p.aux)[(long long)bidx * p.stride_aux + (long long)m * p.ld_aux + n] = u;
+    v = gelu_erf(__bfloat162float(u));
+  } else if (p.epi == CALM_EPI_DGELU) {
+    v *= dgelu_erf(__bfloat162float(reinterpret_cast<const bf16*>(p.aux)[(long long)bidx * p.stride_aux + (long long)m * p.ld_aux + n]));
+  }
+  if (p.c_f32)
+    reinterpret_cast<float*>(p.c)[(long long)split * p.stride_split + (long long)bidx * p.stride_c + (long long)m * p.ldc + n] = v;
+  else
+    reinterpret_cast<bf16*>(p.c)[(long long)bidx * p.stride_c + (long long)m * p.ldc + n] = __float2bfloat16(v);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Host side
+// ---------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// 3-D bf16 tensor map {inner, outer, batch} with a {64, box_outer, 1} box and 128B swizzle.
+int make_map(CUtensorMap* map, const void* base, uint64_t inner, uint64_t outer, uint64_t nbatch, uint64_t ld_elems,
+             uint64_t batch_stride_elems, uint32_t box_outer) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) { calm_set_error("cuTensorMapEncodeTiled entry point not found"); return CALM_ERR_CUDA; }
+  cuuint64_t dims[3] = {inner, outer, nbatch};
+  if (batch_stride_elems == 0 || nbatch == 1) batch_stride_elems = outer * ld_elems;
+  cuuint64_t strides[2] = {ld_elems * 2, batch_stride_elems * 2};
+  cuuint32_t box[3] = {64, box_outer, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    calm_set_error("cuTensorMapEncodeTiled failed (%d): base=%p inner=%llu outer=%llu batch=%llu ld=%llu bstride=%llu box=%u",
+                   (int)r, base, (unsigned long long)inner, (unsigned long long)outer, (unsigned long long)nbatch,
+                   (unsigned long long)ld_elems, (unsigned long long)batch_stride_elems, box_outer);
+    return CALM_ERR_CUDA;
+  }
+  return CALM_OK;
+}
+
+int g_debug_flags = 0;
+int* g_err_flag = nullptr;  // device int written by a trapping kernel (which barrier timed out)
+
+template <int A_MN, int B_MN>
+int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel<A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (e != cudaSuccess) { calm_set_error("gemm: cannot raise dynamic smem: %s", cudaGetErrorString(e)); return CALM_ERR_CUDA; }
+    attr_set = true;
+  }
+  const int grid = p.total_tiles < calm_num_sms() ? p.total_tiles : calm_num_sms();
+  gemm_tcgen05_kernel<A_MN, B_MN><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(ma, mb, p);
+  CALM_CHECK_LAUNCH("calm_gemm(tcgen05)");
+  return CALM_OK;
+}
+
+}  // namespace
+
+extern "C" void calm_set_debug_flags(int32_t flags) { g_debug_flags = flags; }
+extern "C" int32_t calm_get_debug_flags(void) { return g_debug_flags; }
+
+extern "C" int32_t calm_gemm_default_splits(int32_t M, int32_t N, int32_t K, int32_t batch, int32_t reduce_batch) {
+  // Split the contraction so that a small-output GEMM (wgrad) still fills the 148 SMs.
+  const int ntn = (N + BN_MAX - 1) / BN_MAX;
+  int bn = ((N + ntn - 1) / ntn + 15) / 16 * 16;
+  const int tiles = ((M + BM - 1) / BM) * ((N + bn - 1) / bn) * (reduce_batch ? 1 : batch);
+  const int total_kb = ((K + BK - 1) / BK) * (reduce_batch ? batch : 1);
+  int splits = calm_num_sms() / (tiles > 0 ? tiles : 1);
+  if (splits < 1) splits = 1;
+  const int max_by_k = total_kb / 8 > 0 ? total_kb / 8 : 1;  // keep >= 8 k-blocks per split
+  if (splits > max_by_k) splits = max_by_k;
+  if (splits > 32) splits = 32;
+  const int per = (total_kb + splits - 1) / splits;
+  return (total_kb + per - 1) / per;
+}
+
+extern "C" int32_t calm_gemm(const calm_gemm_args* a, cudaStream_t stream) {
+  CALM_CHECK_ARG(a != nullptr, "calm_gemm: null args");
+  CALM_CHECK_ARG(a->M > 0 && a->N > 0 && a->K > 0 && a->batch > 0, "calm_gemm: empty problem M=%d N=%d K=%d batch=%d", a->M, a->N, a->K, a->batch);
+  CALM_CHECK_ARG(a->N % 8 == 0, "calm_gemm: N=%d must be a multiple of 8", a->N);
+  CALM_CHECK_ARG(a->lda % 8 == 0 && a->ldb % 8 == 0 && a->stride_a % 8 == 0 && a->stride_b % 8 == 0,
+                 "calm_gemm: lda/ldb/batch strides must be multiples of 8 elements (TMA 16-byte rule): lda=%lld ldb=%lld", (long long)a->lda, (long long)a->ldb);
+  CALM_CHECK_ARG((reinterpret_cast<uintptr_t>(a->a) & 15) == 0 && (reinterpret_cast<uintptr_t>(a->b) & 15) == 0 &&
+                 (reinterpret_cast<uintptr_t>(a->c) & 15) == 0, "calm_gemm: a/b/c must be 16-byte aligned");
+  CALM_CHECK_ARG(a->ldc % 8 == 0 && a->stride_c % 8 == 0, "calm_gemm: ldc/stride_c must be multiples of 8");
+  CALM_CHECK_ARG(a->epilogue >= 0 && a->epilogue <= 2, "calm_gemm: bad epilogue %d", a->epilogue);
+  CALM_CHECK_ARG(a->epilogue == CALM_EPI_NONE || a->aux != nullptr, "calm_gemm: GELU/dGELU epilogue needs aux");
+  const int splits = a->splits > 0 ? a->splits : 1;
+  CALM_CHECK_ARG(splits == 1 || (a->c_dtype == CALM_F32 && a->epilogue == CALM_EPI_NONE && !a->bias && !a->addend),
+                 "calm_gemm: split-K output must be plain fp32 partials");
+  if (a->addend) CALM_CHECK_ARG(a->ld_addend % 8 == 0 && (reinterpret_cast<uintptr_t>(a->addend) & 15) == 0, "calm_gemm: addend alignment");
+  if (a->aux) CALM_CHECK_ARG(a->ld_aux % 8 == 0 && (reinterpret_cast<uintptr_t>(a->aux) & 15) == 0, "calm_gemm: aux alignment");
+  if (a->bias) CALM_CHECK_ARG((reinterpret_cast<uintptr_t>(a->bias) & 15) == 0, "calm_gemm: bias alignment");
+
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.M = a->M; p.N = a->N; p.K = a->K; p.batch = a->batch;
+  const int ntn = (a->N + BN_MAX - 1) / BN_MAX;
+  p.BN = ((a->N + ntn - 1) / ntn + 15) / 16 * 16;
+  p.tiles_m = (a->M + BM - 1) / BM;
+  p.tiles_n = (a->N + p.BN - 1) / p.BN;
+  p.kblocks = (a->K + BK - 1) / BK;
+  p.reduce_batch = a->reduce_batch ? 1 : 0;
+  p.total_kb = p.kblocks * (p.reduce_batch ? a->batch : 1);
+  p.kb_per_split = (p.total_kb + splits - 1) / splits;
+  p.splits = (p.total_kb + p.kb_per_split - 1) / p.kb_per_split;
+  CALM_CHECK_ARG(p.splits == splits, "calm_gemm: splits=%d leaves empty partials (use calm_gemm_default_splits)", splits);
+  p.total_tiles = p.tiles_m * p.tiles_n * p.splits * (p.reduce_batch ? 1 : a->batch);
+  p.a_bcast = (a->stride_a == 0 && a->batch > 1) ? 1 : 0;
+  p.b_bcast = (a->stride_b == 0 && a->batch > 1) ? 1 : 0;
+  p.stride_split = a->stride_split;
+  p.c = a->c; p.c_f32 = a->c_dtype == CALM_F32; p.ldc = a->ldc; p.stride_c = a->stride_c;
+  p.bias = a->bias;
+  p.addend = a->addend; p.addend_f32 = a->addend_dtype == CALM_F32; p.ld_add = a->ld_addend; p.stride_add = a->stride_addend;
+  p.aux = a->aux; p.ld_aux = a->ld_aux; p.stride_aux = a->stride_aux;
+  p.epi = a->epilogue;
+  p.alpha = a->alpha;
+  p.err_flag = g_err_flag;
+
+  if (g_debug_flags & CALM_DEBUG_SIMT_GEMM) {
+    dim3 block(16, 16), grid((a->N + 15) / 16, (a->M + 15) / 16, p.splits * (p.reduce_batch ? 1 : a->batch));
+    gemm_simt_debug_kernel<<<grid, block, 0, stream>>>(reinterpret_cast<const bf16*>(a->a), reinterpret_cast<const bf16*>(a->b), p,
+                                                        a->lda, a->ldb, a->stride_a, a->stride_b, a->a_major, a->b_major);
+    CALM_CHECK_LAUNCH("calm_gemm(simt-debug)");
+    return CALM_OK;
+  }
+
+  CUtensorMap ma, mb;
+  int rc;
+  const uint64_t nba = p.a_bcast ? 1 : a->batch, nbb = p.b_bcast ? 1 : a->batch;
+  if (a->a_major == CALM_MAJOR_K) rc = make_map(&ma, a->a, a->K, a->M, nba, a->lda, a->stride_a, BM);
+  else                            rc = make_map(&ma, a->a, a->M, a->K, nba, a->lda, a->stride_a, BK);
+  if (rc) return rc;
+  if (a->b_major == CALM_MAJOR_K) rc = make_map(&mb, a->b, a->K, a->N, nbb, a->ldb, a->stride_b, p.BN);
+  else                            rc = make_map(&mb, a->b, a->N, a->K, nbb, a->ldb, a->stride_b, BK);
+  if (rc) return rc;
+
+  if (a->a_major == CALM_MAJOR_K && a->b_major == CALM_MAJOR_K) return launch_tc<0, 0>(ma, mb, p, stream);
+  if (a->a_major == CALM_MAJOR_K && a->b_major == CALM_MAJOR_MN) return launch_tc<0, 1>(ma, mb, p, stream);
+  if (a->a_major == CALM_MAJOR_MN && a->b_major == CALM_MAJOR_K) return launch_tc<1, 0>(ma, mb, p, stream);
+  return launch_tc<1, 1>(ma, mb, p, stream);
+}
+
+extern "C" int32_t calm_set_error_flag_buffer(int32_t* device_int) {
+  g_err_flag = device_int;
+  return CALM_OK;
+}

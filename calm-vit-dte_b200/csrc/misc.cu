@@ -1,0 +1,164 @@
+// Small HBM-bound helpers of the CALM-ViT hot path: token re-tokenisation transposes, bias-gradient column sums,
+// skip-connection adds, casts and the classifier's sequence mean.
+#include "common.cuh"
+#include "../../include/calm_b200.h"
+
+namespace {
+
+// out[b, j, i, :] = in[b, i, j, :] on (B, S, S, 3) fp32: the row<->column token swap of Block.forward
+// (Vi_Tools_CNN_less_V2.py:394-395,397-398). 32x32-pixel tiles staged through shared memory, 12 B pixels.
+__global__ void __launch_bounds__(256)
+token_transpose_kernel(const float* __restrict__ in, float* __restrict__ out, int S) {
+  __shared__ float tile[32][32 * 3 + 1];
+  const int b = blockIdx.z, i0 = blockIdx.y * 32, j0 = blockIdx.x * 32;
+  const float* src = in + (long long)b * S * S * 3;
+  float* dst = out + (long long)b * S * S * 3;
+  for (int idx = threadIdx.x; idx < 32 * 96; idx += 256) {
+    const int r = idx / 96, cc = idx - r * 96;
+    const int i = i0 + r, j = j0 + cc / 3;
+    if (i < S && j < S) tile[r][cc] = src[((long long)i * S + j0) * 3 + cc];
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < 32 * 96; idx += 256) {
+    const int r = idx / 96, cc = idx - r * 96;  // output row j0 + r, output pixel column i0 + cc/3
+    const int j = j0 + r, i = i0 + cc / 3;
+    if (i < S && j < S) dst[((long long)j * S + i0) * 3 + cc] = tile[cc / 3][r * 3 + cc % 3];
+  }
+}
+
+// (B,3,S,S) NCHW -> (B,S,S,3) tokens  (x.permute(0,2,3,1).reshape(B,S,3S), Vi_Tools_CNN_less_V2.py:389-391)
+__global__ void nchw_to_tokens_kernel(const float* __restrict__ in, float* __restrict__ out, long long npix_total, long long plane) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // over B*S*S*3 output elements
+  if (i >= npix_total * 3) return;
+  const long long pix = i / 3;
+  const int ch = (int)(i - pix * 3);
+  const long long b = pix / plane, p = pix - b * plane;
+  out[i] = in[(b * 3 + ch) * plane + p];
+}
+
+// per-CTA column sums of a bf16 (rows, N) matrix
+__global__ void __launch_bounds__(256)
+colsum_kernel(const bf16* __restrict__ x, long long ld, float* __restrict__ partial, long long rows, int N) {
+  // thread t owns columns t, t+256, ...; CTAs stride over rows
+  for (int c = threadIdx.x; c < N; c += 256) {
+    float s = 0.f;
+    for (long long r = blockIdx.x; r < rows; r += gridDim.x) s += __bfloat162float(x[r * ld + c]);
+    partial[(size_t)blockIdx.x * N + c] = s;
+  }
+}
+
+__global__ void reduce_cols_kernel(const float* __restrict__ partial, float* __restrict__ out, int nparts, int n) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n) return;
+  float s = 0.f;
+  for (int p = 0; p < nparts; ++p) s += partial[(size_t)p * n + c];
+  out[c] = s;
+}
+
+__global__ void add3_kernel(const float4* __restrict__ a, const float4* __restrict__ b, const float4* __restrict__ c,
+                            float4* __restrict__ out, long long n4) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    float4 v = a[i];
+    const float4 w = b[i];
+    v.x += w.x; v.y += w.y; v.z += w.z; v.w += w.w;
+    if (c) { const float4 u = c[i]; v.x += u.x; v.y += u.y; v.z += u.z; v.w += u.w; }
+    out[i] = v;
+  }
+}
+
+__global__ void cast_bf16_kernel(const float4* __restrict__ in, uint2* __restrict__ out, long long n4) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 v = in[i];
+    uint2 o; o.x = pack_bf16x2(v.x, v.y); o.y = pack_bf16x2(v.z, v.w);
+    out[i] = o;
+  }
+}
+
+// out[b, d] = mean_s x[b, s, d]
+__global__ void seq_mean_fwd_kernel(const float* __restrict__ x, bf16* __restrict__ out, int S, int D) {
+  const int b = blockIdx.y, d = blockIdx.x * blockDim.x + threadIdx.x;
+  if (d >= D) return;
+  const float* p = x + (long long)b * S * D + d;
+  float s = 0.f;
+  for (int i = 0; i < S; ++i) s += p[(long long)i * D];
+  out[(long long)b * D + d] = __float2bfloat16(s / S);
+}
+__global__ void seq_mean_bwd_kernel(const bf16* __restrict__ dout, float* __restrict__ dx, int S, int D) {
+  const int b = blockIdx.z, s = blockIdx.y, d = blockIdx.x * blockDim.x + threadIdx.x;
+  if (d >= D) return;
+  dx[((long long)b * S + s) * D + d] = __bfloat162float(dout[(long long)b * D + d]) / S;
+}
+
+}  // namespace
+
+extern "C" int32_t calm_token_transpose(const float* in, float* out, int32_t B, int32_t S, cudaStream_t stream) {
+  CALM_CHECK_ARG(B > 0 && S > 0 && in != out, "calm_token_transpose: B=%d S=%d (out of place only)", B, S);
+  dim3 grid((S + 31) / 32, (S + 31) / 32, B);
+  token_transpose_kernel<<<grid, 256, 0, stream>>>(in, out, S);
+  CALM_CHECK_LAUNCH("calm_token_transpose");
+  return CALM_OK;
+}
+
+extern "C" int32_t calm_nchw_to_tokens(const float* in, float* out, int32_t B, int32_t S, cudaStream_t stream) {
+  CALM_CHECK_ARG(B > 0 && S > 0, "calm_nchw_to_tokens: B=%d S=%d", B, S);
+  const long long plane = (long long)S * S, npix = plane * B;
+  nchw_to_tokens_kernel<<<(unsigned)((npix * 3 + 255) / 256), 256, 0, stream>>>(in, out, npix, plane);
+  CALM_CHECK_LAUNCH("calm_nchw_to_tokens");
+  return CALM_OK;
+}
+
+extern "C" int32_t calm_colsum_parts(int64_t rows, int32_t N) {
+  (void)N;
+  const long long cap = 2LL * calm_num_sms();
+  return (int32_t)(rows < cap ? rows : cap);
+}
+
+extern "C" int32_t calm_colsum(const void* x, int64_t ld, float* partial, int32_t nparts, float* out, int64_t rows, int32_t N,
+                               cudaStream_t stream) {
+  CALM_CHECK_ARG(rows > 0 && N > 0, "calm_colsum: rows=%lld N=%d", (long long)rows, N);
+  CALM_CHECK_ARG(nparts == calm_colsum_parts(rows, N), "calm_colsum: nparts=%d expected %d", nparts, calm_colsum_parts(rows, N));
+  colsum_kernel<<<nparts, 256, 0, stream>>>(reinterpret_cast<const bf16*>(x), ld, partial, rows, N);
+  CALM_CHECK_LAUNCH("calm_colsum");
+  reduce_cols_kernel<<<(N + 127) / 128, 128, 0, stream>>>(partial, out, nparts, N);
+  CALM_CHECK_LAUNCH("calm_colsum(reduce)");
+  return CALM_OK;
+}
+
+extern "C" int32_t calm_add3(const float* a, const float* b, const float* c, float* out, int64_t n, cudaStream_t stream) {
+  CALM_CHECK_ARG(n > 0 && n % 4 == 0, "calm_add3: n=%lld must be a positive multiple of 4", (long long)n);
+  const long long n4 = n / 4;
+  long long blocks = (n4 + 255) / 256;
+  const long long cap = 16LL * calm_num_sms();
+  if (blocks > cap) blocks = cap;
+  add3_kernel<<<(unsigned)blocks, 256, 0, stream>>>(reinterpret_cast<const float4*>(a), reinterpret_cast<const float4*>(b),
+                                                    reinterpret_cast<const float4*>(c), reinterpret_cast<float4*>(out), n4);
+  CALM_CHECK_LAUNCH("calm_add3");
+  return CALM_OK;
+}
+
+extern "C" int32_t calm_cast_bf16(const float* in, void* out, int64_t n, cudaStream_t stream) {
+  CALM_CHECK_ARG(n > 0 && n % 4 == 0, "calm_cast_bf16: n=%lld must be a positive multiple of 4", (long long)n);
+  const long long n4 = n / 4;
+  long long blocks = (n4 + 255) / 256;
+  const long long cap = 16LL * calm_num_sms();
+  if (blocks > cap) blocks = cap;
+  cast_bf16_kernel<<<(unsigned)blocks, 256, 0, stream>>>(reinterpret_cast<const float4*>(in), reinterpret_cast<uint2*>(out), n4);
+  CALM_CHECK_LAUNCH("calm_cast_bf16");
+  return CALM_OK;
+}
+
+extern "C" int32_t calm_seq_mean_fwd(const float* x, void* out_bf16, int32_t B, int32_t S, int32_t D, cudaStream_t stream) {
+  CALM_CHECK_ARG(B > 0 && S > 0 && D > 0, "calm_seq_mean_fwd: bad dims");
+  dim3 grid((D + 127) / 128, B);
+  seq_mean_fwd_kernel<<<grid, 128, 0, stream>>>(x, reinterpret_cast<bf16*>(out_bf16), S, D);
+  CALM_CHECK_LAUNCH("calm_seq_mean_fwd");
+  return CALM_OK;
+}
+
+extern "C" int32_t calm_seq_mean_bwd(const void* dout_bf16, float* dx, int32_t B, int32_t S, int32_t D, cudaStream_t stream) {
+  CALM_CHECK_ARG(B > 0 && S > 0 && D > 0, "calm_seq_mean_bwd: bad dims");
+  dim3 grid((D + 127) / 128, S, B);
+  seq_mean_bwd_kernel<<<grid, 128, 0, stream>>>(reinterpret_cast<const bf16*>(dout_bf16), dx, S, D);
+  CALM_CHECK_LAUNCH("calm_seq_mean_bwd");
+  return CALM_OK;
+}

@@ -1,0 +1,181 @@
+/* calm_b200 — C ABI of the B200 (sm_100a) kernel library behind the CALM-ViT drop-in modules.
+ *
+ * The reference (focegueda1998/CALM-ViT-DTE) has no FFI of its own: its hot path is stock PyTorch eager ops inside
+ * CALM-ViT/Vi_Tools_CNN_less_V2.py and CALM-ViT/CALM_ViT_V2.py. Each entry point below replaces the aten op(s) that the
+ * cited reference lines dispatch; the Python modules of the same names in calm-vit-dte_b200/ call these through ctypes.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller (torch caching allocator); the library allocates nothing,
+ *     keeps no pointer across calls, never synchronises the device and only enqueues on `stream`;
+ *   - return value 0 = success, <0 = error (calm_last_error() has the text); nothing throws or exits;
+ *   - "bf16" = __nv_bfloat16 bits, "f32" = IEEE float; row-major with the feature axis innermost unless stated.
+ */
+#ifndef CALM_B200_H_
+#define CALM_B200_H_
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#ifndef __CUDA_RUNTIME_H__
+typedef struct CUstream_st* cudaStream_t;
+#endif
+
+#define CALM_ABI_VERSION 1
+
+enum { CALM_BF16 = 0, CALM_F32 = 1 };
+enum { CALM_MAJOR_K = 0, CALM_MAJOR_MN = 1 };
+enum { CALM_EPI_NONE = 0, CALM_EPI_GELU = 1, CALM_EPI_DGELU = 2 };
+enum { CALM_DEBUG_SIMT_GEMM = 1 };
+
+int32_t calm_abi_version(void);
+const char* calm_last_error(void); /* thread-local, valid until the next failing call on this thread */
+void calm_set_debug_flags(int32_t flags);
+int32_t calm_get_debug_flags(void);
+int32_t calm_set_error_flag_buffer(int32_t* device_int); /* optional: receives the id of a timed-out barrier */
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * GEMM  C[b](M,N) = epi(alpha * A[b](M,K) . B[b](N,K)^T + bias[n] + addend[b](m,n))        tcgen05 + TMA + TMEM
+ * replaces: every sn(Linear) forward/backward contraction (Vi_Tools_CNN_less_V2.py:226-231,251-267,276-277,300,
+ * 305-308,312), the mask logits bmm (:288-290) and linear_mask (:189-194,290), plus their autograd backward.
+ *   a_major/b_major: CALM_MAJOR_K  -> element (r,k) at ptr[r*ld + k];  CALM_MAJOR_MN -> element (r,k) at ptr[k*ld + r]
+ *   stride_* = batch strides in elements (0 = operand shared by all batch entries)
+ *   reduce_batch=1: C = sum over b (the contraction runs over batch x K)
+ *   splits>1: fp32 partial sums, partial s at c + s*stride_split (epilogue must be NONE; caller reduces)
+ *   epilogue GELU : aux <- bf16(pre-activation), C <- gelu_erf(aux)      (mlp.0 / linear_mask.0 forward)
+ *   epilogue DGELU: C <- acc * gelu_erf'(aux)                            (their dgrad)
+ * ------------------------------------------------------------------------------------------------------------------ */
+typedef struct {
+  const void* a; const void* b; void* c;
+  int32_t M, N, K, batch;
+  int64_t lda, ldb, ldc;
+  int64_t stride_a, stride_b, stride_c;
+  int32_t a_major, b_major, c_dtype, epilogue;
+  const float* bias;
+  const void* addend; int32_t addend_dtype; int32_t _pad0; int64_t ld_addend, stride_addend;
+  void* aux; int64_t ld_aux, stride_aux;
+  int32_t reduce_batch, splits; int64_t stride_split;
+  float alpha; int32_t _pad1;
+} calm_gemm_args;
+int32_t calm_gemm(const calm_gemm_args* args, cudaStream_t stream);
+int32_t calm_gemm_default_splits(int32_t M, int32_t N, int32_t K, int32_t batch, int32_t reduce_batch);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Spectral norm, batched over a table of layers: replaces torch/nn/utils/spectral_norm.py:92-114 (one power iteration
+ * v<-norm(W^T u), u<-norm(W v), sigma=u^T W v, W/sigma) for every sn(...) layer hit by a forward
+ * (Vi_Tools_CNN_less_V2.py:137-204,380-384; CALM_ViT_V2.py:50-52,62-66) — 3 launches instead of ~12 per layer.
+ * One table row per layer (device array of calm_sn_layer):
+ * ------------------------------------------------------------------------------------------------------------------ */
+typedef struct {
+  const float* w;      /* weight_orig, (rows, cols) row-major fp32 (conv weights flattened to (out, in*kh*kw)) */
+  float* u;            /* weight_u (rows)  - updated in place when training                                    */
+  float* v;            /* weight_v (cols)  - updated in place when training                                    */
+  const float* rowscale; /* optional LayerScale vector folded into the effective weight rows (or NULL)        */
+  void* w_eff;         /* out: bf16 (rows, cols) = rowscale[r] * W/sigma  — or fp32 when eff_f32               */
+  void* w_eff_t;       /* out: bf16 (cols, rows) transposed copy for dgrad (or NULL)                           */
+  float* grad_w;       /* sn_grad: out fp32 (rows, cols) gradient wrt weight_orig                              */
+  float* grad_rowscale;/* sn_grad: out fp32 (rows) gradient wrt rowscale (or NULL)                             */
+  const float* g_eff;  /* sn_grad: in fp32 partial sums of dL/dW_eff: g_splits x (rows, cols), g_split_stride apart */
+  int32_t rows, cols, g_splits, eff_f32;
+  float* tmp;          /* scratch: >= 32 floats                                                                */
+  float* sigma;        /* out: 1 float                                                                         */
+  int64_t g_split_stride; /* elements between split partials of g_eff (>= rows*cols; layers fused into one GEMM share it) */
+  int32_t ld_t;        /* leading dimension of w_eff_t (>= rows; > rows when several layers share one transposed matrix) */
+  int32_t _pad;
+} calm_sn_layer;
+int32_t calm_sn_forward(const calm_sn_layer* table_dev, int32_t n_layers, int32_t max_rows, int32_t max_cols,
+                        int32_t training, float eps, cudaStream_t stream);
+/* dL/dW_orig = rs*G/sigma - (<rs*G, W>/sigma^2) u v^T ; dL/drowscale[r] = sum_c G[r,c] * W[r,c]/sigma   */
+int32_t calm_sn_backward(const calm_sn_layer* table_dev, int32_t n_layers, int32_t max_rows, int32_t max_cols,
+                         cudaStream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Weight-only LayerNorm (eps 1e-6, no bias): ln_q / ln_kv / ln_2 / ln_final (Vi_Tools_CNN_less_V2.py:131-132,197,494)
+ *   fwd: x f32 (rows, D) -> y bf16 (rows, D) [+ y_f32 optional], mean/rstd f32 (rows)
+ *   bwd: dx f32 = LN'(dy) (+ dres), dw partials (nparts, D) to be summed by the caller-visible finalize
+ * ------------------------------------------------------------------------------------------------------------------ */
+int32_t calm_layernorm_fwd(const float* x, const float* w, void* y, int32_t y_dtype, float* mean, float* rstd,
+                           int64_t rows, int32_t D, float eps, cudaStream_t stream);
+int32_t calm_layernorm_bwd(const void* dy, int32_t dy_dtype, const float* x, const float* w, const float* mean,
+                           const float* rstd, const float* dres, float* dx, float* dw_partial, int32_t nparts,
+                           float* dw, int64_t rows, int32_t D, cudaStream_t stream);
+int32_t calm_layernorm_bwd_parts(int64_t rows, int32_t D);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * RoPE with learned inv_freq (Vi_Tools_CNN_less_V2.py:80-95) fused with the per-head content|rope concat (:278-285).
+ *   out[t, h, 0:dc]     = content[t, h, 0:dc]                      (dc = 0 for the non-reduce blocks)
+ *   out[t, h, dc:dc+dr] = rope(ropein[t, h, 0:dr]) at position s = t % S
+ * bwd also returns d inv_freq partials.
+ * ------------------------------------------------------------------------------------------------------------------ */
+int32_t calm_rope_table(const float* inv_freq, float* cos_sin /* (S, dr/2, 2) */, int32_t S, int32_t half, cudaStream_t stream);
+int32_t calm_rope_fwd(const void* content, int64_t ld_content, const void* ropein, int64_t ld_rope, void* out, int64_t ld_out,
+                      const float* cos_sin, int64_t tokens, int32_t S, int32_t heads, int32_t dc, int32_t dr, cudaStream_t stream);
+int32_t calm_rope_bwd_scratch_floats(int32_t S, int32_t dr);
+int32_t calm_rope_bwd(const void* dout, int64_t ld_dout, const void* out, int64_t ld_out, void* dcontent, int64_t ld_dcontent,
+                      void* dropein, int64_t ld_drope, const float* cos_sin, float* dtheta_scratch /* calm_rope_bwd_scratch_floats */,
+                      float* dinv_freq /* (dr/2) */, int64_t tokens, int32_t S, int32_t heads, int32_t dc, int32_t dr,
+                      cudaStream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Axial attention with a learned additive bias shared by all heads:
+ *   O = softmax(Q K^T / sqrt(hd) + bias[b]) V     replaces F.scaled_dot_product_attention (Vi_Tools_CNN_less_V2.py:293-298)
+ * q/k/v/o: bf16, token-major (B*S, heads*hd) views with leading dims ld_* ; bias bf16 (B, S, S); lse f32 (B, heads, S).
+ * bwd: dq/dk/dv bf16 (same layout), dbias bf16 (B,S,S) = sum_h dS_h, delta f32 (B, heads, S) scratch.
+ * ------------------------------------------------------------------------------------------------------------------ */
+int32_t calm_attention_fwd(const void* q, const void* k, const void* v, const void* bias, void* o, float* lse,
+                           int64_t ld_q, int64_t ld_k, int64_t ld_v, int64_t ld_o, int32_t B, int32_t S, int32_t heads,
+                           int32_t hd, cudaStream_t stream);
+int32_t calm_attention_bwd(const void* q, const void* k, const void* v, const void* bias, const void* o, const void* d_o,
+                           const float* lse, float* delta, void* dq, void* dk, void* dv, void* dbias, int64_t ld_q,
+                           int64_t ld_k, int64_t ld_v, int64_t ld_o, int64_t ld_do, int64_t ld_dq, int64_t ld_dk,
+                           int64_t ld_dv, int32_t B, int32_t S, int32_t heads, int32_t hd, cudaStream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Latent bottleneck sampling (Vi_Tools_CNN_less_V2.py:232-244, 23-30): mv = [mu | rho] bf16 (rows, 2M)
+ *   sigma = softplus(rho)+1e-6 ; z = mu + eps*sigma (eps = NULL in eval) ; zsum = zsum_prev + z ; KL partial sums
+ * ------------------------------------------------------------------------------------------------------------------ */
+int32_t calm_latent_fwd(const void* mv, const float* eps, const float* zsum_prev, float* zsum, void* zsum_bf16,
+                        float* kl_partial /* (nblocks) */, int32_t nblocks, int64_t rows, int32_t Mh, cudaStream_t stream);
+int32_t calm_latent_bwd(const void* mv, const float* eps, const float* dz, float kl_scale, const float* dkl /* scalar on device */,
+                        void* dmv /* bf16 (rows, 2M) */, int64_t rows, int32_t Mh, cudaStream_t stream);
+int32_t calm_latent_blocks(int64_t rows, int32_t Mh);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Per-Block CNN residual on the (B, S, S, 3) token image (Vi_Tools_CNN_less_V2.py:378-385,400-403; CALM_ViT_V2.py:60-67,
+ * 80-83): y = x + conv1x1(gelu(dwconv3x3(gelu(conv1x1(x))))) with 32 hidden channels, fused into one stencil kernel.
+ * weights are the fp32 effective (already /sigma) tensors: w1 (32,3) b1 (32) w2 (32,9) b2 (32) w3 (3,32) b3 (3)
+ * ------------------------------------------------------------------------------------------------------------------ */
+int32_t calm_cnn_fwd(const float* x, float* y, const float* w1, const float* b1, const float* w2, const float* b2,
+                     const float* w3, const float* b3, int32_t B, int32_t S, cudaStream_t stream);
+/* grads: dx f32 (B,S,S,3); parameter-gradient partials gp (nblocks, CALM_CNN_NPARAM) then reduced into gparams */
+#define CALM_CNN_NPARAM 547 /* 96 + 32 + 288 + 32 + 96 + 3 */
+int32_t calm_cnn_bwd(const float* x, const float* dy, float* dx, const float* w1, const float* b1, const float* w2,
+                     const float* b2, const float* w3, const float* b3, float* gpartial, int32_t nblocks, float* gparams,
+                     int32_t B, int32_t S, cudaStream_t stream);
+int32_t calm_cnn_bwd_blocks(int32_t B, int32_t S);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Small memory-bound helpers
+ * ------------------------------------------------------------------------------------------------------------------ */
+/* row<->column re-tokenisation (Vi_Tools_CNN_less_V2.py:394-395,397-398): out[b,j,i,:] = in[b,i,j,:] on (B,S,S,3) f32 */
+int32_t calm_token_transpose(const float* in, float* out, int32_t B, int32_t S, cudaStream_t stream);
+/* first-block row tokenisation (:389-391): (B,3,S,S) NCHW f32 -> (B,S,S,3) ; and its inverse */
+int32_t calm_nchw_to_tokens(const float* in, float* out, int32_t B, int32_t S, cudaStream_t stream);
+/* column sums of a bf16 (rows, N) matrix -> f32 (N): linear_mask bias gradients */
+int32_t calm_colsum(const void* x, int64_t ld, float* partial, int32_t nparts, float* out, int64_t rows, int32_t N, cudaStream_t stream);
+int32_t calm_colsum_parts(int64_t rows, int32_t N);
+/* out = a + b (+ c) elementwise f32 (U-Net skip adds, Vi_Tools_CNN_less_V2.py:513,516,520,522) */
+int32_t calm_add3(const float* a, const float* b, const float* c, float* out, int64_t n, cudaStream_t stream);
+/* f32 -> bf16 cast, and bf16 = bf16(a_f32 + b_f32) */
+int32_t calm_cast_bf16(const float* in, void* out, int64_t n, cudaStream_t stream);
+/* mean over the sequence axis: x f32 (B,S,D) -> bf16/f32 (B,D) (CALM_ViT_V2.py:73-75), and its backward */
+int32_t calm_seq_mean_fwd(const float* x, void* out_bf16, int32_t B, int32_t S, int32_t D, cudaStream_t stream);
+int32_t calm_seq_mean_bwd(const void* dout_bf16, float* dx, int32_t B, int32_t S, int32_t D, cudaStream_t stream);
+/* plain GELU(erf) forward on bf16 (head activation, CALM_ViT_V2.py:51) is covered by the GEMM epilogue. */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CALM_B200_H_ */
