@@ -146,11 +146,20 @@ def latent_fwd(mv, eps, zsum_prev):
     return zsum, zb, part
 
 
-def latent_bwd(mv, eps, dz, kl_scale, dkl):
+def latent_kl(part_q, part_kv, kl_prev, scale):
+    out = torch.empty(1, dtype=f32, device=part_q.device)
+    L.call("calm_latent_kl", ptr(part_q), ptr(part_kv), part_q.numel(), ptr(kl_prev), ptr(out), float(scale))
+    return out
+
+
+def latent_bwd(mv, eps, dz, kl_scale, dkl, dz_bf16=None, want_total=False):
+    """Returns (dmv bf16, dz_total f32 | None): dz_total = dz + dz_bf16 is the gradient wrt the previous running sum."""
     rows, two_m = mv.shape[0], mv.shape[1]
     dmv = torch.empty_like(mv)
-    L.call("calm_latent_bwd", ptr(mv), ptr(eps), ptr(dz), float(kl_scale), ptr(dkl), ptr(dmv), rows, two_m // 2)
-    return dmv
+    tot = torch.empty(rows, two_m // 2, dtype=f32, device=mv.device) if want_total else None
+    L.call("calm_latent_bwd", ptr(mv), ptr(eps), ptr(dz), ptr(dz_bf16), float(kl_scale), ptr(dkl), ptr(dmv), ptr(tot), rows,
+           two_m // 2)
+    return dmv, tot
 
 
 # ------------------------------------------------------------------------------------------------ CNN residual
@@ -160,21 +169,22 @@ def cnn_fwd(x, w1, b1, w2, b2, w3, b3, B, S):
     return y
 
 
-def cnn_bwd(x, dy, w1, b1, w2, b2, w3, b3, B, S):
+def cnn_bwd(x, dy, w1, b1, w2, b2, w3, b3, B, S, gp=None):
     """Returns dx f32 and gparams f32 (547): w1[96] b1[32] w2[288] b2[32] w3[96] b3[3]."""
     nblocks = L.load().calm_cnn_bwd_blocks(B, S)
     dx = torch.empty_like(x)
     part = torch.empty(nblocks * L.CNN_NPARAM, dtype=f32, device=x.device)
-    gp = torch.empty(L.CNN_NPARAM, dtype=f32, device=x.device)
+    if gp is None:
+        gp = torch.empty(L.CNN_NPARAM, dtype=f32, device=x.device)
     L.call("calm_cnn_bwd", ptr(x), ptr(dy), ptr(dx), ptr(w1), ptr(b1), ptr(w2), ptr(b2), ptr(w3), ptr(b3), ptr(part), nblocks,
            ptr(gp), B, S)
     return dx, gp
 
 
 # ------------------------------------------------------------------------------------------------ helpers
-def token_transpose(x, B, S):
+def token_transpose(x, B, S, addend=None):
     out = torch.empty_like(x)
-    L.call("calm_token_transpose", ptr(x), ptr(out), B, S)
+    L.call("calm_token_transpose", ptr(x), ptr(addend), ptr(out), B, S)
     return out
 
 
@@ -202,6 +212,12 @@ def add3(a, b, c=None):
 def cast_bf16(x):
     out = torch.empty(x.shape, dtype=bf16, device=x.device)
     L.call("calm_cast_bf16", ptr(x), ptr(out), x.numel())
+    return out
+
+
+def cast_f32(x):
+    out = torch.empty(x.shape, dtype=f32, device=x.device)
+    L.call("calm_cast_f32", ptr(x), ptr(out), x.numel())
     return out
 
 

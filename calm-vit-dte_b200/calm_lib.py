@@ -69,17 +69,19 @@ PROTOTYPES = {
     "calm_attention_fwd": (i32, [vp, vp, vp, vp, vp, vp, i64, i64, i64, i64, i32, i32, i32, i32, vp]),
     "calm_attention_bwd": (i32, [vp] * 12 + [i64] * 8 + [i32] * 4 + [vp]),
     "calm_latent_fwd": (i32, [vp, vp, vp, vp, vp, vp, i32, i64, i32, vp]),
-    "calm_latent_bwd": (i32, [vp, vp, vp, f32, vp, vp, i64, i32, vp]),
+    "calm_latent_kl": (i32, [vp, vp, i32, vp, vp, f32, vp]),
+    "calm_latent_bwd": (i32, [vp, vp, vp, vp, f32, vp, vp, vp, i64, i32, vp]),
     "calm_latent_blocks": (i32, [i64, i32]),
     "calm_cnn_fwd": (i32, [vp] * 8 + [i32, i32, vp]),
     "calm_cnn_bwd": (i32, [vp] * 10 + [i32, vp, i32, i32, vp]),
     "calm_cnn_bwd_blocks": (i32, [i32, i32]),
-    "calm_token_transpose": (i32, [vp, vp, i32, i32, vp]),
+    "calm_token_transpose": (i32, [vp, vp, vp, i32, i32, vp]),
     "calm_nchw_to_tokens": (i32, [vp, vp, i32, i32, vp]),
     "calm_colsum": (i32, [vp, i64, vp, i32, vp, i64, i32, vp]),
     "calm_colsum_parts": (i32, [i64, i32]),
     "calm_add3": (i32, [vp, vp, vp, vp, i64, vp]),
     "calm_cast_bf16": (i32, [vp, vp, i64, vp]),
+    "calm_cast_f32": (i32, [vp, vp, i64, vp]),
     "calm_seq_mean_fwd": (i32, [vp, vp, i32, i32, i32, vp]),
     "calm_seq_mean_bwd": (i32, [vp, vp, i32, i32, i32, vp]),
 }

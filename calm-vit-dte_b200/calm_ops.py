@@ -1,0 +1,639 @@
+"""Autograd layer of the CALM-ViT hot path: torch.autograd.Functions whose forward/backward launch the sm_100a kernels
+of libcalm_b200.so through the C ABI (calm_kernels -> calm_lib -> ctypes). No arithmetic is done by PyTorch here except
+the autograd engine's own gradient accumulation where one tensor has several consumers.
+
+Numerics are those of the trainers' `autocast(bfloat16)` region (distributed_trainer_cls.py:84): bf16 GEMM/attention
+operands with fp32 accumulation, fp32 LayerNorm statistics / residual stream / latent sampling, fp32 master weights.
+
+Spectral norm: all sn(...) layers of one scope (a Block, a stand-alone VMLA_Block, the ViT head) live in an SNBank —
+ONE batched power-iteration launch per forward writes every bf16 effective weight W/sigma (LayerScale folded in), the
+weight-gradient GEMMs deposit split-K fp32 partials of dL/dW_eff into bank-owned buffers, and ONE batched launch pair
+per backward turns them into dL/dW_orig. The bank's autograd node is ordered after all of its
+consumers by a 1-element `token` tensor every consumer takes as an input.
+"""
+import functools
+import threading
+import weakref
+
+import torch
+
+import calm_kernels as K
+import calm_lib as L
+from calm_lib import MAJOR_MN, EPI_NONE, EPI_GELU, EPI_DGELU
+
+bf16, f32 = torch.bfloat16, torch.float32
+Function = torch.autograd.Function
+
+
+@functools.lru_cache(maxsize=None)
+def _splits(M, N, Kd, batch=1, reduce_batch=False):
+    return K.gemm_default_splits(M, N, Kd, batch, reduce_batch)
+
+
+def _is_sn(m):
+    return hasattr(m, "weight_orig") and hasattr(m, "weight_u") and hasattr(m, "weight_v")
+
+
+# =====================================================================================================================
+# Spectral-norm bank
+# =====================================================================================================================
+def _require_cuda(dev):
+    if dev.type != "cuda":
+        raise L.CalmError("calm_b200 modules run on CUDA only (parameters are on %s); there is no CPU fallback" % dev)
+
+
+class GroupSpec:
+    """A set of sn(...) layers with equal fan-in whose effective weights are stacked row-wise into one GEMM operand."""
+
+    def __init__(self, modules, rowscale=None, conv=False):
+        self.modules = list(modules)
+        self.rowscale = rowscale          # LayerScale Parameter folded into the rows (single-layer groups only)
+        self.conv = conv                  # fp32 effective weight for the fused CNN stencil kernel
+        assert rowscale is None or len(self.modules) == 1
+
+
+class SNBank:
+    def __init__(self, specs):
+        assert specs
+        self.specs = specs
+        self.version = 0
+        self.table = None
+        self.dirty = True
+        self.fingerprint = None
+        self.groups = []
+        self.gid_of = {}
+        self._build()
+
+    # ---- construction -------------------------------------------------------------------------------------------
+    def _build(self):
+        dev = self.specs[0].modules[0].weight_orig.device
+        _require_cuda(dev)
+        self.device = dev
+        self.groups, self.gid_of, self.layers = [], {}, []
+        off = 0
+        for gid, sp in enumerate(self.specs):
+            rows = [m.weight_orig.shape[0] for m in sp.modules]
+            cols = sp.modules[0].weight_orig[0].numel()
+            assert all(m.weight_orig[0].numel() == cols for m in sp.modules), "fused layers need equal fan-in"
+            g = dict(gid=gid, rows=sum(rows), cols=cols, conv=sp.conv, splits=1, g_eff=None, layer_ids=[],
+                     w_eff=torch.empty(sum(rows), cols, dtype=f32 if sp.conv else bf16, device=dev))
+            r0 = 0
+            for m, r in zip(sp.modules, rows):
+                g["layer_ids"].append(len(self.layers))
+                self.layers.append(dict(module=m, gid=gid, row_off=r0, rows=r, cols=cols, grad_off=off, rowscale=sp.rowscale))
+                self.gid_of[id(m)] = gid
+                off += r * cols
+                r0 += r
+            self.groups.append(g)
+        self.rs_layers = [l for l in self.layers if l["rowscale"] is not None]
+        for l in self.rs_layers:
+            l["rs_off"] = off
+            off += l["rows"]
+        self.flat_grad = torch.zeros(off, dtype=f32, device=dev)
+        n = len(self.layers)
+        self.sigma = torch.empty(n, dtype=f32, device=dev)
+        self.tmp = torch.empty(n * 32, dtype=f32, device=dev)
+        self.max_rows = max(l["rows"] for l in self.layers)
+        self.max_cols = max(l["cols"] for l in self.layers)
+        self.params = [l["module"].weight_orig for l in self.layers] + [l["rowscale"] for l in self.rs_layers]
+        self.dirty = True
+        self.fingerprint = self._fingerprint()
+
+    def _fingerprint(self):
+        a, b = self.layers[0]["module"], self.layers[-1]["module"]
+        return (a.weight_orig.data_ptr(), a.weight_u.data_ptr(), b.weight_orig.data_ptr(), b.weight_v.data_ptr())
+
+    def _upload(self):
+        ents = []
+        for i, l in enumerate(self.layers):
+            g = self.groups[l["gid"]]
+            m = l["module"]
+            lo = l["row_off"] * l["cols"]
+            e = dict(w=m.weight_orig, u=m.weight_u, v=m.weight_v, rows=l["rows"], cols=l["cols"], eff_f32=g["conv"],
+                     w_eff=g["w_eff"].view(-1)[lo:], grad_w=self.flat_grad[l["grad_off"]:], tmp=self.tmp[i * 32:],
+                     sigma=self.sigma[i:], g_splits=g["splits"], g_split_stride=g["rows"] * g["cols"])
+            if g["g_eff"] is not None:
+                e["g_eff"] = g["g_eff"].view(-1)[lo:]
+            if l["rowscale"] is not None:
+                e["rowscale"] = l["rowscale"]
+                e["grad_rowscale"] = self.flat_grad[l["rs_off"]:]
+            ents.append(e)
+        self.table = K.sn_table(ents, self.device)
+        self.dirty = False
+
+    # ---- per-step API -------------------------------------------------------------------------------------------
+    def gid(self, module):
+        return self.gid_of[id(module)]
+
+    def weight(self, gid):
+        return self.groups[gid]["w_eff"]
+
+    def cnn_grad_buffer(self, g1, g2, g3):
+        """Persistent 547-float parameter-gradient block of one fused CNN; the conv layers' dW_eff are slices of it."""
+        key = ("cnn", g1)
+        buf = self.__dict__.setdefault("_cnn_gp", {}).get(key)
+        if buf is None:
+            buf = torch.empty(L.CNN_NPARAM, dtype=f32, device=self.device)
+            self._cnn_gp[key] = buf
+            for gid, lo in ((g1, 0), (g2, 128), (g3, 448)):
+                g = self.groups[gid]
+                g["g_eff"] = buf[lo: lo + g["rows"] * g["cols"]].view(1, g["rows"], g["cols"])
+                g["splits"] = 1
+            self.dirty = True
+        return buf
+
+    def wgrad_buffer(self, gid, splits):
+        g = self.groups[gid]
+        if g["g_eff"] is None or g["splits"] != splits:
+            g["g_eff"] = torch.empty(splits, g["rows"], g["cols"], dtype=f32, device=self.device)
+            g["splits"] = splits
+            self.dirty = True
+        return g["g_eff"]
+
+    def begin(self, training):
+        """Runs the batched power iteration; returns the autograd token (None when no parameter needs a gradient)."""
+        if self._fingerprint() != self.fingerprint:
+            self._build()                      # parameters were moved (.to()) or replaced
+        if self.dirty:
+            self._upload()
+        self.version += 1
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.params):
+            return _SNBankFn.apply(self, bool(training), *self.params)
+        K.sn_forward(self.table, len(self.layers), self.max_rows, self.max_cols, training)
+        return None
+
+
+class _SNBankFn(Function):
+    @staticmethod
+    def forward(ctx, bank, training, *params):
+        K.sn_forward(bank.table, len(bank.layers), bank.max_rows, bank.max_cols, training)
+        ctx.bank = bank
+        ctx.version = bank.version
+        return torch.zeros(1, dtype=f32, device=bank.device)
+
+    @staticmethod
+    def backward(ctx, _g):
+        bank = ctx.bank
+        _check_version(bank, ctx.version)
+        for g in bank.groups:
+            if g["g_eff"] is None:
+                raise L.CalmError("an sn(...) layer of this scope received no weight gradient (unused in forward?)")
+        if bank.dirty:
+            bank._upload()
+        K.sn_backward(bank.table, len(bank.layers), bank.max_rows, bank.max_cols)
+        flat = bank.flat_grad.clone()          # persistent scratch -> tensors autograd may keep as .grad
+        grads = [flat[l["grad_off"]: l["grad_off"] + l["rows"] * l["cols"]].view_as(l["module"].weight_orig) for l in bank.layers]
+        grads += [flat[l["rs_off"]: l["rs_off"] + l["rows"]] for l in bank.rs_layers]
+        return (None, None, *grads)
+
+
+def _check_version(bank, version):
+    if bank.version != version:
+        raise L.CalmError("a new forward of this module ran before the backward of the previous one; the spectral-norm "
+                          "bank keeps one set of effective weights (run forward -> backward in order)")
+
+
+_banks = weakref.WeakKeyDictionary()   # owner module -> SNBank (kept out of module __dict__: pickle/deepcopy/state_dict safe)
+_tls = threading.local()
+
+
+class Scope:
+    """Context manager giving the sn(...) layers under `owner` their bank for one forward call."""
+
+    def __init__(self, owner, spec_fn, training):
+        self.owner, self.spec_fn, self.training = owner, spec_fn, training
+
+    def __enter__(self):
+        self.prev = getattr(_tls, "scope", None)
+        bank = _banks.get(self.owner)
+        if bank is None:
+            bank = SNBank(self.spec_fn())
+            _banks[self.owner] = bank
+        self.bank = bank
+        self.token = bank.begin(self.training)
+        _tls.scope = self
+        return self
+
+    def __exit__(self, *exc):
+        _tls.scope = self.prev
+        return False
+
+
+def current_scope():
+    return getattr(_tls, "scope", None)
+
+
+# =====================================================================================================================
+# raw GEMM helpers on bank weights (feature-axis Linear: y = x W^T)
+# =====================================================================================================================
+def _as2d(x):
+    """(…, K) tensor with contiguous last dim and uniformly strided rows -> (rows, K) view + row stride."""
+    if x.dim() == 2:
+        assert x.stride(1) == 1
+        return x, x.shape[0], x.stride(0)
+    x = x.contiguous() if not x.is_contiguous() else x
+    x2 = x.view(-1, x.shape[-1])
+    return x2, x2.shape[0], x2.stride(0)
+
+
+def _lin_fwd(bank, gid, x2, M, lda, out, ldc, **kw):
+    g = bank.groups[gid]
+    K.gemm(x2, g["w_eff"], out, M, g["rows"], g["cols"], lda=lda, ldb=g["cols"], ldc=ldc, **kw)
+
+
+def _lin_dgrad(bank, gid, dy2, M, ld_dy, out, ld_out, **kw):
+    """dX(M, cols) = dY(M, rows) . W(rows, cols) — W read MN-major, no transposed copy."""
+    g = bank.groups[gid]
+    K.gemm(dy2, g["w_eff"], out, M, g["cols"], g["rows"], lda=ld_dy, ldb=g["cols"], ldc=ld_out, b_major=MAJOR_MN, **kw)
+
+
+def _lin_wgrad(bank, gid, dy2, ld_dy, x2, ld_x, M):
+    """dW_eff(rows, cols) = dY^T X — contraction over the M tokens, split-K fp32 partials into the bank."""
+    g = bank.groups[gid]
+    s = _splits(g["rows"], g["cols"], M)
+    buf = bank.wgrad_buffer(gid, s)
+    K.gemm(dy2, x2, buf, g["rows"], g["cols"], M, lda=ld_dy, ldb=ld_x, ldc=g["cols"], a_major=MAJOR_MN, b_major=MAJOR_MN,
+           splits=s, stride_split=g["rows"] * g["cols"])
+
+
+def _bf16_grad(g):
+    return g if g.dtype == bf16 else K.cast_bf16(g.contiguous())
+
+
+# =====================================================================================================================
+# Functions
+# =====================================================================================================================
+class LayerNormFn(Function):
+    """y = LN(x)*w in bf16 (or fp32), plus an alias of x so that the residual consumer's gradient is fused into dx."""
+
+    @staticmethod
+    def forward(ctx, x, w, out_f32):
+        x = x.contiguous()
+        y, mean, rstd = K.layernorm_fwd(x, w, 1e-6, f32 if out_f32 else bf16)
+        ctx.save_for_backward(x, w, mean, rstd)
+        ctx.set_materialize_grads(False)
+        return y, x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, dy, dres):
+        x, w, mean, rstd = ctx.saved_tensors
+        if dy is None:
+            return dres, None, None
+        dx, dw = K.layernorm_bwd(dy.contiguous(), x, w, mean, rstd, dres.contiguous() if dres is not None else None)
+        return dx, dw, None
+
+
+class LinearFn(Function):
+    """y = x W_eff^T (+ addend) for one bank group; x bf16 (…, K); out bf16 or fp32."""
+
+    @staticmethod
+    def forward(ctx, x, token, addend, bank, gid, out_f32):
+        g = bank.groups[gid]
+        x2, M, lda = _as2d(x)
+        out = torch.empty(*x.shape[:-1], g["rows"], dtype=f32 if out_f32 else bf16, device=x.device)
+        kw = {}
+        if addend is not None:
+            a2, _, ld_a = _as2d(addend)
+            kw = dict(addend=a2, ld_addend=ld_a)
+        _lin_fwd(bank, gid, x2, M, lda, out, g["rows"], **kw)
+        ctx.save_for_backward(x)
+        ctx.bank, ctx.gid, ctx.version = bank, gid, bank.version
+        ctx.addend_dtype = addend.dtype if addend is not None else None
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x,) = ctx.saved_tensors
+        bank, gid = ctx.bank, ctx.gid
+        _check_version(bank, ctx.version)
+        g = bank.groups[gid]
+        dyb = _bf16_grad(dy)
+        dy2, M, ld_dy = _as2d(dyb)
+        x2, _, ld_x = _as2d(x)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty(x.shape, dtype=bf16, device=x.device)
+            _lin_dgrad(bank, gid, dy2, M, ld_dy, dx, g["cols"])
+        if ctx.needs_input_grad[1]:
+            _lin_wgrad(bank, gid, dy2, ld_dy, x2, ld_x, M)
+        dadd = None
+        if ctx.needs_input_grad[2]:
+            dadd = dy if ctx.addend_dtype == dy.dtype else (dyb if ctx.addend_dtype == bf16 else K.cast_f32(dy))
+        return dx, None, dadd, None, None, None
+
+
+def _mlp_forward(bank, g1, g2, x2, M, lda, b1, b2, addend2, ld_add, out):
+    """hidden = gelu(x W1^T + b1) ; out = hidden W2^T + b2 + addend. Returns (pre, hidden) for backward."""
+    H = bank.groups[g1]["rows"]
+    pre = torch.empty(M, H, dtype=bf16, device=x2.device)
+    hid = torch.empty(M, H, dtype=bf16, device=x2.device)
+    _lin_fwd(bank, g1, x2, M, lda, hid, H, bias=b1, epilogue=EPI_GELU, aux=pre, ld_aux=H)
+    kw = dict(addend=addend2, ld_addend=ld_add) if addend2 is not None else {}
+    _lin_fwd(bank, g2, hid, M, H, out, bank.groups[g2]["rows"], bias=b2, **kw)
+    return pre, hid
+
+
+def _mlp_backward(bank, g1, g2, dy2, M, ld_dy, x2, ld_x, pre, hid, need_dx, need_w, need_bias):
+    """Returns (dx bf16 | None, db1, db2)."""
+    H, N2, K1 = bank.groups[g1]["rows"], bank.groups[g2]["rows"], bank.groups[g1]["cols"]
+    dpre = torch.empty(M, H, dtype=bf16, device=dy2.device)
+    _lin_dgrad(bank, g2, dy2, M, ld_dy, dpre, H, epilogue=EPI_DGELU, aux=pre, ld_aux=H)
+    db1 = db2 = None
+    if need_w:
+        _lin_wgrad(bank, g2, dy2, ld_dy, hid, H, M)
+        _lin_wgrad(bank, g1, dpre, H, x2, ld_x, M)
+    if need_bias:
+        db2 = K.colsum(dy2, M, N2, ld_dy)
+        db1 = K.colsum(dpre, M, H, H)
+    dx = None
+    if need_dx:
+        dx = torch.empty(M, K1, dtype=bf16, device=dy2.device)
+        _lin_dgrad(bank, g1, dpre, M, H, dx, K1)
+    return dx, db1, db2
+
+
+class MlpFn(Function):
+    """Two sn(Linear)s with an exact GELU between them (mlp: Vi_Tools…:199-205,311-314; cls head: CALM_ViT_V2.py:49-53)."""
+
+    @staticmethod
+    def forward(ctx, x, token, addend, bank, g1, g2, out_f32):
+        x2, M, lda = _as2d(x)
+        N2 = bank.groups[g2]["rows"]
+        out = torch.empty(*x.shape[:-1], N2, dtype=f32 if out_f32 else bf16, device=x.device)
+        a2 = ld_a = None
+        if addend is not None:
+            a2, _, ld_a = _as2d(addend)
+        pre, hid = _mlp_forward(bank, g1, g2, x2, M, lda, None, None, a2, ld_a or 0, out)
+        ctx.save_for_backward(x)
+        ctx.pre, ctx.hid = pre, hid
+        ctx.bank, ctx.g1, ctx.g2, ctx.version = bank, g1, g2, bank.version
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x,) = ctx.saved_tensors
+        bank = ctx.bank
+        _check_version(bank, ctx.version)
+        dyb = _bf16_grad(dy)
+        dy2, M, ld_dy = _as2d(dyb)
+        x2, _, ld_x = _as2d(x)
+        dx, _, _ = _mlp_backward(bank, ctx.g1, ctx.g2, dy2, M, ld_dy, x2, ld_x, ctx.pre, ctx.hid, ctx.needs_input_grad[0],
+                                 ctx.needs_input_grad[1], False)
+        ctx.pre = ctx.hid = None
+        return (dx.view(x.shape) if dx is not None else None), None, (dy if ctx.needs_input_grad[2] else None), None, None, None, None
+
+
+class SeqLinearFn(Function):
+    """sn(Linear)s applied along the SEQUENCE axis of x (B, S1, D): Y_i[b] = W_i (S2_i x S1) . X[b] — batched left-multiply
+    GEMMs, no permute copies (Vi_Tools…:224-229,250-264,304-306). Several layers may share the input (one dX)."""
+
+    @staticmethod
+    def forward(ctx, x, token, bank, *gids):
+        x = x.contiguous()
+        B, S1, D = x.shape
+        outs = []
+        for gid in gids:
+            g = bank.groups[gid]
+            assert g["cols"] == S1
+            y = torch.empty(B, g["rows"], D, dtype=bf16, device=x.device)
+            K.gemm(g["w_eff"], x, y, g["rows"], D, S1, batch=B, lda=S1, ldb=D, ldc=D, stride_a=0, stride_b=S1 * D,
+                   stride_c=g["rows"] * D, b_major=MAJOR_MN)
+            outs.append(y)
+        ctx.save_for_backward(x)
+        ctx.bank, ctx.gids, ctx.version = bank, gids, bank.version
+        ctx.set_materialize_grads(False)
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, *dys):
+        (x,) = ctx.saved_tensors
+        bank = ctx.bank
+        _check_version(bank, ctx.version)
+        B, S1, D = x.shape
+        dx = None
+        for gid, dy in zip(ctx.gids, dys):
+            g = bank.groups[gid]
+            S2 = g["rows"]
+            if dy is None:
+                dy = torch.zeros(B, S2, D, dtype=bf16, device=x.device)
+            dy = _bf16_grad(dy).contiguous()
+            if ctx.needs_input_grad[0]:
+                nx = torch.empty(B, S1, D, dtype=bf16, device=x.device)
+                kw = dict(addend=dx, ld_addend=D, stride_addend=S1 * D) if dx is not None else {}
+                K.gemm(g["w_eff"], dy, nx, S1, D, S2, batch=B, lda=S1, ldb=D, ldc=D, stride_a=0, stride_b=S2 * D,
+                       stride_c=S1 * D, a_major=MAJOR_MN, b_major=MAJOR_MN, **kw)
+                dx = nx
+            if ctx.needs_input_grad[1]:
+                s = _splits(S2, S1, D, B, True)
+                buf = bank.wgrad_buffer(gid, s)
+                K.gemm(dy, x, buf, S2, S1, D, batch=B, lda=D, ldb=D, ldc=S1, stride_a=S2 * D, stride_b=S1 * D,
+                       reduce_batch=True, splits=s, stride_split=S2 * S1)
+        return (dx, None, None) + (None,) * len(ctx.gids)
+
+
+class AttnCoreFn(Function):
+    """RoPE (+ content|rope concat) -> all-head mask logits -> mask MLP over the key axis -> softmax(QK^T/sqrt(hd)+bias)V.
+    (Vi_Tools…:271-299). `roles` maps qc/qr/kc/kr/v to (source index, column offset) inside the bf16 source matrices
+    (fused qkv GEMM outputs or separate projections); gradients are written straight into per-source buffers."""
+
+    @staticmethod
+    def forward(ctx, token, inv_q, inv_k, b1, b2, bank, g1, g2, roles, dims, *srcs):
+        B, S, heads, dc, dr = dims
+        hd = dc + dr
+        D = heads * hd
+        T = B * S
+        src2 = [_as2d(s) for s in srcs]
+
+        def role(name):
+            if roles[name] is None:
+                return None, 0
+            i, off = roles[name]
+            t2, _, ld = src2[i]
+            return t2[:, off:], ld
+
+        cs_q, cs_k = K.rope_table(inv_q, S), K.rope_table(inv_k, S)
+        qc, ld_qc = role("qc"); qr, ld_qr = role("qr")
+        kc, ld_kc = role("kc"); kr, ld_kr = role("kr")
+        v, ld_v = role("v")
+        q = K.rope_fwd(qc, ld_qc, qr, ld_qr, cs_q, T, S, heads, dc, dr)
+        k = K.rope_fwd(kc, ld_kc, kr, ld_kr, cs_k, T, S, heads, dc, dr)
+        logits = torch.empty(B, S, S, dtype=bf16, device=q.device)
+        K.gemm(q, k, logits, S, S, D, batch=B, lda=D, ldb=D, ldc=S, stride_a=S * D, stride_b=S * D, stride_c=S * S)
+        bias = torch.empty(B, S, S, dtype=bf16, device=q.device)
+        pre, hid = _mlp_forward(bank, g1, g2, logits.view(T, S), T, S, b1, b2, None, 0, bias)
+        o, lse = K.attention_fwd(q, k, v, bias, B, S, heads, hd, D, D, ld_v)
+        ctx.save_for_backward(inv_q, inv_k, *srcs)
+        ctx.saved = (q, k, logits, pre, hid, bias, o, lse, cs_q, cs_k)
+        ctx.bank, ctx.g1, ctx.g2, ctx.version = bank, g1, g2, bank.version
+        ctx.roles, ctx.dims = roles, dims
+        return o.view(B, S, D)
+
+    @staticmethod
+    def backward(ctx, d_o):
+        inv_q, inv_k, *srcs = ctx.saved_tensors
+        q, k, logits, pre, hid, bias, o, lse, cs_q, cs_k = ctx.saved
+        bank = ctx.bank
+        _check_version(bank, ctx.version)
+        B, S, heads, dc, dr = ctx.dims
+        hd = dc + dr
+        D = heads * hd
+        T = B * S
+        roles = ctx.roles
+        src2 = [_as2d(s) for s in srcs]
+        dsrc = [torch.empty(s.shape, dtype=bf16, device=s.device) for s in srcs]
+        dsrc2 = [_as2d(d) for d in dsrc]
+
+        def role(name, bufs):
+            if roles[name] is None:
+                return None, 0
+            i, off = roles[name]
+            t2, _, ld = bufs[i]
+            return t2[:, off:], ld
+
+        v, ld_v = role("v", src2)
+        dv, ld_dv = role("v", dsrc2)
+        d_o2, _, ld_do = _as2d(_bf16_grad(d_o))
+        dq = torch.empty(T, D, dtype=bf16, device=q.device)
+        dk = torch.empty(T, D, dtype=bf16, device=q.device)
+        _, _, _, dbias = K.attention_bwd(q, k, v, bias, o, d_o2, lse, B, S, heads, hd, D, D, ld_v, ld_do, dq=dq, dk=dk, dv=dv,
+                                         ld_dq=D, ld_dk=D, ld_dv=ld_dv)
+        need_w = ctx.needs_input_grad[0]
+        dlog, db1, db2 = _mlp_backward(bank, ctx.g1, ctx.g2, dbias.view(T, S), T, S, logits.view(T, S), S, pre, hid, True, need_w, True)
+        # logits = q k^T (all heads, unscaled): dq += dL k ; dk += dL^T q   (accumulated in place through the addend)
+        K.gemm(dlog, k, dq, S, D, S, batch=B, lda=S, ldb=D, ldc=D, stride_a=S * S, stride_b=S * D, stride_c=S * D,
+               b_major=MAJOR_MN, addend=dq, ld_addend=D, stride_addend=S * D)
+        K.gemm(dlog, q, dk, S, D, S, batch=B, lda=S, ldb=D, ldc=D, stride_a=S * S, stride_b=S * D, stride_c=S * D,
+               a_major=MAJOR_MN, b_major=MAJOR_MN, addend=dk, ld_addend=D, stride_addend=S * D)
+        dqc, ld_dqc = role("qc", dsrc2); dqr, ld_dqr = role("qr", dsrc2)
+        dkc, ld_dkc = role("kc", dsrc2); dkr, ld_dkr = role("kr", dsrc2)
+        _, _, dinv_q = K.rope_bwd(dq, D, q, cs_q, T, S, heads, dc, dr, dcontent=dqc, ld_dcontent=ld_dqc, dropein=dqr, ld_drope=ld_dqr)
+        _, _, dinv_k = K.rope_bwd(dk, D, k, cs_k, T, S, heads, dc, dr, dcontent=dkc, ld_dcontent=ld_dkc, dropein=dkr, ld_drope=ld_dkr)
+        ctx.saved = None
+        return (None, dinv_q, dinv_k, db1, db2, None, None, None, None, None, *dsrc)
+
+
+class LatentFn(Function):
+    """Latent bottleneck sampling + ResidualStateManager('sum') running sums and KL (Vi_Tools…:232-244, 23-30)."""
+
+    @staticmethod
+    def forward(ctx, mv_q, mv_kv, eps_q, eps_kv, prev_q, prev_kv, prev_kl):
+        B, R, M2 = mv_q.shape
+        Mh = M2 // 2
+        rows = B * R
+        zq, zq16, pq = K.latent_fwd(mv_q.view(rows, M2), eps_q, prev_q)
+        zkv, zkv16, pkv = K.latent_fwd(mv_kv.view(rows, M2), eps_kv, prev_kv)
+        scale = -0.5 / (rows * Mh)
+        kl = K.latent_kl(pq, pkv, prev_kl, scale)
+        ctx.save_for_backward(mv_q, mv_kv, eps_q, eps_kv)
+        ctx.scale = scale
+        ctx.has_prev = (prev_q is not None, prev_kv is not None, prev_kl is not None)
+        ctx.set_materialize_grads(False)
+        shp = (B, R, Mh)
+        return zq.view(shp), zkv.view(shp), zq16.view(shp), zkv16.view(shp), kl
+
+    @staticmethod
+    def backward(ctx, dzq, dzkv, dzq16, dzkv16, dkl):
+        mv_q, mv_kv, eps_q, eps_kv = ctx.saved_tensors
+        B, R, M2 = mv_q.shape
+        rows = B * R
+        c = lambda t: t.contiguous() if t is not None else None
+        hq, hkv, hkl = ctx.has_prev
+        dmv_q, tq = K.latent_bwd(mv_q.view(rows, M2), eps_q, c(dzq), ctx.scale, dkl, c(dzq16), want_total=hq)
+        dmv_kv, tkv = K.latent_bwd(mv_kv.view(rows, M2), eps_kv, c(dzkv), ctx.scale, dkl, c(dzkv16), want_total=hkv)
+        shp = (B, R, M2 // 2)
+        return (dmv_q.view(B, R, M2), dmv_kv.view(B, R, M2), None, None, (tq.view(shp) if hq else None),
+                (tkv.view(shp) if hkv else None), (dkl if hkl else None))
+
+
+class CnnFn(Function):
+    """Per-Block CNN residual, one fused stencil kernel each way (Vi_Tools…:378-385,400-403; CALM_ViT_V2.py:60-67,80-83)."""
+
+    @staticmethod
+    def forward(ctx, x, token, b1, b2, b3, bank, g1, g2, g3):
+        x = x.contiguous()
+        B, S = x.shape[0], x.shape[1]
+        w1, w2, w3 = bank.weight(g1), bank.weight(g2), bank.weight(g3)
+        y = K.cnn_fwd(x, w1, b1, w2, b2, w3, b3, B, S)
+        ctx.save_for_backward(x, b1, b2, b3)
+        ctx.bank, ctx.gs, ctx.version = bank, (g1, g2, g3), bank.version
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, b1, b2, b3 = ctx.saved_tensors
+        bank = ctx.bank
+        _check_version(bank, ctx.version)
+        g1, g2, g3 = ctx.gs
+        B, S = x.shape[0], x.shape[1]
+        # weight gradients wrt the effective conv weights land in the bank: w1[0:96] w2[128:416] w3[448:544]
+        gp = bank.cnn_grad_buffer(g1, g2, g3)
+        dx, gp = K.cnn_bwd(x, dy.contiguous(), bank.weight(g1), b1, bank.weight(g2), b2, bank.weight(g3), b3, B, S, gp=gp)
+        return dx, None, gp[96:128].clone(), gp[416:448].clone(), gp[544:547].clone(), None, None, None, None
+
+
+class TokenSwapFn(Function):
+    """Row tokens <-> column tokens of the (B,S,S,3) pixel grid (Vi_Tools…:394-395,397-398). Also returns an alias of the
+    input so that the gradient of the other consumer (the cross block's query path) is fused into the backward transpose."""
+
+    @staticmethod
+    def forward(ctx, x):
+        x = x.contiguous()
+        ctx.set_materialize_grads(False)
+        return K.token_transpose(x, x.shape[0], x.shape[1]), x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, dt, dalias):
+        if dt is None:
+            return dalias
+        dt = dt.contiguous()
+        return K.token_transpose(dt, dt.shape[0], dt.shape[1], addend=dalias.contiguous() if dalias is not None else None)
+
+
+class ImageToTokensFn(Function):
+    """(B,3,S,S) image -> S row tokens of width 3S (Vi_Tools…:389-391)."""
+
+    @staticmethod
+    def forward(ctx, img):
+        return K.nchw_to_tokens(img.contiguous().float())
+
+    @staticmethod
+    def backward(ctx, d):
+        B, S, _ = d.shape
+        return d.view(B, S, S, 3).permute(0, 3, 1, 2).contiguous()   # cold path: only if the input image needs a gradient
+
+
+class Add3Fn(Function):
+    """U-Net skip adds (Vi_Tools…:513,516,520,522), out of place."""
+
+    @staticmethod
+    def forward(ctx, a, b, c):
+        ctx.has_c = c is not None
+        return K.add3(a.contiguous(), b.contiguous(), c.contiguous() if c is not None else None)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g, g, (g if ctx.has_c else None)
+
+
+class SeqMeanFn(Function):
+    """Mean over the sequence axis feeding the classifier head (CALM_ViT_V2.py:73-75): fp32 (B,S,D) -> bf16 (B,D)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        ctx.shape = x.shape
+        return K.seq_mean_fwd(x.contiguous())
+
+    @staticmethod
+    def backward(ctx, g):
+        B, S, D = ctx.shape
+        return K.seq_mean_bwd(_bf16_grad(g).contiguous(), B, S, D)
+
+
+class CastBf16Fn(Function):
+    @staticmethod
+    def forward(ctx, x):
+        return K.cast_bf16(x.contiguous())
+
+    @staticmethod
+    def backward(ctx, g):
+        return K.cast_f32(g.contiguous())

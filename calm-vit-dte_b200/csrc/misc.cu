@@ -8,7 +8,7 @@ namespace {
 // out[b, j, i, :] = in[b, i, j, :] on (B, S, S, 3) fp32: the row<->column token swap of Block.forward
 // (Vi_Tools_CNN_less_V2.py:394-395,397-398). 32x32-pixel tiles staged through shared memory, 12 B pixels.
 __global__ void __launch_bounds__(256)
-token_transpose_kernel(const float* __restrict__ in, float* __restrict__ out, int S) {
+token_transpose_kernel(const float* __restrict__ in, const float* __restrict__ addend, float* __restrict__ out, int S) {
   __shared__ float tile[32][32 * 3 + 1];
   const int b = blockIdx.z, i0 = blockIdx.y * 32, j0 = blockIdx.x * 32;
   const float* src = in + (long long)b * S * S * 3;
@@ -22,7 +22,12 @@ token_transpose_kernel(const float* __restrict__ in, float* __restrict__ out, in
   for (int idx = threadIdx.x; idx < 32 * 96; idx += 256) {
     const int r = idx / 96, cc = idx - r * 96;  // output row j0 + r, output pixel column i0 + cc/3
     const int j = j0 + r, i = i0 + cc / 3;
-    if (i < S && j < S) dst[((long long)j * S + i0) * 3 + cc] = tile[cc / 3][r * 3 + cc % 3];
+    if (i < S && j < S) {
+      const long long o = ((long long)j * S + i0) * 3 + cc;
+      float val = tile[cc / 3][r * 3 + cc % 3];
+      if (addend) val += addend[(long long)b * S * S * 3 + o];
+      dst[o] = val;
+    }
   }
 }
 
@@ -74,6 +79,14 @@ __global__ void cast_bf16_kernel(const float4* __restrict__ in, uint2* __restric
   }
 }
 
+__global__ void cast_f32_kernel(const uint2* __restrict__ in, float4* __restrict__ out, long long n4) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const uint2 v = in[i];
+    const float2 a = unpack_bf16x2(v.x), b = unpack_bf16x2(v.y);
+    out[i] = make_float4(a.x, a.y, b.x, b.y);
+  }
+}
+
 // out[b, d] = mean_s x[b, s, d]
 __global__ void seq_mean_fwd_kernel(const float* __restrict__ x, bf16* __restrict__ out, int S, int D) {
   const int b = blockIdx.y, d = blockIdx.x * blockDim.x + threadIdx.x;
@@ -91,10 +104,10 @@ __global__ void seq_mean_bwd_kernel(const bf16* __restrict__ dout, float* __rest
 
 }  // namespace
 
-extern "C" int32_t calm_token_transpose(const float* in, float* out, int32_t B, int32_t S, cudaStream_t stream) {
+extern "C" int32_t calm_token_transpose(const float* in, const float* addend, float* out, int32_t B, int32_t S, cudaStream_t stream) {
   CALM_CHECK_ARG(B > 0 && S > 0 && in != out, "calm_token_transpose: B=%d S=%d (out of place only)", B, S);
   dim3 grid((S + 31) / 32, (S + 31) / 32, B);
-  token_transpose_kernel<<<grid, 256, 0, stream>>>(in, out, S);
+  token_transpose_kernel<<<grid, 256, 0, stream>>>(in, addend, out, S);
   CALM_CHECK_LAUNCH("calm_token_transpose");
   return CALM_OK;
 }
@@ -144,6 +157,17 @@ extern "C" int32_t calm_cast_bf16(const float* in, void* out, int64_t n, cudaStr
   if (blocks > cap) blocks = cap;
   cast_bf16_kernel<<<(unsigned)blocks, 256, 0, stream>>>(reinterpret_cast<const float4*>(in), reinterpret_cast<uint2*>(out), n4);
   CALM_CHECK_LAUNCH("calm_cast_bf16");
+  return CALM_OK;
+}
+
+extern "C" int32_t calm_cast_f32(const void* in, float* out, int64_t n, cudaStream_t stream) {
+  CALM_CHECK_ARG(n > 0 && n % 4 == 0, "calm_cast_f32: n=%lld must be a positive multiple of 4", (long long)n);
+  const long long n4 = n / 4;
+  long long blocks = (n4 + 255) / 256;
+  const long long cap = 16LL * calm_num_sms();
+  if (blocks > cap) blocks = cap;
+  cast_f32_kernel<<<(unsigned)blocks, 256, 0, stream>>>(reinterpret_cast<const uint2*>(in), reinterpret_cast<float4*>(out), n4);
+  CALM_CHECK_LAUNCH("calm_cast_f32");
   return CALM_OK;
 }
 

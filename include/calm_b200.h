@@ -138,8 +138,14 @@ int32_t calm_attention_bwd(const void* q, const void* k, const void* v, const vo
  * ------------------------------------------------------------------------------------------------------------------ */
 int32_t calm_latent_fwd(const void* mv, const float* eps, const float* zsum_prev, float* zsum, void* zsum_bf16,
                         float* kl_partial /* (nblocks) */, int32_t nblocks, int64_t rows, int32_t Mh, cudaStream_t stream);
-int32_t calm_latent_bwd(const void* mv, const float* eps, const float* dz, float kl_scale, const float* dkl /* scalar on device */,
-                        void* dmv /* bf16 (rows, 2M) */, int64_t rows, int32_t Mh, cudaStream_t stream);
+/* running KL total: kl_out = kl_prev (or 0) + scale * (sum part_q + sum part_kv), scale = -0.5 / (rows*M) (:24-26) */
+int32_t calm_latent_kl(const float* part_q, const float* part_kv, int32_t nblocks, const float* kl_prev, float* kl_out,
+                       float scale, cudaStream_t stream);
+/* dz = dz_f32 (grad of the fp32 running sum, or NULL) + dz_bf16 (grad of its bf16 copy, or NULL);
+ * dz_total (optional out, f32) receives that sum = the gradient flowing on to the previous block's running sum */
+int32_t calm_latent_bwd(const void* mv, const float* eps, const float* dz, const void* dz_bf16, float kl_scale,
+                        const float* dkl /* scalar on device or NULL */, void* dmv /* bf16 (rows, 2M) */,
+                        float* dz_total, int64_t rows, int32_t Mh, cudaStream_t stream);
 int32_t calm_latent_blocks(int64_t rows, int32_t Mh);
 
 /* ------------------------------------------------------------------------------------------------------------------
@@ -159,8 +165,9 @@ int32_t calm_cnn_bwd_blocks(int32_t B, int32_t S);
 /* ------------------------------------------------------------------------------------------------------------------
  * Small memory-bound helpers
  * ------------------------------------------------------------------------------------------------------------------ */
-/* row<->column re-tokenisation (Vi_Tools_CNN_less_V2.py:394-395,397-398): out[b,j,i,:] = in[b,i,j,:] on (B,S,S,3) f32 */
-int32_t calm_token_transpose(const float* in, float* out, int32_t B, int32_t S, cudaStream_t stream);
+/* row<->column re-tokenisation (Vi_Tools_CNN_less_V2.py:394-395,397-398): out[b,j,i,:] = in[b,i,j,:] (+ addend[b,j,i,:])
+ * on (B,S,S,3) f32; the optional addend fuses the gradient accumulation of the un-transposed consumer in backward */
+int32_t calm_token_transpose(const float* in, const float* addend, float* out, int32_t B, int32_t S, cudaStream_t stream);
 /* first-block row tokenisation (:389-391): (B,3,S,S) NCHW f32 -> (B,S,S,3) ; and its inverse */
 int32_t calm_nchw_to_tokens(const float* in, float* out, int32_t B, int32_t S, cudaStream_t stream);
 /* column sums of a bf16 (rows, N) matrix -> f32 (N): linear_mask bias gradients */
@@ -170,6 +177,7 @@ int32_t calm_colsum_parts(int64_t rows, int32_t N);
 int32_t calm_add3(const float* a, const float* b, const float* c, float* out, int64_t n, cudaStream_t stream);
 /* f32 -> bf16 cast, and bf16 = bf16(a_f32 + b_f32) */
 int32_t calm_cast_bf16(const float* in, void* out, int64_t n, cudaStream_t stream);
+int32_t calm_cast_f32(const void* in_bf16, float* out, int64_t n, cudaStream_t stream);
 /* mean over the sequence axis: x f32 (B,S,D) -> bf16/f32 (B,D) (CALM_ViT_V2.py:73-75), and its backward */
 int32_t calm_seq_mean_fwd(const float* x, void* out_bf16, int32_t B, int32_t S, int32_t D, cudaStream_t stream);
 int32_t calm_seq_mean_bwd(const void* dout_bf16, float* dx, int32_t B, int32_t S, int32_t D, cudaStream_t stream);

@@ -260,12 +260,16 @@ def test_latent(K):
     assert rel(zb, ref) < 4e-3
     assert abs(part.sum().item() - klsum.item()) < 1e-4 * abs(klsum.item()) + 1e-2
     dz = rnd(rows, Mh, dtype=f32, seed=34)
-    dkl = torch.tensor([0.7], device=dev())
+    dkl = torch.tensor([3.0e4], device=dev())   # large enough that the KL term matters next to dz
     kl_scale = -0.5 / (rows * Mh)
-    dmv = K.latent_bwd(mv, eps, dz, kl_scale, dkl)
-    ((ref * dz).sum() + 0.7 * kl_scale * klsum).backward()
+    dz2 = rnd(rows, Mh, seed=50)
+    dmv, tot = K.latent_bwd(mv, eps, dz, kl_scale, dkl, dz_bf16=dz2, want_total=True)
+    assert rel(tot, dz + dz2.float()) < 1e-6
+    ((ref * (dz + dz2.float())).sum() + 3.0e4 * kl_scale * klsum).backward()
     assert rel(dmv[:, :Mh], mu.grad) < 4e-3
     assert rel(dmv[:, Mh:], rho.grad) < 4e-3
+    klrun = K.latent_kl(part, part, torch.tensor([1.5], device=dev()), kl_scale)
+    assert abs(klrun.item() - (1.5 + 2 * kl_scale * klsum.item())) < 1e-4
     # eval mode: no noise, first block: no previous sum
     z0, _, _ = K.latent_fwd(mv, None, None)
     assert rel(z0, mv[:, :Mh].float()) < 1e-6
@@ -308,6 +312,8 @@ def test_token_helpers(K):
     assert torch.equal(K.add3(a, b), a + b)
     assert rel(K.add3(a, b, c), a + b + c) < 1e-6
     assert torch.equal(K.cast_bf16(a), a.to(bf16))
+    assert torch.equal(K.cast_f32(a.to(bf16)), a.to(bf16).float())
+    assert rel(K.token_transpose(x, B, S, addend=a), t + a) < 1e-7
     m = K.seq_mean_fwd(x)
     assert rel(m, x.mean(1)) < 4e-3
     dm = rnd(B, 3 * S, seed=48)
