@@ -1,0 +1,357 @@
+#!/usr/bin/env python
+"""bench.py — CALM-ViT training images/sec at 224^2 on N B200 GPUs (BASELINE.json's metric), one JSON line on rank 0.
+
+    python bench.py --gpus 1 --steps 10 --warmup 3                     # this repo's CUDA path
+    python bench.py --impl reference --gpus 1 --steps 2 --warmup 1     # the reference algorithm on the host CPU cores
+    torchrun --nproc-per-node N ... bench.py --gpus N ...              # data parallel, one rank per GPU
+
+A "step" is one full training step of the trainer loop (distributed_trainer_cls.py:84-96): forward under autocast(bf16),
+soft-target cross-entropy, scaled backward, unscale, clip-grad-norm 1.0, AdamW, zero_grad — on the trainer config
+(`configs[1]` of BASELINE.json: heads 12, 224x224, dim 672, latent (80,240), 1000 classes, per-GPU batch 256) with
+synthetic ImageNet-shaped data and randomly initialised weights.
+  value    : images/sec, inputs resident in HBM, K steps bracketed by barrier + synchronize, CUDA events, max over ranks
+  e2e      : same step driven from pinned HOST buffers (H2D of the batch + D2H of the loss inside the timed region)
+  roofline : the dominant kernel (tcgen05 GEMM family): algorithmic FLOPs / CUDA-event time per launch, vs the measured
+             sustained bf16 peak of MEASURED_PEAKS.json
+  cpu_baseline : the oracle (a port of the reference path) fwd+bwd on the host cores, a bounded sample (batch 8)
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "calm-vit-dte_b200")
+for p in (PKG, ROOT):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+CFG = dict(heads=12, seq_length=224, in_features=672, dim_step=48, mean_var_hidden=240, seq_len_step=16, seq_len_reduce=80)
+FLOP_PER_IMG = {"cls": 45.43e9, "reg": 45.56e9}     # fwd+bwd algorithmic FLOPs / image
+
+
+def peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        return None
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs (B200_PROFILING.md's clocks line)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *exc):
+        if self.proc is not None:
+            time.sleep(0.15)
+            self.proc.terminate()
+            self.t.join(timeout=2)
+        return False
+
+    def summary(self):
+        sm = sorted(float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit())
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) >= 8 and r[4 + i] == "Active" for r in self.rows)]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
+
+
+def build_model(dev, task):
+    import CALM_ViT_V2 as rvh
+    gen = task == "reg"
+    return rvh.ViT(dev, type=8, out_features=672 if gen else 1000, force_reduce=False, generate=gen, **CFG).to(dev)
+
+
+def synth_batch(B, task, seed):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    x = torch.randn(B, 3, 224, 224, generator=g)
+    y = torch.softmax(torch.randn(B, 1000, generator=g) * 4, -1) if task == "cls" else None   # dense soft labels (CutMix/MixUp)
+    return x, y
+
+
+class Trainer:
+    """The per-rank training step of the reference loop, optionally captured into one CUDA graph (static shapes)."""
+
+    def __init__(self, model, task, dev, B, use_graph):
+        from torch.amp import GradScaler
+        self.model, self.task, self.dev = model, task, dev
+        self.params = [p for p in model.parameters()]
+        self.opt = torch.optim.AdamW(self.params, lr=3.1e-3, weight_decay=0.02, betas=(0.9, 0.98), fused=True, capturable=True)
+        self.scaler = GradScaler(enabled=True)
+        self.x = torch.zeros(B, 3, 224, 224, device=dev)
+        self.y = torch.zeros(B, 1000, device=dev) if task == "cls" else None
+        self.loss = torch.zeros((), device=dev)
+        self.graph = None
+        self.use_graph = use_graph
+
+    def _step(self):
+        with torch.autocast(device_type="cuda", dtype=torch.bfloat16):
+            y_hat, kl = self.model(self.x)
+            if self.task == "cls":
+                loss = torch.nn.functional.cross_entropy(y_hat.squeeze(), self.y)
+            else:
+                img = y_hat.reshape(-1, 224, 224, 3).permute(0, 3, 1, 2)
+                loss = torch.nn.functional.huber_loss(img, self.x, delta=1.0) + kl * 0.1
+        self.scaler.scale(loss).backward()
+        self.scaler.unscale_(self.opt)
+        torch.nn.utils.clip_grad_norm_(self.params, max_norm=1, error_if_nonfinite=False)
+        self.scaler.step(self.opt)
+        self.scaler.update()
+        self.opt.zero_grad()
+        self.loss.copy_(loss.detach())
+
+    def capture(self):
+        """3 eager steps on a side stream (allocator + lazy state warm-up), then capture one step."""
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(3):
+                self._step()
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        if not self.use_graph:
+            return
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self._step()
+        self.graph = g
+
+    def step(self):
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self._step()
+
+
+def cpu_baseline(model, max_seconds=20.0):
+    """Oracle fwd+bwd (fp32, batch 8, all host cores): BASELINE.json configs[0], a bounded sample of the workload."""
+    from oracle import calm_oracle as O
+    sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+    P = O.params_from_state_dict(sd)
+    x, y = synth_batch(8, "cls", 0)
+    y = torch.randint(0, 1000, (8,))
+
+    def one():
+        for p in P.values():
+            p.grad = None
+        t = time.perf_counter()
+        O.train_step_cls(P, CFG["heads"], x, y, training=True)
+        return time.perf_counter() - t
+    one()
+    ts, t0 = [], time.perf_counter()
+    while len(ts) < 3 or (time.perf_counter() - t0 < max_seconds and len(ts) < 10):
+        ts.append(one())
+    best = min(ts)
+    return {"value": 8 / best, "unit": "images/sec", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": "oracle fwd+bwd, fp32, batch 8 at 224^2 (BASELINE configs[0]), best of %d, %d torch threads" % (len(ts), torch.get_num_threads())}
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference algorithm (oracle port) on the host cores; rank 0 only."""
+    if rank != 0:
+        return
+    torch.manual_seed(0)
+    from oracle import calm_oracle as O
+    # weights: a random reference-layout state of the same config (nothing of the product path is involved here)
+    P = O.params_from_state_dict(O.random_state(O.state_shapes(out_features=1000, generate=False, **CFG)))
+    Bs = 8
+    x, y = synth_batch(Bs, "cls", 2006)
+
+    def one():
+        for p in P.values():
+            p.grad = None
+        O.train_step_cls(P, CFG["heads"], x, y, training=True)
+    for _ in range(max(1, min(args.warmup, 2))):
+        one()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        one()
+    dt = (time.perf_counter() - t0) / args.steps
+    val = Bs / dt
+    line = {"impl": "reference", "metric": "train images/sec at 224^2", "value": val, "unit": "images/sec", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "CALM-ViT cls trainer config 224^2, fwd+bwd on host CPU cores, bounded sample: batch %d per step" % Bs},
+            "cpu_baseline": {"value": val, "unit": "images/sec", "cores": torch.get_num_threads(), "kind": "port",
+                             "sample": "oracle (port of the reference path) fwd+bwd fp32, batch %d/step, %d steps" % (Bs, args.steps)},
+            "e2e": {"value": val, "unit": "images/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=256)
+    ap.add_argument("--task", default="cls", choices=["cls", "reg"])
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-profile", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback for the product path)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group(backend="nccl", device_id=dev)
+    import calm_lib
+    torch.manual_seed(0)                      # identical initial weights on every rank (then broadcast from rank 0 anyway)
+    model = build_model(dev, args.task)
+    model.train()
+    B = args.batch
+    use_graph = not args.no_graph and world == 1
+    wrapped = model
+    if world > 1:
+        from calm_ddp import DataParallel
+        wrapped = DataParallel(model)
+    tr = Trainer(wrapped, args.task, dev, B, use_graph)
+    xh, yh = synth_batch(B, args.task, 2006 + rank)
+    xh, yh = xh.pin_memory(), (yh.pin_memory() if yh is not None else None)
+    tr.x.copy_(xh)
+    if yh is not None:
+        tr.y.copy_(yh)
+    torch.manual_seed(1234 + rank)            # per-rank latent noise stream (the reference never seeds inside train())
+    graph_note = None
+    try:
+        tr.capture()
+    except Exception as e:                    # capture problems must not kill the measurement: fall back to eager launches
+        graph_note = "cuda graph capture failed (%s); eager launches" % (repr(e)[:160])
+        tr.graph = None
+        torch.cuda.synchronize()
+    for _ in range(max(args.warmup, 3)):
+        tr.step()
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing -------------------------------------------------------------------------------------
+    n0 = calm_lib.launch_count
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clocks:
+        e0.record()
+        for _ in range(args.steps):
+            tr.step()
+        e1.record()
+        barrier()
+    ms = e0.elapsed_time(e1)
+    launches_py = calm_lib.launch_count - n0
+    # ---- end-to-end from pinned host buffers ----------------------------------------------------------------------
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    last = 0.0
+    for _ in range(args.steps):
+        tr.x.copy_(xh, non_blocking=True)
+        if yh is not None:
+            tr.y.copy_(yh, non_blocking=True)
+        tr.step()
+        last = tr.loss.item()                 # device -> host read of the step's result
+    f1.record()
+    barrier()
+    ms_e2e = f0.elapsed_time(f1)
+    t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = t.tolist()
+    ms_step = ms / args.steps
+    value = B * world * args.steps / (ms / 1e3)
+    e2e_value = B * world * args.steps / (ms_e2e / 1e3)
+
+    # ---- one extra eager step with CUDA events around every C-ABI launch: per-kernel-family time and work -----------
+    roof, breakdown, launches_per_step = None, None, None
+    if not args.no_profile:
+        calm_lib.profile = []
+        n1 = calm_lib.launch_count
+        tr._step()
+        torch.cuda.synchronize()
+        launches_per_step = calm_lib.launch_count - n1
+        prof, calm_lib.profile = calm_lib.profile, None
+        fam = {}
+        for name, work, a, b in prof:
+            d = fam.setdefault(name, {"ms": 0.0, "work": 0.0, "n": 0})
+            d["ms"] += a.elapsed_time(b)
+            d["work"] += work
+            d["n"] += 1
+        tot = sum(d["ms"] for d in fam.values())
+        breakdown = {k: {"ms": round(v["ms"], 3), "n": v["n"], "share": round(v["ms"] / tot, 4),
+                         "rate": (v["work"] / (v["ms"] * 1e-3) if v["work"] and v["ms"] > 0 else None)} for k, v in fam.items()}
+        pk = peaks()
+        g = fam.get("calm_gemm")
+        if g and g["ms"] > 0:
+            ach = g["work"] / (g["ms"] * 1e-3) / 1e12
+            peak = (pk or {}).get("bf16_tflops_sustained", 1400.0)
+            roof = {"bound": "tensor", "kernel": "gemm_tcgen05_kernel (calm_gemm, %d launches/step, %.1f%% of kernel time)" % (g["n"], 100 * g["ms"] / tot),
+                    "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
+                    "peak_source": "measured (MEASURED_PEAKS.json bf16_tflops_sustained)" if pk else "fallback (B200_PROFILING.md)"}
+    line = {
+        "metric": "train images/sec at 224^2", "value": value, "unit": "images/sec", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": "CALM-ViT %s trainer config (distributed_trainer_%s.py): 224x224x3, heads 12, dim 672, latent (80,240), "
+                               "per-GPU batch %d, full training step (fwd+loss+bwd+unscale+clip+AdamW)" % (args.task, args.task, B),
+                   "parallelism": "dp%d" % world, "global_batch": B * world, "cuda_graph": tr.graph is not None,
+                   "l2": "inputs larger than L2 (batch 154 MB, activations GBs per step); no explicit flush"},
+        "model_flops_frac_of_bf16_peak": value * FLOP_PER_IMG[args.task] / world / ((peaks() or {}).get("bf16_tflops_sustained", 1400.0) * 1e12),
+        "e2e": {"value": e2e_value, "unit": "images/sec", "h2d_bytes_per_step": xh.numel() * 4 + (yh.numel() * 4 if yh is not None else 0),
+                "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": (launches_per_step or launches_py // max(args.steps, 1)) * args.steps,
+        "gpu_launches_per_step": launches_per_step,
+        "clocks": clocks.summary(), "loss": last,
+    }
+    if graph_note:
+        line["config"]["note"] = graph_note
+    if roof:
+        line["roofline"] = roof
+    if world > 1:
+        line["buffers_in_sync"] = wrapped.check_buffers()
+    if rank == 0:
+        if breakdown is not None:
+            os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+            json.dump(breakdown, open(os.path.join(ROOT, "gpurun_out", "bench_kernel_breakdown.json"), "w"), indent=1)
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(model)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -41,7 +41,7 @@ def gemm(a, b, c, M, N, K, *, lda, ldb, ldc, batch=1, stride_a=0, stride_b=0, st
     g.aux, g.ld_aux, g.stride_aux = ptr(aux), ld_aux, stride_aux
     g.reduce_batch, g.splits, g.stride_split = int(reduce_batch), splits, stride_split
     g.alpha = alpha
-    L.call("calm_gemm", C.byref(g))
+    L.call("calm_gemm", C.byref(g), work=2.0 * M * N * K * batch)
     return c
 
 
@@ -57,7 +57,8 @@ def layernorm_fwd(x, w, eps=1e-6, out_dtype=bf16):
     y = torch.empty(x.shape, dtype=out_dtype, device=x.device)
     mean = torch.empty(rows, dtype=f32, device=x.device)
     rstd = torch.empty(rows, dtype=f32, device=x.device)
-    L.call("calm_layernorm_fwd", ptr(x), ptr(w), ptr(y), _dt(y), ptr(mean), ptr(rstd), rows, D, eps)
+    L.call("calm_layernorm_fwd", ptr(x), ptr(w), ptr(y), _dt(y), ptr(mean), ptr(rstd), rows, D, eps,
+           work=float(rows) * D * (4 + y.element_size()))
     return y, mean, rstd
 
 
@@ -111,7 +112,7 @@ def attention_fwd(q, k, v, bias, B, S, heads, hd, ld_q, ld_k, ld_v):
     o = torch.empty(B * S, heads * hd, dtype=bf16, device=q.device)
     lse = torch.empty(B, heads, S, dtype=f32, device=q.device)
     L.call("calm_attention_fwd", ptr(q), ptr(k), ptr(v), ptr(bias), ptr(o), ptr(lse), ld_q, ld_k, ld_v, o.stride(0), B, S,
-           heads, hd)
+           heads, hd, work=4.0 * B * heads * S * S * hd)
     return o, lse
 
 
@@ -128,7 +129,8 @@ def attention_bwd(q, k, v, bias, o, d_o, lse, B, S, heads, hd, ld_q, ld_k, ld_v,
     dbias = torch.empty(B, S, S, dtype=bf16, device=dev)
     delta = torch.empty(B, heads, S, dtype=f32, device=dev)
     L.call("calm_attention_bwd", ptr(q), ptr(k), ptr(v), ptr(bias), ptr(o), ptr(d_o), ptr(lse), ptr(delta), ptr(dq), ptr(dk),
-           ptr(dv), ptr(dbias), ld_q, ld_k, ld_v, o.stride(0), ld_do, ld_dq, ld_dk, ld_dv, B, S, heads, hd)
+           ptr(dv), ptr(dbias), ld_q, ld_k, ld_v, o.stride(0), ld_do, ld_dq, ld_dk, ld_dv, B, S, heads, hd,
+           work=10.0 * B * heads * S * S * hd)
     return dq, dk, dv, dbias
 
 

@@ -144,11 +144,23 @@ def stream():
     return torch.cuda.current_stream().cuda_stream
 
 
-def call(name, *args):
-    """Invoke an int32-returning entry point on the current torch stream (appended as last argument)."""
+profile = None   # bench.py's per-kernel timing pass sets this to a list; entries: (name, work, start_event, end_event)
+
+
+def call(name, *args, work=0.0):
+    """Invoke an int32-returning entry point on the current torch stream (appended as last argument).
+    `work` = algorithmic FLOPs (contractions) or bytes (memory-bound kernels) of this launch, used only by the
+    optional CUDA-event profiling pass."""
     global launch_count
     lib = load()
-    rc = getattr(lib, name)(*args, stream())
+    if profile is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = getattr(lib, name)(*args, stream())
+        e1.record()
+        profile.append((name, work, e0, e1))
+    else:
+        rc = getattr(lib, name)(*args, stream())
     launch_count += 1
     if rc != 0:
         raise CalmError("%s failed (rc=%d): %s" % (name, rc, last_error()))

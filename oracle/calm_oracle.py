@@ -257,3 +257,103 @@ def train_step_reg(P, heads, img, training=True, noise=None):
     loss = F.huber_loss(rec, img, delta=1.0) + 0.1 * kl
     loss.backward()
     return loss.detach(), y.detach()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# state_dict layout of the reference, derived from the constructor arguments alone
+# ---------------------------------------------------------------------------------------------------------------------
+def _sn(shapes, name, out_f, in_f, bias=False, conv_tail=None):
+    """Entries an sn(Linear/Conv2d) contributes, in torch's registration order: [bias], weight_orig, weight_u, weight_v."""
+    w = (out_f, in_f) if conv_tail is None else (out_f, in_f) + tuple(conv_tail)
+    fan = in_f if conv_tail is None else in_f * conv_tail[0] * conv_tail[1]
+    if bias:
+        shapes[name + ".bias"] = (out_f,)
+    shapes[name + ".weight_orig"] = w
+    shapes[name + ".weight_u"] = (out_f,)
+    shapes[name + ".weight_v"] = (fan,)
+
+
+def _vmla_shapes(shapes, pre, heads, d1, d2, M, S1, R, S2, mlp_dim, is_cross):
+    reduce, t_reduce = d1 != d2, S1 != S2                                    # force_reduce=False (Vi_Tools…:128-129)
+    hd_half = d2 // heads // 2
+    shapes[pre + "ls_att"] = (d2,)
+    shapes[pre + "ls_mlp"] = (d2,)
+    shapes[pre + "ln_q.weight"] = (d1,)
+    if is_cross:
+        shapes[pre + "ln_kv.weight"] = (d1,)
+    if t_reduce:
+        _sn(shapes, pre + "t_encoder_q", R, S1); _sn(shapes, pre + "t_encoder_kv", R, S1)
+    if reduce:
+        _sn(shapes, pre + "encoder_q", 2 * M, d1); _sn(shapes, pre + "encoder_kv", 2 * M, d1)
+    if t_reduce:
+        for n in ("t_qz_upsample", "t_kz_upsample", "t_vz_upsample", "t_qr_proj"):
+            _sn(shapes, pre + n, S2, R)
+        _sn(shapes, pre + "t_kr_proj", S2, S1)
+    d_in = M if reduce else d2
+    _sn(shapes, pre + "q_proj", heads * hd_half if reduce else heads * 2 * hd_half, d_in)
+    _sn(shapes, pre + "k_proj", heads * hd_half if reduce else heads * 2 * hd_half, d_in)
+    _sn(shapes, pre + "v_proj", d2, d_in)
+    if reduce:
+        _sn(shapes, pre + "qr_proj", heads * hd_half, M); _sn(shapes, pre + "kr_proj", heads * hd_half, d1)
+    if t_reduce:
+        _sn(shapes, pre + "input_t_proj", S2, S1)
+    if reduce:
+        _sn(shapes, pre + "input_proj", d2, d1)
+    d_rope = hd_half if reduce else 2 * hd_half
+    shapes[pre + "rope_q.inv_freq"] = (len(range(0, d_rope, 2)),)
+    shapes[pre + "rope_k.inv_freq"] = (len(range(0, d_rope, 2)),)
+    _sn(shapes, pre + "linear_mask.0", 2 * S2, S2, bias=True); _sn(shapes, pre + "linear_mask.2", S2, 2 * S2, bias=True)
+    _sn(shapes, pre + "out_proj", d2, d2)
+    shapes[pre + "ln_2.weight"] = (d2,)
+    _sn(shapes, pre + "mlp.0", mlp_dim, d2); _sn(shapes, pre + "mlp.3", d2, mlp_dim)
+
+
+def _cnn_shapes(shapes, pre, hidden=32):
+    _sn(shapes, pre + "0", hidden, 3, bias=True, conv_tail=(1, 1))
+    _sn(shapes, pre + "2", hidden, 1, bias=True, conv_tail=(3, 3))
+    _sn(shapes, pre + "4", 3, hidden, bias=True, conv_tail=(1, 1))
+
+
+def state_shapes(heads, seq_length, in_features, dim_step, mean_var_hidden, seq_len_step, seq_len_reduce, out_features,
+                 generate, **_):
+    """{key: shape} of ViT(type=8).state_dict(), in order (CALM_ViT_V2.py:22-67; Vi_Tools…:98-205,317-385,407-494)."""
+    shapes = {}
+    S, D, M, R = seq_length, in_features, mean_var_hidden, seq_len_reduce
+    plan = [("encoder_blocks.%d." % i, -1) for i in range(3)] + [("block_bottle_neck_1.", 0), ("block_bottle_neck_2.", 0)] + \
+           [("decoder_blocks.%d." % i, +1) for i in range(3)]
+    for name, sign in plan:
+        pre = "autoencoder." + name
+        D2, S2 = D + sign * dim_step * 3, S + sign * seq_len_step * 3
+        _vmla_shapes(shapes, pre + "encoder.", heads, D, D, M, S, R, S, 2 * D, False)
+        _vmla_shapes(shapes, pre + "decoder.", heads, D, D, M, S, R, S, 2 * D, False)
+        _vmla_shapes(shapes, pre + "cross.", heads, D, D2, M, S, R, S2, 2 * D2, True)
+        _cnn_shapes(shapes, pre + "proj.")
+        D, S = D2, S2
+    shapes["autoencoder.ln_final.weight"] = (D,)
+    if generate:
+        _cnn_shapes(shapes, "proj.")
+    else:
+        _sn(shapes, "head.0", 2 * in_features, in_features); _sn(shapes, "head.2", out_features, 2 * in_features)
+    return shapes
+
+
+def random_state(shapes, seed=0):
+    """Random reference-layout state (for timing the CPU baseline): U(-1,1)/sqrt(fan_in) weights, unit u/v, ones elsewhere."""
+    g = torch.Generator().manual_seed(seed)
+    sd = {}
+    for k, shp in shapes.items():
+        if k.endswith("weight_orig"):
+            fan = 1
+            for s in shp[1:]:
+                fan *= s
+            sd[k] = (torch.rand(shp, generator=g) * 2 - 1) / math.sqrt(fan)
+        elif k.endswith("weight_u") or k.endswith("weight_v"):
+            sd[k] = F.normalize(torch.randn(shp, generator=g), dim=0)
+        elif k.endswith("inv_freq"):
+            half = shp[0]
+            sd[k] = 1.0 / (10000.0 ** (torch.arange(0, 2 * half, 2).float() / (2 * half)))
+        elif k.endswith(".bias"):
+            sd[k] = torch.zeros(shp)
+        else:
+            sd[k] = torch.ones(shp)
+    return sd

@@ -79,6 +79,16 @@ def test_oracle_matches_reference_golden(name):
     assert all(torch.equal(P[k], before[k]) for k in meta["buf_keys"])
 
 
+@pytest.mark.parametrize("name", ["tiny_cls", "tiny_gen", "small_cls", "small_gen"])
+def test_oracle_state_layout_matches_reference(name):
+    """oracle.state_shapes re-derives the reference's state_dict keys, order and shapes from the ctor arguments alone."""
+    _, meta = load_fixture(name)
+    cfg = meta["config"]
+    shapes = O.state_shapes(**cfg)
+    assert list(shapes.keys()) == list(meta["shapes"].keys())
+    assert all(list(shapes[k]) == meta["shapes"][k] for k in shapes)
+
+
 def test_oracle_kl_and_shapes():
     z, meta = load_fixture("tiny_gen")
     cfg = meta["config"]
@@ -92,11 +102,21 @@ def test_oracle_kl_and_shapes():
 @pytest.mark.skipif(not os.path.exists("/root/reference/CALM-ViT/CALM_ViT_V2.py"), reason="reference only exists in the build container")
 def test_oracle_matches_live_reference_rng_order():
     """Same torch seed right before each forward -> the oracle consumes torch.randn_like in the reference's order."""
+    # the product modules carry the same names by design: import the reference in isolation, then restore sys.modules
+    names = ("CALM_ViT_V2", "Vi_Tools_CNN_less_V2")
+    saved = {n: sys.modules.pop(n) for n in names if n in sys.modules}
     sys.path.insert(0, "/root/reference/CALM-ViT")
     for n in ("matplotlib", "matplotlib.pyplot"):
         sys.modules.setdefault(n, types.ModuleType(n))
     sys.modules["matplotlib"].pyplot = sys.modules["matplotlib.pyplot"]
-    import CALM_ViT_V2 as rvh
+    try:
+        import CALM_ViT_V2 as rvh
+        assert rvh.__file__.startswith("/root/reference/")
+    finally:
+        sys.path.remove("/root/reference/CALM-ViT")
+        for n in names:
+            sys.modules.pop(n, None)
+        sys.modules.update(saved)
     cfg = synth.CONFIGS["tiny_cls"]
     kw = {k: v for k, v in cfg.items() if k != "batch"}
     torch.manual_seed(3)
