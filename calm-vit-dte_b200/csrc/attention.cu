@@ -35,17 +35,34 @@ __device__ __forceinline__ void mma16816(float* c, const uint32_t* a, uint32_t b
 __device__ __forceinline__ uint32_t sm_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 // Load a TILE x hd slab (rows row0.. of a token-major matrix, head offset already applied) into smem [TILE][P],
-// zero-filling rows >= nvalid and columns >= hd.
+// zero-filling rows >= nvalid and columns >= hd. 8-byte (4 x bf16) accesses: hd % 4 == 0 and ld % 4 == 0 are required.
 template <int HDP>
 __device__ __forceinline__ void load_tile(bf16* dst, const bf16* __restrict__ src, long long ld, int nvalid, int hd) {
   constexpr int P = HDP + 8;
-  constexpr int WPR = HDP / 2;  // 32-bit words per padded row
-  uint32_t* d32 = reinterpret_cast<uint32_t*>(dst);
-  for (int idx = threadIdx.x; idx < TILE * WPR; idx += ATT_THREADS) {
-    const int r = idx / WPR, w = idx - r * WPR;
-    uint32_t val = 0u;
-    if (r < nvalid && 2 * w < hd) val = *reinterpret_cast<const uint32_t*>(src + (long long)r * ld + 2 * w);
-    d32[r * (P / 2) + w] = val;
+  constexpr int V = HDP / 4;  // uint2 per padded row
+  const int hv = hd >> 2;
+#pragma unroll 4
+  for (int it = 0; it < (TILE * V + ATT_THREADS - 1) / ATT_THREADS; ++it) {
+    const int idx = threadIdx.x + it * ATT_THREADS;
+    if (idx < TILE * V) {
+      const int r = idx / V, c = idx - r * V;
+      uint2 val = make_uint2(0u, 0u);
+      if (r < nvalid && c < hv) val = *reinterpret_cast<const uint2*>(src + (long long)r * ld + 4 * c);
+      *reinterpret_cast<uint2*>(dst + r * P + 4 * c) = val;
+    }
+  }
+}
+
+// Load the 64 x 64 block (rows q0.., columns k0..) of one image's (S, S) bias matrix into smem [TILE][BP], zero-filled.
+constexpr int BP = TILE + 8;
+__device__ __forceinline__ void load_bias_tile(bf16* dst, const bf16* __restrict__ bias_b, int S, int q0, int k0) {
+#pragma unroll 4
+  for (int it = 0; it < (TILE * (TILE / 4)) / ATT_THREADS; ++it) {
+    const int idx = threadIdx.x + it * ATT_THREADS;
+    const int r = idx >> 4, c = idx & 15;
+    uint2 val = make_uint2(0u, 0u);
+    if (q0 + r < S && k0 + 4 * c < S) val = *reinterpret_cast<const uint2*>(bias_b + (long long)(q0 + r) * S + k0 + 4 * c);
+    *reinterpret_cast<uint2*>(dst + r * BP + 4 * c) = val;
   }
 }
 
@@ -99,7 +116,7 @@ __device__ __forceinline__ void mma_p_t(float (*c)[4], const float (*pm)[4], con
 // forward: grid (ceil(S/64), heads, B)
 // ---------------------------------------------------------------------------------------------------------------
 template <int HDP>
-__global__ void __launch_bounds__(ATT_THREADS)
+__global__ void __launch_bounds__(ATT_THREADS, 4)
 attn_fwd_kernel(const bf16* __restrict__ q, const bf16* __restrict__ k, const bf16* __restrict__ v, const bf16* __restrict__ bias,
                 bf16* __restrict__ o, float* __restrict__ lse, long long ld_q, long long ld_k, long long ld_v, long long ld_o,
                 int S, int heads, int hd, float scale_log2) {
@@ -108,6 +125,7 @@ attn_fwd_kernel(const bf16* __restrict__ q, const bf16* __restrict__ k, const bf
   bf16* Qs = reinterpret_cast<bf16*>(att_smem);
   bf16* Ks = Qs + TILE * P;
   bf16* Vs = Ks + TILE * P;
+  bf16* Bs = Vs + TILE * P;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int q0 = blockIdx.x * TILE, h = blockIdx.y, b = blockIdx.z;
   const long long tok0 = (long long)b * S;
@@ -128,6 +146,7 @@ attn_fwd_kernel(const bf16* __restrict__ q, const bf16* __restrict__ k, const bf
     __syncthreads();
     load_tile<HDP>(Ks, k + (tok0 + kb0) * ld_k + (long long)h * hd, ld_k, S - kb0, hd);
     load_tile<HDP>(Vs, v + (tok0 + kb0) * ld_v + (long long)h * hd, ld_v, S - kb0, hd);
+    load_bias_tile(Bs, bias_b, S, q0, kb0);
     __syncthreads();
     float s[8][4];
 #pragma unroll
@@ -140,12 +159,8 @@ attn_fwd_kernel(const bf16* __restrict__ q, const bf16* __restrict__ k, const bf
       const int key = kb0 + nt * 8 + (lane & 3) * 2;
 #pragma unroll
       for (int hh = 0; hh < 2; ++hh) {
-        const int row = row_lo + hh * 8;
-        float b0 = 0.f, b1 = 0.f;
-        if (row < S && key < S) {
-          const float2 bb = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(bias_b + (long long)row * S + key));
-          b0 = bb.x; b1 = bb.y;
-        }
+        const float2 bb = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(Bs + (warp * 16 + (lane >> 2) + hh * 8) * BP + nt * 8 + (lane & 3) * 2));
+        const float b0 = bb.x, b1 = bb.y;
         float v0 = s[nt][2 * hh] * scale_log2 + b0 * LOG2E;
         float v1 = s[nt][2 * hh + 1] * scale_log2 + b1 * LOG2E;
         if (key >= S) v0 = -INFINITY;
@@ -202,31 +217,30 @@ attn_fwd_kernel(const bf16* __restrict__ q, const bf16* __restrict__ k, const bf
   }
 }
 
-// delta[b,h,s] = sum_c dO[t, h*hd + c] * O[t, h*hd + c]   (one warp per (token, head))
+// delta[b,h,s] = sum_c dO[t, h*hd + c] * O[t, h*hd + c]   (one thread per (token, head): adjacent threads read adjacent
+// 2*hd-byte segments of the same token row, so the warp's accesses are contiguous)
 __global__ void attn_delta_kernel(const bf16* __restrict__ o, const bf16* __restrict__ d_o, float* __restrict__ delta, long long ld_o,
                                   long long ld_do, long long tokens, int S, int heads, int hd) {
-  const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
+  const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (w >= tokens * heads) return;
   const long long t = w / heads;
   const int h = (int)(w - t * heads);
-  const bf16* op = o + t * ld_o + (long long)h * hd;
-  const bf16* dp = d_o + t * ld_do + (long long)h * hd;
+  const uint2* op = reinterpret_cast<const uint2*>(o + t * ld_o + (long long)h * hd);
+  const uint2* dp = reinterpret_cast<const uint2*>(d_o + t * ld_do + (long long)h * hd);
   float acc = 0.f;
-  for (int c = lane * 2; c < hd; c += 64) {
-    const float2 a = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(op + c));
-    const float2 g = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(dp + c));
-    acc += a.x * g.x + a.y * g.y;
+  for (int c = 0; c < (hd >> 2); ++c) {
+    const uint2 a = op[c], g = dp[c];
+    const float2 a0 = unpack_bf16x2(a.x), a1 = unpack_bf16x2(a.y), g0 = unpack_bf16x2(g.x), g1 = unpack_bf16x2(g.y);
+    acc += a0.x * g0.x + a0.y * g0.y + a1.x * g1.x + a1.y * g1.y;
   }
-  acc = warp_sum(acc);
-  if (lane == 0) delta[((t / S) * heads + h) * S + (t % S)] = acc;
+  delta[((t / S) * heads + h) * S + (t % S)] = acc;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
 // backward, query-major: dQ.  grid (ceil(S/64), heads, B)
 // ---------------------------------------------------------------------------------------------------------------
 template <int HDP>
-__global__ void __launch_bounds__(ATT_THREADS)
+__global__ void __launch_bounds__(ATT_THREADS, 3)
 attn_bwd_dq_kernel(const bf16* __restrict__ q, const bf16* __restrict__ k, const bf16* __restrict__ v, const bf16* __restrict__ bias,
                    const bf16* __restrict__ d_o, const float* __restrict__ lse, const float* __restrict__ delta, bf16* __restrict__ dq,
                    long long ld_q, long long ld_k, long long ld_v, long long ld_do, long long ld_dq, int S, int heads, int hd,
@@ -237,6 +251,7 @@ attn_bwd_dq_kernel(const bf16* __restrict__ q, const bf16* __restrict__ k, const
   bf16* dOs = Qs + TILE * P;
   bf16* Ks = dOs + TILE * P;
   bf16* Vs = Ks + TILE * P;
+  bf16* Bs = Vs + TILE * P;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int q0 = blockIdx.x * TILE, h = blockIdx.y, b = blockIdx.z;
   const long long tok0 = (long long)b * S;
@@ -266,6 +281,7 @@ attn_bwd_dq_kernel(const bf16* __restrict__ q, const bf16* __restrict__ k, const
     __syncthreads();
     load_tile<HDP>(Ks, k + (tok0 + kb0) * ld_k + (long long)h * hd, ld_k, S - kb0, hd);
     load_tile<HDP>(Vs, v + (tok0 + kb0) * ld_v + (long long)h * hd, ld_v, S - kb0, hd);
+    load_bias_tile(Bs, bias_b, S, q0, kb0);
     __syncthreads();
     float s[8][4], dp[8][4];
 #pragma unroll
@@ -278,12 +294,9 @@ attn_bwd_dq_kernel(const bf16* __restrict__ q, const bf16* __restrict__ k, const
 #pragma unroll
       for (int hh = 0; hh < 2; ++hh) {
         const int row = row_lo + hh * 8;
-        float b0 = 0.f, b1 = 0.f;
         const bool ok = row < S && key < S;
-        if (ok) {
-          const float2 bb = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(bias_b + (long long)row * S + key));
-          b0 = bb.x; b1 = bb.y;
-        }
+        const float2 bb = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(Bs + (warp * 16 + (lane >> 2) + hh * 8) * BP + nt * 8 + (lane & 3) * 2));
+        const float b0 = bb.x, b1 = bb.y;
         const float p0 = ok ? exp2f(s[nt][2 * hh] * scale_log2 + b0 * LOG2E - lse2[hh]) : 0.f;
         const float p1 = (ok && key + 1 < S) ? exp2f(s[nt][2 * hh + 1] * scale_log2 + b1 * LOG2E - lse2[hh]) : 0.f;
         s[nt][2 * hh] = p0 * (dp[nt][2 * hh] - dlt[hh]);          // dS
@@ -311,7 +324,7 @@ attn_bwd_dq_kernel(const bf16* __restrict__ q, const bf16* __restrict__ k, const
 // Works on transposed tiles (keys x queries) so that P^T / dS^T feed the next MMA straight from registers.
 // ---------------------------------------------------------------------------------------------------------------
 template <int HDP>
-__global__ void __launch_bounds__(ATT_THREADS)
+__global__ void __launch_bounds__(ATT_THREADS, 2)
 attn_bwd_dkv_kernel(const bf16* __restrict__ q, const bf16* __restrict__ k, const bf16* __restrict__ v, const bf16* __restrict__ bias,
                     const bf16* __restrict__ d_o, const float* __restrict__ lse, const float* __restrict__ delta, bf16* __restrict__ dk,
                     bf16* __restrict__ dv, bf16* __restrict__ dbias, long long ld_q, long long ld_k, long long ld_v, long long ld_do,
@@ -323,7 +336,8 @@ attn_bwd_dkv_kernel(const bf16* __restrict__ q, const bf16* __restrict__ k, cons
   bf16* Vs = Ks + TILE * P;
   bf16* Qs = Vs + TILE * P;
   bf16* dOs = Qs + TILE * P;
-  float* lse_s = reinterpret_cast<float*>(dOs + TILE * P);  // TILE
+  bf16* Bs = dOs + TILE * P;                                 // TILE x BP bias block [query][key]
+  float* lse_s = reinterpret_cast<float*>(Bs + TILE * BP);   // TILE
   float* dlt_s = lse_s + TILE;                               // TILE
   float* db_s = dlt_s + TILE;                                // s_pad x DBP   [query][key]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -351,6 +365,7 @@ attn_bwd_dkv_kernel(const bf16* __restrict__ q, const bf16* __restrict__ k, cons
       __syncthreads();
       load_tile<HDP>(Qs, q + (tok0 + q0) * ld_q + (long long)h * hd, ld_q, S - q0, hd);
       load_tile<HDP>(dOs, d_o + (tok0 + q0) * ld_do + (long long)h * hd, ld_do, S - q0, hd);
+      load_bias_tile(Bs, bias_b, S, q0, k0);
       if (threadIdx.x < TILE) {
         const int row = q0 + threadIdx.x;
         const long long idx = ((long long)b * heads + h) * S + row;
@@ -372,7 +387,7 @@ attn_bwd_dkv_kernel(const bf16* __restrict__ q, const bf16* __restrict__ k, cons
           const int qrow = q0 + ql;
           float p = 0.f;
           if (key < S && qrow < S) {
-            const float bb = __bfloat162float(bias_b[(long long)qrow * S + key]);
+            const float bb = __bfloat162float(Bs[ql * BP + (key - k0)]);
             p = exp2f(st[nt][e] * scale_log2 + bb * LOG2E - lse_s[ql]);
           }
           st[nt][e] = p;                                   // P^T
@@ -410,10 +425,10 @@ attn_bwd_dkv_kernel(const bf16* __restrict__ q, const bf16* __restrict__ k, cons
   }
 }
 
-template <int HDP> size_t fwd_smem() { return (size_t)3 * TILE * (HDP + 8) * sizeof(bf16); }
-template <int HDP> size_t dq_smem() { return (size_t)4 * TILE * (HDP + 8) * sizeof(bf16); }
+template <int HDP> size_t fwd_smem() { return (size_t)(3 * TILE * (HDP + 8) + TILE * BP) * sizeof(bf16); }
+template <int HDP> size_t dq_smem() { return (size_t)(4 * TILE * (HDP + 8) + TILE * BP) * sizeof(bf16); }
 template <int HDP> size_t dkv_smem(int s_pad) {
-  return (size_t)4 * TILE * (HDP + 8) * sizeof(bf16) + 2 * TILE * sizeof(float) + (size_t)s_pad * (TILE + 1) * sizeof(float);
+  return (size_t)(4 * TILE * (HDP + 8) + TILE * BP) * sizeof(bf16) + 2 * TILE * sizeof(float) + (size_t)s_pad * (TILE + 1) * sizeof(float);
 }
 
 template <typename K>
@@ -474,8 +489,8 @@ int launch_bwd(const void* q, const void* k, const void* v, const void* bias, co
 
 int check_common(const char* name, int B, int S, int heads, int hd) {
   CALM_CHECK_ARG(B > 0 && S > 0 && heads > 0 && hd > 0, "%s: empty problem", name);
-  CALM_CHECK_ARG(hd % 2 == 0 && hd <= 128, "%s: head_dim=%d must be even and <= 128", name, hd);
-  CALM_CHECK_ARG(S % 2 == 0, "%s: S=%d must be even", name, S);
+  CALM_CHECK_ARG(hd % 4 == 0 && hd <= 128, "%s: head_dim=%d must be a multiple of 4 and <= 128", name, hd);
+  CALM_CHECK_ARG(S % 4 == 0, "%s: S=%d must be a multiple of 4", name, S);
   return CALM_OK;
 }
 
@@ -497,6 +512,7 @@ extern "C" int32_t calm_attention_fwd(const void* q, const void* k, const void* 
   int rc = check_common("calm_attention_fwd", B, S, heads, hd);
   if (rc) return rc;
   CALM_CHECK_ARG(ld_q % 2 == 0 && ld_k % 2 == 0 && ld_v % 2 == 0 && ld_o % 2 == 0, "calm_attention_fwd: leading dims must be even");
+  CALM_CHECK_ARG(ld_q % 4 == 0 && ld_k % 4 == 0 && ld_v % 4 == 0, "calm_attention_fwd: q/k/v leading dims must be multiples of 4");
   DISPATCH_HDP(hd, return launch_fwd<HDP>(q, k, v, bias, o, lse, ld_q, ld_k, ld_v, ld_o, B, S, heads, hd, stream));
   return CALM_OK;
 }
@@ -509,9 +525,11 @@ extern "C" int32_t calm_attention_bwd(const void* q, const void* k, const void* 
   if (rc) return rc;
   CALM_CHECK_ARG(ld_q % 2 == 0 && ld_k % 2 == 0 && ld_v % 2 == 0 && ld_o % 2 == 0 && ld_do % 2 == 0 && ld_dq % 2 == 0 &&
                  ld_dk % 2 == 0 && ld_dv % 2 == 0, "calm_attention_bwd: leading dims must be even");
+  CALM_CHECK_ARG(ld_q % 4 == 0 && ld_k % 4 == 0 && ld_v % 4 == 0 && ld_o % 4 == 0 && ld_do % 4 == 0,
+                 "calm_attention_bwd: q/k/v/o/dO leading dims must be multiples of 4");
   const long long tokens = (long long)B * S;
-  const long long warps = tokens * heads;
-  attn_delta_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, stream>>>(
+  const long long nthr = tokens * heads;
+  attn_delta_kernel<<<(unsigned)((nthr + 255) / 256), 256, 0, stream>>>(
       reinterpret_cast<const bf16*>(o), reinterpret_cast<const bf16*>(d_o), delta, ld_o, ld_do, tokens, S, heads, hd);
   CALM_CHECK_LAUNCH("calm_attention_bwd(delta)");
   DISPATCH_HDP(hd, return launch_bwd<HDP>(q, k, v, bias, d_o, lse, delta, dq, dk, dv, dbias, ld_q, ld_k, ld_v, ld_do, ld_dq, ld_dk,

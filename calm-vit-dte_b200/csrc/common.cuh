@@ -65,13 +65,23 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
   return r;
 }
 
-// exact (erf) GELU and its derivative, fp32
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
-__device__ __forceinline__ float dgelu_erf(float x) {
-  const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752f));
-  const float pdf = 0.3989422804014327f * __expf(-0.5f * x * x);
-  return cdf + x * pdf;
+// exact-erf GELU and its derivative in fp32: Phi(x) = 1 - 0.5 erfc(x/sqrt2) with erfc from Abramowitz-Stegun 7.1.26
+// (|abs err| < 1.5e-7; one MUFU.RCP + one MUFU.EX2 — ~2.5x cheaper than erff, and the derivative reuses the exponential)
+__device__ __forceinline__ void gelu_pair(float x, float& g, float& dg) {
+  const float z = fabsf(x) * 0.70710678118654752f;
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  const float e = __expf(-z * z);    // exp(-x^2/2)
+  const float q = 0.5f * p * t * e;  // Phi(-|x|)
+  const float phi = x >= 0.f ? 1.0f - q : q;
+  g = x * phi;
+  dg = fmaf(x * 0.3989422804014327f, e, phi);
 }
+__device__ __forceinline__ float gelu_erf(float x) { float g, dg; gelu_pair(x, g, dg); return g; }
+__device__ __forceinline__ float dgelu_erf(float x) { float g, dg; gelu_pair(x, g, dg); return dg; }
 
 __device__ __forceinline__ float bf16_bits_to_float(uint16_t b) { return __uint_as_float(((uint32_t)b) << 16); }
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {

@@ -108,12 +108,95 @@ ln_bwd_kernel(const void* __restrict__ dy, const float* __restrict__ x, const fl
   }
 }
 
-__global__ void reduce_partials_kernel(const float* __restrict__ partial, float* __restrict__ out, int nparts, int n) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= n) return;
+// Register-resident variant for D <= 128*VPL: each row is read ONCE (x, dy stay in registers between the statistics and
+// the output pass), a lane owns fixed columns so the dw accumulators live in registers too (no shared-memory
+// read-modify-write per element); shared memory is only used to combine the 8 warps of a CTA at the very end.
+template <int VPL, bool DY_F32>
+__global__ void __launch_bounds__(LN_THREADS)
+ln_bwd_reg_kernel(const void* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ w,
+                  const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ dres,
+                  float* __restrict__ dx, float* __restrict__ dw_partial, long long rows, int D) {
+  extern __shared__ float acc_s[];  // LN_WARPS * D
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nv = D >> 2;
+  float4 wv[VPL], dwa[VPL];
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int idx = lane + 32 * i;
+    wv[i] = idx < nv ? reinterpret_cast<const float4*>(w)[idx] : make_float4(0.f, 0.f, 0.f, 0.f);
+    dwa[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  const float invD = 1.0f / D;
+  for (long long row = (long long)blockIdx.x * LN_WARPS + warp; row < rows; row += (long long)gridDim.x * LN_WARPS) {
+    const float mu = mean[row], rs = rstd[row];
+    float4 hv[VPL], dv[VPL];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int idx = lane + 32 * i;
+      if (idx < nv) {
+        const float4 xv = reinterpret_cast<const float4*>(x + row * D)[idx];
+        dv[i] = load_dy4<DY_F32>(dy, row, D, idx);
+        hv[i] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
+      } else {
+        dv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        hv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      const float g0 = dv[i].x * wv[i].x, g1 = dv[i].y * wv[i].y, g2 = dv[i].z * wv[i].z, g3 = dv[i].w * wv[i].w;
+      s1 += g0 + g1 + g2 + g3;
+      s2 += g0 * hv[i].x + g1 * hv[i].y + g2 * hv[i].z + g3 * hv[i].w;
+      dwa[i].x = fmaf(dv[i].x, hv[i].x, dwa[i].x); dwa[i].y = fmaf(dv[i].y, hv[i].y, dwa[i].y);
+      dwa[i].z = fmaf(dv[i].z, hv[i].z, dwa[i].z); dwa[i].w = fmaf(dv[i].w, hv[i].w, dwa[i].w);
+    }
+    const float c2 = warp_sum(s1) * invD, c1 = warp_sum(s2) * invD;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int idx = lane + 32 * i;
+      if (idx < nv) {
+        float4 o;
+        o.x = rs * (dv[i].x * wv[i].x - c2 - hv[i].x * c1);
+        o.y = rs * (dv[i].y * wv[i].y - c2 - hv[i].y * c1);
+        o.z = rs * (dv[i].z * wv[i].z - c2 - hv[i].z * c1);
+        o.w = rs * (dv[i].w * wv[i].w - c2 - hv[i].w * c1);
+        if (dres) {
+          const float4 r = reinterpret_cast<const float4*>(dres + row * D)[idx];
+          o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+        }
+        reinterpret_cast<float4*>(dx + row * D)[idx] = o;
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int idx = lane + 32 * i;
+    if (idx < nv) reinterpret_cast<float4*>(acc_s + (size_t)warp * D)[idx] = dwa[i];
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < D; c += LN_THREADS) {
+    float s = 0.f;
+#pragma unroll
+    for (int wv2 = 0; wv2 < LN_WARPS; ++wv2) s += acc_s[(size_t)wv2 * D + c];
+    dw_partial[(size_t)blockIdx.x * D + c] = s;
+  }
+}
+
+// out[c] = sum_p partial[p][c]: 32 columns per CTA, 8 row-groups reduced through shared memory (deterministic)
+__global__ void __launch_bounds__(256)
+reduce_partials_kernel(const float* __restrict__ partial, float* __restrict__ out, int nparts, int n) {
+  __shared__ float red[8][33];
+  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cx;
   float s = 0.f;
-  for (int p = 0; p < nparts; ++p) s += partial[(size_t)p * n + c];
-  out[c] = s;
+  if (c < n)
+    for (int p = ry; p < nparts; p += 8) s += partial[(size_t)p * n + c];
+  red[ry][cx] = s;
+  __syncthreads();
+  if (ry == 0 && c < n) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += red[k][cx];
+    out[c] = t;
+  }
 }
 
 }  // namespace
@@ -131,7 +214,7 @@ extern "C" int32_t calm_layernorm_fwd(const float* x, const float* w, void* y, i
 extern "C" int32_t calm_layernorm_bwd_parts(int64_t rows, int32_t D) {
   (void)D;
   long long need = (rows + LN_WARPS - 1) / LN_WARPS;
-  const long long cap = 2LL * calm_num_sms();
+  const long long cap = 4LL * calm_num_sms();
   return (int32_t)(need < cap ? need : cap);
 }
 
@@ -141,18 +224,23 @@ extern "C" int32_t calm_layernorm_bwd(const void* dy, int32_t dy_dtype, const fl
   CALM_CHECK_ARG(rows > 0 && D > 0 && D % 4 == 0, "calm_layernorm_bwd: rows=%lld D=%d", (long long)rows, D);
   CALM_CHECK_ARG(nparts == calm_layernorm_bwd_parts(rows, D), "calm_layernorm_bwd: nparts=%d, expected %d", nparts, calm_layernorm_bwd_parts(rows, D));
   const size_t smem = (size_t)LN_WARPS * D * sizeof(float);
-  static size_t configured[2] = {0, 0};
-  const int which = dy_dtype == CALM_F32 ? 1 : 0;
-  if (smem > 48 * 1024 && smem > configured[which]) {
-    cudaError_t e = which ? cudaFuncSetAttribute(ln_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
-                          : cudaFuncSetAttribute(ln_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) { calm_set_error("calm_layernorm_bwd: smem %zu: %s", smem, cudaGetErrorString(e)); return CALM_ERR_CUDA; }
-    configured[which] = smem;
-  }
-  if (which) ln_bwd_kernel<true><<<nparts, LN_THREADS, smem, stream>>>(dy, x, w, mean, rstd, dres, dx, dw_partial, rows, D);
-  else       ln_bwd_kernel<false><<<nparts, LN_THREADS, smem, stream>>>(dy, x, w, mean, rstd, dres, dx, dw_partial, rows, D);
+  const bool f32 = dy_dtype == CALM_F32;
+  const int vpl = (D / 4 + 31) / 32;  // float4 per lane and row
+#define LN_BWD_LAUNCH(KERNEL)                                                                                         \
+  do {                                                                                                                \
+    if (smem > 48 * 1024) {                                                                                           \
+      cudaError_t e = cudaFuncSetAttribute(KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);           \
+      if (e != cudaSuccess) { calm_set_error("calm_layernorm_bwd: smem %zu: %s", smem, cudaGetErrorString(e)); return CALM_ERR_CUDA; } \
+    }                                                                                                                 \
+    KERNEL<<<nparts, LN_THREADS, smem, stream>>>(dy, x, w, mean, rstd, dres, dx, dw_partial, rows, D);                 \
+  } while (0)
+  if (vpl <= 3) { if (f32) LN_BWD_LAUNCH((ln_bwd_reg_kernel<3, true>)); else LN_BWD_LAUNCH((ln_bwd_reg_kernel<3, false>)); }
+  else if (vpl <= 6) { if (f32) LN_BWD_LAUNCH((ln_bwd_reg_kernel<6, true>)); else LN_BWD_LAUNCH((ln_bwd_reg_kernel<6, false>)); }
+  else if (vpl <= 12) { if (f32) LN_BWD_LAUNCH((ln_bwd_reg_kernel<12, true>)); else LN_BWD_LAUNCH((ln_bwd_reg_kernel<12, false>)); }
+  else { if (f32) LN_BWD_LAUNCH((ln_bwd_kernel<true>)); else LN_BWD_LAUNCH((ln_bwd_kernel<false>)); }
+#undef LN_BWD_LAUNCH
   CALM_CHECK_LAUNCH("calm_layernorm_bwd");
-  reduce_partials_kernel<<<(D + 127) / 128, 128, 0, stream>>>(dw_partial, dw, nparts, D);
+  reduce_partials_kernel<<<(D + 31) / 32, 256, 0, stream>>>(dw_partial, dw, nparts, D);
   CALM_CHECK_LAUNCH("calm_layernorm_bwd(reduce)");
   return CALM_OK;
 }

@@ -41,23 +41,48 @@ __global__ void nchw_to_tokens_kernel(const float* __restrict__ in, float* __res
   out[i] = in[(b * 3 + ch) * plane + p];
 }
 
-// per-CTA column sums of a bf16 (rows, N) matrix
+// per-CTA column sums of a bf16 (rows, N) matrix: a thread owns 2 adjacent columns (one 4-byte load per row), rows are
+// strided over the CTAs and unrolled 4x for memory-level parallelism
 __global__ void __launch_bounds__(256)
 colsum_kernel(const bf16* __restrict__ x, long long ld, float* __restrict__ partial, long long rows, int N) {
-  // thread t owns columns t, t+256, ...; CTAs stride over rows
-  for (int c = threadIdx.x; c < N; c += 256) {
-    float s = 0.f;
-    for (long long r = blockIdx.x; r < rows; r += gridDim.x) s += __bfloat162float(x[r * ld + c]);
-    partial[(size_t)blockIdx.x * N + c] = s;
+  for (int c = 2 * threadIdx.x; c < N; c += 512) {
+    float s0 = 0.f, s1 = 0.f;
+    long long r = blockIdx.x;
+    const long long step = gridDim.x;
+    for (; r + 3 * step < rows; r += 4 * step) {
+      const float2 a = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(x + r * ld + c));
+      const float2 b = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(x + (r + step) * ld + c));
+      const float2 d = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(x + (r + 2 * step) * ld + c));
+      const float2 e = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(x + (r + 3 * step) * ld + c));
+      s0 += (a.x + b.x) + (d.x + e.x);
+      s1 += (a.y + b.y) + (d.y + e.y);
+    }
+    for (; r < rows; r += step) {
+      const float2 a = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(x + r * ld + c));
+      s0 += a.x; s1 += a.y;
+    }
+    partial[(size_t)blockIdx.x * N + c] = s0;
+    partial[(size_t)blockIdx.x * N + c + 1] = s1;
   }
 }
 
-__global__ void reduce_cols_kernel(const float* __restrict__ partial, float* __restrict__ out, int nparts, int n) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= n) return;
+// out[c] = sum_p partial[p][c]: 32 columns per CTA, 8 row-groups combined through shared memory (deterministic)
+__global__ void __launch_bounds__(256)
+reduce_cols_kernel(const float* __restrict__ partial, float* __restrict__ out, int nparts, int n) {
+  __shared__ float red[8][33];
+  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cx;
   float s = 0.f;
-  for (int p = 0; p < nparts; ++p) s += partial[(size_t)p * n + c];
-  out[c] = s;
+  if (c < n)
+    for (int p = ry; p < nparts; p += 8) s += partial[(size_t)p * n + c];
+  red[ry][cx] = s;
+  __syncthreads();
+  if (ry == 0 && c < n) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += red[k][cx];
+    out[c] = t;
+  }
 }
 
 __global__ void add3_kernel(const float4* __restrict__ a, const float4* __restrict__ b, const float4* __restrict__ c,
@@ -128,11 +153,11 @@ extern "C" int32_t calm_colsum_parts(int64_t rows, int32_t N) {
 
 extern "C" int32_t calm_colsum(const void* x, int64_t ld, float* partial, int32_t nparts, float* out, int64_t rows, int32_t N,
                                cudaStream_t stream) {
-  CALM_CHECK_ARG(rows > 0 && N > 0, "calm_colsum: rows=%lld N=%d", (long long)rows, N);
+  CALM_CHECK_ARG(rows > 0 && N > 0 && N % 2 == 0 && ld % 2 == 0, "calm_colsum: rows=%lld N=%d ld=%lld (N, ld must be even)", (long long)rows, N, (long long)ld);
   CALM_CHECK_ARG(nparts == calm_colsum_parts(rows, N), "calm_colsum: nparts=%d expected %d", nparts, calm_colsum_parts(rows, N));
   colsum_kernel<<<nparts, 256, 0, stream>>>(reinterpret_cast<const bf16*>(x), ld, partial, rows, N);
   CALM_CHECK_LAUNCH("calm_colsum");
-  reduce_cols_kernel<<<(N + 127) / 128, 128, 0, stream>>>(partial, out, nparts, N);
+  reduce_cols_kernel<<<(N + 31) / 32, 256, 0, stream>>>(partial, out, nparts, N);
   CALM_CHECK_LAUNCH("calm_colsum(reduce)");
   return CALM_OK;
 }

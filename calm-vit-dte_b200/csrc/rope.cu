@@ -20,28 +20,49 @@ __global__ void rope_table_kernel(const float* __restrict__ inv_freq, float* __r
   cs[2 * i + 1] = sn;
 }
 
-__global__ void rope_fwd_kernel(const bf16* __restrict__ content, long long ld_content, const bf16* __restrict__ ropein,
-                                long long ld_rope, bf16* __restrict__ out, long long ld_out, const float* __restrict__ cs,
-                                long long tokens, int S, int heads, int dc, int dr) {
+// One CTA per ROPE_TPC consecutive tokens; a thread resolves its (head, element) once and then walks the CTA's tokens, so the
+// index arithmetic is amortised and ROPE_TPC independent load chains are in flight per thread.
+constexpr int ROPE_TPC = 8;
+__global__ void __launch_bounds__(256)
+rope_fwd_kernel(const bf16* __restrict__ content, long long ld_content, const bf16* __restrict__ ropein, long long ld_rope,
+                bf16* __restrict__ out, long long ld_out, const float* __restrict__ cs, long long tokens, int S, int heads,
+                int dc, int dr) {
   const int half = dr >> 1;
-  const int per_head = dc + half;             // work items per (token, head): dc copies + half rotations
+  const int per_head = dc + half;  // work items per (token, head): dc copies + half rotations
   const int per_tok = heads * per_head;
-  const long long total = tokens * per_tok;
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
-    const long long t = idx / per_tok;
-    const int rem = (int)(idx - t * per_tok);
-    const int h = rem / per_head, i = rem - h * per_head;
-    bf16* o = out + t * ld_out + (long long)h * (dc + dr);
+  const long long t0 = (long long)blockIdx.x * ROPE_TPC;
+  const int nt = (int)min((long long)ROPE_TPC, tokens - t0);
+  const int p0 = (int)(t0 % S);
+  const float2* cs2 = reinterpret_cast<const float2*>(cs);
+  for (int w = threadIdx.x; w < per_tok; w += blockDim.x) {
+    const int h = w / per_head, i = w - h * per_head;
     if (i < dc) {
-      o[i] = content[t * ld_content + (long long)h * dc + i];
+#pragma unroll
+      for (int k = 0; k < ROPE_TPC; ++k)
+        if (k < nt) out[(t0 + k) * ld_out + (long long)h * (dc + dr) + i] = content[(t0 + k) * ld_content + (long long)h * dc + i];
     } else {
       const int j = i - dc;
-      const int pos = (int)(t % S);
-      const float c = cs[2 * (pos * half + j)], s = cs[2 * (pos * half + j) + 1];
-      const bf16* r = ropein + t * ld_rope + (long long)h * dr;
-      const float x1 = __bfloat162float(r[j]), x2 = __bfloat162float(r[j + half]);
-      o[dc + j] = __float2bfloat16(x1 * c - x2 * s);
-      o[dc + j + half] = __float2bfloat16(x2 * c + x1 * s);
+      float x1[ROPE_TPC], x2[ROPE_TPC];
+      float2 csv[ROPE_TPC];
+#pragma unroll
+      for (int k = 0; k < ROPE_TPC; ++k) {
+        if (k < nt) {
+          int pos = p0 + k;
+          if (pos >= S) pos -= S;
+          const bf16* r = ropein + (t0 + k) * ld_rope + (long long)h * dr;
+          x1[k] = __bfloat162float(r[j]);
+          x2[k] = __bfloat162float(r[j + half]);
+          csv[k] = cs2[pos * half + j];
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < ROPE_TPC; ++k) {
+        if (k < nt) {
+          bf16* o = out + (t0 + k) * ld_out + (long long)h * (dc + dr) + dc;
+          o[j] = __float2bfloat16(x1[k] * csv[k].x - x2[k] * csv[k].y);
+          o[j + half] = __float2bfloat16(x2[k] * csv[k].x + x1[k] * csv[k].y);
+        }
+      }
     }
   }
 }
@@ -118,10 +139,8 @@ extern "C" int32_t calm_rope_fwd(const void* content, int64_t ld_content, const 
                                  int32_t dr, cudaStream_t stream) {
   CALM_CHECK_ARG(tokens > 0 && S > 0 && heads > 0 && dr > 0 && dr % 2 == 0 && dc >= 0, "calm_rope_fwd: bad dims");
   CALM_CHECK_ARG(dc == 0 || content != nullptr, "calm_rope_fwd: content missing");
-  const long long total = tokens * heads * (dc + dr / 2);
-  long long blocks = (total + 255) / 256;
-  const long long cap = 16LL * calm_num_sms();
-  if (blocks > cap) blocks = cap;
+  CALM_CHECK_ARG(S >= ROPE_TPC, "calm_rope_fwd: S=%d too short", S);
+  const long long blocks = (tokens + ROPE_TPC - 1) / ROPE_TPC;
   rope_fwd_kernel<<<(unsigned)blocks, 256, 0, stream>>>(reinterpret_cast<const bf16*>(content), ld_content,
                                                          reinterpret_cast<const bf16*>(ropein), ld_rope,
                                                          reinterpret_cast<bf16*>(out), ld_out, cos_sin, tokens, S, heads, dc, dr);

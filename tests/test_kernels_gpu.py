@@ -35,6 +35,7 @@ def K():
 GEMM_SHAPES = [
     # M, N, K
     (128, 64, 64), (300, 264, 240), (256, 672, 672), (1000, 1344, 672), (513, 240, 528), (96, 16, 80), (128, 1000, 1344),
+    (384, 480, 240), (200, 528, 176), (130, 8, 64),   # BN=240 (tile width not a multiple of the 32-column epilogue chunk), tails
 ]
 
 
