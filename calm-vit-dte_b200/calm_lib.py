@@ -67,7 +67,7 @@ PROTOTYPES = {
     "calm_rope_bwd_scratch_floats": (i32, [i32, i32]),
     "calm_rope_bwd": (i32, [vp, i64, vp, i64, vp, i64, vp, i64, vp, vp, vp, i64, i32, i32, i32, i32, vp]),
     "calm_attention_fwd": (i32, [vp, vp, vp, vp, vp, vp, i64, i64, i64, i64, i32, i32, i32, i32, vp]),
-    "calm_attention_bwd": (i32, [vp] * 12 + [i64] * 8 + [i32] * 4 + [vp]),
+    "calm_attention_bwd": (i32, [vp] * 13 + [i64] * 8 + [i32] * 4 + [vp]),
     "calm_latent_fwd": (i32, [vp, vp, vp, vp, vp, vp, i32, i64, i32, vp]),
     "calm_latent_kl": (i32, [vp, vp, i32, vp, vp, f32, vp]),
     "calm_latent_bwd": (i32, [vp, vp, vp, vp, f32, vp, vp, vp, i64, i32, vp]),

@@ -11,6 +11,7 @@
 // that are not multiples of 16 (56, 44, 20, ...) are zero-padded in shared memory only.
 #include "common.cuh"
 #include "../../include/calm_b200.h"
+#include "attention_tc.h"
 #include <math.h>
 
 namespace {
@@ -513,12 +514,18 @@ extern "C" int32_t calm_attention_fwd(const void* q, const void* k, const void* 
   if (rc) return rc;
   CALM_CHECK_ARG(ld_q % 2 == 0 && ld_k % 2 == 0 && ld_v % 2 == 0 && ld_o % 2 == 0, "calm_attention_fwd: leading dims must be even");
   CALM_CHECK_ARG(ld_q % 4 == 0 && ld_k % 4 == 0 && ld_v % 4 == 0, "calm_attention_fwd: q/k/v leading dims must be multiples of 4");
+  {
+    const int64_t lds[3] = {ld_q, ld_k, ld_v};
+    const void* ptrs[4] = {q, k, v, bias};
+    if (!(calm_get_debug_flags() & CALM_DEBUG_LEGACY_ATTENTION) && calm_attention_tc_eligible(B, S, heads, hd, lds, 3, ptrs, 4))
+      return calm_attention_fwd_tc(q, k, v, bias, o, lse, ld_q, ld_k, ld_v, ld_o, B, S, heads, hd, stream);
+  }
   DISPATCH_HDP(hd, return launch_fwd<HDP>(q, k, v, bias, o, lse, ld_q, ld_k, ld_v, ld_o, B, S, heads, hd, stream));
   return CALM_OK;
 }
 
 extern "C" int32_t calm_attention_bwd(const void* q, const void* k, const void* v, const void* bias, const void* o, const void* d_o,
-                                      const float* lse, float* delta, void* dq, void* dk, void* dv, void* dbias, int64_t ld_q,
+                                      const float* lse, float* delta, void* dq, void* dk, void* dv, void* dbias, float* dbias_acc, int64_t ld_q,
                                       int64_t ld_k, int64_t ld_v, int64_t ld_o, int64_t ld_do, int64_t ld_dq, int64_t ld_dk,
                                       int64_t ld_dv, int32_t B, int32_t S, int32_t heads, int32_t hd, cudaStream_t stream) {
   int rc = check_common("calm_attention_bwd", B, S, heads, hd);
@@ -532,6 +539,13 @@ extern "C" int32_t calm_attention_bwd(const void* q, const void* k, const void* 
   attn_delta_kernel<<<(unsigned)((nthr + 255) / 256), 256, 0, stream>>>(
       reinterpret_cast<const bf16*>(o), reinterpret_cast<const bf16*>(d_o), delta, ld_o, ld_do, tokens, S, heads, hd);
   CALM_CHECK_LAUNCH("calm_attention_bwd(delta)");
+  {
+    const int64_t lds[4] = {ld_q, ld_k, ld_v, ld_do};
+    const void* ptrs[6] = {q, k, v, d_o, bias, dbias};
+    if (dbias_acc && !(calm_get_debug_flags() & CALM_DEBUG_LEGACY_ATTENTION) && calm_attention_tc_eligible(B, S, heads, hd, lds, 4, ptrs, 6))
+      return calm_attention_bwd_tc(q, k, v, bias, d_o, lse, delta, dq, dk, dv, dbias, dbias_acc, ld_q, ld_k, ld_v, ld_do, ld_dq, ld_dk,
+                                   ld_dv, B, S, heads, hd, stream);
+  }
   DISPATCH_HDP(hd, return launch_bwd<HDP>(q, k, v, bias, d_o, lse, delta, dq, dk, dv, dbias, ld_q, ld_k, ld_v, ld_do, ld_dq, ld_dk,
                                           ld_dv, B, S, heads, hd, stream));
   return CALM_OK;

@@ -1,0 +1,555 @@
+// Axial attention with a shared additive bias on the Blackwell tensor cores (tcgen05 + TMEM + TMA), forward and backward.
+//   O = softmax(Q K^T / sqrt(hd) + bias[b]) V        (Vi_Tools_CNN_less_V2.py:293-298; bias = linear_mask(...), :288-291)
+//
+// The sequences of this model are short (S = image side <= 256 at 224^2: 224/176/128/80), so a whole key axis fits one
+// TMEM accumulator: S = Q K^T for a 128-query tile is ONE tcgen05.mma chain into <= 256 fp32 columns, the softmax needs no
+// online rescaling, and P (bf16) goes back to shared memory as the A operand of the P.V MMA. One thread owns one query row
+// (= one TMEM lane), so row max / row sum are plain register reductions — no shuffles.
+//
+// Roles per CTA (160 threads, one CTA per SM, persistent): warps 0-3 = 128 row workers (softmax, epilogues; warp w reads
+// TMEM lanes 32w..32w+31), warp 4 lane 0 = controller (TMA loads + MMA issue). Hand-offs are mbarriers:
+//   bar_kv / bar_q : TMA transaction barriers          bar_mma : tcgen05.commit -> workers      bar_work : 128 worker arrivals -> controller
+//
+// Layouts: Q/K/V/dO tiles are TMA boxes {64 columns, rows} with the 128-byte swizzle, i.e. directly the K-major UMMA
+// operand layout (rows of 128 B). Head dims 56/44/20 are not multiples of the 16-wide MMA K step: the box still brings 64
+// columns (the tail belongs to the next head), the workers zero the tail of the Q (and dO) rows in shared memory, and the
+// MMA runs over hd rounded up to 16 — the garbage tail of K/V then multiplies zeros.
+// V (keys x hd) serves as the MN-major B operand of P.V; in backward the same P / dS tiles serve K-major (dQ = dS K) and
+// MN-major (dK = dS^T Q, dV = P^T dO) without a second copy.
+//
+// Backward: per image the CTA walks the 12 heads; per head and 128-query tile
+//   S = Q K^T and dP = dO V^T in key parts of <= 96 columns  ->  P = exp2(S c + bias - lse), dS = P (dP - delta)
+//   dQ = dS K (complete per tile), dK += dS^T Q, dV += P^T dO (accumulated in TMEM over the query tiles)
+// TMEM budget (512 columns): S part 96 | dP part 96 | dQ 64 | dK 2 x 64 | dV 2 x 64.
+// dbias[b] = sum over heads of dS is accumulated by the row's owner thread in an fp32 scratch matrix (same thread, same
+// row for every head: no atomics, deterministic) and written as bf16 by the last head.
+#include "tcgen05.cuh"
+#include "attention_tc.h"
+
+namespace {
+
+using namespace tc;
+
+constexpr int NTHREADS = 160;
+constexpr int NWORKERS = 128;
+constexpr float LOG2E = 1.4426950408889634f;
+constexpr float LN2 = 0.6931471805599453f;
+constexpr int KV_BYTES = 256 * 128;     // up to 256 keys x 64 columns bf16
+constexpr int QT_BYTES = 128 * 128;     // 128 query rows x 64 columns
+constexpr int P_BYTES = 4 * 16384;      // 128 rows x 256 key columns bf16 = 4 swizzle atoms of [128][64]
+constexpr int TMEM_COLS = 512;
+
+struct Common {
+  int B, S, heads, hd;
+  float scale, scale_log2;
+  const bf16* bias;          // (B, S, S)
+  int* err_flag;
+};
+
+// A TMA box must start on a 16-byte boundary of the row, but a head starts at column h*hd (8-byte granularity when
+// hd % 8 == 4: 44, 20, ...). The box therefore starts at the aligned-down column; the head's columns sit at
+// [shift, shift + hd) of the 64-column tile, shift in {0, 4}, and the MMAs run over hdp = roundup16(shift + hd) columns.
+struct HeadCols { int col0, shift, hdp; };
+__device__ __forceinline__ HeadCols head_cols(int h, int hd) {
+  HeadCols hc;
+  const int c = h * hd;
+  hc.col0 = c & ~7;
+  hc.shift = c - hc.col0;
+  hc.hdp = (hc.shift + hd + 15) & ~15;
+  return hc;
+}
+// zero the columns of row r that do not belong to the head: [0, shift) and [shift + hd, hdp)   (8-byte units)
+__device__ __forceinline__ void zero_outside(uint8_t* tile, int r, const HeadCols& hc, int hd) {
+  if (hc.shift) *reinterpret_cast<uint2*>(tile + swz128(r, 0)) = make_uint2(0u, 0u);
+  for (int c = hc.shift + hd; c < hc.hdp; c += 4)
+    *reinterpret_cast<uint2*>(tile + swz128(r, c >> 3) + ((c & 4) << 1)) = make_uint2(0u, 0u);
+}
+// store TMEM columns [c0, c0+16) (already scaled) of a row whose head occupies TMEM columns [shift, shift+hd)
+__device__ __forceinline__ void store_cols16(bf16* row, const uint32_t* v, int c0, const HeadCols& hc, int hd, float mul) {
+#pragma unroll
+  for (int j = 0; j < 16; j += 4) {
+    const int g = c0 + j - hc.shift;
+    if (g >= 0 && g < hd) {
+      uint2 u;
+      u.x = pack_bf16x2(__uint_as_float(v[j]) * mul, __uint_as_float(v[j + 1]) * mul);
+      u.y = pack_bf16x2(__uint_as_float(v[j + 2]) * mul, __uint_as_float(v[j + 3]) * mul);
+      *reinterpret_cast<uint2*>(row + g) = u;
+    }
+  }
+}
+
+__device__ __forceinline__ void unpack16(const uint4& a, const uint4& b, float* f) {
+  float2 t;
+  t = unpack_bf16x2(a.x); f[0] = t.x; f[1] = t.y;   t = unpack_bf16x2(a.y); f[2] = t.x; f[3] = t.y;
+  t = unpack_bf16x2(a.z); f[4] = t.x; f[5] = t.y;   t = unpack_bf16x2(a.w); f[6] = t.x; f[7] = t.y;
+  t = unpack_bf16x2(b.x); f[8] = t.x; f[9] = t.y;   t = unpack_bf16x2(b.y); f[10] = t.x; f[11] = t.y;
+  t = unpack_bf16x2(b.z); f[12] = t.x; f[13] = t.y; t = unpack_bf16x2(b.w); f[14] = t.x; f[15] = t.y;
+}
+__device__ __forceinline__ uint4 pack8f(const float* f) {
+  uint4 u;
+  u.x = pack_bf16x2(f[0], f[1]); u.y = pack_bf16x2(f[2], f[3]); u.z = pack_bf16x2(f[4], f[5]); u.w = pack_bf16x2(f[6], f[7]);
+  return u;
+}
+// write 16 consecutive key columns [kc, kc+16) of row r into a [128][256] bf16 tile made of 4 swizzled atoms
+__device__ __forceinline__ void store_row16(uint8_t* tile, int r, int kc, const float* f) {
+  uint8_t* atom = tile + (kc >> 6) * 16384;
+  const int g = (kc & 63) >> 3;
+  *reinterpret_cast<uint4*>(atom + swz128(r, g)) = pack8f(f);
+  *reinterpret_cast<uint4*>(atom + swz128(r, g + 1)) = pack8f(f + 8);
+}
+
+// ====================================================================================================================
+// forward
+// ====================================================================================================================
+struct FwdParams {
+  Common c;
+  bf16* o; long long ld_o;
+  float* lse;  // (B, heads, S), natural log
+};
+
+__global__ void __launch_bounds__(NTHREADS, 1)
+attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap mQ, const __grid_constant__ CUtensorMap mK, const __grid_constant__ CUtensorMap mV,
+                   const FwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sK = smem;
+  uint8_t* sV = sK + KV_BYTES;
+  uint8_t* sQ = sV + KV_BYTES;
+  uint8_t* sP = sQ + QT_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + P_BYTES);  // kv, q, mma, work
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+  const uint32_t bar_kv = smem_u32(&bars[0]), bar_q = smem_u32(&bars[1]), bar_mma = smem_u32(&bars[2]), bar_work = smem_u32(&bars[3]);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const Common& c = p.c;
+  const int S = c.S, hd = c.hd;
+
+  if (threadIdx.x == NWORKERS) {
+    prefetch_tensormap(&mQ); prefetch_tensormap(&mK); prefetch_tensormap(&mV);
+    mbar_init(bar_kv, 1); mbar_init(bar_q, 1); mbar_init(bar_mma, 1); mbar_init(bar_work, NWORKERS);
+    fence_barrier_init();
+  }
+  if (warp == 4) tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
+  fence_before();
+  __syncthreads();
+  fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const int ntiles = (S + 127) >> 7;
+  const int items = c.B * c.heads;
+
+  if (warp == 4) {
+    // ============================ controller: TMA + MMA issue ============================
+    if (lane == 0) {
+      uint32_t ph_kv = 0, ph_q = 0, ph_work = 0;
+      const uint32_t id_s = idesc_bf16(128, S, 0, 0);      // S = Q K^T : both K-major
+      for (int it = blockIdx.x; it < items; it += gridDim.x) {
+        const int b = it / c.heads, h = it - b * c.heads;
+        const HeadCols hc = head_cols(h, hd);
+        const int hdp = hc.hdp;
+        const uint32_t id_o = idesc_bf16(128, hdp, 0, 1);  // O = P V   : A K-major, B (V: keys x hd) MN-major
+        mbar_expect_tx(bar_kv, 2u * S * 128u);
+        tma_load_2d(smem_u32(sK), &mK, bar_kv, hc.col0, b * S);
+        tma_load_2d(smem_u32(sV), &mV, bar_kv, hc.col0, b * S);
+        for (int i = 0; i < ntiles; ++i) {
+          mbar_expect_tx(bar_q, QT_BYTES);
+          tma_load_2d(smem_u32(sQ), &mQ, bar_q, hc.col0, b * S + i * 128);
+          if (i == 0) { mbar_wait(bar_kv, ph_kv, c.err_flag, 11); ph_kv ^= 1; }
+          mbar_wait(bar_q, ph_q, c.err_flag, 12); ph_q ^= 1;
+          mbar_wait(bar_work, ph_work, c.err_flag, 13); ph_work ^= 1;   // A: Q tail zeroed
+          fence_after();
+          for (int ks = 0; ks < hdp / 16; ++ks)
+            mma_bf16(tmem, smem_desc(smem_u32(sQ) + ks * 32, 16, 1024), smem_desc(smem_u32(sK) + ks * 32, 16, 1024), id_s, ks > 0);
+          commit(bar_mma);
+          mbar_wait(bar_work, ph_work, c.err_flag, 14); ph_work ^= 1;   // B: P written
+          fence_after();
+          for (int kk = 0; kk < S / 16; ++kk)
+            mma_bf16(tmem + 256, smem_desc(smem_u32(sP) + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024),
+                     smem_desc(smem_u32(sV) + kk * 2048, 8192, 1024), id_o, kk > 0);
+          commit(bar_mma);
+          mbar_wait(bar_work, ph_work, c.err_flag, 15); ph_work ^= 1;   // C: epilogue done, Q / P / TMEM free
+        }
+      }
+    }
+  } else {
+    // ============================ workers: one query row per thread ============================
+    const int r = threadIdx.x;
+    const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
+    uint32_t ph_kv = 0, ph_q = 0, ph_mma = 0;
+    for (int it = blockIdx.x; it < items; it += gridDim.x) {
+      const int b = it / c.heads, h = it - b * c.heads;
+      const HeadCols hc = head_cols(h, hd);
+      const int hdp = hc.hdp;
+      for (int i = 0; i < ntiles; ++i) {
+        const int q = i * 128 + r;
+        const bool valid = q < S;
+        if (i == 0) { mbar_wait(bar_kv, ph_kv, c.err_flag, 21); ph_kv ^= 1; }
+        mbar_wait(bar_q, ph_q, c.err_flag, 22); ph_q ^= 1;
+        zero_outside(sQ, r, hc, hd);
+        fence_proxy_async();
+        mbar_arrive(bar_work);                                            // A
+        // the row's bias (S bf16 = up to 32 x 16 B) is requested now and lives in registers for both softmax passes:
+        // its latency overlaps the Q.K^T MMA, and the chunk loops below touch only TMEM and registers
+        const bf16* brow = c.bias + ((long long)b * S + (valid ? q : 0)) * S;
+        uint4 bb[32];
+#pragma unroll
+        for (int ch = 0; ch < 16; ++ch) {
+          if (ch * 16 < S) {
+            bb[2 * ch] = *reinterpret_cast<const uint4*>(brow + ch * 16);
+            bb[2 * ch + 1] = *reinterpret_cast<const uint4*>(brow + ch * 16 + 8);
+          }
+        }
+        mbar_wait(bar_mma, ph_mma, c.err_flag, 23); ph_mma ^= 1;
+        fence_after();
+        // pass 1: row maximum of x = s * scale*log2e + bias*log2e
+        float mx = -INFINITY;
+#pragma unroll
+        for (int ch = 0; ch < 16; ++ch) {
+          if (ch * 16 < S) {
+            uint32_t sr[16];
+            tmem_ld16(trow + ch * 16, sr);
+            tmem_ld_wait();
+            float bf[16];
+            unpack16(bb[2 * ch], bb[2 * ch + 1], bf);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) mx = fmaxf(mx, fmaf(__uint_as_float(sr[j]), c.scale_log2, bf[j] * LOG2E));
+          }
+        }
+        // pass 2: P = exp2(x - max), row sum, bf16 P into the swizzled A-operand tile
+        float l = 0.f;
+#pragma unroll
+        for (int ch = 0; ch < 16; ++ch) {
+          if (ch * 16 < S) {
+            uint32_t sr[16];
+            tmem_ld16(trow + ch * 16, sr);
+            tmem_ld_wait();
+            float bf[16], pv[16];
+            unpack16(bb[2 * ch], bb[2 * ch + 1], bf);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              pv[j] = exp2f(fmaf(__uint_as_float(sr[j]), c.scale_log2, fmaf(bf[j], LOG2E, -mx)));
+              l += pv[j];
+            }
+            store_row16(sP, r, ch * 16, pv);
+          }
+        }
+        fence_proxy_async();
+        fence_before();
+        mbar_arrive(bar_work);                                            // B
+        mbar_wait(bar_mma, ph_mma, c.err_flag, 24); ph_mma ^= 1;
+        fence_after();
+        const float inv = 1.0f / l;
+        bf16* orow = p.o + ((long long)b * S + q) * p.ld_o + (long long)h * hd;
+        for (int c0 = 0; c0 < hdp; c0 += 16) {
+          uint32_t orr[16];
+          tmem_ld16(trow + 256 + c0, orr);
+          tmem_ld_wait();
+          if (valid) store_cols16(orow, orr, c0, hc, hd, inv);
+        }
+        if (valid) p.lse[((long long)b * c.heads + h) * S + q] = (mx + log2f(l)) * LN2;
+        fence_before();
+        mbar_arrive(bar_work);                                            // C
+      }
+    }
+  }
+  fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    fence_after();
+    tmem_dealloc(tmem, TMEM_COLS);
+  }
+}
+
+// ====================================================================================================================
+// backward
+// ====================================================================================================================
+struct BwdParams {
+  Common c;
+  const float* lse; const float* delta;  // (B, heads, S)
+  bf16* dq; bf16* dk; bf16* dv; long long ld_dq, ld_dk, ld_dv;
+  bf16* dbias;                            // (B, S, S) bf16 out
+  float* dbias_acc;                       // (B, S, S) fp32 scratch
+};
+
+constexpr int KPART = 96;  // key columns per S / dP part (TMEM: 2 x 96 + 64 + 4 x 64 = 512)
+
+__global__ void __launch_bounds__(NTHREADS, 1)
+attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap mQ, const __grid_constant__ CUtensorMap mK, const __grid_constant__ CUtensorMap mV,
+                   const __grid_constant__ CUtensorMap mDO, const BwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sK = smem;
+  uint8_t* sV = sK + KV_BYTES;
+  uint8_t* sQ = sV + KV_BYTES;
+  uint8_t* sDO = sQ + QT_BYTES;
+  uint8_t* sP = sDO + QT_BYTES;
+  uint8_t* sDS = sP + P_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sDS + P_BYTES);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+  const uint32_t bar_kv = smem_u32(&bars[0]), bar_q = smem_u32(&bars[1]), bar_mma = smem_u32(&bars[2]), bar_work = smem_u32(&bars[3]);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const Common& c = p.c;
+  const int S = c.S, hd = c.hd, heads = c.heads;
+
+  if (threadIdx.x == NWORKERS) {
+    prefetch_tensormap(&mQ); prefetch_tensormap(&mK); prefetch_tensormap(&mV); prefetch_tensormap(&mDO);
+    mbar_init(bar_kv, 1); mbar_init(bar_q, 1); mbar_init(bar_mma, 1); mbar_init(bar_work, NWORKERS);
+    fence_barrier_init();
+  }
+  if (warp == 4) tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
+  fence_before();
+  __syncthreads();
+  fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const int ntiles = (S + 127) >> 7;          // query tiles == key M-tiles
+  const int nparts = (S + KPART - 1) / KPART;
+  constexpr uint32_t T_S = 0, T_DP = 96, T_DQ = 192, T_DK = 256, T_DV = 384;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      uint32_t ph_kv = 0, ph_q = 0, ph_work = 0;
+      for (int b = blockIdx.x; b < c.B; b += gridDim.x) {
+        for (int h = 0; h < heads; ++h) {
+          const HeadCols hc = head_cols(h, hd);
+          const int hdp = hc.hdp;
+          const uint32_t id_dq = idesc_bf16(128, hdp, 0, 1);   // dQ = dS K     : A K-major, B (K: keys x hd) MN-major
+          const uint32_t id_dkv = idesc_bf16(128, hdp, 1, 1);  // dK = dS^T Q   : A MN-major, B (Q: queries x hd) MN-major
+          mbar_expect_tx(bar_kv, 2u * S * 128u);
+          tma_load_2d(smem_u32(sK), &mK, bar_kv, hc.col0, b * S);
+          tma_load_2d(smem_u32(sV), &mV, bar_kv, hc.col0, b * S);
+          for (int i = 0; i < ntiles; ++i) {
+            mbar_expect_tx(bar_q, 2 * QT_BYTES);
+            tma_load_2d(smem_u32(sQ), &mQ, bar_q, hc.col0, b * S + i * 128);
+            tma_load_2d(smem_u32(sDO), &mDO, bar_q, hc.col0, b * S + i * 128);
+            if (i == 0) { mbar_wait(bar_kv, ph_kv, c.err_flag, 31); ph_kv ^= 1; }
+            mbar_wait(bar_q, ph_q, c.err_flag, 32); ph_q ^= 1;
+            for (int part = 0; part < nparts; ++part) {
+              mbar_wait(bar_work, ph_work, c.err_flag, 33); ph_work ^= 1;   // tails zeroed (part 0) / previous part consumed
+              fence_after();
+              const int k0 = part * KPART, w = min(KPART, S - k0);
+              const uint32_t id_s = idesc_bf16(128, w, 0, 0);
+              for (int ks = 0; ks < hdp / 16; ++ks)
+                mma_bf16(tmem + T_S, smem_desc(smem_u32(sQ) + ks * 32, 16, 1024),
+                         smem_desc(smem_u32(sK) + k0 * 128 + ks * 32, 16, 1024), id_s, ks > 0);
+              for (int ks = 0; ks < hdp / 16; ++ks)
+                mma_bf16(tmem + T_DP, smem_desc(smem_u32(sDO) + ks * 32, 16, 1024),
+                         smem_desc(smem_u32(sV) + k0 * 128 + ks * 32, 16, 1024), id_s, ks > 0);
+              commit(bar_mma);
+            }
+            mbar_wait(bar_work, ph_work, c.err_flag, 34); ph_work ^= 1;     // P and dS of this query tile complete
+            fence_after();
+            for (int kk = 0; kk < S / 16; ++kk)     // dQ_i = dS_i K   (contraction over the keys)
+              mma_bf16(tmem + T_DQ, smem_desc(smem_u32(sDS) + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024),
+                       smem_desc(smem_u32(sK) + kk * 2048, 8192, 1024), id_dq, kk > 0);
+            for (int t = 0; t < ntiles; ++t) {      // dK_t += dS_i^T Q_i ; dV_t += P_i^T dO_i   (contraction over this tile's 128 queries)
+              for (int kq = 0; kq < 8; ++kq) {
+                const uint32_t acc = (i > 0 || kq > 0) ? 1u : 0u;
+                mma_bf16(tmem + T_DK + 64 * t, smem_desc(smem_u32(sDS) + 2 * t * 16384 + kq * 2048, 16384, 1024),
+                         smem_desc(smem_u32(sQ) + kq * 2048, 8192, 1024), id_dkv, acc);
+                mma_bf16(tmem + T_DV + 64 * t, smem_desc(smem_u32(sP) + 2 * t * 16384 + kq * 2048, 16384, 1024),
+                         smem_desc(smem_u32(sDO) + kq * 2048, 8192, 1024), id_dkv, acc);
+              }
+            }
+            commit(bar_mma);
+            mbar_wait(bar_work, ph_work, c.err_flag, 35); ph_work ^= 1;     // epilogues done: Q/dO/P/dS tiles and dQ columns free
+          }
+        }
+      }
+    }
+  } else {
+    const int r = threadIdx.x;
+    const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
+    uint32_t ph_kv = 0, ph_q = 0, ph_mma = 0;
+    for (int b = blockIdx.x; b < c.B; b += gridDim.x) {
+      for (int h = 0; h < heads; ++h) {
+        const HeadCols hc = head_cols(h, hd);
+        const int hdp = hc.hdp;
+        for (int i = 0; i < ntiles; ++i) {
+          const int q = i * 128 + r;
+          const bool valid = q < S;
+          if (i == 0) { mbar_wait(bar_kv, ph_kv, c.err_flag, 41); ph_kv ^= 1; }
+          mbar_wait(bar_q, ph_q, c.err_flag, 42); ph_q ^= 1;
+          zero_outside(sQ, r, hc, hd);
+          zero_outside(sDO, r, hc, hd);
+          const long long stat = ((long long)b * heads + h) * S + (valid ? q : 0);
+          const float lse2 = p.lse[stat] * LOG2E, dl = p.delta[stat];
+          const long long rowoff = ((long long)b * S + (valid ? q : 0)) * S;
+          fence_proxy_async();
+          mbar_arrive(bar_work);
+          for (int part = 0; part < nparts; ++part) {
+            const int k0 = part * KPART, w = min(KPART, S - k0);
+            // global operands of this part first (bias row segment, running dbias sums): in flight while the MMAs run
+            uint4 bb[12];
+            float4 ac[24];
+            const bool have_acc = h > 0 && valid;
+#pragma unroll
+            for (int ch = 0; ch < 6; ++ch) {
+              if (ch * 16 < w) {
+                const int kc = k0 + ch * 16;
+                bb[2 * ch] = *reinterpret_cast<const uint4*>(c.bias + rowoff + kc);
+                bb[2 * ch + 1] = *reinterpret_cast<const uint4*>(c.bias + rowoff + kc + 8);
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                  ac[4 * ch + j] = have_acc ? reinterpret_cast<const float4*>(p.dbias_acc + rowoff + kc)[j] : make_float4(0.f, 0.f, 0.f, 0.f);
+              }
+            }
+            mbar_wait(bar_mma, ph_mma, c.err_flag, 43); ph_mma ^= 1;
+            fence_after();
+#pragma unroll
+            for (int ch = 0; ch < 6; ++ch) {
+              if (ch * 16 < w) {
+                const int cc = ch * 16, kc = k0 + cc;
+                uint32_t sr[16], dr[16];
+                tmem_ld16(trow + T_S + cc, sr);
+                tmem_ld16(trow + T_DP + cc, dr);
+                tmem_ld_wait();
+                float bf[16], pv[16], ds[16], acc[16];
+                unpack16(bb[2 * ch], bb[2 * ch + 1], bf);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  acc[4 * j] = ac[4 * ch + j].x; acc[4 * j + 1] = ac[4 * ch + j].y; acc[4 * j + 2] = ac[4 * ch + j].z; acc[4 * j + 3] = ac[4 * ch + j].w;
+                }
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                  const float pj = valid ? exp2f(fmaf(__uint_as_float(sr[j]), c.scale_log2, fmaf(bf[j], LOG2E, -lse2))) : 0.f;
+                  pv[j] = pj;
+                  ds[j] = pj * (__uint_as_float(dr[j]) - dl);   // rows beyond S contribute exact zeros to dK / dV
+                  acc[j] += ds[j];
+                }
+                store_row16(sP, r, kc, pv);
+                store_row16(sDS, r, kc, ds);
+                if (valid) {
+                  if (h == heads - 1) {
+                    uint4* op = reinterpret_cast<uint4*>(p.dbias + rowoff + kc);
+                    op[0] = pack8f(acc); op[1] = pack8f(acc + 8);
+                  } else {
+                    float4* ap = reinterpret_cast<float4*>(p.dbias_acc + rowoff + kc);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) ap[j] = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
+                  }
+                }
+              }
+            }
+            fence_proxy_async();
+            fence_before();
+            mbar_arrive(bar_work);
+          }
+          mbar_wait(bar_mma, ph_mma, c.err_flag, 44); ph_mma ^= 1;
+          fence_after();
+          // dQ rows of this tile
+          {
+            bf16* row = p.dq + ((long long)b * S + q) * p.ld_dq + (long long)h * hd;
+            for (int c0 = 0; c0 < hdp; c0 += 16) {
+              uint32_t v[16];
+              tmem_ld16(trow + T_DQ + c0, v);
+              tmem_ld_wait();
+              if (valid) store_cols16(row, v, c0, hc, hd, c.scale);
+            }
+          }
+          if (i == ntiles - 1) {
+            // dK / dV: TMEM lanes are key rows of M-tile t
+            for (int t = 0; t < ntiles; ++t) {
+              const int key = t * 128 + r;
+              const bool kvalid = key < S;
+              bf16* krow = p.dk + ((long long)b * S + key) * p.ld_dk + (long long)h * hd;
+              bf16* vrow = p.dv + ((long long)b * S + key) * p.ld_dv + (long long)h * hd;
+              for (int c0 = 0; c0 < hdp; c0 += 16) {
+                uint32_t kk[16], vv[16];
+                tmem_ld16(trow + T_DK + 64 * t + c0, kk);
+                tmem_ld16(trow + T_DV + 64 * t + c0, vv);
+                tmem_ld_wait();
+                if (kvalid) {
+                  store_cols16(krow, kk, c0, hc, hd, c.scale);
+                  store_cols16(vrow, vv, c0, hc, hd, 1.0f);
+                }
+              }
+            }
+          }
+          fence_before();
+          mbar_arrive(bar_work);
+        }
+      }
+    }
+  }
+  fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    fence_after();
+    tmem_dealloc(tmem, TMEM_COLS);
+  }
+}
+
+constexpr size_t FWD_SMEM = 2 * KV_BYTES + QT_BYTES + P_BYTES + 256 + 1024;
+constexpr size_t BWD_SMEM = 2 * KV_BYTES + 2 * QT_BYTES + 2 * P_BYTES + 256 + 1024;
+
+int fill_common(Common& c, const void* bias, int B, int S, int heads, int hd) {
+  c.B = B; c.S = S; c.heads = heads; c.hd = hd;
+  c.scale = 1.0f / sqrtf((float)hd);
+  c.scale_log2 = c.scale * LOG2E;
+  c.bias = reinterpret_cast<const bf16*>(bias);
+  c.err_flag = g_calm_err_flag;
+  return CALM_OK;
+}
+
+}  // namespace
+
+bool calm_attention_tc_eligible(int B, int S, int heads, int hd, const int64_t* lds, int nlds, const void* const* ptrs, int nptrs) {
+  if (B <= 0 || heads <= 0 || S < 16 || S > 256 || (S & 15) || hd < 4 || hd > 64 || (hd & 3)) return false;
+  if ((hd & 7) && hd > 60) return false;                // a head shifted by 4 columns must still fit the 64-column box
+  for (int i = 0; i < nlds; ++i)
+    if (lds[i] % 8) return false;                       // TMA: row pitch multiple of 16 bytes
+  for (int i = 0; i < nptrs; ++i)
+    if (reinterpret_cast<uintptr_t>(ptrs[i]) & 15) return false;
+  return true;
+}
+
+int calm_attention_fwd_tc(const void* q, const void* k, const void* v, const void* bias, void* o, float* lse, int64_t ld_q, int64_t ld_k,
+                          int64_t ld_v, int64_t ld_o, int B, int S, int heads, int hd, cudaStream_t stream) {
+  FwdParams p;
+  fill_common(p.c, bias, B, S, heads, hd);
+  p.o = reinterpret_cast<bf16*>(o); p.ld_o = ld_o; p.lse = lse;
+  CUtensorMap mQ, mK, mV;
+  int rc;
+  const uint64_t rows = (uint64_t)B * S, cols = (uint64_t)heads * hd;
+  if ((rc = tc::make_map_2d(&mQ, q, cols, rows, ld_q, 128))) return rc;
+  if ((rc = tc::make_map_2d(&mK, k, cols, rows, ld_k, S))) return rc;
+  if ((rc = tc::make_map_2d(&mV, v, cols, rows, ld_v, S))) return rc;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FWD_SMEM);
+    if (e != cudaSuccess) { calm_set_error("calm_attention_fwd(tcgen05): smem: %s", cudaGetErrorString(e)); return CALM_ERR_CUDA; }
+    configured = true;
+  }
+  const int items = B * heads;
+  const int grid = items < calm_num_sms() ? items : calm_num_sms();
+  attn_fwd_tc_kernel<<<grid, NTHREADS, FWD_SMEM, stream>>>(mQ, mK, mV, p);
+  CALM_CHECK_LAUNCH("calm_attention_fwd(tcgen05)");
+  return CALM_OK;
+}
+
+int calm_attention_bwd_tc(const void* q, const void* k, const void* v, const void* bias, const void* d_o, const float* lse,
+                          const float* delta, void* dq, void* dk, void* dv, void* dbias, float* dbias_acc, int64_t ld_q, int64_t ld_k,
+                          int64_t ld_v, int64_t ld_do, int64_t ld_dq, int64_t ld_dk, int64_t ld_dv, int B, int S, int heads, int hd,
+                          cudaStream_t stream) {
+  BwdParams p;
+  fill_common(p.c, bias, B, S, heads, hd);
+  p.lse = lse; p.delta = delta;
+  p.dq = reinterpret_cast<bf16*>(dq); p.dk = reinterpret_cast<bf16*>(dk); p.dv = reinterpret_cast<bf16*>(dv);
+  p.ld_dq = ld_dq; p.ld_dk = ld_dk; p.ld_dv = ld_dv;
+  p.dbias = reinterpret_cast<bf16*>(dbias); p.dbias_acc = dbias_acc;
+  CUtensorMap mQ, mK, mV, mDO;
+  int rc;
+  const uint64_t rows = (uint64_t)B * S, cols = (uint64_t)heads * hd;
+  if ((rc = tc::make_map_2d(&mQ, q, cols, rows, ld_q, 128))) return rc;
+  if ((rc = tc::make_map_2d(&mK, k, cols, rows, ld_k, S))) return rc;
+  if ((rc = tc::make_map_2d(&mV, v, cols, rows, ld_v, S))) return rc;
+  if ((rc = tc::make_map_2d(&mDO, d_o, cols, rows, ld_do, 128))) return rc;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(attn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BWD_SMEM);
+    if (e != cudaSuccess) { calm_set_error("calm_attention_bwd(tcgen05): smem: %s", cudaGetErrorString(e)); return CALM_ERR_CUDA; }
+    configured = true;
+  }
+  const int grid = B < calm_num_sms() ? B : calm_num_sms();
+  attn_bwd_tc_kernel<<<grid, NTHREADS, BWD_SMEM, stream>>>(mQ, mK, mV, mDO, p);
+  CALM_CHECK_LAUNCH("calm_attention_bwd(tcgen05)");
+  return CALM_OK;
+}

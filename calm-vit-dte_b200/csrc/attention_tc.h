@@ -1,0 +1,13 @@
+// Internal interface between attention.cu (C-ABI entry points, legacy mma.sync kernels for long sequences / wide heads)
+// and attention_sm100.cu (tcgen05 kernels for S <= 256, head_dim <= 64).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+bool calm_attention_tc_eligible(int B, int S, int heads, int hd, const int64_t* lds, int nlds, const void* const* ptrs, int nptrs);
+int calm_attention_fwd_tc(const void* q, const void* k, const void* v, const void* bias, void* o, float* lse, int64_t ld_q, int64_t ld_k,
+                          int64_t ld_v, int64_t ld_o, int B, int S, int heads, int hd, cudaStream_t stream);
+int calm_attention_bwd_tc(const void* q, const void* k, const void* v, const void* bias, const void* d_o, const float* lse,
+                          const float* delta, void* dq, void* dk, void* dv, void* dbias, float* dbias_acc, int64_t ld_q, int64_t ld_k,
+                          int64_t ld_v, int64_t ld_do, int64_t ld_dq, int64_t ld_dk, int64_t ld_dv, int B, int S, int heads, int hd,
+                          cudaStream_t stream);

@@ -11,6 +11,7 @@
 #define CALM_ERR_UNSUPPORTED (-3)
 
 void calm_set_error(const char* fmt, ...);
+extern int* g_calm_err_flag;
 
 #define CALM_CHECK_ARG(cond, ...)                    \
   do {                                               \

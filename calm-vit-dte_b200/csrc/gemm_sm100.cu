@@ -508,7 +508,7 @@ int make_map(CUtensorMap* map, const void* base, uint64_t inner, uint64_t outer,
 }
 
 int g_debug_flags = 0;
-int* g_err_flag = nullptr;  // device int written by a trapping kernel (which barrier timed out)
+
 
 template <int A_MN, int B_MN>
 int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, cudaStream_t stream) {
@@ -585,7 +585,7 @@ extern "C" int32_t calm_gemm(const calm_gemm_args* a, cudaStream_t stream) {
   p.aux = a->aux; p.ld_aux = a->ld_aux; p.stride_aux = a->stride_aux;
   p.epi = a->epilogue;
   p.alpha = a->alpha;
-  p.err_flag = g_err_flag;
+  p.err_flag = g_calm_err_flag;
 
   if (g_debug_flags & CALM_DEBUG_SIMT_GEMM) {
     dim3 block(16, 16), grid((a->N + 15) / 16, (a->M + 15) / 16, p.splits * (p.reduce_batch ? 1 : a->batch));
@@ -611,7 +611,3 @@ extern "C" int32_t calm_gemm(const calm_gemm_args* a, cudaStream_t stream) {
   return launch_tc<1, 1>(ma, mb, p, stream);
 }
 
-extern "C" int32_t calm_set_error_flag_buffer(int32_t* device_int) {
-  g_err_flag = device_int;
-  return CALM_OK;
-}

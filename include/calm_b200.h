@@ -28,7 +28,7 @@ typedef struct CUstream_st* cudaStream_t;
 enum { CALM_BF16 = 0, CALM_F32 = 1 };
 enum { CALM_MAJOR_K = 0, CALM_MAJOR_MN = 1 };
 enum { CALM_EPI_NONE = 0, CALM_EPI_GELU = 1, CALM_EPI_DGELU = 2 };
-enum { CALM_DEBUG_SIMT_GEMM = 1 };
+enum { CALM_DEBUG_SIMT_GEMM = 1, CALM_DEBUG_LEGACY_ATTENTION = 2 };
 
 int32_t calm_abi_version(void);
 const char* calm_last_error(void); /* thread-local, valid until the next failing call on this thread */
@@ -122,13 +122,17 @@ int32_t calm_rope_bwd(const void* dout, int64_t ld_dout, const void* out, int64_
  * Axial attention with a learned additive bias shared by all heads:
  *   O = softmax(Q K^T / sqrt(hd) + bias[b]) V     replaces F.scaled_dot_product_attention (Vi_Tools_CNN_less_V2.py:293-298)
  * q/k/v/o: bf16, token-major (B*S, heads*hd) views with leading dims ld_* ; bias bf16 (B, S, S); lse f32 (B, heads, S).
- * bwd: dq/dk/dv bf16 (same layout), dbias bf16 (B,S,S) = sum_h dS_h, delta f32 (B, heads, S) scratch.
+ * bwd: dq/dk/dv bf16 (same layout), dbias bf16 (B,S,S) = sum_h dS_h, delta f32 (B, heads, S) scratch,
+ *      dbias_acc f32 (B,S,S) scratch for the per-head accumulation (NULL forces the legacy kernels).
+ * Two implementations behind these entry points: tcgen05/TMEM/TMA kernels (attention_sm100.cu) when S <= 256, S % 16 == 0,
+ * head_dim <= 64, 16-byte aligned operands; warp-level mma.sync kernels (attention.cu) otherwise (384^2 / 512^2 configs) or
+ * when calm_set_debug_flags(CALM_DEBUG_LEGACY_ATTENTION) is set.
  * ------------------------------------------------------------------------------------------------------------------ */
 int32_t calm_attention_fwd(const void* q, const void* k, const void* v, const void* bias, void* o, float* lse,
                            int64_t ld_q, int64_t ld_k, int64_t ld_v, int64_t ld_o, int32_t B, int32_t S, int32_t heads,
                            int32_t hd, cudaStream_t stream);
 int32_t calm_attention_bwd(const void* q, const void* k, const void* v, const void* bias, const void* o, const void* d_o,
-                           const float* lse, float* delta, void* dq, void* dk, void* dv, void* dbias, int64_t ld_q,
+                           const float* lse, float* delta, void* dq, void* dk, void* dv, void* dbias, float* dbias_acc, int64_t ld_q,
                            int64_t ld_k, int64_t ld_v, int64_t ld_o, int64_t ld_do, int64_t ld_dq, int64_t ld_dk,
                            int64_t ld_dv, int32_t B, int32_t S, int32_t heads, int32_t hd, cudaStream_t stream);
 

@@ -220,9 +220,21 @@ def test_rope(K, B, S, h, dc, dr):
 
 
 # ------------------------------------------------------------------------------------------------------ attention
+@pytest.mark.parametrize("legacy", [False, True])
 @pytest.mark.parametrize("B,S,h,hd", [(2, 224, 12, 56), (2, 176, 12, 44), (3, 128, 12, 32), (2, 80, 12, 20), (2, 16, 12, 4),
-                                       (1, 384, 12, 96)])
-def test_attention(K, B, S, h, hd):
+                                       (1, 384, 12, 96), (5, 160, 12, 40), (3, 256, 4, 64)])
+def test_attention(K, B, S, h, hd, legacy):
+    """legacy=False: tcgen05/TMEM/TMA kernels where eligible (S <= 256, hd <= 64); legacy=True: the mma.sync kernels
+    (also what the 384^2 / 512^2 shapes use)."""
+    import calm_lib
+    calm_lib.load().calm_set_debug_flags(2 if legacy else 0)
+    try:
+        _attention_case(K, B, S, h, hd)
+    finally:
+        calm_lib.load().calm_set_debug_flags(0)
+
+
+def _attention_case(K, B, S, h, hd):
     D = h * hd
     qkv = rnd(B * S, 3 * D, seed=28)
     q, k, v = qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:]
