@@ -152,6 +152,7 @@ class Trainer:
 def cpu_baseline(model, max_seconds=20.0):
     """Oracle fwd+bwd (fp32, batch 8, all host cores): BASELINE.json configs[0], a bounded sample of the workload."""
     from oracle import calm_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
     sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
     P = O.params_from_state_dict(sd)
     x, y = synth_batch(8, "cls", 0)
@@ -176,6 +177,7 @@ def run_reference(args, rank, world):
     """--impl reference: the reference algorithm (oracle port) on the host cores; rank 0 only."""
     if rank != 0:
         return
+    torch.set_num_threads(os.cpu_count() or 1)      # torchrun exports OMP_NUM_THREADS=1: use every host core anyway
     torch.manual_seed(0)
     from oracle import calm_oracle as O
     # weights: a random reference-layout state of the same config (nothing of the product path is involved here)
@@ -305,12 +307,18 @@ def main():
         launches_per_step = calm_lib.launch_count - n1
         prof, calm_lib.profile = calm_lib.profile, None
         fam = {}
-        for name, work, a, b in prof:
+        shapes = {}
+        for name, work, a, b, *tag in prof:
+            if tag and tag[0]:
+                d = shapes.setdefault(tag[0], {"ms": 0.0, "work": 0.0, "n": 0})
+                d["ms"] += a.elapsed_time(b); d["work"] += work; d["n"] += 1
             d = fam.setdefault(name, {"ms": 0.0, "work": 0.0, "n": 0})
             d["ms"] += a.elapsed_time(b)
             d["work"] += work
             d["n"] += 1
         tot = sum(d["ms"] for d in fam.values())
+        top_shapes = sorted(shapes.items(), key=lambda t: -t[1]["ms"])[:60]
+        breakdown_shapes = [{"shape": k, "ms": round(v["ms"], 3), "n": v["n"], "tflops": round(v["work"] / (v["ms"] * 1e9), 1)} for k, v in top_shapes]
         breakdown = {k: {"ms": round(v["ms"], 3), "n": v["n"], "share": round(v["ms"] / tot, 4),
                          "rate": (v["work"] / (v["ms"] * 1e-3) if v["work"] and v["ms"] > 0 else None)} for k, v in fam.items()}
         pk = peaks()
@@ -346,6 +354,7 @@ def main():
         if breakdown is not None:
             os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
             json.dump(breakdown, open(os.path.join(ROOT, "gpurun_out", "bench_kernel_breakdown.json"), "w"), indent=1)
+            json.dump(breakdown_shapes, open(os.path.join(ROOT, "gpurun_out", "bench_gemm_shapes.json"), "w"), indent=1)
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(model)
         print(json.dumps(line), flush=True)

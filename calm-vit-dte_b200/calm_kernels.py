@@ -41,7 +41,12 @@ def gemm(a, b, c, M, N, K, *, lda, ldb, ldc, batch=1, stride_a=0, stride_b=0, st
     g.aux, g.ld_aux, g.stride_aux = ptr(aux), ld_aux, stride_aux
     g.reduce_batch, g.splits, g.stride_split = int(reduce_batch), splits, stride_split
     g.alpha = alpha
-    L.call("calm_gemm", C.byref(g), work=2.0 * M * N * K * batch)
+    tag = None
+    if L.profile is not None:
+        tag = "M%d N%d K%d b%d %s%s%s%s%s" % (M, N, K, batch, "AK" if a_major == MAJOR_K else "AM", "BK" if b_major == MAJOR_K else "BM",
+                                               " f32" if c.dtype == f32 else "", " add" if addend is not None else "",
+                                               (" epi%d" % epilogue if epilogue else "") + (" red" if reduce_batch else "") + (" s%d" % splits if splits > 1 else ""))
+    L.call("calm_gemm", C.byref(g), work=2.0 * M * N * K * batch, tag=tag)
     return c
 
 

@@ -147,7 +147,7 @@ def stream():
 profile = None   # bench.py's per-kernel timing pass sets this to a list; entries: (name, work, start_event, end_event)
 
 
-def call(name, *args, work=0.0):
+def call(name, *args, work=0.0, tag=None):
     """Invoke an int32-returning entry point on the current torch stream (appended as last argument).
     `work` = algorithmic FLOPs (contractions) or bytes (memory-bound kernels) of this launch, used only by the
     optional CUDA-event profiling pass."""
@@ -158,7 +158,7 @@ def call(name, *args, work=0.0):
         e0.record()
         rc = getattr(lib, name)(*args, stream())
         e1.record()
-        profile.append((name, work, e0, e1))
+        profile.append((name, work, e0, e1, tag))
     else:
         rc = getattr(lib, name)(*args, stream())
     launch_count += 1
