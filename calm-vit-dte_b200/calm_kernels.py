@@ -243,26 +243,50 @@ def seq_mean_bwd(dout, B, S, D):
 
 
 # ------------------------------------------------------------------------------------------------ spectral norm
+class SnTable:
+    """Device-side description of a scope's sn(...) layers: the calm_sn_layer table, the (layer, row-chunk) work items and
+    the scratch the kernels need. Holds references to every tensor whose pointer is baked into the table."""
+
+    def __init__(self, entries, device):
+        n = len(entries)
+        arr = (L.SnLayer * n)()
+        items = []
+        self.keep = [entries]
+        for i, e in enumerate(entries):
+            rows, cols = e["rows"], e["cols"]
+            chunk = max(4, min(rows, -(-16384 // cols)))          # ~16 K weights per item: a few hundred CTAs per scope
+            nit = -(-rows // chunk)
+            for j in range(nit):
+                items.append((i, j * chunk, min(rows, (j + 1) * chunk), j))
+            tpart = torch.empty(nit * cols, dtype=f32, device=device)
+            svec = torch.empty(rows, dtype=f32, device=device)
+            self.keep += [tpart, svec]
+            s = arr[i]
+            for name in ("w", "u", "v", "rowscale", "w_eff", "grad_w", "grad_rowscale", "g_eff", "sigma"):
+                t = e.get(name)
+                setattr(s, name, ptr(t) if t is not None else None)
+            s.tpart, s.svec = ptr(tpart), ptr(svec)
+            s.rows, s.cols = rows, cols
+            s.g_splits = e.get("g_splits", 1)
+            s.eff_f32 = int(e.get("eff_f32", 0))
+            s.g_split_stride = e.get("g_split_stride", rows * cols)
+            s.item_count = nit
+        it = (L.SnItem * len(items))()
+        for j, (li, rb, re, loc) in enumerate(items):
+            it[j].layer, it[j].row_begin, it[j].row_end, it[j].local_index = li, rb, re, loc
+        self.n_layers, self.n_items = n, len(items)
+        self.table = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(device)
+        self.items = torch.frombuffer(bytearray(bytes(it)), dtype=torch.uint8).to(device)
+
+
 def sn_table(entries, device):
-    """entries: list of dicts with the calm_sn_layer fields (tensors or ints). Returns the device table (uint8 tensor)."""
-    arr = (L.SnLayer * len(entries))()
-    for i, e in enumerate(entries):
-        s = arr[i]
-        for name in ("w", "u", "v", "rowscale", "w_eff", "w_eff_t", "grad_w", "grad_rowscale", "g_eff", "tmp", "sigma"):
-            t = e.get(name)
-            setattr(s, name, ptr(t) if t is not None else None)
-        s.rows, s.cols = e["rows"], e["cols"]
-        s.g_splits = e.get("g_splits", 1)
-        s.eff_f32 = int(e.get("eff_f32", 0))
-        s.g_split_stride = e.get("g_split_stride", e["rows"] * e["cols"])
-        s.ld_t = e.get("ld_t", e["rows"])
-    host = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
-    return host.to(device)
+    """entries: list of dicts with the calm_sn_layer fields (tensors or ints)."""
+    return SnTable(entries, device)
 
 
 def sn_forward(table, n_layers, max_rows, max_cols, training, eps=1e-12):
-    L.call("calm_sn_forward", ptr(table), n_layers, max_rows, max_cols, int(training), eps)
+    L.call("calm_sn_forward", ptr(table.table), table.n_layers, ptr(table.items), table.n_items, int(training), eps)
 
 
 def sn_backward(table, n_layers, max_rows, max_cols):
-    L.call("calm_sn_backward", ptr(table), n_layers, max_rows, max_cols)
+    L.call("calm_sn_backward", ptr(table.table), table.n_layers, ptr(table.items), table.n_items)

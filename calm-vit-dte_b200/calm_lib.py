@@ -40,12 +40,17 @@ class GemmArgs(C.Structure):
 class SnLayer(C.Structure):
     """Mirror of calm_sn_layer (include/calm_b200.h)."""
     _fields_ = [
-        ("w", vp), ("u", vp), ("v", vp), ("rowscale", vp), ("w_eff", vp), ("w_eff_t", vp),
-        ("grad_w", vp), ("grad_rowscale", vp), ("g_eff", vp),
+        ("w", vp), ("u", vp), ("v", vp), ("rowscale", vp), ("w_eff", vp),
+        ("grad_w", vp), ("grad_rowscale", vp), ("g_eff", vp), ("tpart", vp), ("svec", vp), ("sigma", vp),
+        ("g_split_stride", i64),
         ("rows", i32), ("cols", i32), ("g_splits", i32), ("eff_f32", i32),
-        ("tmp", vp), ("sigma", vp),
-        ("g_split_stride", i64), ("ld_t", i32), ("_pad", i32),
+        ("item_count", i32), ("_pad", i32),
     ]
+
+
+class SnItem(C.Structure):
+    """Mirror of calm_sn_item."""
+    _fields_ = [("layer", i32), ("row_begin", i32), ("row_end", i32), ("local_index", i32)]
 
 
 # name -> (restype, argtypes); every symbol include/calm_b200.h declares
@@ -57,8 +62,8 @@ PROTOTYPES = {
     "calm_set_error_flag_buffer": (i32, [vp]),
     "calm_gemm": (i32, [C.POINTER(GemmArgs), vp]),
     "calm_gemm_default_splits": (i32, [i32, i32, i32, i32, i32]),
-    "calm_sn_forward": (i32, [vp, i32, i32, i32, i32, f32, vp]),
-    "calm_sn_backward": (i32, [vp, i32, i32, i32, vp]),
+    "calm_sn_forward": (i32, [vp, i32, vp, i32, i32, f32, vp]),
+    "calm_sn_backward": (i32, [vp, i32, vp, i32, vp]),
     "calm_layernorm_fwd": (i32, [vp, vp, vp, i32, vp, vp, i64, i32, f32, vp]),
     "calm_layernorm_bwd": (i32, [vp, i32, vp, vp, vp, vp, vp, vp, vp, i32, vp, i64, i32, vp]),
     "calm_layernorm_bwd_parts": (i32, [i64, i32]),

@@ -82,17 +82,16 @@ class SNBank:
                 g["layer_ids"].append(len(self.layers))
                 self.layers.append(dict(module=m, gid=gid, row_off=r0, rows=r, cols=cols, grad_off=off, rowscale=sp.rowscale))
                 self.gid_of[id(m)] = gid
-                off += r * cols
+                off += (r * cols + 3) & ~3          # keep every layer's gradient block 16-byte aligned
                 r0 += r
             self.groups.append(g)
         self.rs_layers = [l for l in self.layers if l["rowscale"] is not None]
         for l in self.rs_layers:
             l["rs_off"] = off
-            off += l["rows"]
+            off += (l["rows"] + 3) & ~3
         self.flat_grad = torch.zeros(off, dtype=f32, device=dev)
         n = len(self.layers)
         self.sigma = torch.empty(n, dtype=f32, device=dev)
-        self.tmp = torch.empty(n * 32, dtype=f32, device=dev)
         self.max_rows = max(l["rows"] for l in self.layers)
         self.max_cols = max(l["cols"] for l in self.layers)
         self.params = [l["module"].weight_orig for l in self.layers] + [l["rowscale"] for l in self.rs_layers]
@@ -110,8 +109,7 @@ class SNBank:
             m = l["module"]
             lo = l["row_off"] * l["cols"]
             e = dict(w=m.weight_orig, u=m.weight_u, v=m.weight_v, rows=l["rows"], cols=l["cols"], eff_f32=g["conv"],
-                     w_eff=g["w_eff"].view(-1)[lo:], grad_w=self.flat_grad[l["grad_off"]:], tmp=self.tmp[i * 32:],
-                     sigma=self.sigma[i:], g_splits=g["splits"], g_split_stride=g["rows"] * g["cols"])
+                     w_eff=g["w_eff"].view(-1)[lo:], grad_w=self.flat_grad[l["grad_off"]:], sigma=self.sigma[i:], g_splits=g["splits"], g_split_stride=g["rows"] * g["cols"])
             if g["g_eff"] is not None:
                 e["g_eff"] = g["g_eff"].view(-1)[lo:]
             if l["rowscale"] is not None:

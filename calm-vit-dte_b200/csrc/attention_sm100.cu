@@ -6,8 +6,10 @@
 // online rescaling, and P (bf16) goes back to shared memory as the A operand of the P.V MMA. One thread owns one query row
 // (= one TMEM lane), so row max / row sum are plain register reductions — no shuffles.
 //
-// Roles per CTA (160 threads, one CTA per SM, persistent): warps 0-3 = 128 row workers (softmax, epilogues; warp w reads
-// TMEM lanes 32w..32w+31), warp 4 lane 0 = controller (TMA loads + MMA issue). Hand-offs are mbarriers:
+// Roles per CTA (288 threads, one CTA per SM, persistent): warps 0-7 = row workers (softmax, epilogues): warp w reads TMEM
+// lanes 32(w%4)..32(w%4)+31, the two warps of a lane quadrant take alternate 16-column chunks of every row (row max / row
+// sum of the forward are combined through two floats of shared memory per row); warp 8 lane 0 = controller (TMA loads +
+// MMA issue). Hand-offs are mbarriers:
 //   bar_kv / bar_q : TMA transaction barriers          bar_mma : tcgen05.commit -> workers      bar_work : 128 worker arrivals -> controller
 //
 // Layouts: Q/K/V/dO tiles are TMA boxes {64 columns, rows} with the 128-byte swizzle, i.e. directly the K-major UMMA
@@ -30,8 +32,9 @@ namespace {
 
 using namespace tc;
 
-constexpr int NTHREADS = 160;
-constexpr int NWORKERS = 128;
+constexpr int NWORKERS = 256;            // 8 worker warps: warps w and w+4 share TMEM lane quadrant w%4 and split the columns
+constexpr int NTHREADS = NWORKERS + 32;  // + controller warp (warp 8)
+constexpr int CTRL_WARP = NWORKERS / 32;
 constexpr float LOG2E = 1.4426950408889634f;
 constexpr float LN2 = 0.6931471805599453f;
 constexpr int KV_BYTES = 256 * 128;     // up to 256 keys x 64 columns bf16
@@ -116,7 +119,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap mQ, const __grid_constant
   uint8_t* sV = sK + KV_BYTES;
   uint8_t* sQ = sV + KV_BYTES;
   uint8_t* sP = sQ + QT_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + P_BYTES);  // kv, q, mma, work
+  float* xchg = reinterpret_cast<float*>(sP + P_BYTES);          // [2][2][128]: row max / row sum halves of the two column groups
+  uint64_t* bars = reinterpret_cast<uint64_t*>(xchg + 512);      // kv, q, mma, work
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
   const uint32_t bar_kv = smem_u32(&bars[0]), bar_q = smem_u32(&bars[1]), bar_mma = smem_u32(&bars[2]), bar_work = smem_u32(&bars[3]);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -128,7 +132,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap mQ, const __grid_constant
     mbar_init(bar_kv, 1); mbar_init(bar_q, 1); mbar_init(bar_mma, 1); mbar_init(bar_work, NWORKERS);
     fence_barrier_init();
   }
-  if (warp == 4) tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
+  if (warp == CTRL_WARP) tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
   fence_before();
   __syncthreads();
   fence_after();
@@ -136,7 +140,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap mQ, const __grid_constant
   const int ntiles = (S + 127) >> 7;
   const int items = c.B * c.heads;
 
-  if (warp == 4) {
+  if (warp == CTRL_WARP) {
     // ============================ controller: TMA + MMA issue ============================
     if (lane == 0) {
       uint32_t ph_kv = 0, ph_q = 0, ph_work = 0;
@@ -170,9 +174,10 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap mQ, const __grid_constant
       }
     }
   } else {
-    // ============================ workers: one query row per thread ============================
-    const int r = threadIdx.x;
-    const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
+    // ============================ workers: a query row is shared by two threads (alternate 16-column chunks) ============================
+    const int grp = warp >> 2;                    // 0: even chunks, 1: odd chunks
+    const int r = (warp & 3) * 32 + lane;         // query row within the tile == TMEM lane
+    const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16);
     uint32_t ph_kv = 0, ph_q = 0, ph_mma = 0;
     for (int it = blockIdx.x; it < items; it += gridDim.x) {
       const int b = it / c.heads, h = it - b * c.heads;
@@ -183,68 +188,76 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap mQ, const __grid_constant
         const bool valid = q < S;
         if (i == 0) { mbar_wait(bar_kv, ph_kv, c.err_flag, 21); ph_kv ^= 1; }
         mbar_wait(bar_q, ph_q, c.err_flag, 22); ph_q ^= 1;
-        zero_outside(sQ, r, hc, hd);
+        if (grp == 0) zero_outside(sQ, r, hc, hd);
         fence_proxy_async();
         mbar_arrive(bar_work);                                            // A
-        // the row's bias (S bf16 = up to 32 x 16 B) is requested now and lives in registers for both softmax passes:
-        // its latency overlaps the Q.K^T MMA, and the chunk loops below touch only TMEM and registers
+        // this thread's half of the row's bias (chunks grp, grp+2, ...) is requested now and lives in registers for both
+        // softmax passes: its latency overlaps the Q.K^T MMA, and the chunk loops below touch only TMEM and registers
         const bf16* brow = c.bias + ((long long)b * S + (valid ? q : 0)) * S;
-        uint4 bb[32];
+        uint4 bb[16];
 #pragma unroll
-        for (int ch = 0; ch < 16; ++ch) {
-          if (ch * 16 < S) {
-            bb[2 * ch] = *reinterpret_cast<const uint4*>(brow + ch * 16);
-            bb[2 * ch + 1] = *reinterpret_cast<const uint4*>(brow + ch * 16 + 8);
+        for (int j = 0; j < 8; ++j) {
+          const int kc = (2 * j + grp) * 16;
+          if (kc < S) {
+            bb[2 * j] = *reinterpret_cast<const uint4*>(brow + kc);
+            bb[2 * j + 1] = *reinterpret_cast<const uint4*>(brow + kc + 8);
           }
         }
         mbar_wait(bar_mma, ph_mma, c.err_flag, 23); ph_mma ^= 1;
         fence_after();
-        // pass 1: row maximum of x = s * scale*log2e + bias*log2e
+        // pass 1: maximum of x = s * scale*log2e + bias*log2e over this thread's chunks, then over the row
         float mx = -INFINITY;
 #pragma unroll
-        for (int ch = 0; ch < 16; ++ch) {
-          if (ch * 16 < S) {
+        for (int j = 0; j < 8; ++j) {
+          const int kc = (2 * j + grp) * 16;
+          if (kc < S) {
             uint32_t sr[16];
-            tmem_ld16(trow + ch * 16, sr);
+            tmem_ld16(trow + kc, sr);
             tmem_ld_wait();
             float bf[16];
-            unpack16(bb[2 * ch], bb[2 * ch + 1], bf);
+            unpack16(bb[2 * j], bb[2 * j + 1], bf);
 #pragma unroll
-            for (int j = 0; j < 16; ++j) mx = fmaxf(mx, fmaf(__uint_as_float(sr[j]), c.scale_log2, bf[j] * LOG2E));
+            for (int jj = 0; jj < 16; ++jj) mx = fmaxf(mx, fmaf(__uint_as_float(sr[jj]), c.scale_log2, bf[jj] * LOG2E));
           }
         }
-        // pass 2: P = exp2(x - max), row sum, bf16 P into the swizzled A-operand tile
+        xchg[grp * 128 + r] = mx;
+        asm volatile("bar.sync 1, %0;" ::"n"(NWORKERS) : "memory");
+        mx = fmaxf(mx, xchg[(grp ^ 1) * 128 + r]);
+        // pass 2: P = exp2(x - max), partial row sum, bf16 P into the swizzled A-operand tile
         float l = 0.f;
 #pragma unroll
-        for (int ch = 0; ch < 16; ++ch) {
-          if (ch * 16 < S) {
+        for (int j = 0; j < 8; ++j) {
+          const int kc = (2 * j + grp) * 16;
+          if (kc < S) {
             uint32_t sr[16];
-            tmem_ld16(trow + ch * 16, sr);
+            tmem_ld16(trow + kc, sr);
             tmem_ld_wait();
             float bf[16], pv[16];
-            unpack16(bb[2 * ch], bb[2 * ch + 1], bf);
+            unpack16(bb[2 * j], bb[2 * j + 1], bf);
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              pv[j] = exp2f(fmaf(__uint_as_float(sr[j]), c.scale_log2, fmaf(bf[j], LOG2E, -mx)));
-              l += pv[j];
+            for (int jj = 0; jj < 16; ++jj) {
+              pv[jj] = exp2f(fmaf(__uint_as_float(sr[jj]), c.scale_log2, fmaf(bf[jj], LOG2E, -mx)));
+              l += pv[jj];
             }
-            store_row16(sP, r, ch * 16, pv);
+            store_row16(sP, r, kc, pv);
           }
         }
+        xchg[256 + grp * 128 + r] = l;
         fence_proxy_async();
         fence_before();
         mbar_arrive(bar_work);                                            // B
-        mbar_wait(bar_mma, ph_mma, c.err_flag, 24); ph_mma ^= 1;
+        mbar_wait(bar_mma, ph_mma, c.err_flag, 24); ph_mma ^= 1;           // (all 256 workers arrived at B before the MMA ran)
         fence_after();
+        l += xchg[256 + (grp ^ 1) * 128 + r];
         const float inv = 1.0f / l;
         bf16* orow = p.o + ((long long)b * S + q) * p.ld_o + (long long)h * hd;
-        for (int c0 = 0; c0 < hdp; c0 += 16) {
+        for (int c0 = grp * 16; c0 < hdp; c0 += 32) {
           uint32_t orr[16];
           tmem_ld16(trow + 256 + c0, orr);
           tmem_ld_wait();
           if (valid) store_cols16(orow, orr, c0, hc, hd, inv);
         }
-        if (valid) p.lse[((long long)b * c.heads + h) * S + q] = (mx + log2f(l)) * LN2;
+        if (valid && grp == 0) p.lse[((long long)b * c.heads + h) * S + q] = (mx + log2f(l)) * LN2;
         fence_before();
         mbar_arrive(bar_work);                                            // C
       }
@@ -252,7 +265,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap mQ, const __grid_constant
   }
   fence_before();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == CTRL_WARP) {
     fence_after();
     tmem_dealloc(tmem, TMEM_COLS);
   }
@@ -294,7 +307,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap mQ, const __grid_constant
     mbar_init(bar_kv, 1); mbar_init(bar_q, 1); mbar_init(bar_mma, 1); mbar_init(bar_work, NWORKERS);
     fence_barrier_init();
   }
-  if (warp == 4) tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
+  if (warp == CTRL_WARP) tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
   fence_before();
   __syncthreads();
   fence_after();
@@ -303,7 +316,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap mQ, const __grid_constant
   const int nparts = (S + KPART - 1) / KPART;
   constexpr uint32_t T_S = 0, T_DP = 96, T_DQ = 192, T_DK = 256, T_DV = 384;
 
-  if (warp == 4) {
+  if (warp == CTRL_WARP) {
     if (lane == 0) {
       uint32_t ph_kv = 0, ph_q = 0, ph_work = 0;
       for (int b = blockIdx.x; b < c.B; b += gridDim.x) {
@@ -355,8 +368,9 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap mQ, const __grid_constant
       }
     }
   } else {
-    const int r = threadIdx.x;
-    const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
+    const int grp = warp >> 2;                    // 0: even 16-column chunks, 1: odd chunks
+    const int r = (warp & 3) * 32 + lane;         // row within the tile == TMEM lane
+    const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16);
     uint32_t ph_kv = 0, ph_q = 0, ph_mma = 0;
     for (int b = blockIdx.x; b < c.B; b += gridDim.x) {
       for (int h = 0; h < heads; ++h) {
@@ -367,8 +381,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap mQ, const __grid_constant
           const bool valid = q < S;
           if (i == 0) { mbar_wait(bar_kv, ph_kv, c.err_flag, 41); ph_kv ^= 1; }
           mbar_wait(bar_q, ph_q, c.err_flag, 42); ph_q ^= 1;
-          zero_outside(sQ, r, hc, hd);
-          zero_outside(sDO, r, hc, hd);
+          if (grp == 0) zero_outside(sQ, r, hc, hd);
+          else zero_outside(sDO, r, hc, hd);
           const long long stat = ((long long)b * heads + h) * S + (valid ? q : 0);
           const float lse2 = p.lse[stat] * LOG2E, dl = p.delta[stat];
           const long long rowoff = ((long long)b * S + (valid ? q : 0)) * S;
@@ -377,13 +391,15 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap mQ, const __grid_constant
           for (int part = 0; part < nparts; ++part) {
             const int k0 = part * KPART, w = min(KPART, S - k0);
             // global operands of this part first (bias row segment, running dbias sums): in flight while the MMAs run
-            uint4 bb[12];
-            float4 ac[24];
+            uint4 bb[6];
+            float4 ac[12];
             const bool have_acc = h > 0 && valid;
 #pragma unroll
-            for (int ch = 0; ch < 6; ++ch) {
-              if (ch * 16 < w) {
-                const int kc = k0 + ch * 16;
+            for (int j = 0; j < 3; ++j) {
+              const int ch = j;           // register slot
+              const int cc = (2 * j + grp) * 16;
+              if (cc < w) {
+                const int kc = k0 + cc;
                 bb[2 * ch] = *reinterpret_cast<const uint4*>(c.bias + rowoff + kc);
                 bb[2 * ch + 1] = *reinterpret_cast<const uint4*>(c.bias + rowoff + kc + 8);
 #pragma unroll
@@ -394,9 +410,11 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap mQ, const __grid_constant
             mbar_wait(bar_mma, ph_mma, c.err_flag, 43); ph_mma ^= 1;
             fence_after();
 #pragma unroll
-            for (int ch = 0; ch < 6; ++ch) {
-              if (ch * 16 < w) {
-                const int cc = ch * 16, kc = k0 + cc;
+            for (int j = 0; j < 3; ++j) {
+              const int ch = j;
+              const int cc = (2 * j + grp) * 16;
+              if (cc < w) {
+                const int kc = k0 + cc;
                 uint32_t sr[16], dr[16];
                 tmem_ld16(trow + T_S + cc, sr);
                 tmem_ld16(trow + T_DP + cc, dr);
@@ -437,7 +455,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap mQ, const __grid_constant
           // dQ rows of this tile
           {
             bf16* row = p.dq + ((long long)b * S + q) * p.ld_dq + (long long)h * hd;
-            for (int c0 = 0; c0 < hdp; c0 += 16) {
+            for (int c0 = grp * 16; c0 < hdp; c0 += 32) {
               uint32_t v[16];
               tmem_ld16(trow + T_DQ + c0, v);
               tmem_ld_wait();
@@ -451,7 +469,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap mQ, const __grid_constant
               const bool kvalid = key < S;
               bf16* krow = p.dk + ((long long)b * S + key) * p.ld_dk + (long long)h * hd;
               bf16* vrow = p.dv + ((long long)b * S + key) * p.ld_dv + (long long)h * hd;
-              for (int c0 = 0; c0 < hdp; c0 += 16) {
+              for (int c0 = grp * 16; c0 < hdp; c0 += 32) {
                 uint32_t kk[16], vv[16];
                 tmem_ld16(trow + T_DK + 64 * t + c0, kk);
                 tmem_ld16(trow + T_DV + 64 * t + c0, vv);
@@ -471,13 +489,13 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap mQ, const __grid_constant
   }
   fence_before();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == CTRL_WARP) {
     fence_after();
     tmem_dealloc(tmem, TMEM_COLS);
   }
 }
 
-constexpr size_t FWD_SMEM = 2 * KV_BYTES + QT_BYTES + P_BYTES + 256 + 1024;
+constexpr size_t FWD_SMEM = 2 * KV_BYTES + QT_BYTES + P_BYTES + 2048 + 256 + 1024;
 constexpr size_t BWD_SMEM = 2 * KV_BYTES + 2 * QT_BYTES + 2 * P_BYTES + 256 + 1024;
 
 int fill_common(Common& c, const void* bias, int B, int S, int heads, int hd) {

@@ -1,250 +1,239 @@
-// Batched spectral normalisation for every sn(...) layer of the model in ONE launch per direction.
+// Batched spectral normalisation for every sn(...) layer of a scope (one Block: ~40 layers, 5 M weights).
 // Replaces the per-layer forward-pre-hook of torch.nn.utils.spectral_norm (torch/nn/utils/spectral_norm.py:92-114):
 //     v <- normalize(W^T u) ; u <- normalize(W v) ; sigma = u . (W v) ; W_eff = W / sigma
-// (same update order, eps and in-place buffer semantics), and writes the bf16 operand copies the tcgen05 GEMMs read:
-// W_eff (rows, cols) for forward/wgrad and its transpose (cols, rows) for dgrad. An optional LayerScale vector is folded
-// into the rows of W_eff (out_proj*ls_att, mlp.3*ls_mlp: Vi_Tools_CNN_less_V2.py:300,314).
-// HBM-bound: each fp32 W is read ~3x (2nd/3rd read from L2), one CTA per layer, deterministic (no atomics).
+// (same update order, eps and in-place buffer semantics) and writes the bf16 operands the tcgen05 GEMMs read. An optional
+// LayerScale vector is folded into the rows of W_eff (out_proj*ls_att, mlp.3*ls_mlp: Vi_Tools_CNN_less_V2.py:300,314).
+//
+// v2: the work is cut into (layer, row-chunk) ITEMS so that the big matrices are streamed by many CTAs; the two global
+// reductions of the power iteration become two tiny per-layer kernels. Five launches per scope (three in eval mode):
+//   A  item : partial t = u_chunk^T W_chunk                     (W read #1, HBM)
+//   B  layer: t = sum of partials ; v = t / max(|t|, eps)
+//   C  item : s_chunk = W_chunk v                               (W read #2, L2)
+//   D  layer: u = s / max(|s|, eps) ; sigma = |s|^2 / max(|s|, eps)      (eval: sigma = u . s with the stored u)
+//   E  item : W_eff_chunk = rowscale * W_chunk / sigma -> bf16 | fp32   (W read #3, L2)
+// Backward:  H = rowscale (.) sum_splits G ;  dW = H/sigma - (<H,W>/sigma^2) u v^T ;
+// d rowscale[r] = <G[r,:], W[r,:]>/sigma — item kernel (H + partial dots), then item kernel (rank-1 correction).
+// All reductions are fixed-order: results are deterministic.
 #include "common.cuh"
 #include "../../include/calm_b200.h"
 
 namespace {
 
-constexpr int SN_THREADS = 512;
+constexpr int SN_THREADS = 256;
 constexpr int SN_WARPS = SN_THREADS / 32;
 
-// t[c] = sum_r u[r] * W[r,c]   (u in smem, result in smem t[cols]); scratch part[SN_WARPS][32*VEC]
-template <int VEC>
-__device__ void wt_u(const float* __restrict__ W, const float* u_s, float* t_s, float* part, int rows, int cols) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int chunk = 32 * VEC;
-  for (int c0 = 0; c0 < cols; c0 += chunk) {
-    const int c = c0 + lane * VEC;
-    float acc[VEC];
-#pragma unroll
-    for (int j = 0; j < VEC; ++j) acc[j] = 0.f;
-    if (c < cols) {
+__device__ __forceinline__ float block_sum256(float v, float* red) { return block_sum(v, red); }
+
+// ---- A: partial t[c] = sum_{r in chunk} u[r] W[r,c]
+__global__ void __launch_bounds__(SN_THREADS)
+sn_a_kernel(const calm_sn_layer* __restrict__ table, const calm_sn_item* __restrict__ items) {
+  const calm_sn_item it = items[blockIdx.x];
+  const calm_sn_layer L = table[it.layer];
+  const int cols = L.cols;
+  float* tp = L.tpart + (size_t)it.local_index * cols;
+  if ((cols & 3) == 0) {
+    for (int c4 = threadIdx.x; c4 < (cols >> 2); c4 += SN_THREADS) {
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 4
-      for (int r = warp; r < rows; r += SN_WARPS) {
-        const float ur = u_s[r];
-        if constexpr (VEC == 4) {
-          const float4 w = *reinterpret_cast<const float4*>(W + (size_t)r * cols + c);
-          acc[0] += ur * w.x; acc[1] += ur * w.y; acc[2] += ur * w.z; acc[3] += ur * w.w;
-        } else {
-          acc[0] += ur * W[(size_t)r * cols + c];
-        }
+      for (int r = it.row_begin; r < it.row_end; ++r) {
+        const float ur = L.u[r];
+        const float4 w = reinterpret_cast<const float4*>(L.w + (size_t)r * cols)[c4];
+        acc.x = fmaf(ur, w.x, acc.x); acc.y = fmaf(ur, w.y, acc.y); acc.z = fmaf(ur, w.z, acc.z); acc.w = fmaf(ur, w.w, acc.w);
       }
+      reinterpret_cast<float4*>(tp)[c4] = acc;
     }
-#pragma unroll
-    for (int j = 0; j < VEC; ++j) part[warp * chunk + lane * VEC + j] = acc[j];
-    __syncthreads();
-    for (int i = threadIdx.x; i < chunk; i += SN_THREADS) {
-      float s = 0.f;
-#pragma unroll
-      for (int w = 0; w < SN_WARPS; ++w) s += part[w * chunk + i];
-      if (c0 + i < cols) t_s[c0 + i] = s;
+  } else {
+    for (int c = threadIdx.x; c < cols; c += SN_THREADS) {
+      float acc = 0.f;
+      for (int r = it.row_begin; r < it.row_end; ++r) acc = fmaf(L.u[r], L.w[(size_t)r * cols + c], acc);
+      tp[c] = acc;
     }
-    __syncthreads();
   }
 }
 
-// s[r] = sum_c W[r,c] * v[c]   (v in smem, result in smem s[rows])
-__device__ void w_v(const float* __restrict__ W, const float* v_s, float* s_s, int rows, int cols) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int r = warp; r < rows; r += SN_WARPS) {
-    const float* wr = W + (size_t)r * cols;
+// ---- B: v = normalize(sum of partials)
+__global__ void __launch_bounds__(SN_THREADS)
+sn_b_kernel(const calm_sn_layer* __restrict__ table, float eps) {
+  __shared__ float red[32];
+  const calm_sn_layer L = table[blockIdx.x];
+  const int cols = L.cols;
+  float ss = 0.f;
+  for (int c = threadIdx.x; c < cols; c += SN_THREADS) {
+    float t = 0.f;
+    for (int k = 0; k < L.item_count; ++k) t += L.tpart[(size_t)k * cols + c];
+    L.v[c] = t;  // un-normalised for the moment (only this CTA touches v)
+    ss = fmaf(t, t, ss);
+  }
+  ss = block_sum256(ss, red);
+  const float inv = 1.0f / fmaxf(sqrtf(ss), eps);
+  for (int c = threadIdx.x; c < cols; c += SN_THREADS) L.v[c] *= inv;  // same thread wrote the element
+}
+
+// ---- C: s[r] = W[r,:] . v   (warp per row)
+__global__ void __launch_bounds__(SN_THREADS)
+sn_c_kernel(const calm_sn_layer* __restrict__ table, const calm_sn_item* __restrict__ items) {
+  const calm_sn_item it = items[blockIdx.x];
+  const calm_sn_layer L = table[it.layer];
+  const int cols = L.cols, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int r = it.row_begin + warp; r < it.row_end; r += SN_WARPS) {
+    const float* wr = L.w + (size_t)r * cols;
     float acc = 0.f;
     if ((cols & 3) == 0) {
-      for (int c = lane * 4; c < cols; c += 128) {
-        const float4 w = *reinterpret_cast<const float4*>(wr + c);
-        acc += w.x * v_s[c] + w.y * v_s[c + 1] + w.z * v_s[c + 2] + w.w * v_s[c + 3];
+      for (int c4 = lane; c4 < (cols >> 2); c4 += 32) {
+        const float4 w = reinterpret_cast<const float4*>(wr)[c4];
+        const float4 v = reinterpret_cast<const float4*>(L.v)[c4];
+        acc += w.x * v.x + w.y * v.y + w.z * v.z + w.w * v.w;
       }
     } else {
-      for (int c = lane; c < cols; c += 32) acc += wr[c] * v_s[c];
+      for (int c = lane; c < cols; c += 32) acc = fmaf(wr[c], L.v[c], acc);
     }
     acc = warp_sum(acc);
-    if (lane == 0) s_s[r] = acc;
+    if (lane == 0) L.svec[r] = acc;
   }
-  __syncthreads();
 }
 
-__device__ float sumsq_smem(const float* x, int n, float* red) {
-  float a = 0.f;
-  for (int i = threadIdx.x; i < n; i += SN_THREADS) a += x[i] * x[i];
-  return block_sum(a, red);
-}
-
+// ---- D: u, sigma
 __global__ void __launch_bounds__(SN_THREADS)
-sn_forward_kernel(const calm_sn_layer* __restrict__ table, int training, float eps, int max_rows, int max_cols) {
-  extern __shared__ float sm[];
-  const calm_sn_layer L = table[blockIdx.x];
-  const int rows = L.rows, cols = L.cols;
-  float* u_s = sm;                       // rows  (also holds s = W v)
-  float* v_s = sm + max_rows;            // cols  (also holds t = W^T u)
-  float* part = sm + max_rows + max_cols;  // SN_WARPS*128 floats of reduction scratch
+sn_d_kernel(const calm_sn_layer* __restrict__ table, int training, float eps) {
   __shared__ float red[32];
-  __shared__ float tile[32][33];
-
-  for (int i = threadIdx.x; i < rows; i += SN_THREADS) u_s[i] = L.u[i];
-  for (int i = threadIdx.x; i < cols; i += SN_THREADS) v_s[i] = L.v[i];
-  __syncthreads();
-
-  float sigma;
+  const calm_sn_layer L = table[blockIdx.x];
+  const int rows = L.rows;
+  float acc = 0.f;
   if (training) {
-    // v <- normalize(W^T u)
-    if ((cols & 3) == 0) wt_u<4>(L.w, u_s, v_s, part, rows, cols);
-    else                 wt_u<1>(L.w, u_s, v_s, part, rows, cols);
-    const float nv = sqrtf(sumsq_smem(v_s, cols, red));
-    const float inv_nv = 1.0f / fmaxf(nv, eps);
-    for (int i = threadIdx.x; i < cols; i += SN_THREADS) { const float x = v_s[i] * inv_nv; v_s[i] = x; L.v[i] = x; }
-    __syncthreads();
-    // u <- normalize(W v) ; sigma = u . (W v)
-    w_v(L.w, v_s, u_s, rows, cols);
-    const float ss = sumsq_smem(u_s, rows, red);
-    const float ns = sqrtf(ss);
-    const float inv_ns = 1.0f / fmaxf(ns, eps);
-    for (int i = threadIdx.x; i < rows; i += SN_THREADS) L.u[i] = u_s[i] * inv_ns;
-    sigma = ss * inv_ns;
+    for (int r = threadIdx.x; r < rows; r += SN_THREADS) { const float s = L.svec[r]; acc = fmaf(s, s, acc); }
+    const float ss = block_sum256(acc, red);
+    const float inv = 1.0f / fmaxf(sqrtf(ss), eps);
+    for (int r = threadIdx.x; r < rows; r += SN_THREADS) L.u[r] = L.svec[r] * inv;
+    if (threadIdx.x == 0) *L.sigma = ss * inv;
   } else {
-    // sigma = u . (W v) with the stored buffers
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    float acc_total = 0.f;
-    for (int r = warp; r < rows; r += SN_WARPS) {
-      const float* wr = L.w + (size_t)r * cols;
-      float acc = 0.f;
-      for (int c = lane; c < cols; c += 32) acc += wr[c] * v_s[c];
-      acc = warp_sum(acc);
-      if (lane == 0) acc_total += acc * u_s[r];
-    }
-    sigma = block_sum(acc_total, red);
+    for (int r = threadIdx.x; r < rows; r += SN_THREADS) acc = fmaf(L.u[r], L.svec[r], acc);
+    const float sg = block_sum256(acc, red);
+    if (threadIdx.x == 0) *L.sigma = sg;
   }
-  if (threadIdx.x == 0) *L.sigma = sigma;
-  const float inv_sigma = 1.0f / sigma;
+}
 
-  // W_eff = rowscale * W / sigma  -> bf16 (rows, cols) [+ transposed bf16 (cols, rows)] or fp32
+// ---- E: W_eff = rowscale * W / sigma
+__global__ void __launch_bounds__(SN_THREADS)
+sn_e_kernel(const calm_sn_layer* __restrict__ table, const calm_sn_item* __restrict__ items) {
+  const calm_sn_item it = items[blockIdx.x];
+  const calm_sn_layer L = table[it.layer];
+  const int cols = L.cols;
+  const float inv_sigma = 1.0f / (*L.sigma);
+  const size_t base = (size_t)it.row_begin * cols;
+  const int n = (it.row_end - it.row_begin) * cols;
   if (L.eff_f32) {
     float* out = reinterpret_cast<float*>(L.w_eff);
-    for (int i = threadIdx.x; i < rows * cols; i += SN_THREADS) {
-      const float rs = L.rowscale ? L.rowscale[i / cols] : 1.f;
-      out[i] = L.w[i] * inv_sigma * rs;
+    for (int i = threadIdx.x; i < n; i += SN_THREADS) {
+      const float rs = L.rowscale ? L.rowscale[it.row_begin + i / cols] : 1.f;
+      out[base + i] = L.w[base + i] * inv_sigma * rs;
     }
-    return;
-  }
-  bf16* out = reinterpret_cast<bf16*>(L.w_eff);
-  bf16* out_t = reinterpret_cast<bf16*>(L.w_eff_t);
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 16
-  for (int r0 = 0; r0 < rows; r0 += 32) {
-    for (int c0 = 0; c0 < cols; c0 += 32) {
-#pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        const int r = r0 + ty + j * 16, c = c0 + tx;
-        float val = 0.f;
-        if (r < rows && c < cols) {
-          const float rs = L.rowscale ? L.rowscale[r] : 1.f;
-          val = L.w[(size_t)r * cols + c] * inv_sigma * rs;
-          out[(size_t)r * cols + c] = __float2bfloat16(val);
-        }
-        tile[ty + j * 16][tx] = val;
-      }
-      __syncthreads();
-      if (out_t) {
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          const int c = c0 + ty + j * 16, r = r0 + tx;
-          if (r < rows && c < cols) out_t[(size_t)c * L.ld_t + r] = __float2bfloat16(tile[tx][ty + j * 16]);
-        }
-      }
-      __syncthreads();
+  } else if ((cols & 3) == 0) {
+    bf16* out = reinterpret_cast<bf16*>(L.w_eff);
+    const int c4n = cols >> 2;
+    for (int i = threadIdx.x; i < (n >> 2); i += SN_THREADS) {
+      const int r = it.row_begin + i / c4n;
+      const float sc = inv_sigma * (L.rowscale ? L.rowscale[r] : 1.f);
+      const float4 w = reinterpret_cast<const float4*>(L.w + base)[i];
+      uint2 o;
+      o.x = pack_bf16x2(w.x * sc, w.y * sc); o.y = pack_bf16x2(w.z * sc, w.w * sc);
+      reinterpret_cast<uint2*>(out + base)[i] = o;
+    }
+  } else {
+    bf16* out = reinterpret_cast<bf16*>(L.w_eff);
+    for (int i = threadIdx.x; i < n; i += SN_THREADS) {
+      const float rs = L.rowscale ? L.rowscale[it.row_begin + i / cols] : 1.f;
+      out[base + i] = __float2bfloat16(L.w[base + i] * inv_sigma * rs);
     }
   }
 }
 
-// ------------------------------------------------------------------------------------------------------------
-// backward:  H = rs (.) sum_s G_s ;  dW = H/sigma - (<H,W>/sigma^2) u v^T ;  d rs[r] = sum_c G[r,c] W[r,c]/sigma
-// grid (n_layers, SN_BWD_CHUNKS); kernel A writes H into grad_w and per-chunk partial dots into tmp.
-// ------------------------------------------------------------------------------------------------------------
-constexpr int SN_BWD_CHUNKS = 16;
-constexpr int SN_BWD_THREADS = 256;
-
-__global__ void __launch_bounds__(SN_BWD_THREADS)
-sn_backward_a_kernel(const calm_sn_layer* __restrict__ table) {
-  const calm_sn_layer L = table[blockIdx.x];
-  const int rows = L.rows, cols = L.cols;
-  const int rpc = (rows + SN_BWD_CHUNKS - 1) / SN_BWD_CHUNKS;
-  const int r_begin = blockIdx.y * rpc, r_end = min(rows, r_begin + rpc);
+// ---- backward A: H = rowscale * sum_splits G -> grad_w ; per-item partial <H, W> ; d rowscale
+__global__ void __launch_bounds__(SN_THREADS)
+sn_bwd_a_kernel(const calm_sn_layer* __restrict__ table, const calm_sn_item* __restrict__ items) {
   __shared__ float red[32];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = SN_BWD_THREADS / 32;
+  const calm_sn_item it = items[blockIdx.x];
+  const calm_sn_layer L = table[it.layer];
+  const int cols = L.cols, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const size_t plane = (size_t)L.g_split_stride;
+  const float inv_sigma = 1.0f / (*L.sigma);
   float dot = 0.f;
-  for (int r = r_begin + warp; r < r_end; r += nwarps) {
+  for (int r = it.row_begin + warp; r < it.row_end; r += SN_WARPS) {
     const float rs = L.rowscale ? L.rowscale[r] : 1.f;
+    const size_t rowoff = (size_t)r * cols;
     float rowdot = 0.f;
-    for (int c = lane; c < cols; c += 32) {
-      const size_t idx = (size_t)r * cols + c;
-      float g = 0.f;
-      for (int s = 0; s < L.g_splits; ++s) g += L.g_eff[s * plane + idx];
-      const float w = L.w[idx];
-      rowdot += g * w;
-      L.grad_w[idx] = g * rs;
+    if ((cols & 3) == 0) {
+      for (int c4 = lane; c4 < (cols >> 2); c4 += 32) {
+        float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int s = 0; s < L.g_splits; ++s) {
+          const float4 p = reinterpret_cast<const float4*>(L.g_eff + s * plane + rowoff)[c4];
+          g.x += p.x; g.y += p.y; g.z += p.z; g.w += p.w;
+        }
+        const float4 w = reinterpret_cast<const float4*>(L.w + rowoff)[c4];
+        rowdot += g.x * w.x + g.y * w.y + g.z * w.z + g.w * w.w;
+        reinterpret_cast<float4*>(L.grad_w + rowoff)[c4] = make_float4(g.x * rs, g.y * rs, g.z * rs, g.w * rs);
+      }
+    } else {
+      for (int c = lane; c < cols; c += 32) {
+        float g = 0.f;
+        for (int s = 0; s < L.g_splits; ++s) g += L.g_eff[s * plane + rowoff + c];
+        rowdot = fmaf(g, L.w[rowoff + c], rowdot);
+        L.grad_w[rowoff + c] = g * rs;
+      }
     }
     rowdot = warp_sum(rowdot);
     if (lane == 0) {
-      if (L.grad_rowscale) L.grad_rowscale[r] = rowdot / (*L.sigma);
+      if (L.grad_rowscale) L.grad_rowscale[r] = rowdot * inv_sigma;
       dot += rowdot * rs;
     }
   }
-  dot = block_sum(dot, red);
-  if (threadIdx.x == 0) L.tmp[blockIdx.y] = dot;
+  dot = block_sum256(dot, red);
+  if (threadIdx.x == 0) L.tpart[it.local_index] = dot;  // tpart is free again in backward: one float per item
 }
 
-__global__ void __launch_bounds__(SN_BWD_THREADS)
-sn_backward_b_kernel(const calm_sn_layer* __restrict__ table) {
-  const calm_sn_layer L = table[blockIdx.x];
-  const int rows = L.rows, cols = L.cols;
-  const int rpc = (rows + SN_BWD_CHUNKS - 1) / SN_BWD_CHUNKS;
-  const int r_begin = blockIdx.y * rpc, r_end = min(rows, r_begin + rpc);
-  if (r_begin >= r_end) return;
+// ---- backward B: grad_w = H / sigma - (<H,W> / sigma^2) u v^T
+__global__ void __launch_bounds__(SN_THREADS)
+sn_bwd_b_kernel(const calm_sn_layer* __restrict__ table, const calm_sn_item* __restrict__ items) {
+  const calm_sn_item it = items[blockIdx.x];
+  const calm_sn_layer L = table[it.layer];
+  const int cols = L.cols;
   float dot = 0.f;
-#pragma unroll
-  for (int i = 0; i < SN_BWD_CHUNKS; ++i) dot += L.tmp[i];
-  const float sigma = *L.sigma;
-  const float inv_sigma = 1.0f / sigma;
+  for (int k = 0; k < L.item_count; ++k) dot += L.tpart[k];
+  const float inv_sigma = 1.0f / (*L.sigma);
   const float coef = dot * inv_sigma * inv_sigma;
-  const int n = (r_end - r_begin) * cols;
-  for (int i = threadIdx.x; i < n; i += SN_BWD_THREADS) {
-    const int r = r_begin + i / cols, c = i % cols;
-    const size_t idx = (size_t)r * cols + c;
-    L.grad_w[idx] = L.grad_w[idx] * inv_sigma - coef * L.u[r] * L.v[c];
+  const size_t base = (size_t)it.row_begin * cols;
+  const int n = (it.row_end - it.row_begin) * cols;
+  for (int i = threadIdx.x; i < n; i += SN_THREADS) {
+    const int r = it.row_begin + i / cols, c = i % cols;
+    L.grad_w[base + i] = L.grad_w[base + i] * inv_sigma - coef * L.u[r] * L.v[c];
   }
 }
 
 }  // namespace
 
-extern "C" int32_t calm_sn_forward(const calm_sn_layer* table_dev, int32_t n_layers, int32_t max_rows, int32_t max_cols,
+extern "C" int32_t calm_sn_forward(const calm_sn_layer* table_dev, int32_t n_layers, const calm_sn_item* items_dev, int32_t n_items,
                                    int32_t training, float eps, cudaStream_t stream) {
-  CALM_CHECK_ARG(table_dev != nullptr && n_layers > 0, "calm_sn_forward: empty table");
-  CALM_CHECK_ARG(max_rows > 0 && max_cols > 0, "calm_sn_forward: bad max dims");
-  const int mr = (max_rows + 3) & ~3, mc = (max_cols + 3) & ~3;
-  const size_t smem = (size_t)(mr + mc + SN_WARPS * 128) * sizeof(float);
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(sn_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) { calm_set_error("calm_sn_forward: smem %zu: %s", smem, cudaGetErrorString(e)); return CALM_ERR_CUDA; }
-    configured = smem;
+  CALM_CHECK_ARG(table_dev != nullptr && n_layers > 0 && items_dev != nullptr && n_items >= n_layers, "calm_sn_forward: empty table");
+  if (training) {
+    sn_a_kernel<<<n_items, SN_THREADS, 0, stream>>>(table_dev, items_dev);
+    CALM_CHECK_LAUNCH("calm_sn_forward(A)");
+    sn_b_kernel<<<n_layers, SN_THREADS, 0, stream>>>(table_dev, eps);
+    CALM_CHECK_LAUNCH("calm_sn_forward(B)");
   }
-  sn_forward_kernel<<<n_layers, SN_THREADS, smem, stream>>>(table_dev, training, eps, mr, mc);
-  CALM_CHECK_LAUNCH("calm_sn_forward");
+  sn_c_kernel<<<n_items, SN_THREADS, 0, stream>>>(table_dev, items_dev);
+  CALM_CHECK_LAUNCH("calm_sn_forward(C)");
+  sn_d_kernel<<<n_layers, SN_THREADS, 0, stream>>>(table_dev, training, eps);
+  CALM_CHECK_LAUNCH("calm_sn_forward(D)");
+  sn_e_kernel<<<n_items, SN_THREADS, 0, stream>>>(table_dev, items_dev);
+  CALM_CHECK_LAUNCH("calm_sn_forward(E)");
   return CALM_OK;
 }
 
-extern "C" int32_t calm_sn_backward(const calm_sn_layer* table_dev, int32_t n_layers, int32_t max_rows, int32_t max_cols,
+extern "C" int32_t calm_sn_backward(const calm_sn_layer* table_dev, int32_t n_layers, const calm_sn_item* items_dev, int32_t n_items,
                                     cudaStream_t stream) {
-  CALM_CHECK_ARG(table_dev != nullptr && n_layers > 0, "calm_sn_backward: empty table");
-  (void)max_rows; (void)max_cols;
-  dim3 grid(n_layers, SN_BWD_CHUNKS);
-  sn_backward_a_kernel<<<grid, SN_BWD_THREADS, 0, stream>>>(table_dev);
+  CALM_CHECK_ARG(table_dev != nullptr && n_layers > 0 && items_dev != nullptr && n_items >= n_layers, "calm_sn_backward: empty table");
+  sn_bwd_a_kernel<<<n_items, SN_THREADS, 0, stream>>>(table_dev, items_dev);
   CALM_CHECK_LAUNCH("calm_sn_backward(a)");
-  sn_backward_b_kernel<<<grid, SN_BWD_THREADS, 0, stream>>>(table_dev);
+  sn_bwd_b_kernel<<<n_items, SN_THREADS, 0, stream>>>(table_dev, items_dev);
   CALM_CHECK_LAUNCH("calm_sn_backward(b)");
   return CALM_OK;
 }

@@ -65,7 +65,7 @@ int32_t calm_gemm_default_splits(int32_t M, int32_t N, int32_t K, int32_t batch,
 /* ------------------------------------------------------------------------------------------------------------------
  * Spectral norm, batched over a table of layers: replaces torch/nn/utils/spectral_norm.py:92-114 (one power iteration
  * v<-norm(W^T u), u<-norm(W v), sigma=u^T W v, W/sigma) for every sn(...) layer hit by a forward
- * (Vi_Tools_CNN_less_V2.py:137-204,380-384; CALM_ViT_V2.py:50-52,62-66) — 3 launches instead of ~12 per layer.
+ * (Vi_Tools_CNN_less_V2.py:137-204,380-384; CALM_ViT_V2.py:50-52,62-66) — 5 launches per scope (~40 layers) instead of ~12 per layer.
  * One table row per layer (device array of calm_sn_layer):
  * ------------------------------------------------------------------------------------------------------------------ */
 typedef struct {
@@ -73,22 +73,24 @@ typedef struct {
   float* u;            /* weight_u (rows)  - updated in place when training                                    */
   float* v;            /* weight_v (cols)  - updated in place when training                                    */
   const float* rowscale; /* optional LayerScale vector folded into the effective weight rows (or NULL)        */
-  void* w_eff;         /* out: bf16 (rows, cols) = rowscale[r] * W/sigma  — or fp32 when eff_f32               */
-  void* w_eff_t;       /* out: bf16 (cols, rows) transposed copy for dgrad (or NULL)                           */
-  float* grad_w;       /* sn_grad: out fp32 (rows, cols) gradient wrt weight_orig                              */
-  float* grad_rowscale;/* sn_grad: out fp32 (rows) gradient wrt rowscale (or NULL)                             */
-  const float* g_eff;  /* sn_grad: in fp32 partial sums of dL/dW_eff: g_splits x (rows, cols), g_split_stride apart */
-  int32_t rows, cols, g_splits, eff_f32;
-  float* tmp;          /* scratch: >= 32 floats                                                                */
+  void* w_eff;         /* out: bf16 (rows, cols) = rowscale[r] * W/sigma  - or fp32 when eff_f32               */
+  float* grad_w;       /* sn_backward: out fp32 (rows, cols) gradient wrt weight_orig                           */
+  float* grad_rowscale;/* sn_backward: out fp32 (rows) gradient wrt rowscale (or NULL)                          */
+  const float* g_eff;  /* sn_backward: in fp32 partial sums of dL/dW_eff: g_splits x (rows, cols), g_split_stride apart */
+  float* tpart;        /* scratch: item_count x cols floats (partial W^T u per row chunk; partial dots in backward) */
+  float* svec;         /* scratch: rows floats (W v)                                                            */
   float* sigma;        /* out: 1 float                                                                         */
-  int64_t g_split_stride; /* elements between split partials of g_eff (>= rows*cols; layers fused into one GEMM share it) */
-  int32_t ld_t;        /* leading dimension of w_eff_t (>= rows; > rows when several layers share one transposed matrix) */
+  int64_t g_split_stride; /* elements between split partials of g_eff (layers stacked into one GEMM operand share it) */
+  int32_t rows, cols, g_splits, eff_f32;
+  int32_t item_count;  /* number of row-chunk items of this layer                                              */
   int32_t _pad;
 } calm_sn_layer;
-int32_t calm_sn_forward(const calm_sn_layer* table_dev, int32_t n_layers, int32_t max_rows, int32_t max_cols,
+/* one CTA-sized piece of work: rows [row_begin, row_end) of layer `layer`; local_index = its rank within the layer */
+typedef struct { int32_t layer, row_begin, row_end, local_index; } calm_sn_item;
+int32_t calm_sn_forward(const calm_sn_layer* table_dev, int32_t n_layers, const calm_sn_item* items_dev, int32_t n_items,
                         int32_t training, float eps, cudaStream_t stream);
 /* dL/dW_orig = rs*G/sigma - (<rs*G, W>/sigma^2) u v^T ; dL/drowscale[r] = sum_c G[r,c] * W[r,c]/sigma   */
-int32_t calm_sn_backward(const calm_sn_layer* table_dev, int32_t n_layers, int32_t max_rows, int32_t max_cols,
+int32_t calm_sn_backward(const calm_sn_layer* table_dev, int32_t n_layers, const calm_sn_item* items_dev, int32_t n_items,
                          cudaStream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
