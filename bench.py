@@ -199,7 +199,9 @@ def run_reference(args, rank, world):
     line = {"impl": "reference", "metric": "train images/sec at 224^2", "value": val, "unit": "images/sec", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "CALM-ViT cls trainer config 224^2, fwd+bwd on host CPU cores, bounded sample: batch %d per step" % Bs},
+            "config": {"workload": "CALM-ViT cls trainer config (distributed_trainer_cls.py): 224x224x3, heads 12, dim 672, latent (80,240), "
+                                   "1000 classes; reference algorithm (oracle port) fwd+bwd on the host CPU cores",
+                       "sample": "bounded sample of the workload: batch %d per step instead of 256" % Bs},
             "cpu_baseline": {"value": val, "unit": "images/sec", "cores": torch.get_num_threads(), "kind": "port",
                              "sample": "oracle (port of the reference path) fwd+bwd fp32, batch %d/step, %d steps" % (Bs, args.steps)},
             "e2e": {"value": val, "unit": "images/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}

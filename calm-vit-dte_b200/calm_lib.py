@@ -59,6 +59,7 @@ PROTOTYPES = {
     "calm_last_error": (C.c_char_p, []),
     "calm_set_debug_flags": (None, [i32]),
     "calm_get_debug_flags": (i32, []),
+    "calm_debug_set_gemm_bn": (None, [i32]),
     "calm_set_error_flag_buffer": (i32, [vp]),
     "calm_gemm": (i32, [C.POINTER(GemmArgs), vp]),
     "calm_gemm_default_splits": (i32, [i32, i32, i32, i32, i32]),

@@ -508,6 +508,7 @@ int make_map(CUtensorMap* map, const void* base, uint64_t inner, uint64_t outer,
 }
 
 int g_debug_flags = 0;
+int g_bn_override = 0;  // tuning hook (calm_debug_set_gemm_bn): force the N tile width
 
 
 template <int A_MN, int B_MN>
@@ -527,6 +528,7 @@ int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p,
 }  // namespace
 
 extern "C" void calm_set_debug_flags(int32_t flags) { g_debug_flags = flags; }
+extern "C" void calm_debug_set_gemm_bn(int32_t bn) { g_bn_override = bn; }
 extern "C" int32_t calm_get_debug_flags(void) { return g_debug_flags; }
 
 extern "C" int32_t calm_gemm_default_splits(int32_t M, int32_t N, int32_t K, int32_t batch, int32_t reduce_batch) {
@@ -567,6 +569,7 @@ extern "C" int32_t calm_gemm(const calm_gemm_args* a, cudaStream_t stream) {
   p.M = a->M; p.N = a->N; p.K = a->K; p.batch = a->batch;
   const int ntn = (a->N + BN_MAX - 1) / BN_MAX;
   p.BN = ((a->N + ntn - 1) / ntn + 15) / 16 * 16;
+  if (g_bn_override >= 16 && g_bn_override <= BN_MAX && g_bn_override % 16 == 0) p.BN = g_bn_override < ((a->N + 15) / 16 * 16) ? g_bn_override : (a->N + 15) / 16 * 16;
   p.tiles_m = (a->M + BM - 1) / BM;
   p.tiles_n = (a->N + p.BN - 1) / p.BN;
   p.kblocks = (a->K + BK - 1) / BK;

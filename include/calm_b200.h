@@ -34,6 +34,7 @@ int32_t calm_abi_version(void);
 const char* calm_last_error(void); /* thread-local, valid until the next failing call on this thread */
 void calm_set_debug_flags(int32_t flags);
 int32_t calm_get_debug_flags(void);
+void calm_debug_set_gemm_bn(int32_t bn); /* tuning hook: force the GEMM N-tile width (0 = automatic) */
 int32_t calm_set_error_flag_buffer(int32_t* device_int); /* optional: receives the id of a timed-out barrier */
 
 /* ------------------------------------------------------------------------------------------------------------------
