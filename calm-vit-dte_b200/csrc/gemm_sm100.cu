@@ -43,6 +43,7 @@ struct GemmParams {
   int BN, tiles_m, tiles_n, kblocks;
   int reduce_batch, splits, kb_per_split, total_kb;
   int total_tiles;
+  int tiles_mp, total_pairs;   // pair mode: M tiles are processed two at a time by a 2-CTA cluster sharing the B tile
   int a_bcast, b_bcast;
   long long stride_split;
   void* c; int c_f32; long long ldc, stride_c;
@@ -96,6 +97,20 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
       "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
+}
+// multicast variant: the box lands at the same smem offset of every CTA in `mask`, each one's mbarrier gets the bytes
+__device__ __forceinline__ void tma_load_3d_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4, %5}], [%2], %6;"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit_mc(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -241,10 +256,12 @@ __device__ __forceinline__ void epi_finish(const GemmParams& p, const EpiPre& e,
 }
 
 struct TileCoord { int m_t, n_t, b, split; };
-__device__ __forceinline__ TileCoord decode_tile(const GemmParams& p, int t) {
+template <int PAIR>
+__device__ __forceinline__ TileCoord decode_tile(const GemmParams& p, int t, int crank) {
   TileCoord c;
   c.n_t = t % p.tiles_n; t /= p.tiles_n;
-  c.m_t = t % p.tiles_m; t /= p.tiles_m;
+  if (PAIR) { c.m_t = 2 * (t % p.tiles_mp) + crank; t /= p.tiles_mp; }   // may be == tiles_m (phantom tile of an odd count)
+  else { c.m_t = t % p.tiles_m; t /= p.tiles_m; }
   if (p.reduce_batch) { c.b = 0; c.split = t; }
   else { c.b = t % p.batch; c.split = t / p.batch; }
   return c;
@@ -253,9 +270,14 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmParams& p, int t) {
 // ---------------------------------------------------------------------------------------------------------
 // The tcgen05 kernel
 // ---------------------------------------------------------------------------------------------------------
-template <int A_MN, int B_MN>
+// PAIR = 1: launched as clusters of 2 CTAs that work on two M tiles of the same N tile in lock-step; each CTA fetches half
+// of the B (weight) tile and TMA-multicasts it into both CTAs' shared memory, which cuts the L2 -> SM fill traffic of a
+// 128 x 256 tile from 48 KB to 32 KB per k-block. Stage release needs both consumers: the MMA warp's tcgen05.commit is
+// multicast to both CTAs' "empty" barriers (count 2).
+template <int A_MN, int B_MN, int PAIR>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmBh,
+                    const GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
@@ -274,7 +296,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if (warp == WARP_MMA && lane == 0) {
     for (int i = 0; i < STAGES; ++i) {
       mbar_init(smem_u32(&bars[i]), 1);
-      mbar_init(smem_u32(&bars[STAGES + i]), 1);
+      mbar_init(smem_u32(&bars[STAGES + i]), PAIR ? 2 : 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(smem_u32(&bars[2 * STAGES + i]), 1);
@@ -288,8 +310,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   }
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();   // the peer's barriers exist before anything is multicast into this CTA
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const int crank = PAIR ? (int)(blockIdx.x & 1) : 0;
+  const int w_first = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int w_stride = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int w_total = PAIR ? p.total_pairs : p.total_tiles;
 
   const int nb_boxes = (p.BN + 63) / 64;
   const uint32_t b_bytes = B_MN ? (uint32_t)nb_boxes * (BK * 128) : (uint32_t)p.BN * (BK * 2);
@@ -299,8 +326,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     // ===================== TMA producer =====================
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
-        const TileCoord tc = decode_tile(p, t);
+      for (int t = w_first; t < w_total; t += w_stride) {
+        const TileCoord tc = decode_tile<PAIR>(p, t, crank);
         const int m0 = tc.m_t * BM, n0 = tc.n_t * p.BN;
         const int kb_begin = tc.split * p.kb_per_split;
         const int kb_end = min(kb_begin + p.kb_per_split, p.total_kb);
@@ -320,7 +347,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           } else {
             tma_load_3d(sa, &tmA, full, k0, m0, ba);
           }
-          if (B_MN) {
+          if (PAIR) {
+            if (B_MN) {   // 64-wide slabs alternate between the two CTAs
+              for (int i = crank; i < nb_boxes; i += 2) tma_load_3d_mc(sb + i * (BK * 128), &tmB, full, n0 + 64 * i, k0, bb, 3);
+            } else {      // rows [crank * BN/2, (crank + 1) * BN/2) of the tile
+              const int half_rows = p.BN >> 1;
+              tma_load_3d_mc(sb + crank * half_rows * 128, &tmBh, full, k0, n0 + crank * half_rows, bb, 3);
+            }
+          } else if (B_MN) {
             for (int i = 0; i < nb_boxes; ++i) tma_load_3d(sb + i * (BK * 128), &tmB, full, n0 + 64 * i, k0, bb);
           } else {
             tma_load_3d(sb, &tmB, full, k0, n0, bb);
@@ -336,8 +370,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                              ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
-      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
-        const TileCoord tc = decode_tile(p, t);
+      for (int t = w_first; t < w_total; t += w_stride) {
+        const TileCoord tc = decode_tile<PAIR>(p, t, crank);
         const int kb_begin = tc.split * p.kb_per_split;
         const int kb_end = min(kb_begin + p.kb_per_split, p.total_kb);
         mbar_wait(smem_u32(&bars[2 * STAGES + 2 + acc]), acc_phase ^ 1, p.err_flag, 2);
@@ -354,7 +388,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             const uint64_t bdesc = B_MN ? make_smem_desc(sb + k * 2048, BK * 128, 1024) : make_smem_desc(sb + k * 32, 16, 1024);
             tc_mma_bf16(tmem_d, adesc, bdesc, idesc, (ci > kb_begin || k > 0) ? 1u : 0u);
           }
-          tc_commit(smem_u32(&bars[STAGES + stage]));  // frees this smem stage when the MMAs above retire
+          if (PAIR) tc_commit_mc(smem_u32(&bars[STAGES + stage]), 3);  // both CTAs' producers wait for both consumers
+          else tc_commit(smem_u32(&bars[STAGES + stage]));             // frees this smem stage when the MMAs above retire
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
         tc_commit(smem_u32(&bars[2 * STAGES + acc]));  // accumulator ready for the epilogue
@@ -366,8 +401,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int q = warp & 3;             // TMEM lane quadrant this warp may access
     const int half = warp >> 2;   // which half of the tile's 32-column chunks this warp owns
     int acc = 0; uint32_t acc_phase = 0;
-    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
-      const TileCoord tc = decode_tile(p, t);
+    for (int t = w_first; t < w_total; t += w_stride) {
+      const TileCoord tc = decode_tile<PAIR>(p, t, crank);
       const int m0 = tc.m_t * BM, n0 = tc.n_t * p.BN;
       const int ncols = min(p.BN, p.N - n0);
       const int nch = (ncols + 31) >> 5;
@@ -410,6 +445,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();   // no multicast write / commit may target a CTA that has already exited
   if (warp == WARP_ALLOC) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
@@ -512,15 +548,33 @@ int g_bn_override = 0;  // tuning hook (calm_debug_set_gemm_bn): force the N til
 
 
 template <int A_MN, int B_MN>
-int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, cudaStream_t stream) {
+int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mbh, const GemmParams& p, bool pair, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel<A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel<A_MN, B_MN, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tcgen05_kernel<A_MN, B_MN, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     if (e != cudaSuccess) { calm_set_error("gemm: cannot raise dynamic smem: %s", cudaGetErrorString(e)); return CALM_ERR_CUDA; }
     attr_set = true;
   }
+  if (pair) {
+    const int max_clusters = calm_num_sms() / 2;
+    const int clusters = p.total_pairs < max_clusters ? p.total_pairs : max_clusters;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(2 * clusters);
+    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.dynamicSmemBytes = SMEM_BYTES;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<A_MN, B_MN, 1>, ma, mb, mbh, p);
+    if (e != cudaSuccess) { calm_set_error("calm_gemm(tcgen05, cluster): launch failed: %s", cudaGetErrorString(e)); return CALM_ERR_CUDA; }
+    return CALM_OK;
+  }
   const int grid = p.total_tiles < calm_num_sms() ? p.total_tiles : calm_num_sms();
-  gemm_tcgen05_kernel<A_MN, B_MN><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(ma, mb, p);
+  gemm_tcgen05_kernel<A_MN, B_MN, 0><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(ma, mb, mbh, p);
   CALM_CHECK_LAUNCH("calm_gemm(tcgen05)");
   return CALM_OK;
 }
@@ -579,6 +633,11 @@ extern "C" int32_t calm_gemm(const calm_gemm_args* a, cudaStream_t stream) {
   p.splits = (p.total_kb + p.kb_per_split - 1) / p.kb_per_split;
   CALM_CHECK_ARG(p.splits == splits, "calm_gemm: splits=%d leaves empty partials (use calm_gemm_default_splits)", splits);
   p.total_tiles = p.tiles_m * p.tiles_n * p.splits * (p.reduce_batch ? 1 : a->batch);
+  p.tiles_mp = (p.tiles_m + 1) / 2;
+  p.total_pairs = p.tiles_mp * p.tiles_n * p.splits * (p.reduce_batch ? 1 : a->batch);
+  // pair (cluster + multicast) mode pays off on many-wave problems (measured: +9 % on the 57344 x 2016 x 672 GEMM, nothing on
+  // one-wave problems, where the coarser work unit and the phantom tile of an odd M-tile count cost more than they save)
+  const bool pair = !(g_debug_flags & CALM_DEBUG_NO_CLUSTER) && (g_debug_flags & CALM_DEBUG_FORCE_CLUSTER || (p.total_pairs >= 2 * calm_num_sms() && (p.tiles_m % 2 == 0 || p.tiles_m >= 32))) && p.tiles_m >= 2;
   p.a_bcast = (a->stride_a == 0 && a->batch > 1) ? 1 : 0;
   p.b_bcast = (a->stride_b == 0 && a->batch > 1) ? 1 : 0;
   p.stride_split = a->stride_split;
@@ -608,9 +667,14 @@ extern "C" int32_t calm_gemm(const calm_gemm_args* a, cudaStream_t stream) {
   else                            rc = make_map(&mb, a->b, a->N, a->K, nbb, a->ldb, a->stride_b, BK);
   if (rc) return rc;
 
-  if (a->a_major == CALM_MAJOR_K && a->b_major == CALM_MAJOR_K) return launch_tc<0, 0>(ma, mb, p, stream);
-  if (a->a_major == CALM_MAJOR_K && a->b_major == CALM_MAJOR_MN) return launch_tc<0, 1>(ma, mb, p, stream);
-  if (a->a_major == CALM_MAJOR_MN && a->b_major == CALM_MAJOR_K) return launch_tc<1, 0>(ma, mb, p, stream);
-  return launch_tc<1, 1>(ma, mb, p, stream);
+  CUtensorMap mbh = mb;   // K-major B, pair mode: half-height box (BN/2 rows) for the multicast halves
+  if (pair && a->b_major == CALM_MAJOR_K) {
+    rc = make_map(&mbh, a->b, a->K, a->N, nbb, a->ldb, a->stride_b, p.BN / 2);
+    if (rc) return rc;
+  }
+  if (a->a_major == CALM_MAJOR_K && a->b_major == CALM_MAJOR_K) return launch_tc<0, 0>(ma, mb, mbh, p, pair, stream);
+  if (a->a_major == CALM_MAJOR_K && a->b_major == CALM_MAJOR_MN) return launch_tc<0, 1>(ma, mb, mbh, p, pair, stream);
+  if (a->a_major == CALM_MAJOR_MN && a->b_major == CALM_MAJOR_K) return launch_tc<1, 0>(ma, mb, mbh, p, pair, stream);
+  return launch_tc<1, 1>(ma, mb, mbh, p, pair, stream);
 }
 

@@ -28,7 +28,7 @@ typedef struct CUstream_st* cudaStream_t;
 enum { CALM_BF16 = 0, CALM_F32 = 1 };
 enum { CALM_MAJOR_K = 0, CALM_MAJOR_MN = 1 };
 enum { CALM_EPI_NONE = 0, CALM_EPI_GELU = 1, CALM_EPI_DGELU = 2 };
-enum { CALM_DEBUG_SIMT_GEMM = 1, CALM_DEBUG_LEGACY_ATTENTION = 2 };
+enum { CALM_DEBUG_SIMT_GEMM = 1, CALM_DEBUG_LEGACY_ATTENTION = 2, CALM_DEBUG_NO_CLUSTER = 4, CALM_DEBUG_FORCE_CLUSTER = 8 };
 
 int32_t calm_abi_version(void);
 const char* calm_last_error(void); /* thread-local, valid until the next failing call on this thread */

@@ -155,6 +155,34 @@ def test_gemm_strided_views(K):
     assert rel(dx, dk.float() @ w[D:2 * D].float()) < 4e-3
 
 
+@pytest.mark.parametrize("a_mn,b_mn", [(0, 0), (0, 1), (1, 0), (1, 1)])
+@pytest.mark.parametrize("M,N,Kd", [(20480, 240, 240), (19000, 528, 176), (18952, 96, 80)])
+def test_gemm_pair_mode(K, M, N, Kd, a_mn, b_mn):
+    """Large-M problems run as 2-CTA clusters that share the B tile through TMA multicast (odd tile counts included);
+    the result must be bit-identical to the single-CTA schedule (same MMA order per tile)."""
+    import calm_lib
+    a = rnd(M, Kd, seed=51)
+    b = rnd(N, Kd, scale=0.1, seed=52)
+    A = a.t().contiguous() if a_mn else a            # MN-major: element (m, k) at [k * ld + m]
+    Bm = b.t().contiguous() if b_mn else b
+    bias = rnd(N, dtype=f32, seed=53)
+    outs = []
+    for flags in (8, 4):                             # 8 = CALM_DEBUG_FORCE_CLUSTER, 4 = CALM_DEBUG_NO_CLUSTER
+        calm_lib.load().calm_set_debug_flags(flags)
+        try:
+            c = torch.full((M, N), float("nan"), dtype=bf16, device=dev())
+            aux = torch.empty(M, N, dtype=bf16, device=dev())
+            K.gemm(A, Bm, c, M, N, Kd, lda=M if a_mn else Kd, ldb=N if b_mn else Kd, ldc=N, a_major=a_mn, b_major=b_mn, bias=bias,
+                   epilogue=K.EPI_GELU, aux=aux, ld_aux=N)
+            outs.append((c, aux))
+        finally:
+            calm_lib.load().calm_set_debug_flags(0)
+    pre = a.float() @ b.float().t() + bias
+    assert rel(outs[0][1], pre) < 4e-3
+    assert rel(outs[0][0], torch.nn.functional.gelu(outs[0][1].float())) < 4e-3
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+
+
 def test_gemm_rejects_bad_args(K):
     import calm_lib
     a, b = rnd(64, 64), rnd(60, 64)
