@@ -158,8 +158,9 @@ def test_gemm_strided_views(K):
 @pytest.mark.parametrize("a_mn,b_mn", [(0, 0), (0, 1), (1, 0), (1, 1)])
 @pytest.mark.parametrize("M,N,Kd", [(20480, 240, 240), (19000, 528, 176), (18952, 96, 80)])
 def test_gemm_pair_mode(K, M, N, Kd, a_mn, b_mn):
-    """Large-M problems run as 2-CTA clusters that share the B tile through TMA multicast (odd tile counts included);
-    the result must be bit-identical to the single-CTA schedule (same MMA order per tile)."""
+    """Large-M problems run as 2-CTA clusters: tcgen05.mma.cta_group::2 over a 256-row tile pair with half of B in each CTA
+    (flag 8), or cta_group::1 with the B tile TMA-multicast (flags 8|16); odd tile counts included. Both must be bit-identical
+    to the single-CTA schedule (same k order per output element)."""
     import calm_lib
     a = rnd(M, Kd, seed=51)
     b = rnd(N, Kd, scale=0.1, seed=52)
@@ -167,7 +168,7 @@ def test_gemm_pair_mode(K, M, N, Kd, a_mn, b_mn):
     Bm = b.t().contiguous() if b_mn else b
     bias = rnd(N, dtype=f32, seed=53)
     outs = []
-    for flags in (8, 4):                             # 8 = CALM_DEBUG_FORCE_CLUSTER, 4 = CALM_DEBUG_NO_CLUSTER
+    for flags in (8, 4, 8 | 16):                     # FORCE_CLUSTER, NO_CLUSTER, FORCE_CLUSTER | PAIR_MULTICAST
         calm_lib.load().calm_set_debug_flags(flags)
         try:
             c = torch.full((M, N), float("nan"), dtype=bf16, device=dev())
@@ -181,6 +182,49 @@ def test_gemm_pair_mode(K, M, N, Kd, a_mn, b_mn):
     assert rel(outs[0][1], pre) < 4e-3
     assert rel(outs[0][0], torch.nn.functional.gelu(outs[0][1].float())) < 4e-3
     assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+    assert torch.equal(outs[2][0], outs[1][0]) and torch.equal(outs[2][1], outs[1][1])
+
+
+@pytest.mark.parametrize("M,N,Kd,nb", [(300, 264, 240, 1), (1000, 1344, 128, 1), (130, 8, 64, 1), (224, 224, 96, 5), (96, 40, 80, 3)])
+@pytest.mark.parametrize("form", ["bf16", "f32", "f32+add", "bf16+add_inplace", "gelu", "dgelu", "bf16<-f32add"])
+def test_gemm_epilogue_forms(K, M, N, Kd, nb, form):
+    """The TMA-staged epilogue (forced: flag 64) and the row-owner direct epilogue (flag 32) must agree bit for
+    bit on every operand mix, ragged tiles and batches included; the last form has no staged variant and checks the fallback."""
+    import calm_lib
+    a, b = rnd(nb * M, Kd, seed=61), rnd(nb * N, Kd, scale=0.1, seed=62)
+    bias = rnd(N, dtype=f32, seed=63)
+    outs = []
+    for flags in (64, 32):                          # FORCE_STAGED_EPILOGUE, DIRECT_EPILOGUE
+        calm_lib.load().calm_set_debug_flags(flags)
+        try:
+            cdt = f32 if form in ("f32", "f32+add") else bf16
+            c = torch.full((nb * M, N), float("nan"), dtype=cdt, device=dev())
+            kw = dict(lda=Kd, ldb=Kd, ldc=N, batch=nb, stride_a=M * Kd, stride_b=N * Kd, stride_c=M * N, bias=bias, alpha=0.75)
+            extra = None
+            if form == "f32+add":
+                kw.update(addend=rnd(nb * M, N, dtype=f32, seed=64), ld_addend=N, stride_addend=M * N)
+            elif form == "bf16+add_inplace":
+                c = rnd(nb * M, N, seed=65)
+                kw.update(addend=c, ld_addend=N, stride_addend=M * N)
+            elif form == "bf16<-f32add":
+                kw.update(addend=rnd(nb * M, N, dtype=f32, seed=64), ld_addend=N, stride_addend=M * N)
+            elif form == "gelu":
+                extra = torch.full((nb * M, N), float("nan"), dtype=bf16, device=dev())
+                kw.update(epilogue=K.EPI_GELU, aux=extra, ld_aux=N, stride_aux=M * N)
+            elif form == "dgelu":
+                extra = rnd(nb * M, N, seed=66)
+                kw.update(epilogue=K.EPI_DGELU, aux=extra, ld_aux=N, stride_aux=M * N)
+            K.gemm(a, b, c, M, N, Kd, **kw)
+            outs.append((c, extra))
+        finally:
+            calm_lib.load().calm_set_debug_flags(0)
+    assert not torch.isnan(outs[0][0].float()).any()
+    assert torch.equal(outs[0][0], outs[1][0])
+    if form == "gelu":
+        assert torch.equal(outs[0][1], outs[1][1])
+    if form in ("bf16", "f32"):
+        ref = 0.75 * torch.bmm(a.view(nb, M, Kd).float(), b.view(nb, N, Kd).float().transpose(1, 2)).reshape(nb * M, N) + bias
+        assert rel(outs[0][0], ref) < (1e-5 if form == "f32" else 4e-3)
 
 
 def test_gemm_rejects_bad_args(K):

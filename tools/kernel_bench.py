@@ -179,6 +179,9 @@ def bench_misc():
 
 if __name__ == "__main__":
     which = sys.argv[1:] or ["gemm", "attn", "cnn", "ln", "misc"]
+    if os.environ.get("KB_FLAGS"):   # library debug flags (include/calm_b200.h) for A/B experiments
+        import calm_lib
+        calm_lib.load().calm_set_debug_flags(int(os.environ["KB_FLAGS"], 0))
     for w in which:
         globals()["bench_" + w]()
         torch.cuda.empty_cache()
