@@ -40,7 +40,7 @@ constexpr int TMEM_COLS = 512;
 // Epilogue staging: every epilogue warp owns a small ring of 2 KB slots (32 rows x 64 B = 16 fp32 | 32 bf16 columns, 64B swizzle)
 // through which its output (and residual addend / saved pre-activation input) moves by TMA. Carved out of the operand-ring budget.
 constexpr int EPI_SLOT_BYTES = 2048;
-constexpr int EPI_MAX_SLOTS = 4;
+constexpr int EPI_MAX_SLOTS = 5;
 constexpr int EPI_BAR_OFFSET = 32;   // index (in 8-byte words) of the first epilogue load barrier inside the 1 KB barrier block
 
 struct GemmParams {
@@ -158,11 +158,13 @@ __device__ __forceinline__ void tc_mma_bf16_2sm(uint32_t tmem_d, uint64_t adesc,
 __device__ __forceinline__ void tc_commit_2sm(uint32_t bar, uint16_t mask) {
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask) : "memory");
 }
+// (default .release.cta semantics: the .release.cluster form costs a MEMBAR.ALL + ERRBAR per arrive, 15 % of all warp samples
+// of the 57344 x 2016 x 672 GEMM; nothing but TMEM reads, already fenced by tcgen05.fence, is ordered by this arrive)
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t local_bar, uint32_t cta_rank) {
   asm volatile(
       "{\n\t.reg .b32 ra;\n\t"
       "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
-      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}"
       ::"r"(local_bar), "r"(cta_rank) : "memory");
 }
 __device__ __forceinline__ void cluster_sync_all() {
@@ -339,6 +341,27 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmParams& p, int t, int
 // Slot ring per warp: unit g uses unit-slot g % NU; its bulk group must have finished READING shared memory before the
 // slot is written again (cp.async.bulk.wait_group.read), the load for unit g + 1 is in flight while unit g is combined.
 // ---------------------------------------------------------------------------------------------------------
+// The TMA units of one tile that belong to one epilogue warp.
+struct EpiTile { int n0, row0, b, split, ncols, nun_tma, u_begin, u_end; bool live, my_tail; };
+template <int PAIR, bool F32>
+__device__ __forceinline__ EpiTile epi_tile(const GemmParams& p, int t, int crank, int q, int half) {
+  const TileCoord tc = decode_tile<PAIR>(p, t, crank);
+  EpiTile e;
+  e.n0 = tc.n_t * p.BN; e.row0 = tc.m_t * BM + q * 32; e.b = tc.b; e.split = tc.split;
+  e.ncols = min(p.BN, p.N - e.n0);
+  // bf16 units are 32 columns wide; a tile width BN = 16 (mod 32) leaves a 16-column tail unit that a 32-column box would
+  // write into the next tile's columns: that one unit takes the row-owner direct form.
+  e.nun_tma = F32 ? (e.ncols + 15) / 16 : min((e.ncols + 31) / 32, p.BN / 32);
+  const bool has_tail = !F32 && e.ncols > e.nun_tma * 32;
+  const int nun = e.nun_tma + (has_tail ? 1 : 0);
+  e.u_begin = half == 0 ? 0 : (nun + 1) >> 1;
+  const int u_end_all = half == 0 ? (nun + 1) >> 1 : nun;
+  e.u_end = min(u_end_all, e.nun_tma);
+  e.my_tail = has_tail && u_end_all == nun && e.u_begin <= e.nun_tma;
+  e.live = e.row0 < p.M;                               // phantom tiles of pair mode and rows past M have nothing to move
+  return e;
+}
+
 template <int PAIR, bool F32>
 __device__ __forceinline__ void epilogue_tma(const GemmParams& p, const CUtensorMap* tmC, const CUtensorMap* tmAdd, const CUtensorMap* tmAux,
                                              uint8_t* smem, uint64_t* bars, uint32_t tmem_base, int warp, int lane, int crank,
@@ -355,42 +378,58 @@ __device__ __forceinline__ void epilogue_tma(const GemmParams& p, const CUtensor
   uint64_t* lbar = bars + EPI_BAR_OFFSET + warp * EPI_MAX_SLOTS;
   const int sw = (lane >> 1) & 3;                      // 64B swizzle: 16-byte granule index ^= bits [7:8] of the address
   uint8_t* my_row = stage_ptr + lane * 64;
-  uint32_t g = 0;                                      // units this warp has processed (slot rotation, barrier parity)
+  uint32_t g = 0;                                      // units this warp has processed
+  uint32_t us = 0, us_par = 0;                         // unit slot g % NU and its use parity (g / NU) & 1
   int acc = 0; uint32_t acc_phase = 0;
 
-  for (int t = w_first; t < w_total; t += w_stride) {
-    const TileCoord tc = decode_tile<PAIR>(p, t, crank);
-    const int m0 = tc.m_t * BM, n0 = tc.n_t * p.BN;
-    const int ncols = min(p.BN, p.N - n0);
-    // bf16 units are 32 columns wide; a tile width BN = 16 (mod 32) leaves a 16-column tail unit that a 32-column box would
-    // write into the next tile's columns: that one unit takes the row-owner direct form below.
-    const int nun_tma = F32 ? (ncols + 15) / 16 : min((ncols + 31) / 32, p.BN / 32);
-    const bool has_tail = !F32 && ncols > nun_tma * 32;
-    const int nun = nun_tma + (has_tail ? 1 : 0);
-    const int u_begin = half == 0 ? 0 : (nun + 1) >> 1, u_end_all = half == 0 ? (nun + 1) >> 1 : nun;
-    const int u_end = min(u_end_all, nun_tma);
-    const bool my_tail = has_tail && u_end_all == nun && u_begin <= nun_tma;
-    const int row0 = m0 + q * 32;
-    const bool live = row0 < p.M;                      // phantom tiles of pair mode and rows past M have nothing to move
-    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * BN_MAX;
-
-    auto issue_load = [&](uint32_t gi, int u) {        // lane 0: slot of unit gi free again -> request its input
-      const uint32_t us = gi % NU;
-      bulk_wait_read<1>();
-      const uint32_t lb = smem_u32(&lbar[us]);
+  // Input units (residual / saved pre-activation) are requested EPI_LOOKAHEAD units ahead of the one being combined, across
+  // tile boundaries: an HBM miss is ~1.5 us, a unit's arithmetic ~0.3 us. Lane 0 walks the same unit sequence with a second cursor.
+  constexpr uint32_t EPI_LOOKAHEAD = 3;                // < NU - 1 (= 4): the slot of unit g + 3 was last used by unit g - 2
+  int la_t = w_first, la_u = 0;
+  uint32_t la_g = 0, la_us = 0;
+  EpiTile la;
+  auto la_seek = [&]() {                               // first tile at or after la_t with a unit for this warp
+    for (; la_t < w_total; la_t += w_stride) {
+      la = epi_tile<PAIR, F32>(p, la_t, crank, q, half);
+      if (la.live && la.u_begin < la.u_end) { la_u = la.u_begin; return; }
+    }
+  };
+  auto pump = [&](uint32_t upto) {                     // lane 0: request the inputs of units [la_g, upto)
+    while (la_g < upto && la_t < w_total) {
+      bulk_wait_read<1>();                             // all stores but the newest have left their slots
+      const uint32_t lb = smem_u32(&lbar[la_us]);
       mbar_expect_tx(lb, EPI_SLOT_BYTES);
-      tma_load_4d(smem_u32(stage_ptr + us * EPI_SLOT_BYTES), tmL, lb, n0 + u * UC, row0, tc.b, 0);
+      tma_load_4d(smem_u32(stage_ptr + la_us * EPI_SLOT_BYTES), tmL, lb, la.n0 + la_u * UC, la.row0, la.b, 0);
+      ++la_g;
+      if (++la_us == NU) la_us = 0;
+      if (++la_u == la.u_end) { la_t += w_stride; la_seek(); }
+    }
+  };
+  if (has_load && lane == 0) la_seek();
+
+  for (int t = w_first; t < w_total; t += w_stride) {
+    const EpiTile e = epi_tile<PAIR, F32>(p, t, crank, q, half);
+    const int n0 = e.n0, row0 = e.row0, u_begin = e.u_begin, u_end = e.u_end;
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * BN_MAX;
+    if (has_load && lane == 0) pump(g + EPI_LOOKAHEAD);   // overlaps the wait for the accumulator
+    bool released = false;
+    auto release_acc = [&]() {                         // this warp has read the last of its accumulator columns out of TMEM
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (PAIR == 2 && crank != 0) mbar_arrive_remote(smem_u32(&bars[2 * STAGES + 2 + acc]), 0);  // the leader issues the MMAs
+        else mbar_arrive(smem_u32(&bars[2 * STAGES + 2 + acc]));
+      }
+      released = true;
     };
-    if (live && has_load && u_begin < u_end && lane == 0) issue_load(g, u_begin);   // overlaps the wait for the accumulator
 
     mbar_wait(smem_u32(&bars[2 * STAGES + acc]), acc_phase, p.err_flag, 4);
     tc_fence_after();
-    if (live) {
-      for (int u = u_begin; u < u_end; ++u, ++g) {
-        const uint32_t us = g % NU;
+    if (e.live) {
+      for (int u = u_begin; u < u_end; ++u) {
         uint8_t* slot = my_row + us * per_unit * EPI_SLOT_BYTES;
         if (has_load) {
-          if (u + 1 < u_end && lane == 0) issue_load(g + 1, u + 1);
+          if (lane == 0) pump(g + 1 + EPI_LOOKAHEAD);
         } else {
           if (lane == 0) { if (gelu) bulk_wait_read<1>(); else bulk_wait_read<2>(); }
           __syncwarp();
@@ -398,8 +437,9 @@ __device__ __forceinline__ void epilogue_tma(const GemmParams& p, const CUtensor
         uint32_t r[UC];
         tmem_ld16(taddr + u * UC, r);
         if (!F32) tmem_ld16(taddr + u * UC + 16, r + 16);
-        if (has_load) mbar_wait(smem_u32(&lbar[us]), (g / NU) & 1, p.err_flag, 5);
+        if (has_load) mbar_wait(smem_u32(&lbar[us]), us_par, p.err_flag, 5);
         tmem_ld_wait();
+        if (u + 1 == u_end && !e.my_tail) release_acc();   // the MMA warp may refill this accumulator while the unit is finished
         float v[UC];
 #pragma unroll
         for (int j = 0; j < UC; ++j) v[j] = __uint_as_float(r[j]) * p.alpha;
@@ -458,37 +498,35 @@ __device__ __forceinline__ void epilogue_tma(const GemmParams& p, const CUtensor
         if (lane == 0) {
           const uint32_t src = smem_u32(stage_ptr + us * per_unit * EPI_SLOT_BYTES);
           if (gelu) {
-            tma_store_4d(tmAux, src, n0 + u * UC, row0, tc.b, 0);
-            tma_store_4d(tmC, src + EPI_SLOT_BYTES, n0 + u * UC, row0, tc.b, 0);
+            tma_store_4d(tmAux, src, n0 + u * UC, row0, e.b, 0);
+            tma_store_4d(tmC, src + EPI_SLOT_BYTES, n0 + u * UC, row0, e.b, 0);
           } else {
-            tma_store_4d(tmC, src, n0 + u * UC, row0, tc.b, tc.split);
+            tma_store_4d(tmC, src, n0 + u * UC, row0, e.b, e.split);
           }
           bulk_commit();
         }
+        ++g;
+        if (++us == NU) { us = 0; us_par ^= 1; }
       }
-      if (my_tail) {
-        const int c = nun_tma * 32;
+      if (e.my_tail) {
+        const int c = e.nun_tma * 32;
         const long long row = (long long)row0 + lane;
-        const int nvalid = row < p.M ? min(16, ncols - c) : 0;
+        const int nvalid = row < p.M ? min(16, e.ncols - c) : 0;
         EpiPre pre;
-        epi_prefetch(p, pre, row, n0 + c, tc.b, nvalid);
+        epi_prefetch(p, pre, row, n0 + c, e.b, nvalid);
         uint32_t r[16];
         tmem_ld16(taddr + c, r);
         tmem_ld_wait();
+        release_acc();
         if (nvalid > 0) {
           float v[32];
 #pragma unroll
           for (int j = 0; j < 16; ++j) { v[j] = __uint_as_float(r[j]); v[16 + j] = 0.f; }
-          epi_finish(p, pre, v, row, n0 + c, tc.b, tc.split, nvalid);
+          epi_finish(p, pre, v, row, n0 + c, e.b, e.split, nvalid);
         }
       }
     }
-    tc_fence_before();
-    __syncwarp();
-    if (lane == 0) {
-      if (PAIR == 2 && crank != 0) mbar_arrive_remote(smem_u32(&bars[2 * STAGES + 2 + acc]), 0);  // the leader issues the MMAs
-      else mbar_arrive(smem_u32(&bars[2 * STAGES + 2 + acc]));
-    }
+    if (!released) release_acc();
     if (++acc == 2) { acc = 0; acc_phase ^= 1; }
   }
   if (lane == 0) bulk_wait_all();   // staging memory must outlive the last store's read
@@ -952,7 +990,8 @@ extern "C" int32_t calm_gemm(const calm_gemm_args* a, cudaStream_t stream) {
   // per-tile latency cost 5-25 %, and fp32 split-K partials (one exposed epilogue per CTA) are better off writing directly.
   const bool want_tma = (g_debug_flags & CALM_DEBUG_FORCE_STAGED_EPILOGUE) || ((a->addend || pair == 2) && !(a->c_dtype == CALM_F32 && !a->addend));
   p.epi_tma = !(g_debug_flags & CALM_DEBUG_DIRECT_EPILOGUE) && want_tma && add_ok && act_ok && a->stride_split % 4 == 0;
-  p.epi_slots = !p.epi_tma ? 0 : a->epilogue == CALM_EPI_GELU ? 4 : 3;
+  // slots per epilogue warp: 3 in-flight stores; GELU stores two slots per unit; units with an input keep 3 loads in flight
+  p.epi_slots = !p.epi_tma ? 0 : (a->addend || a->epilogue == CALM_EPI_DGELU) ? 5 : a->epilogue == CALM_EPI_GELU ? 4 : 3;
   {
     const int bn_cta = pair == 2 ? p.BN / 2 : p.BN;   // B columns staged per CTA
     const int b_bytes = a->b_major == CALM_MAJOR_K ? bn_cta * BK * 2 : ((bn_cta + 63) / 64) * BK * 128;

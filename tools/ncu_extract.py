@@ -29,3 +29,7 @@ for r in rows[2:]:
         if w in hdr:
             i = hdr.index(w)
             print("   %-85s %s %s" % (w, r[i], units[i]))
+    if len(sys.argv) > 2:   # extra: every metric whose name contains one of the given substrings
+        for i, h in enumerate(hdr):
+            if h not in WANT and any(k in h for k in sys.argv[2:]):
+                print("   %-85s %s %s" % (h, r[i], units[i]))
