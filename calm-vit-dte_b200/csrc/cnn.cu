@@ -31,6 +31,40 @@ __device__ __forceinline__ float gelu_fast(float x) {
   return g;
 }
 
+
+// Sum N register values over the 32 lanes with N - 1 + log2(32/N)... shuffles instead of 5 N: at every butterfly step a lane
+// keeps one half of its values and ships the other half to its partner. On return v[0] of lane L holds the all-lane sum of
+// value (L >> (5 - log2 N)): the lanes of a group all hold the same total, in the same (fixed) summation order.
+__device__ __forceinline__ void warp_sum16(float (&v)[16], int lane) {
+#pragma unroll
+  for (int step = 0; step < 4; ++step) {
+    const int off = 16 >> step, half = 8 >> step;
+    const bool hi = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < half; ++i) {
+      const float send = hi ? v[i] : v[i + half];
+      const float keep = hi ? v[i + half] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
+}
+__device__ __forceinline__ void warp_sum8(float (&v)[8], int lane) {
+#pragma unroll
+  for (int step = 0; step < 3; ++step) {
+    const int off = 16 >> step, half = 4 >> step;
+    const bool hi = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < half; ++i) {
+      const float send = hi ? v[i] : v[i + half];
+      const float keep = hi ? v[i + half] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  v[0] += __shfl_xor_sync(0xffffffffu, v[0], 2);
+  v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
+}
+
 __device__ __forceinline__ void load_weights(float* wsm, const CnnW& W) {
   for (int i = threadIdx.x; i < CH; i += NT) {
     wsm[i * 4 + 0] = W.w1[i * 3 + 0]; wsm[i * 4 + 1] = W.w1[i * 3 + 1]; wsm[i * 4 + 2] = W.w1[i * 3 + 2]; wsm[i * 4 + 3] = W.b1[i];
@@ -291,17 +325,15 @@ cnn_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, float*
           }
           *reinterpret_cast<float4*>(dp2s + k * dp_plane + c_rr * DPP + 4 * c_g) = make_float4(dpv[0], dpv[1], dpv[2], dpv[3]);
         }
-        // per-warp reduction of the 13 per-channel sums (all lanes take part; inactive lanes hold zeros)
-        float v[13] = {gw2[0], gw2[1], gw2[2], gw2[3], gw2[4], gw2[5], gw2[6], gw2[7], gw2[8], gb2, gw3[0], gw3[1], gw3[2]};
-#pragma unroll
-        for (int q = 0; q < 13; ++q) v[q] = warp_sum(v[q]);
-        if (lane == 0) {
-#pragma unroll
-          for (int q = 0; q < 13; ++q) myacc[ch * 17 + 4 + q] += v[q];
-        }
+        // per-warp reduction of the 13 per-channel sums (all lanes take part; inactive lanes hold zeros): lane L ends up
+        // with the total of value L >> 1, the even lanes of the first 13 pairs add it to the warp's accumulator row
+        float v[16] = {gw2[0], gw2[1], gw2[2], gw2[3], gw2[4], gw2[5], gw2[6], gw2[7], gw2[8], gb2, gw3[0], gw3[1], gw3[2], 0.f, 0.f, 0.f};
+        warp_sum16(v, lane);
+        if (!(lane & 1) && lane < 26) myacc[ch * 17 + 4 + (lane >> 1)] += v[0];
       }
       __syncthreads();
       // ---------------- phase D
+      float dsum[4 * BCC];
 #pragma unroll
       for (int k = 0; k < BCC; ++k) {
         const int ch = chunk * BCC + k;
@@ -338,14 +370,11 @@ cnn_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, float*
             gb1 += dp1;
           }
         }
-        float v[4] = {gw1[0], gw1[1], gw1[2], gb1};
-#pragma unroll
-        for (int q = 0; q < 4; ++q) v[q] = warp_sum(v[q]);
-        if (lane == 0) {
-#pragma unroll
-          for (int q = 0; q < 4; ++q) myacc[ch * 17 + q] += v[q];
-        }
+        dsum[4 * k] = gw1[0]; dsum[4 * k + 1] = gw1[1]; dsum[4 * k + 2] = gw1[2]; dsum[4 * k + 3] = gb1;
       }
+      static_assert(BCC == 2, "phase D reduces the 2 x 4 sums of a chunk in one 8-value butterfly");
+      warp_sum8(dsum, lane);   // lane L: total of value L >> 2 = (channel (L >> 4), slot (L >> 2) & 3)
+      if (!(lane & 3)) myacc[(chunk * BCC + (lane >> 4)) * 17 + ((lane >> 2) & 3)] += dsum[0];
       // no barrier here: the next phase B writes h1 (last read before the barrier above) and the OTHER g1 buffer;
       // dp2 is rewritten only after the next barrier
     }
