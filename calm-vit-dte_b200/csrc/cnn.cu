@@ -14,6 +14,7 @@
 // exponential. Parameter gradients: per-warp shuffle reductions per channel into per-warp shared accumulators (no atomics,
 // deterministic), one partial row per CTA, then a second-stage reduce.
 #include "common.cuh"
+#include <stdlib.h>
 #include "../../include/calm_b200.h"
 
 namespace {
@@ -201,9 +202,9 @@ constexpr int B_DP2 = BCC * (BTH + 2) * DPP;       // 1872
 constexpr int WACC = 548;                          // per-warp accumulators: 32 x 17 + 3 (+1 pad)
 constexpr int BWD_SMEM_FLOATS = B_XS + B_DYS + B_H1 + B_G1 + B_DP2 + WSM + NW * WACC;
 
-__global__ void __launch_bounds__(NT, 3)
-cnn_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dx, CnnW W,
-               float* __restrict__ gpartial, int B, int S, int tiles_x, int tiles_y, int th) {
+__device__ __forceinline__ void
+cnn_bwd_body(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dx, const CnnW& W,
+             float* __restrict__ gpartial, int B, int S, int tiles_x, int tiles_y, int th) {
   extern __shared__ __align__(16) float sm[];
   float* xs = sm;
   float* dys = xs + B_XS;
@@ -221,7 +222,11 @@ cnn_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, float*
   const int h1_plane = (BTH + 4) * H1P, g1_plane = BTH * G1P, dp_plane = (BTH + 2) * DPP;
   // phase C task: row rr (0..th+1) of the 1-halo region, 4-pixel group gc (0..8)
   const bool c_active = tid < 9 * (th + 2);
-  const int c_rr = tid / 9, c_g = tid - c_rr * 9;
+  // row and 4-pixel group packed into one opaque register: ptxas otherwise re-derives tid / 9 inside the channel loop
+  unsigned c_pack = (unsigned)(tid / 9) | (unsigned)(tid % 9) << 8;
+  asm volatile("" : "+r"(c_pack));
+#define c_rr ((int)(c_pack & 255u))
+#define c_g ((int)(c_pack >> 8))
   // phase D task: row dr (0..th-1), group dg (0..7)
   const bool d_active = tid < 8 * th;
   const int d_r = tid >> 3, d_g = tid & 7;
@@ -247,6 +252,19 @@ cnn_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, float*
     float dxa[4][3];
 #pragma unroll
     for (int j = 0; j < 4; ++j) dxa[j][0] = dxa[j][1] = dxa[j][2] = 0.f;
+    // phase C pixel classes of this thread are the same for all 32 channels: bit j = inside the image (and the 1-pixel halo
+    // columns of the tile), bit 4 + j = owned by this tile
+    unsigned cmask = 0;
+    {
+      const int rloc = c_rr - 1, gy = ty0 + rloc;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int cloc = 4 * c_g + j - 1, gx = tx0 + cloc;
+        const bool valid = cloc <= BT && gy >= 0 && gy < S && gx >= 0 && gx < S;
+        const bool owned = valid && rloc >= 0 && rloc < th && cloc >= 0 && cloc < BT;
+        cmask |= (valid ? 1u : 0u) << j | (owned ? 16u : 0u) << j;
+      }
+    }
 
     for (int chunk = 0; chunk < CH / BCC; ++chunk) {
       float* g1b = g1s + (chunk & 1) * BCC * g1_plane;
@@ -291,13 +309,10 @@ cnn_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, float*
           const float4 w3 = *reinterpret_cast<const float4*>(wsm + 512 + ch * 4);
           const float w2[9] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w, wc.x};
           float dpv[4];
-          const int rloc = c_rr - 1;
-          const int gy = ty0 + rloc;
+          const float* dyp = dys + (c_rr * (BT + 2) + 4 * c_g) * 3;   // pixel cloc = 4 c_g + j - 1 sits at column cloc + 1
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            const int cloc = 4 * c_g + j - 1;  // -1 .. 34
-            const int gx = tx0 + cloc;
-            const bool valid = cloc <= BT && gy >= 0 && gy < S && gx >= 0 && gx < S;
+            const bool valid = (cmask >> j) & 1u;
             float pre = wc.y;
 #pragma unroll
             for (int ky = 0; ky < 3; ++ky)
@@ -305,16 +320,12 @@ cnn_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, float*
               for (int kx = 0; kx < 3; ++kx) pre = fmaf(w2[ky * 3 + kx], r[ky][j + kx], pre);
             float h2, d2;
             gelu_pair(pre, h2, d2);
-            float d0 = 0.f, d1 = 0.f, d2y = 0.f;
-            if (valid) {
-              const float* dp = dys + (c_rr * (BT + 2) + (cloc + 1)) * 3;
-              d0 = dp[0]; d1 = dp[1]; d2y = dp[2];
-            }
-            // (the two right-most columns of the last group read uninitialised plane padding: force 0, never NaN)
+            // dy is zero outside the image; the two right-most pixels of the last group lie past the halo and read whatever
+            // follows in shared memory (planes, other rows): their product is discarded, never a NaN in dp2
+            const float d0 = dyp[3 * j], d1 = dyp[3 * j + 1], d2y = dyp[3 * j + 2];
             const float dpre = valid ? (w3.x * d0 + w3.y * d1 + w3.z * d2y) * d2 : 0.f;
             dpv[j] = dpre;
-            const bool owned = valid && rloc >= 0 && rloc < th && cloc >= 0 && cloc < BT;
-            if (owned) {
+            if ((cmask >> (4 + j)) & 1u) {
               gw3[0] = fmaf(d0, h2, gw3[0]); gw3[1] = fmaf(d1, h2, gw3[1]); gw3[2] = fmaf(d2y, h2, gw3[2]);
               gb2 += dpre;
 #pragma unroll
@@ -422,6 +433,21 @@ cnn_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, float*
   }
 }
 
+#undef c_rr
+#undef c_g
+
+// two register budgets of the same body: 3 CTAs/SM (80 registers, a few spills) or 2 CTAs/SM (no spills)
+__global__ void __launch_bounds__(NT, 3)
+cnn_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dx, CnnW W,
+               float* __restrict__ gpartial, int B, int S, int tiles_x, int tiles_y, int th) {
+  cnn_bwd_body(x, dy, dx, W, gpartial, B, S, tiles_x, tiles_y, th);
+}
+__global__ void __launch_bounds__(NT, 2)
+cnn_bwd_kernel_occ2(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dx, CnnW W,
+                    float* __restrict__ gpartial, int B, int S, int tiles_x, int tiles_y, int th) {
+  cnn_bwd_body(x, dy, dx, W, gpartial, B, S, tiles_x, tiles_y, th);
+}
+
 __global__ void cnn_reduce_kernel(const float* __restrict__ partial, float* __restrict__ out, int nparts, int n) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= n) return;
@@ -457,10 +483,18 @@ extern "C" int32_t calm_cnn_fwd(const float* x, float* y, const float* w1, const
   return CALM_OK;
 }
 
+namespace {
+int bwd_ctas_per_sm() {
+  static int v = 0;
+  if (!v) { const char* e = getenv("CALM_CNN_BWD_OCC"); v = (e && e[0] == '2') ? 2 : 3; }
+  return v;
+}
+}  // namespace
+
 extern "C" int32_t calm_cnn_bwd_blocks(int32_t B, int32_t S) {
   const int th = bwd_tile_height(S);
   const long long total = (long long)B * ((S + BT - 1) / BT) * ((S + th - 1) / th);
-  const long long cap = 3LL * calm_num_sms();
+  const long long cap = (long long)bwd_ctas_per_sm() * calm_num_sms();
   return (int32_t)(total < cap ? total : cap);
 }
 
@@ -475,11 +509,13 @@ extern "C" int32_t calm_cnn_bwd(const float* x, const float* dy, float* dx, cons
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(cnn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(cnn_bwd_kernel_occ2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { calm_set_error("calm_cnn_bwd: smem %zu: %s", smem, cudaGetErrorString(e)); return CALM_ERR_CUDA; }
     configured = true;
   }
   CnnW W{w1, b1, w2, b2, w3, b3};
-  cnn_bwd_kernel<<<nblocks, NT, smem, stream>>>(x, dy, dx, W, gpartial, B, S, tiles_x, tiles_y, th);
+  if (bwd_ctas_per_sm() == 2) cnn_bwd_kernel_occ2<<<nblocks, NT, smem, stream>>>(x, dy, dx, W, gpartial, B, S, tiles_x, tiles_y, th);
+  else cnn_bwd_kernel<<<nblocks, NT, smem, stream>>>(x, dy, dx, W, gpartial, B, S, tiles_x, tiles_y, th);
   CALM_CHECK_LAUNCH("calm_cnn_bwd");
   cnn_reduce_kernel<<<(CALM_CNN_NPARAM + 127) / 128, 128, 0, stream>>>(gpartial, gparams, nblocks, CALM_CNN_NPARAM);
   CALM_CHECK_LAUNCH("calm_cnn_bwd(reduce)");
