@@ -20,11 +20,11 @@
 // MN-major (dK = dS^T Q, dV = P^T dO) without a second copy.
 //
 // Backward: per image the CTA walks the 12 heads; per head and 128-query tile
-//   S = Q K^T and dP = dO V^T in key parts of <= 96 columns  ->  P = exp2(S c + bias - lse), dS = P (dP - delta)
+//   S = Q K^T and dP = dO V^T in key parts of <= 64 columns, two parts in flight  ->  P = exp2(S c + bias - lse), dS = P (dP - delta)
 //   dQ = dS K (complete per tile), dK += dS^T Q, dV += P^T dO (accumulated in TMEM over the query tiles)
-// TMEM budget (512 columns): S part 96 | dP part 96 | dQ 64 | dK 2 x 64 | dV 2 x 64.
+// TMEM budget (512 columns): 2 x (S part 64 | dP part 64), dQ reuses the first S part | dK 2 x 64 | dV 2 x 64.
 // dbias[b] = sum over heads of dS is accumulated by the row's owner thread in an fp32 scratch matrix (same thread, same
-// row for every head: no atomics, deterministic) and written as bf16 by the last head.
+// address for every head, updates issued in head order: deterministic) and written as bf16 by the last head.
 #include "tcgen05.cuh"
 #include "attention_tc.h"
 
@@ -236,7 +236,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap mQ, const __grid_constant
             unpack16(bb[2 * j], bb[2 * j + 1], bf);
 #pragma unroll
             for (int jj = 0; jj < 16; ++jj) {
-              pv[jj] = exp2f(fmaf(__uint_as_float(sr[jj]), c.scale_log2, fmaf(bf[jj], LOG2E, -mx)));
+              pv[jj] = ex2_approx(fmaf(__uint_as_float(sr[jj]), c.scale_log2, fmaf(bf[jj], LOG2E, -mx)));
               l += pv[jj];
             }
             store_row16(sP, r, kc, pv);
@@ -282,8 +282,26 @@ struct BwdParams {
   float* dbias_acc;                       // (B, S, S) fp32 scratch
 };
 
-constexpr int KPART = 96;  // key columns per S / dP part (TMEM: 2 x 96 + 64 + 4 x 64 = 512)
+constexpr int KPART = 64;  // key columns per S / dP part; two parts in flight (TMEM: 2 x (64 + 64) | dK 2 x 64 | dV 2 x 64)
 
+// fire-and-forget fp32 vector add into global memory (performed at the L2, no value returned -> no load latency in the thread)
+__device__ __forceinline__ void red_add_f32x4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1) : "memory");
+}
+
+// Pipeline of one (image, head, 128-query tile):
+//   controller: S/dP MMAs of parts 0 and 1 at once (two TMEM buffers); the MMAs of part p + 2 as soon as the workers have
+//               drained buffer p & 1 (bar_free) -> the tensor core and the mbarrier round trip run under the workers'
+//               exp2 / dS arithmetic of the other buffer instead of in series with it.
+//   workers   : per part wait bar_sd[buf] -> P, dS -> bf16 tiles in shared memory, dbias accumulation, arrive bar_free[buf].
+//   tile end  : dQ = dS K (into the drained buffer 0), dK += dS^T Q, dV += P^T dO; commit bar_fin -> workers store dQ
+//               (and dK / dV after the last query tile) -> bar_tile.
+// dbias: head 0 stores, heads 1..H-2 use red.global.add (no read), the last head reads the sum back (L2, .cg) and writes
+// bf16. One thread owns an address for all heads and issues its updates in head order: deterministic.
+// The bias row segment of the NEXT part (next tile / head / image at a tile's last part) is requested one part ahead.
 __global__ void __launch_bounds__(NTHREADS, 1)
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap mQ, const __grid_constant__ CUtensorMap mK, const __grid_constant__ CUtensorMap mV,
                    const __grid_constant__ CUtensorMap mDO, const BwdParams p) {
@@ -296,15 +314,17 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap mQ, const __grid_constant
   uint8_t* sP = sDO + QT_BYTES;
   uint8_t* sDS = sP + P_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sDS + P_BYTES);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
-  const uint32_t bar_kv = smem_u32(&bars[0]), bar_q = smem_u32(&bars[1]), bar_mma = smem_u32(&bars[2]), bar_work = smem_u32(&bars[3]);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  const uint32_t bar_kv = smem_u32(&bars[0]), bar_q = smem_u32(&bars[1]), bar_fin = smem_u32(&bars[2]), bar_tile = smem_u32(&bars[3]);
+  const uint32_t bar_sd0 = smem_u32(&bars[4]), bar_free0 = smem_u32(&bars[6]);   // [buf] at +8 bytes
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const Common& c = p.c;
   const int S = c.S, hd = c.hd, heads = c.heads;
 
   if (threadIdx.x == NWORKERS) {
     prefetch_tensormap(&mQ); prefetch_tensormap(&mK); prefetch_tensormap(&mV); prefetch_tensormap(&mDO);
-    mbar_init(bar_kv, 1); mbar_init(bar_q, 1); mbar_init(bar_mma, 1); mbar_init(bar_work, NWORKERS);
+    mbar_init(bar_kv, 1); mbar_init(bar_q, 1); mbar_init(bar_fin, 1); mbar_init(bar_tile, NWORKERS);
+    mbar_init(bar_sd0, 1); mbar_init(bar_sd0 + 8, 1); mbar_init(bar_free0, NWORKERS); mbar_init(bar_free0 + 8, NWORKERS);
     fence_barrier_init();
   }
   if (warp == CTRL_WARP) tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
@@ -314,11 +334,11 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap mQ, const __grid_constant
   const uint32_t tmem = *tmem_slot;
   const int ntiles = (S + 127) >> 7;          // query tiles == key M-tiles
   const int nparts = (S + KPART - 1) / KPART;
-  constexpr uint32_t T_S = 0, T_DP = 96, T_DQ = 192, T_DK = 256, T_DV = 384;
+  constexpr uint32_t T_SD = 0 /* buffer b: S at 128 b, dP at 128 b + 64 */, T_DQ = 0 /* aliases buffer 0 */, T_DK = 256, T_DV = 384;
 
   if (warp == CTRL_WARP) {
     if (lane == 0) {
-      uint32_t ph_kv = 0, ph_q = 0, ph_work = 0;
+      uint32_t ph_kv = 0, ph_q = 0, ph_tile = 0, ph_free[2] = {0, 0};
       for (int b = blockIdx.x; b < c.B; b += gridDim.x) {
         for (int h = 0; h < heads; ++h) {
           const HeadCols hc = head_cols(h, hd);
@@ -332,22 +352,47 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap mQ, const __grid_constant
             mbar_expect_tx(bar_q, 2 * QT_BYTES);
             tma_load_2d(smem_u32(sQ), &mQ, bar_q, hc.col0, b * S + i * 128);
             tma_load_2d(smem_u32(sDO), &mDO, bar_q, hc.col0, b * S + i * 128);
+            {  // what the next iteration will load: pulled into the L2 now, its TMA then costs an L2 hit instead of an HBM miss
+              if (i + 1 < ntiles) {
+                tma_prefetch_2d(&mQ, hc.col0, b * S + (i + 1) * 128);
+                tma_prefetch_2d(&mDO, hc.col0, b * S + (i + 1) * 128);
+              } else {
+                int nb = b, nh = h + 1;
+                if (nh == heads) { nh = 0; nb = b + (int)gridDim.x; }
+                if (nb < c.B) {
+                  const HeadCols nc = head_cols(nh, hd);
+                  tma_prefetch_2d(&mK, nc.col0, nb * S);
+                  tma_prefetch_2d(&mV, nc.col0, nb * S);
+                  tma_prefetch_2d(&mQ, nc.col0, nb * S);
+                  tma_prefetch_2d(&mDO, nc.col0, nb * S);
+                }
+              }
+            }
             if (i == 0) { mbar_wait(bar_kv, ph_kv, c.err_flag, 31); ph_kv ^= 1; }
             mbar_wait(bar_q, ph_q, c.err_flag, 32); ph_q ^= 1;
+            mbar_wait(bar_tile, ph_tile, c.err_flag, 33); ph_tile ^= 1;         // Q / dO tails zeroed
+            fence_after();
             for (int part = 0; part < nparts; ++part) {
-              mbar_wait(bar_work, ph_work, c.err_flag, 33); ph_work ^= 1;   // tails zeroed (part 0) / previous part consumed
-              fence_after();
+              const int buf = part & 1;
+              if (part >= 2) {                                                  // workers drained this buffer (part - 2)
+                mbar_wait(bar_free0 + 8 * buf, ph_free[buf], c.err_flag, 34); ph_free[buf] ^= 1;
+                fence_after();
+              }
               const int k0 = part * KPART, w = min(KPART, S - k0);
               const uint32_t id_s = idesc_bf16(128, w, 0, 0);
+              const uint32_t ts = tmem + T_SD + 128u * buf;
               for (int ks = 0; ks < hdp / 16; ++ks)
-                mma_bf16(tmem + T_S, smem_desc(smem_u32(sQ) + ks * 32, 16, 1024),
+                mma_bf16(ts, smem_desc(smem_u32(sQ) + ks * 32, 16, 1024),
                          smem_desc(smem_u32(sK) + k0 * 128 + ks * 32, 16, 1024), id_s, ks > 0);
               for (int ks = 0; ks < hdp / 16; ++ks)
-                mma_bf16(tmem + T_DP, smem_desc(smem_u32(sDO) + ks * 32, 16, 1024),
+                mma_bf16(ts + 64, smem_desc(smem_u32(sDO) + ks * 32, 16, 1024),
                          smem_desc(smem_u32(sV) + k0 * 128 + ks * 32, 16, 1024), id_s, ks > 0);
-              commit(bar_mma);
+              commit(bar_sd0 + 8 * buf);
             }
-            mbar_wait(bar_work, ph_work, c.err_flag, 34); ph_work ^= 1;     // P and dS of this query tile complete
+            for (int part = max(0, nparts - 2); part < nparts; ++part) {       // the last parts: P and dS of the tile complete
+              const int buf = part & 1;
+              mbar_wait(bar_free0 + 8 * buf, ph_free[buf], c.err_flag, 35); ph_free[buf] ^= 1;
+            }
             fence_after();
             for (int kk = 0; kk < S / 16; ++kk)     // dQ_i = dS_i K   (contraction over the keys)
               mma_bf16(tmem + T_DQ, smem_desc(smem_u32(sDS) + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024),
@@ -361,8 +406,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap mQ, const __grid_constant
                          smem_desc(smem_u32(sDO) + kq * 2048, 8192, 1024), id_dkv, acc);
               }
             }
-            commit(bar_mma);
-            mbar_wait(bar_work, ph_work, c.err_flag, 35); ph_work ^= 1;     // epilogues done: Q/dO/P/dS tiles and dQ columns free
+            commit(bar_fin);
+            mbar_wait(bar_tile, ph_tile, c.err_flag, 36); ph_tile ^= 1;         // epilogues done: Q/dO/P/dS tiles and TMEM free
           }
         }
       }
@@ -371,11 +416,28 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap mQ, const __grid_constant
     const int grp = warp >> 2;                    // 0: even 16-column chunks, 1: odd chunks
     const int r = (warp & 3) * 32 + lane;         // row within the tile == TMEM lane
     const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16);
-    uint32_t ph_kv = 0, ph_q = 0, ph_mma = 0;
+    uint32_t ph_kv = 0, ph_q = 0, ph_fin = 0, ph_sd[2] = {0, 0};
+    // bias row segment of a part: this thread's chunks (2 j + grp) * 16, j = 0, 1, of key columns [part * 64, part * 64 + 64)
+    uint4 bcur[4], bnxt[4];
+    auto load_bias = [&](uint4* dst, int bb, int ii, int part) {
+      const int qq = ii * 128 + r;
+      const bf16* brow = c.bias + ((long long)bb * S + (qq < S ? qq : 0)) * S + part * KPART;
+      const int w = min(KPART, S - part * KPART);
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int cc = (2 * j + grp) * 16;
+        if (cc < w) {
+          dst[2 * j] = *reinterpret_cast<const uint4*>(brow + cc);
+          dst[2 * j + 1] = *reinterpret_cast<const uint4*>(brow + cc + 8);
+        }
+      }
+    };
+    if ((int)blockIdx.x < c.B) load_bias(bcur, blockIdx.x, 0, 0);
     for (int b = blockIdx.x; b < c.B; b += gridDim.x) {
       for (int h = 0; h < heads; ++h) {
         const HeadCols hc = head_cols(h, hd);
         const int hdp = hc.hdp;
+        const bool first = h == 0, last = h == heads - 1;
         for (int i = 0; i < ntiles; ++i) {
           const int q = i * 128 + r;
           const bool valid = q < S;
@@ -383,74 +445,84 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap mQ, const __grid_constant
           mbar_wait(bar_q, ph_q, c.err_flag, 42); ph_q ^= 1;
           if (grp == 0) zero_outside(sQ, r, hc, hd);
           else zero_outside(sDO, r, hc, hd);
+          fence_proxy_async();
+          mbar_arrive(bar_tile);
           const long long stat = ((long long)b * heads + h) * S + (valid ? q : 0);
           const float lse2 = p.lse[stat] * LOG2E, dl = p.delta[stat];
           const long long rowoff = ((long long)b * S + (valid ? q : 0)) * S;
-          fence_proxy_async();
-          mbar_arrive(bar_work);
           for (int part = 0; part < nparts; ++part) {
+            const int buf = part & 1;
             const int k0 = part * KPART, w = min(KPART, S - k0);
-            // global operands of this part first (bias row segment, running dbias sums): in flight while the MMAs run
-            uint4 bb[6];
-            float4 ac[12];
-            const bool have_acc = h > 0 && valid;
+            // next part's bias (next tile / head / image after the tile's last part)
+            {
+              int nb = b, ni = i, np = part + 1;
+              if (np == nparts) {
+                np = 0;
+                if (++ni == ntiles) { ni = 0; if (last) nb = b + (int)gridDim.x; }
+              }
+              if (nb < c.B) load_bias(bnxt, nb, ni, np);
+            }
+            // the last head reads the running sum back (written by this same thread, so far only through the L2)
+            float4 ac[8];
+            if (last && !first && valid) {
 #pragma unroll
-            for (int j = 0; j < 3; ++j) {
-              const int ch = j;           // register slot
-              const int cc = (2 * j + grp) * 16;
-              if (cc < w) {
-                const int kc = k0 + cc;
-                bb[2 * ch] = *reinterpret_cast<const uint4*>(c.bias + rowoff + kc);
-                bb[2 * ch + 1] = *reinterpret_cast<const uint4*>(c.bias + rowoff + kc + 8);
+              for (int j = 0; j < 2; ++j) {
+                const int cc = (2 * j + grp) * 16;
+                if (cc < w) {
 #pragma unroll
-                for (int j = 0; j < 4; ++j)
-                  ac[4 * ch + j] = have_acc ? reinterpret_cast<const float4*>(p.dbias_acc + rowoff + kc)[j] : make_float4(0.f, 0.f, 0.f, 0.f);
+                  for (int e = 0; e < 4; ++e) ac[4 * j + e] = __ldcg(reinterpret_cast<const float4*>(p.dbias_acc + rowoff + k0 + cc) + e);
+                }
               }
             }
-            mbar_wait(bar_mma, ph_mma, c.err_flag, 43); ph_mma ^= 1;
+            mbar_wait(bar_sd0 + 8 * buf, ph_sd[buf], c.err_flag, 43); ph_sd[buf] ^= 1;
             fence_after();
 #pragma unroll
-            for (int j = 0; j < 3; ++j) {
-              const int ch = j;
+            for (int j = 0; j < 2; ++j) {
               const int cc = (2 * j + grp) * 16;
               if (cc < w) {
                 const int kc = k0 + cc;
                 uint32_t sr[16], dr[16];
-                tmem_ld16(trow + T_S + cc, sr);
-                tmem_ld16(trow + T_DP + cc, dr);
+                tmem_ld16(trow + T_SD + 128u * buf + cc, sr);
+                tmem_ld16(trow + T_SD + 128u * buf + 64 + cc, dr);
                 tmem_ld_wait();
-                float bf[16], pv[16], ds[16], acc[16];
-                unpack16(bb[2 * ch], bb[2 * ch + 1], bf);
+                float bf[16], pv[16], ds[16];
+                unpack16(bcur[2 * j], bcur[2 * j + 1], bf);
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  acc[4 * j] = ac[4 * ch + j].x; acc[4 * j + 1] = ac[4 * ch + j].y; acc[4 * j + 2] = ac[4 * ch + j].z; acc[4 * j + 3] = ac[4 * ch + j].w;
-                }
-#pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                  const float pj = valid ? exp2f(fmaf(__uint_as_float(sr[j]), c.scale_log2, fmaf(bf[j], LOG2E, -lse2))) : 0.f;
-                  pv[j] = pj;
-                  ds[j] = pj * (__uint_as_float(dr[j]) - dl);   // rows beyond S contribute exact zeros to dK / dV
-                  acc[j] += ds[j];
+                for (int e = 0; e < 16; ++e) {
+                  const float pj = valid ? ex2_approx(fmaf(__uint_as_float(sr[e]), c.scale_log2, fmaf(bf[e], LOG2E, -lse2))) : 0.f;
+                  pv[e] = pj;
+                  ds[e] = pj * (__uint_as_float(dr[e]) - dl);   // rows beyond S contribute exact zeros to dK / dV
                 }
                 store_row16(sP, r, kc, pv);
                 store_row16(sDS, r, kc, ds);
                 if (valid) {
-                  if (h == heads - 1) {
-                    uint4* op = reinterpret_cast<uint4*>(p.dbias + rowoff + kc);
-                    op[0] = pack8f(acc); op[1] = pack8f(acc + 8);
-                  } else {
-                    float4* ap = reinterpret_cast<float4*>(p.dbias_acc + rowoff + kc);
+                  float* ap = p.dbias_acc + rowoff + kc;
+                  if (last) {
+                    if (!first) {
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) ap[j] = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
+                      for (int e = 0; e < 4; ++e) {
+                        ds[4 * e] += ac[4 * j + e].x; ds[4 * e + 1] += ac[4 * j + e].y; ds[4 * e + 2] += ac[4 * j + e].z; ds[4 * e + 3] += ac[4 * j + e].w;
+                      }
+                    }
+                    uint4* op = reinterpret_cast<uint4*>(p.dbias + rowoff + kc);
+                    op[0] = pack8f(ds); op[1] = pack8f(ds + 8);
+                  } else if (first) {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) reinterpret_cast<float4*>(ap)[e] = make_float4(ds[4 * e], ds[4 * e + 1], ds[4 * e + 2], ds[4 * e + 3]);
+                  } else {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) red_add_f32x4(ap + 4 * e, ds[4 * e], ds[4 * e + 1], ds[4 * e + 2], ds[4 * e + 3]);
                   }
                 }
               }
             }
             fence_proxy_async();
             fence_before();
-            mbar_arrive(bar_work);
+            mbar_arrive(bar_free0 + 8 * buf);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) bcur[e] = bnxt[e];
           }
-          mbar_wait(bar_mma, ph_mma, c.err_flag, 44); ph_mma ^= 1;
+          mbar_wait(bar_fin, ph_fin, c.err_flag, 44); ph_fin ^= 1;
           fence_after();
           // dQ rows of this tile
           {
@@ -482,7 +554,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap mQ, const __grid_constant
             }
           }
           fence_before();
-          mbar_arrive(bar_work);
+          mbar_arrive(bar_tile);
         }
       }
     }
