@@ -133,9 +133,10 @@ def attention_bwd(q, k, v, bias, o, d_o, lse, B, S, heads, hd, ld_q, ld_k, ld_v,
         dv = torch.empty(B * S, D, dtype=bf16, device=dev); ld_dv = D
     dbias = torch.empty(B, S, S, dtype=bf16, device=dev)
     delta = torch.empty(B, heads, S, dtype=f32, device=dev)
-    dbias_acc = torch.empty(B, S, S, dtype=f32, device=dev)   # per-head accumulation scratch of the tcgen05 path
+    # per-head dS scratch of the tcgen05 path (summed over the heads by its second kernel)
+    scratch = torch.empty(L.load().calm_attention_bwd_scratch_bytes(B, S, heads, hd), dtype=torch.uint8, device=dev)
     L.call("calm_attention_bwd", ptr(q), ptr(k), ptr(v), ptr(bias), ptr(o), ptr(d_o), ptr(lse), ptr(delta), ptr(dq), ptr(dk),
-           ptr(dv), ptr(dbias), ptr(dbias_acc), ld_q, ld_k, ld_v, o.stride(0), ld_do, ld_dq, ld_dk, ld_dv, B, S, heads, hd,
+           ptr(dv), ptr(dbias), ptr(scratch), ld_q, ld_k, ld_v, o.stride(0), ld_do, ld_dq, ld_dk, ld_dv, B, S, heads, hd,
            work=10.0 * B * heads * S * S * hd)
     return dq, dk, dv, dbias
 

@@ -60,6 +60,7 @@ PROTOTYPES = {
     "calm_set_debug_flags": (None, [i32]),
     "calm_get_debug_flags": (i32, []),
     "calm_debug_set_gemm_bn": (None, [i32]),
+    "calm_debug_set_trace_buffer": (None, [vp, i32]),
     "calm_set_error_flag_buffer": (i32, [vp]),
     "calm_gemm": (i32, [C.POINTER(GemmArgs), vp]),
     "calm_gemm_default_splits": (i32, [i32, i32, i32, i32, i32]),
@@ -73,6 +74,7 @@ PROTOTYPES = {
     "calm_rope_bwd_scratch_floats": (i32, [i32, i32]),
     "calm_rope_bwd": (i32, [vp, i64, vp, i64, vp, i64, vp, i64, vp, vp, vp, i64, i32, i32, i32, i32, vp]),
     "calm_attention_fwd": (i32, [vp, vp, vp, vp, vp, vp, i64, i64, i64, i64, i32, i32, i32, i32, vp]),
+    "calm_attention_bwd_scratch_bytes": (i64, [i32, i32, i32, i32]),
     "calm_attention_bwd": (i32, [vp] * 13 + [i64] * 8 + [i32] * 4 + [vp]),
     "calm_latent_fwd": (i32, [vp, vp, vp, vp, vp, vp, i32, i64, i32, vp]),
     "calm_latent_kl": (i32, [vp, vp, i32, vp, vp, f32, vp]),

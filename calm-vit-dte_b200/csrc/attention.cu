@@ -524,8 +524,13 @@ extern "C" int32_t calm_attention_fwd(const void* q, const void* k, const void* 
   return CALM_OK;
 }
 
+extern "C" int64_t calm_attention_bwd_scratch_bytes(int32_t B, int32_t S, int32_t heads, int32_t hd) {
+  (void)hd;
+  return (int64_t)calm_attention_bwd_tc_scratch_bytes(B, S, heads);
+}
+
 extern "C" int32_t calm_attention_bwd(const void* q, const void* k, const void* v, const void* bias, const void* o, const void* d_o,
-                                      const float* lse, float* delta, void* dq, void* dk, void* dv, void* dbias, float* dbias_acc, int64_t ld_q,
+                                      const float* lse, float* delta, void* dq, void* dk, void* dv, void* dbias, void* ds_scratch, int64_t ld_q,
                                       int64_t ld_k, int64_t ld_v, int64_t ld_o, int64_t ld_do, int64_t ld_dq, int64_t ld_dk,
                                       int64_t ld_dv, int32_t B, int32_t S, int32_t heads, int32_t hd, cudaStream_t stream) {
   int rc = check_common("calm_attention_bwd", B, S, heads, hd);
@@ -542,8 +547,8 @@ extern "C" int32_t calm_attention_bwd(const void* q, const void* k, const void* 
   {
     const int64_t lds[4] = {ld_q, ld_k, ld_v, ld_do};
     const void* ptrs[6] = {q, k, v, d_o, bias, dbias};
-    if (dbias_acc && !(calm_get_debug_flags() & CALM_DEBUG_LEGACY_ATTENTION) && calm_attention_tc_eligible(B, S, heads, hd, lds, 4, ptrs, 6))
-      return calm_attention_bwd_tc(q, k, v, bias, d_o, lse, delta, dq, dk, dv, dbias, dbias_acc, ld_q, ld_k, ld_v, ld_do, ld_dq, ld_dk,
+    if (ds_scratch && !(calm_get_debug_flags() & CALM_DEBUG_LEGACY_ATTENTION) && calm_attention_tc_eligible(B, S, heads, hd, lds, 4, ptrs, 6))
+      return calm_attention_bwd_tc(q, k, v, bias, d_o, lse, delta, dq, dk, dv, dbias, ds_scratch, ld_q, ld_k, ld_v, ld_do, ld_dq, ld_dk,
                                    ld_dv, B, S, heads, hd, stream);
   }
   DISPATCH_HDP(hd, return launch_bwd<HDP>(q, k, v, bias, d_o, lse, delta, dq, dk, dv, dbias, ld_q, ld_k, ld_v, ld_do, ld_dq, ld_dk,

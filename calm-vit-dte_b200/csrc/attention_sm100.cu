@@ -32,6 +32,10 @@ namespace {
 
 using namespace tc;
 
+// `if (leader)` inside the (warp-uniform) controller loops: elect.sync is evaluated at every use, so ptxas knows the branch runs on
+// exactly one lane and needs no ELECT / R2UR.BROADCAST loop to feed the uniform-register operands of tcgen05.mma / TMA.
+#define leader (elect_one() != 0u)
+
 constexpr int NWORKERS = 256;            // 8 worker warps: warps w and w+4 share TMEM lane quadrant w%4 and split the columns
 constexpr int NTHREADS = NWORKERS + 32;  // + controller warp (warp 8)
 constexpr int CTRL_WARP = NWORKERS / 32;
@@ -101,6 +105,35 @@ __device__ __forceinline__ void store_row16(uint8_t* tile, int r, int kc, const 
   *reinterpret_cast<uint4*>(atom + swz128(r, g + 1)) = pack8f(f + 8);
 }
 
+
+// Epilogue store of a [128][hdp] fp32 TMEM tile as bf16 rows of `hd` columns: the row-owner thread drops its 16-column chunks
+// into a swizzled [128][64] bf16 staging atom, the two warps of the lane quadrant meet on a named barrier, then each warp
+// writes 16 of the quadrant's rows with lanes walking ALONG the rows (8 bytes per lane, two rows per instruction): 2-4 cache
+// lines per store instruction instead of 32 (one per lane) when every thread writes its own row.
+__device__ __forceinline__ void stage_cols16(uint8_t* atom, int r, const uint32_t* v, int c0, float mul) {
+  float f[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]) * mul;
+  *reinterpret_cast<uint4*>(atom + swz128(r, c0 >> 3)) = pack8f(f);
+  *reinterpret_cast<uint4*>(atom + swz128(r, (c0 >> 3) + 1)) = pack8f(f + 8);
+}
+__device__ __forceinline__ void quad_sync(int quad) { asm volatile("bar.sync %0, 64;" ::"r"(2 + quad) : "memory"); }
+// rows [row_begin, row_begin + 16) of the tile (tile-relative), global row g = g0 + row (valid while g < g_end)
+__device__ __forceinline__ void store_rows16(const uint8_t* atom, bf16* base, long long ld, int row_begin, long long g0, long long g_end,
+                                             const HeadCols& hc, int hd, int lane) {
+  const int unit = lane & 15, sub = lane >> 4;    // 8-byte unit along the row, row of the pair
+  const int c = hc.shift + 4 * unit;              // tile column of the unit
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int row = row_begin + 2 * k + sub;
+    const long long g = g0 + row;
+    if (4 * unit < hd && g < g_end) {
+      const uint2 u = *reinterpret_cast<const uint2*>(atom + swz128(row, c >> 3) + ((c & 4) << 1));
+      *reinterpret_cast<uint2*>(base + g * ld + 4 * unit) = u;
+    }
+  }
+}
+
 // ====================================================================================================================
 // forward
 // ====================================================================================================================
@@ -142,33 +175,37 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap mQ, const __grid_constant
 
   if (warp == CTRL_WARP) {
     // ============================ controller: TMA + MMA issue ============================
-    if (lane == 0) {
+    {
+      // The whole warp walks the control flow (loop counters, descriptors and barrier addresses stay warp-uniform, so they live
+      // in uniform registers); only the instructions with side effects are issued by lane 0. Under `if (lane == 0) { loops }`
+      // ptxas moves every tcgen05.mma operand through an ELECT / R2UR.BROADCAST loop: ~20 instructions per MMA.
       uint32_t ph_kv = 0, ph_q = 0, ph_work = 0;
       const uint32_t id_s = idesc_bf16(128, S, 0, 0);      // S = Q K^T : both K-major
+      // descriptors of the (fixed) tiles, built once: per MMA only the low word advances by (byte offset >> 4)
+      const uint64_t dQk = smem_desc(smem_u32(sQ), 16, 1024), dKk = smem_desc(smem_u32(sK), 16, 1024);
+      const uint64_t dPk = smem_desc(smem_u32(sP), 16, 1024), dVmn = smem_desc(smem_u32(sV), 8192, 1024);
       for (int it = blockIdx.x; it < items; it += gridDim.x) {
         const int b = it / c.heads, h = it - b * c.heads;
         const HeadCols hc = head_cols(h, hd);
         const int hdp = hc.hdp;
         const uint32_t id_o = idesc_bf16(128, hdp, 0, 1);  // O = P V   : A K-major, B (V: keys x hd) MN-major
-        mbar_expect_tx(bar_kv, 2u * S * 128u);
-        tma_load_2d(smem_u32(sK), &mK, bar_kv, hc.col0, b * S);
-        tma_load_2d(smem_u32(sV), &mV, bar_kv, hc.col0, b * S);
+        if (leader) mbar_expect_tx(bar_kv, 2u * S * 128u);
+        if (leader) tma_load_2d(smem_u32(sK), &mK, bar_kv, hc.col0, b * S);
+        if (leader) tma_load_2d(smem_u32(sV), &mV, bar_kv, hc.col0, b * S);
         for (int i = 0; i < ntiles; ++i) {
-          mbar_expect_tx(bar_q, QT_BYTES);
-          tma_load_2d(smem_u32(sQ), &mQ, bar_q, hc.col0, b * S + i * 128);
+          if (leader) mbar_expect_tx(bar_q, QT_BYTES);
+          if (leader) tma_load_2d(smem_u32(sQ), &mQ, bar_q, hc.col0, b * S + i * 128);
           if (i == 0) { mbar_wait(bar_kv, ph_kv, c.err_flag, 11); ph_kv ^= 1; }
           mbar_wait(bar_q, ph_q, c.err_flag, 12); ph_q ^= 1;
           mbar_wait(bar_work, ph_work, c.err_flag, 13); ph_work ^= 1;   // A: Q tail zeroed
           fence_after();
-          for (int ks = 0; ks < hdp / 16; ++ks)
-            mma_bf16(tmem, smem_desc(smem_u32(sQ) + ks * 32, 16, 1024), smem_desc(smem_u32(sK) + ks * 32, 16, 1024), id_s, ks > 0);
-          commit(bar_mma);
+          for (int ks = 0; ks < hdp / 16; ++ks) if (leader) mma_bf16(tmem, dQk + 2 * ks, dKk + 2 * ks, id_s, ks > 0);
+          if (leader) commit(bar_mma);
           mbar_wait(bar_work, ph_work, c.err_flag, 14); ph_work ^= 1;   // B: P written
           fence_after();
           for (int kk = 0; kk < S / 16; ++kk)
-            mma_bf16(tmem + 256, smem_desc(smem_u32(sP) + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024),
-                     smem_desc(smem_u32(sV) + kk * 2048, 8192, 1024), id_o, kk > 0);
-          commit(bar_mma);
+            if (leader) mma_bf16(tmem + 256, dPk + (uint32_t)((kk >> 2) * 1024 + (kk & 3) * 2), dVmn + (uint32_t)(kk * 128), id_o, kk > 0);
+          if (leader) commit(bar_mma);
           mbar_wait(bar_work, ph_work, c.err_flag, 15); ph_work ^= 1;   // C: epilogue done, Q / P / TMEM free
         }
       }
@@ -278,16 +315,29 @@ struct BwdParams {
   Common c;
   const float* lse; const float* delta;  // (B, heads, S)
   bf16* dq; bf16* dk; bf16* dv; long long ld_dq, ld_dk, ld_dv;
-  bf16* dbias;                            // (B, S, S) bf16 out
-  float* dbias_acc;                       // (B, S, S) fp32 scratch
+  unsigned long long* trace; int trace_cap;   // bring-up: CTA 0 time stamps (calm_debug_set_trace_buffer), null in production
 };
+
+// trace[0] = event count, then (event id, globaltimer ns) pairs; id = role * 1000 + point * 10 + part
+__device__ __forceinline__ void trace_evt(const BwdParams& p, int id) {
+  if (p.trace != nullptr && blockIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    const unsigned long long i = atomicAdd(p.trace, 1ULL);
+    if ((int)i < p.trace_cap) { p.trace[1 + 2 * i] = (unsigned long long)id; p.trace[2 + 2 * i] = t; }
+  }
+}
 
 constexpr int KPART = 64;  // key columns per S / dP part; two parts in flight (TMEM: 2 x (64 + 64) | dK 2 x 64 | dV 2 x 64)
 
-// fire-and-forget fp32 vector add into global memory (performed at the L2, no value returned -> no load latency in the thread)
-__device__ __forceinline__ void red_add_f32x4(float* addr, float a, float b, float c, float d) {
-  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+// bulk tensor store of a swizzled [128][64] bf16 atom (shared -> global, rows / columns beyond the tensor are clipped)
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(src), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int c0, int c1) {
   asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1) : "memory");
 }
@@ -299,12 +349,14 @@ __device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int c0, 
 //   workers   : per part wait bar_sd[buf] -> P, dS -> bf16 tiles in shared memory, dbias accumulation, arrive bar_free[buf].
 //   tile end  : dQ = dS K (into the drained buffer 0), dK += dS^T Q, dV += P^T dO; commit bar_fin -> workers store dQ
 //               (and dK / dV after the last query tile) -> bar_tile.
-// dbias: head 0 stores, heads 1..H-2 use red.global.add (no read), the last head reads the sum back (L2, .cg) and writes
-// bf16. One thread owns an address for all heads and issues its updates in head order: deterministic.
+// dbias = sum over heads of dS: the bf16 dS tile the MMAs consume is also TMA-stored, per head, into a (B, H, S, S) scratch;
+// dbias_reduce_kernel sums the heads afterwards. (Accumulating in the row-owner threads cost one 128-byte line per lane and
+// instruction: 8 warps x 8 scattered 16-byte RMWs per part kept the L1 busy for ~2 us of every part; the TMA store moves
+// whole swizzle atoms and costs the workers nothing.)
 // The bias row segment of the NEXT part (next tile / head / image at a tile's last part) is requested one part ahead.
 __global__ void __launch_bounds__(NTHREADS, 1)
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap mQ, const __grid_constant__ CUtensorMap mK, const __grid_constant__ CUtensorMap mV,
-                   const __grid_constant__ CUtensorMap mDO, const BwdParams p) {
+                   const __grid_constant__ CUtensorMap mDO, const __grid_constant__ CUtensorMap mDS, const BwdParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sK = smem;
@@ -322,7 +374,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap mQ, const __grid_constant
   const int S = c.S, hd = c.hd, heads = c.heads;
 
   if (threadIdx.x == NWORKERS) {
-    prefetch_tensormap(&mQ); prefetch_tensormap(&mK); prefetch_tensormap(&mV); prefetch_tensormap(&mDO);
+    prefetch_tensormap(&mQ); prefetch_tensormap(&mK); prefetch_tensormap(&mV); prefetch_tensormap(&mDO); prefetch_tensormap(&mDS);
     mbar_init(bar_kv, 1); mbar_init(bar_q, 1); mbar_init(bar_fin, 1); mbar_init(bar_tile, NWORKERS);
     mbar_init(bar_sd0, 1); mbar_init(bar_sd0 + 8, 1); mbar_init(bar_free0, NWORKERS); mbar_init(bar_free0 + 8, NWORKERS);
     fence_barrier_init();
@@ -337,86 +389,119 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap mQ, const __grid_constant
   constexpr uint32_t T_SD = 0 /* buffer b: S at 128 b, dP at 128 b + 64 */, T_DQ = 0 /* aliases buffer 0 */, T_DK = 256, T_DV = 384;
 
   if (warp == CTRL_WARP) {
-    if (lane == 0) {
-      uint32_t ph_kv = 0, ph_q = 0, ph_tile = 0, ph_free[2] = {0, 0};
+    {
+      // The whole warp walks the control flow (loop counters, descriptors and barrier addresses stay warp-uniform, so they live
+      // in uniform registers); only the instructions with side effects are issued by lane 0. Under `if (lane == 0) { loops }`
+      // ptxas moves every tcgen05.mma operand through an ELECT / R2UR.BROADCAST loop: ~20 instructions per MMA.
+      uint32_t ph_kv = 0, ph_q = 0, ph_tile = 0, ph_fin = 0, ph_free[2] = {0, 0};
+      // The tiles never move: their UMMA descriptors are built once, an MMA's operand is base + (byte offset >> 4) in the
+      // low word (the 14-bit address field cannot carry: every tile lies below 256 KB). One thread issues ~80 MMAs per
+      // query tile; rebuilding two descriptors per MMA made that thread, not the tensor core, the critical path.
+      const uint64_t dQk = smem_desc(smem_u32(sQ), 16, 1024), dKk = smem_desc(smem_u32(sK), 16, 1024);        // K-major (S = Q K^T)
+      const uint64_t dDOk = smem_desc(smem_u32(sDO), 16, 1024), dVk = smem_desc(smem_u32(sV), 16, 1024);      // K-major (dP = dO V^T)
+      const uint64_t dDSk = smem_desc(smem_u32(sDS), 16, 1024);                                                // K-major A of dQ = dS K
+      const uint64_t dKmn = smem_desc(smem_u32(sK), 8192, 1024);                                               // MN-major B of dQ
+      const uint64_t dDSmn = smem_desc(smem_u32(sDS), 16384, 1024), dPmn = smem_desc(smem_u32(sP), 16384, 1024);  // MN-major A of dK / dV
+      const uint64_t dQmn = smem_desc(smem_u32(sQ), 8192, 1024), dDOmn = smem_desc(smem_u32(sDO), 8192, 1024);    // MN-major B of dK / dV
+      // loads of one (image, head, tile): Q and dO always, K and V with the head's first tile; the following tile goes to the L2
+      auto issue_loads = [&](int bb, int hh, int ii) {
+        const HeadCols lc = head_cols(hh, hd);
+        if (ii == 0) {
+          if (leader) mbar_expect_tx(bar_kv, 2u * S * 128u);
+          if (leader) tma_load_2d(smem_u32(sK), &mK, bar_kv, lc.col0, bb * S);
+          if (leader) tma_load_2d(smem_u32(sV), &mV, bar_kv, lc.col0, bb * S);
+        }
+        if (leader) mbar_expect_tx(bar_q, 2 * QT_BYTES);
+        if (leader) tma_load_2d(smem_u32(sQ), &mQ, bar_q, lc.col0, bb * S + ii * 128);
+        if (leader) tma_load_2d(smem_u32(sDO), &mDO, bar_q, lc.col0, bb * S + ii * 128);
+        if (ii + 1 < ntiles) {
+          if (leader) tma_prefetch_2d(&mQ, lc.col0, bb * S + (ii + 1) * 128);
+          if (leader) tma_prefetch_2d(&mDO, lc.col0, bb * S + (ii + 1) * 128);
+        } else {
+          int nb = bb, nh = hh + 1;
+          if (nh == heads) { nh = 0; nb = bb + (int)gridDim.x; }
+          if (nb < c.B) {
+            const HeadCols nc = head_cols(nh, hd);
+            if (leader) tma_prefetch_2d(&mK, nc.col0, nb * S);
+            if (leader) tma_prefetch_2d(&mV, nc.col0, nb * S);
+            if (leader) tma_prefetch_2d(&mQ, nc.col0, nb * S);
+            if (leader) tma_prefetch_2d(&mDO, nc.col0, nb * S);
+          }
+        }
+      };
+      if ((int)blockIdx.x < c.B) issue_loads(blockIdx.x, 0, 0);
       for (int b = blockIdx.x; b < c.B; b += gridDim.x) {
         for (int h = 0; h < heads; ++h) {
           const HeadCols hc = head_cols(h, hd);
           const int hdp = hc.hdp;
+          const int nks = hdp / 16;
           const uint32_t id_dq = idesc_bf16(128, hdp, 0, 1);   // dQ = dS K     : A K-major, B (K: keys x hd) MN-major
           const uint32_t id_dkv = idesc_bf16(128, hdp, 1, 1);  // dK = dS^T Q   : A MN-major, B (Q: queries x hd) MN-major
-          mbar_expect_tx(bar_kv, 2u * S * 128u);
-          tma_load_2d(smem_u32(sK), &mK, bar_kv, hc.col0, b * S);
-          tma_load_2d(smem_u32(sV), &mV, bar_kv, hc.col0, b * S);
+          const uint32_t id_s_full = idesc_bf16(128, KPART, 0, 0), id_s_tail = idesc_bf16(128, S - (nparts - 1) * KPART, 0, 0);
           for (int i = 0; i < ntiles; ++i) {
-            mbar_expect_tx(bar_q, 2 * QT_BYTES);
-            tma_load_2d(smem_u32(sQ), &mQ, bar_q, hc.col0, b * S + i * 128);
-            tma_load_2d(smem_u32(sDO), &mDO, bar_q, hc.col0, b * S + i * 128);
-            {  // what the next iteration will load: pulled into the L2 now, its TMA then costs an L2 hit instead of an HBM miss
-              if (i + 1 < ntiles) {
-                tma_prefetch_2d(&mQ, hc.col0, b * S + (i + 1) * 128);
-                tma_prefetch_2d(&mDO, hc.col0, b * S + (i + 1) * 128);
-              } else {
-                int nb = b, nh = h + 1;
-                if (nh == heads) { nh = 0; nb = b + (int)gridDim.x; }
-                if (nb < c.B) {
-                  const HeadCols nc = head_cols(nh, hd);
-                  tma_prefetch_2d(&mK, nc.col0, nb * S);
-                  tma_prefetch_2d(&mV, nc.col0, nb * S);
-                  tma_prefetch_2d(&mQ, nc.col0, nb * S);
-                  tma_prefetch_2d(&mDO, nc.col0, nb * S);
-                }
-              }
+            if (i == 0) {
+              mbar_wait(bar_kv, ph_kv, c.err_flag, 31); ph_kv ^= 1;
+              mbar_wait(bar_tile, ph_tile, c.err_flag, 33); ph_tile ^= 1;       // the workers zeroed the K / V column tails of this head
             }
-            if (i == 0) { mbar_wait(bar_kv, ph_kv, c.err_flag, 31); ph_kv ^= 1; }
             mbar_wait(bar_q, ph_q, c.err_flag, 32); ph_q ^= 1;
-            mbar_wait(bar_tile, ph_tile, c.err_flag, 33); ph_tile ^= 1;         // Q / dO tails zeroed
             fence_after();
+            if (leader) trace_evt(p, 1010);
+            if (lane == 0) bulk_wait_read0();                                   // the previous tile's dS stores have left sDS
             for (int part = 0; part < nparts; ++part) {
               const int buf = part & 1;
               if (part >= 2) {                                                  // workers drained this buffer (part - 2)
                 mbar_wait(bar_free0 + 8 * buf, ph_free[buf], c.err_flag, 34); ph_free[buf] ^= 1;
                 fence_after();
               }
-              const int k0 = part * KPART, w = min(KPART, S - k0);
-              const uint32_t id_s = idesc_bf16(128, w, 0, 0);
+              if (leader) trace_evt(p, 1020 + part);
+              const uint32_t id_s = part == nparts - 1 ? id_s_tail : id_s_full;
               const uint32_t ts = tmem + T_SD + 128u * buf;
-              for (int ks = 0; ks < hdp / 16; ++ks)
-                mma_bf16(ts, smem_desc(smem_u32(sQ) + ks * 32, 16, 1024),
-                         smem_desc(smem_u32(sK) + k0 * 128 + ks * 32, 16, 1024), id_s, ks > 0);
-              for (int ks = 0; ks < hdp / 16; ++ks)
-                mma_bf16(ts + 64, smem_desc(smem_u32(sDO) + ks * 32, 16, 1024),
-                         smem_desc(smem_u32(sV) + k0 * 128 + ks * 32, 16, 1024), id_s, ks > 0);
-              commit(bar_sd0 + 8 * buf);
+              const uint32_t koff = (uint32_t)(part * KPART * 128) >> 4;      // key rows of this part inside the K / V tiles
+              for (int ks = 0; ks < nks; ++ks) if (leader) mma_bf16(ts, dQk + 2 * ks, dKk + koff + 2 * ks, id_s, ks > 0);
+              for (int ks = 0; ks < nks; ++ks) if (leader) mma_bf16(ts + 64, dDOk + 2 * ks, dVk + koff + 2 * ks, id_s, ks > 0);
+              if (leader) commit(bar_sd0 + 8 * buf);
             }
             for (int part = max(0, nparts - 2); part < nparts; ++part) {       // the last parts: P and dS of the tile complete
               const int buf = part & 1;
               mbar_wait(bar_free0 + 8 * buf, ph_free[buf], c.err_flag, 35); ph_free[buf] ^= 1;
             }
             fence_after();
-            for (int kk = 0; kk < S / 16; ++kk)     // dQ_i = dS_i K   (contraction over the keys)
-              mma_bf16(tmem + T_DQ, smem_desc(smem_u32(sDS) + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024),
-                       smem_desc(smem_u32(sK) + kk * 2048, 8192, 1024), id_dq, kk > 0);
+            for (int a = 0; a < nparts; ++a)                                    // dS_h of this tile -> scratch[b, h, i * 128 .., a * 64 ..]
+              if (lane == 0) tma_store_3d(&mDS, smem_u32(sDS) + a * 16384, a * 64, i * 128, b * heads + h);
+            if (lane == 0) bulk_commit();
+            if (leader) trace_evt(p, 1030);
+            for (int kk = 0; kk < S / 16; ++kk)     // dQ_i = dS_i K   (contraction over the keys): 16 keys = 32 B of a K-major row, 2048 B of MN-major K
+              if (leader) mma_bf16(tmem + T_DQ, dDSk + (uint32_t)((kk >> 2) * 1024 + (kk & 3) * 2), dKmn + (uint32_t)(kk * 128), id_dq, kk > 0);
             for (int t = 0; t < ntiles; ++t) {      // dK_t += dS_i^T Q_i ; dV_t += P_i^T dO_i   (contraction over this tile's 128 queries)
               for (int kq = 0; kq < 8; ++kq) {
                 const uint32_t acc = (i > 0 || kq > 0) ? 1u : 0u;
-                mma_bf16(tmem + T_DK + 64 * t, smem_desc(smem_u32(sDS) + 2 * t * 16384 + kq * 2048, 16384, 1024),
-                         smem_desc(smem_u32(sQ) + kq * 2048, 8192, 1024), id_dkv, acc);
-                mma_bf16(tmem + T_DV + 64 * t, smem_desc(smem_u32(sP) + 2 * t * 16384 + kq * 2048, 16384, 1024),
-                         smem_desc(smem_u32(sDO) + kq * 2048, 8192, 1024), id_dkv, acc);
+                const uint32_t aoff = (uint32_t)(2 * t * 1024 + kq * 128), boff = (uint32_t)(kq * 128);
+                if (leader) mma_bf16(tmem + T_DK + 64 * t, dDSmn + aoff, dQmn + boff, id_dkv, acc);
+                if (leader) mma_bf16(tmem + T_DV + 64 * t, dPmn + aoff, dDOmn + boff, id_dkv, acc);
               }
             }
-            commit(bar_fin);
-            mbar_wait(bar_tile, ph_tile, c.err_flag, 36); ph_tile ^= 1;         // epilogues done: Q/dO/P/dS tiles and TMEM free
+            if (leader) commit(bar_fin);
+            if (leader) trace_evt(p, 1040);
+            // Q / dO (and, after a head's last tile, K / V) are free as soon as these MMAs have retired: the next loads run under
+            // the workers' store epilogue
+            mbar_wait(bar_fin, ph_fin, c.err_flag, 37); ph_fin ^= 1;
+            {
+              int nb = b, nh = h, ni = i + 1;
+              if (ni == ntiles) { ni = 0; if (++nh == heads) { nh = 0; nb = b + (int)gridDim.x; } }
+              if (nb < c.B) issue_loads(nb, nh, ni);
+            }
+            mbar_wait(bar_tile, ph_tile, c.err_flag, 36); ph_tile ^= 1;         // epilogues done: P / dS tiles and TMEM free
+            if (leader) trace_evt(p, 1050);
           }
         }
       }
+      if (lane == 0) bulk_wait0();
     }
   } else {
     const int grp = warp >> 2;                    // 0: even 16-column chunks, 1: odd chunks
     const int r = (warp & 3) * 32 + lane;         // row within the tile == TMEM lane
     const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16);
-    uint32_t ph_kv = 0, ph_q = 0, ph_fin = 0, ph_sd[2] = {0, 0};
+    uint32_t ph_kv = 0, ph_fin = 0, ph_sd[2] = {0, 0};
     // bias row segment of a part: this thread's chunks (2 j + grp) * 16, j = 0, 1, of key columns [part * 64, part * 64 + 64)
     uint4 bcur[4], bnxt[4];
     auto load_bias = [&](uint4* dst, int bb, int ii, int part) {
@@ -437,19 +522,23 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap mQ, const __grid_constant
       for (int h = 0; h < heads; ++h) {
         const HeadCols hc = head_cols(h, hd);
         const int hdp = hc.hdp;
-        const bool first = h == 0, last = h == heads - 1;
+        const bool last = h == heads - 1;
         for (int i = 0; i < ntiles; ++i) {
           const int q = i * 128 + r;
           const bool valid = q < S;
-          if (i == 0) { mbar_wait(bar_kv, ph_kv, c.err_flag, 41); ph_kv ^= 1; }
-          mbar_wait(bar_q, ph_q, c.err_flag, 42); ph_q ^= 1;
-          if (grp == 0) zero_outside(sQ, r, hc, hd);
-          else zero_outside(sDO, r, hc, hd);
-          fence_proxy_async();
-          mbar_arrive(bar_tile);
+          if (i == 0) {
+            // The 64-column boxes also bring the neighbouring heads' columns. Zeroing them in K and V (once per head) is enough:
+            // S = Q K^T and dP = dO V^T then ignore the tails of Q and dO, and the tails only reach dQ / dK / dV columns nobody stores.
+            mbar_wait(bar_kv, ph_kv, c.err_flag, 41); ph_kv ^= 1;
+            if (threadIdx.x == 0) trace_evt(p, 2000);
+            uint8_t* tile = grp == 0 ? sK : sV;
+            for (int row = r; row < S; row += 128) zero_outside(tile, row, hc, hd);
+            fence_proxy_async();
+            mbar_arrive(bar_tile);
+            if (threadIdx.x == 0) trace_evt(p, 2010);
+          }
           const long long stat = ((long long)b * heads + h) * S + (valid ? q : 0);
           const float lse2 = p.lse[stat] * LOG2E, dl = p.delta[stat];
-          const long long rowoff = ((long long)b * S + (valid ? q : 0)) * S;
           for (int part = 0; part < nparts; ++part) {
             const int buf = part & 1;
             const int k0 = part * KPART, w = min(KPART, S - k0);
@@ -462,20 +551,10 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap mQ, const __grid_constant
               }
               if (nb < c.B) load_bias(bnxt, nb, ni, np);
             }
-            // the last head reads the running sum back (written by this same thread, so far only through the L2)
-            float4 ac[8];
-            if (last && !first && valid) {
-#pragma unroll
-              for (int j = 0; j < 2; ++j) {
-                const int cc = (2 * j + grp) * 16;
-                if (cc < w) {
-#pragma unroll
-                  for (int e = 0; e < 4; ++e) ac[4 * j + e] = __ldcg(reinterpret_cast<const float4*>(p.dbias_acc + rowoff + k0 + cc) + e);
-                }
-              }
-            }
+            if (threadIdx.x == 0) trace_evt(p, 2020 + part);
             mbar_wait(bar_sd0 + 8 * buf, ph_sd[buf], c.err_flag, 43); ph_sd[buf] ^= 1;
             fence_after();
+            if (threadIdx.x == 0) trace_evt(p, 2030 + part);
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
               const int cc = (2 * j + grp) * 16;
@@ -495,66 +574,56 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap mQ, const __grid_constant
                 }
                 store_row16(sP, r, kc, pv);
                 store_row16(sDS, r, kc, ds);
-                if (valid) {
-                  float* ap = p.dbias_acc + rowoff + kc;
-                  if (last) {
-                    if (!first) {
-#pragma unroll
-                      for (int e = 0; e < 4; ++e) {
-                        ds[4 * e] += ac[4 * j + e].x; ds[4 * e + 1] += ac[4 * j + e].y; ds[4 * e + 2] += ac[4 * j + e].z; ds[4 * e + 3] += ac[4 * j + e].w;
-                      }
-                    }
-                    uint4* op = reinterpret_cast<uint4*>(p.dbias + rowoff + kc);
-                    op[0] = pack8f(ds); op[1] = pack8f(ds + 8);
-                  } else if (first) {
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) reinterpret_cast<float4*>(ap)[e] = make_float4(ds[4 * e], ds[4 * e + 1], ds[4 * e + 2], ds[4 * e + 3]);
-                  } else {
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) red_add_f32x4(ap + 4 * e, ds[4 * e], ds[4 * e + 1], ds[4 * e + 2], ds[4 * e + 3]);
-                  }
-                }
               }
             }
+            if (threadIdx.x == 0) trace_evt(p, 2040 + part);
             fence_proxy_async();
             fence_before();
             mbar_arrive(bar_free0 + 8 * buf);
+            if (threadIdx.x == 0) trace_evt(p, 2050 + part);
 #pragma unroll
             for (int e = 0; e < 4; ++e) bcur[e] = bnxt[e];
           }
           mbar_wait(bar_fin, ph_fin, c.err_flag, 44); ph_fin ^= 1;
           fence_after();
-          // dQ rows of this tile
+          if (threadIdx.x == 0) trace_evt(p, 2060);
+          // dQ rows of this tile: TMEM -> staging atom 0 of sP (free: the dV MMAs have retired; sDS is still being read by the
+          // dS store) -> coalesced rows. After the head's last tile the same for dK_t (atoms t) and dV_t (atoms 2 + t).
           {
-            bf16* row = p.dq + ((long long)b * S + q) * p.ld_dq + (long long)h * hd;
+            const int quad = warp & 3;
+            const int row_begin = quad * 32 + grp * 16;
+            const long long g_end = (long long)b * S + S;
             for (int c0 = grp * 16; c0 < hdp; c0 += 32) {
               uint32_t v[16];
               tmem_ld16(trow + T_DQ + c0, v);
               tmem_ld_wait();
-              if (valid) store_cols16(row, v, c0, hc, hd, c.scale);
+              stage_cols16(sP, r, v, c0, c.scale);
             }
-          }
-          if (i == ntiles - 1) {
-            // dK / dV: TMEM lanes are key rows of M-tile t
-            for (int t = 0; t < ntiles; ++t) {
-              const int key = t * 128 + r;
-              const bool kvalid = key < S;
-              bf16* krow = p.dk + ((long long)b * S + key) * p.ld_dk + (long long)h * hd;
-              bf16* vrow = p.dv + ((long long)b * S + key) * p.ld_dv + (long long)h * hd;
-              for (int c0 = grp * 16; c0 < hdp; c0 += 32) {
-                uint32_t kk[16], vv[16];
-                tmem_ld16(trow + T_DK + 64 * t + c0, kk);
-                tmem_ld16(trow + T_DV + 64 * t + c0, vv);
-                tmem_ld_wait();
-                if (kvalid) {
-                  store_cols16(krow, kk, c0, hc, hd, c.scale);
-                  store_cols16(vrow, vv, c0, hc, hd, 1.0f);
+            quad_sync(quad);
+            store_rows16(sP, p.dq + (long long)h * hd, p.ld_dq, row_begin, (long long)b * S + i * 128, g_end, hc, hd, lane);
+            if (i == ntiles - 1) {
+              quad_sync(quad);                                   // atom 0 is reused
+              for (int t = 0; t < ntiles; ++t) {                 // TMEM lanes are key rows of M-tile t
+                for (int c0 = grp * 16; c0 < hdp; c0 += 32) {
+                  uint32_t kk[16], vv[16];
+                  tmem_ld16(trow + T_DK + 64 * t + c0, kk);
+                  tmem_ld16(trow + T_DV + 64 * t + c0, vv);
+                  tmem_ld_wait();
+                  stage_cols16(sP + t * 16384, r, kk, c0, c.scale);
+                  stage_cols16(sP + (2 + t) * 16384, r, vv, c0, 1.0f);
                 }
               }
+              quad_sync(quad);
+              for (int t = 0; t < ntiles; ++t) {
+                store_rows16(sP + t * 16384, p.dk + (long long)h * hd, p.ld_dk, row_begin, (long long)b * S + t * 128, g_end, hc, hd, lane);
+                store_rows16(sP + (2 + t) * 16384, p.dv + (long long)h * hd, p.ld_dv, row_begin, (long long)b * S + t * 128, g_end, hc, hd, lane);
+              }
             }
+            quad_sync(quad);   // the staging rows are rewritten (P of the next tile) by the partner warp
           }
           fence_before();
           mbar_arrive(bar_tile);
+          if (threadIdx.x == 0) trace_evt(p, 2070);
         }
       }
     }
@@ -565,6 +634,46 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap mQ, const __grid_constant
     fence_after();
     tmem_dealloc(tmem, TMEM_COLS);
   }
+}
+
+// dbias[b, q, k] = sum_h dS[b, h, q, k]  (bf16 in, fp32 sum in head order, bf16 out); 8 elements (16 bytes) per thread
+__global__ void dbias_reduce_kernel(const bf16* __restrict__ ds, bf16* __restrict__ dbias, int heads, long long ss8 /* S * S / 8 */,
+                                    long long total8 /* B * S * S / 8 */) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total8) return;
+  const long long b = i / ss8, r = i - b * ss8;
+  const uint4* src = reinterpret_cast<const uint4*>(ds) + b * heads * ss8 + r;
+  float acc[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+  for (int h0 = 0; h0 < heads; h0 += 4) {      // 4 independent 16-byte loads in flight
+    uint4 u[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) u[j] = h0 + j < heads ? __ldcs(src + (long long)(h0 + j) * ss8) : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float2 t;
+      t = unpack_bf16x2(u[j].x); acc[0] += t.x; acc[1] += t.y;
+      t = unpack_bf16x2(u[j].y); acc[2] += t.x; acc[3] += t.y;
+      t = unpack_bf16x2(u[j].z); acc[4] += t.x; acc[5] += t.y;
+      t = unpack_bf16x2(u[j].w); acc[6] += t.x; acc[7] += t.y;
+    }
+  }
+  reinterpret_cast<uint4*>(dbias)[i] = pack8f(acc);
+}
+
+// 3-D bf16 map {S cols, S rows, B * heads} over the per-head dS scratch, box {64, 128, 1}, 128B swizzle
+int make_map_ds(CUtensorMap* map, void* base, uint64_t S, uint64_t bh) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) { calm_set_error("cuTensorMapEncodeTiled entry point not found"); return CALM_ERR_CUDA; }
+  cuuint64_t dims[3] = {S, S, bh};
+  cuuint64_t strides[2] = {S * 2, S * S * 2};
+  cuuint32_t box[3] = {64, 128, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { calm_set_error("cuTensorMapEncodeTiled(dS scratch) failed (%d)", (int)r); return CALM_ERR_CUDA; }
+  return CALM_OK;
 }
 
 constexpr size_t FWD_SMEM = 2 * KV_BYTES + QT_BYTES + P_BYTES + 2048 + 256 + 1024;
@@ -615,8 +724,17 @@ int calm_attention_fwd_tc(const void* q, const void* k, const void* v, const voi
   return CALM_OK;
 }
 
+static unsigned long long* g_trace_buf = nullptr;
+static int g_trace_cap = 0;
+extern "C" void calm_debug_set_trace_buffer(void* device_u64, int32_t capacity_events) {
+  g_trace_buf = reinterpret_cast<unsigned long long*>(device_u64);
+  g_trace_cap = capacity_events;
+}
+
+size_t calm_attention_bwd_tc_scratch_bytes(int B, int S, int heads) { return (size_t)2 * B * heads * S * S; }
+
 int calm_attention_bwd_tc(const void* q, const void* k, const void* v, const void* bias, const void* d_o, const float* lse,
-                          const float* delta, void* dq, void* dk, void* dv, void* dbias, float* dbias_acc, int64_t ld_q, int64_t ld_k,
+                          const float* delta, void* dq, void* dk, void* dv, void* dbias, void* ds_scratch, int64_t ld_q, int64_t ld_k,
                           int64_t ld_v, int64_t ld_do, int64_t ld_dq, int64_t ld_dk, int64_t ld_dv, int B, int S, int heads, int hd,
                           cudaStream_t stream) {
   BwdParams p;
@@ -624,14 +742,15 @@ int calm_attention_bwd_tc(const void* q, const void* k, const void* v, const voi
   p.lse = lse; p.delta = delta;
   p.dq = reinterpret_cast<bf16*>(dq); p.dk = reinterpret_cast<bf16*>(dk); p.dv = reinterpret_cast<bf16*>(dv);
   p.ld_dq = ld_dq; p.ld_dk = ld_dk; p.ld_dv = ld_dv;
-  p.dbias = reinterpret_cast<bf16*>(dbias); p.dbias_acc = dbias_acc;
-  CUtensorMap mQ, mK, mV, mDO;
+  p.trace = g_trace_buf; p.trace_cap = g_trace_cap;
+  CUtensorMap mQ, mK, mV, mDO, mDS;
   int rc;
   const uint64_t rows = (uint64_t)B * S, cols = (uint64_t)heads * hd;
   if ((rc = tc::make_map_2d(&mQ, q, cols, rows, ld_q, 128))) return rc;
   if ((rc = tc::make_map_2d(&mK, k, cols, rows, ld_k, S))) return rc;
   if ((rc = tc::make_map_2d(&mV, v, cols, rows, ld_v, S))) return rc;
   if ((rc = tc::make_map_2d(&mDO, d_o, cols, rows, ld_do, 128))) return rc;
+  if ((rc = make_map_ds(&mDS, ds_scratch, (uint64_t)S, (uint64_t)B * heads))) return rc;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(attn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BWD_SMEM);
@@ -639,7 +758,11 @@ int calm_attention_bwd_tc(const void* q, const void* k, const void* v, const voi
     configured = true;
   }
   const int grid = B < calm_num_sms() ? B : calm_num_sms();
-  attn_bwd_tc_kernel<<<grid, NTHREADS, BWD_SMEM, stream>>>(mQ, mK, mV, mDO, p);
+  attn_bwd_tc_kernel<<<grid, NTHREADS, BWD_SMEM, stream>>>(mQ, mK, mV, mDO, mDS, p);
   CALM_CHECK_LAUNCH("calm_attention_bwd(tcgen05)");
+  const long long ss8 = (long long)S * S / 8, total8 = ss8 * B;
+  dbias_reduce_kernel<<<(unsigned)((total8 + 255) / 256), 256, 0, stream>>>(reinterpret_cast<const bf16*>(ds_scratch),
+                                                                            reinterpret_cast<bf16*>(dbias), heads, ss8, total8);
+  CALM_CHECK_LAUNCH("calm_attention_bwd(dbias reduce)");
   return CALM_OK;
 }

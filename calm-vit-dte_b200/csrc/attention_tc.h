@@ -8,6 +8,7 @@ bool calm_attention_tc_eligible(int B, int S, int heads, int hd, const int64_t* 
 int calm_attention_fwd_tc(const void* q, const void* k, const void* v, const void* bias, void* o, float* lse, int64_t ld_q, int64_t ld_k,
                           int64_t ld_v, int64_t ld_o, int B, int S, int heads, int hd, cudaStream_t stream);
 int calm_attention_bwd_tc(const void* q, const void* k, const void* v, const void* bias, const void* d_o, const float* lse,
-                          const float* delta, void* dq, void* dk, void* dv, void* dbias, float* dbias_acc, int64_t ld_q, int64_t ld_k,
+                          const float* delta, void* dq, void* dk, void* dv, void* dbias, void* ds_scratch, int64_t ld_q, int64_t ld_k,
                           int64_t ld_v, int64_t ld_do, int64_t ld_dq, int64_t ld_dk, int64_t ld_dv, int B, int S, int heads, int hd,
                           cudaStream_t stream);
+size_t calm_attention_bwd_tc_scratch_bytes(int B, int S, int heads);

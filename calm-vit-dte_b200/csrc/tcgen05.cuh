@@ -41,6 +41,12 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* er
     }
   }
 }
+// true on exactly one lane of the (converged) warp
+__device__ __forceinline__ uint32_t elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred;
+}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 // generic-proxy writes to shared memory (st.shared by threads) -> visible to the async proxy (tcgen05.mma / TMA reads)
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }

@@ -37,6 +37,8 @@ int32_t calm_abi_version(void);
 const char* calm_last_error(void); /* thread-local, valid until the next failing call on this thread */
 void calm_set_debug_flags(int32_t flags);
 int32_t calm_get_debug_flags(void);
+void calm_debug_set_trace_buffer(void* device_u64, int32_t capacity_events); /* bring-up: attention-backward CTA 0 writes
+   [count, (event id, globaltimer ns)...] into this zero-initialised device buffer of 1 + 2 * capacity u64; NULL disables */
 void calm_debug_set_gemm_bn(int32_t bn); /* tuning hook: force the GEMM N-tile width (0 = automatic) */
 int32_t calm_set_error_flag_buffer(int32_t* device_int); /* optional: receives the id of a timed-out barrier */
 
@@ -129,7 +131,8 @@ int32_t calm_rope_bwd(const void* dout, int64_t ld_dout, const void* out, int64_
  *   O = softmax(Q K^T / sqrt(hd) + bias[b]) V     replaces F.scaled_dot_product_attention (Vi_Tools_CNN_less_V2.py:293-298)
  * q/k/v/o: bf16, token-major (B*S, heads*hd) views with leading dims ld_* ; bias bf16 (B, S, S); lse f32 (B, heads, S).
  * bwd: dq/dk/dv bf16 (same layout), dbias bf16 (B,S,S) = sum_h dS_h, delta f32 (B, heads, S) scratch,
- *      dbias_acc f32 (B,S,S) scratch for the per-head accumulation (NULL forces the legacy kernels).
+ *      ds_scratch: calm_attention_bwd_scratch_bytes(...) bytes, 16-byte aligned: the tcgen05 path stores every head's dS there
+ *      (bf16, (B, heads, S, S)) and sums the heads with a second kernel (NULL forces the legacy kernels).
  * Two implementations behind these entry points: tcgen05/TMEM/TMA kernels (attention_sm100.cu) when S <= 256, S % 16 == 0,
  * head_dim <= 64, 16-byte aligned operands; warp-level mma.sync kernels (attention.cu) otherwise (384^2 / 512^2 configs) or
  * when calm_set_debug_flags(CALM_DEBUG_LEGACY_ATTENTION) is set.
@@ -137,8 +140,9 @@ int32_t calm_rope_bwd(const void* dout, int64_t ld_dout, const void* out, int64_
 int32_t calm_attention_fwd(const void* q, const void* k, const void* v, const void* bias, void* o, float* lse,
                            int64_t ld_q, int64_t ld_k, int64_t ld_v, int64_t ld_o, int32_t B, int32_t S, int32_t heads,
                            int32_t hd, cudaStream_t stream);
+int64_t calm_attention_bwd_scratch_bytes(int32_t B, int32_t S, int32_t heads, int32_t hd);
 int32_t calm_attention_bwd(const void* q, const void* k, const void* v, const void* bias, const void* o, const void* d_o,
-                           const float* lse, float* delta, void* dq, void* dk, void* dv, void* dbias, float* dbias_acc, int64_t ld_q,
+                           const float* lse, float* delta, void* dq, void* dk, void* dv, void* dbias, void* ds_scratch, int64_t ld_q,
                            int64_t ld_k, int64_t ld_v, int64_t ld_o, int64_t ld_do, int64_t ld_dq, int64_t ld_dk,
                            int64_t ld_dv, int32_t B, int32_t S, int32_t heads, int32_t hd, cudaStream_t stream);
 
