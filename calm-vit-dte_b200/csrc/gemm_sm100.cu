@@ -167,6 +167,14 @@ __device__ __forceinline__ void mbar_arrive_remote(uint32_t local_bar, uint32_t 
       "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}"
       ::"r"(local_bar), "r"(cta_rank) : "memory");
 }
+// true on exactly one lane of the converged warp. `if (elect_one())` around a batch of TMA / tcgen05 instructions inside warp-uniform
+// loops lets ptxas keep their operands in uniform registers; under `if (lane == 0) { loops }` every operand of every MMA goes
+// through an ELECT / R2UR.BROADCAST loop (~20 instructions per MMA on the one thread that must stay ahead of the tensor core).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0u;
+}
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
@@ -608,7 +616,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
   if (warp == WARP_TMA) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    {
       int stage = 0; uint32_t phase = 0;
       for (int t = w_first; t < w_total; t += w_stride) {
         const TileCoord tc = decode_tile<PAIR>(p, t, crank);
@@ -624,42 +632,43 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           const uint32_t full = smem_u32(&bars[stage]);
           const uint32_t sa = smem_u32(smem_a + stage * A_STAGE_BYTES);
           const uint32_t sb = smem_u32(smem_b + stage * B_STAGE_BYTES);
-          if (PAIR == 2) {
-            // both CTAs load their A rows and their half of B; all bytes are accounted on the LEADER's full barrier
-            if (crank == 0) mbar_expect_tx(full, stage_tx);
-            const uint32_t lfull = mapa_u32(full, 0);
-            if (A_MN) {
-              tma_load_3d_2sm(sa, &tmA, lfull, m0, k0, ba);
-              tma_load_3d_2sm(sa + BK * 128, &tmA, lfull, m0 + 64, k0, ba);
+          if (elect_one()) {
+            if (PAIR == 2) {
+              // both CTAs load their A rows and their half of B; all bytes are accounted on the LEADER's full barrier
+              if (crank == 0) mbar_expect_tx(full, stage_tx);
+              const uint32_t lfull = mapa_u32(full, 0);
+              if (A_MN) {
+                tma_load_3d_2sm(sa, &tmA, lfull, m0, k0, ba);
+                tma_load_3d_2sm(sa + BK * 128, &tmA, lfull, m0 + 64, k0, ba);
+              } else {
+                tma_load_3d_2sm(sa, &tmA, lfull, k0, m0, ba);
+              }
+              if (B_MN) {
+                for (int i = 0; i < nbh_boxes; ++i) tma_load_3d_2sm(sb + i * (BK * 128), &tmB, lfull, n0 + crank * half_n + 64 * i, k0, bb);
+              } else {
+                tma_load_3d_2sm(sb, &tmBh, lfull, k0, n0 + crank * half_n, bb);
+              }
             } else {
-              tma_load_3d_2sm(sa, &tmA, lfull, k0, m0, ba);
+              mbar_expect_tx(full, stage_tx);
+              if (A_MN) {
+                tma_load_3d(sa, &tmA, full, m0, k0, ba);
+                tma_load_3d(sa + BK * 128, &tmA, full, m0 + 64, k0, ba);
+              } else {
+                tma_load_3d(sa, &tmA, full, k0, m0, ba);
+              }
+              if (PAIR) {
+                if (B_MN) {   // 64-wide slabs alternate between the two CTAs
+                  for (int i = crank; i < nb_boxes; i += 2) tma_load_3d_mc(sb + i * (BK * 128), &tmB, full, n0 + 64 * i, k0, bb, 3);
+                } else {      // rows [crank * BN/2, (crank + 1) * BN/2) of the tile
+                  const int half_rows = p.BN >> 1;
+                  tma_load_3d_mc(sb + crank * half_rows * 128, &tmBh, full, k0, n0 + crank * half_rows, bb, 3);
+                }
+              } else if (B_MN) {
+                for (int i = 0; i < nb_boxes; ++i) tma_load_3d(sb + i * (BK * 128), &tmB, full, n0 + 64 * i, k0, bb);
+              } else {
+                tma_load_3d(sb, &tmB, full, k0, n0, bb);
+              }
             }
-            if (B_MN) {
-              for (int i = 0; i < nbh_boxes; ++i) tma_load_3d_2sm(sb + i * (BK * 128), &tmB, lfull, n0 + crank * half_n + 64 * i, k0, bb);
-            } else {
-              tma_load_3d_2sm(sb, &tmBh, lfull, k0, n0 + crank * half_n, bb);
-            }
-            if (++stage == nstages) { stage = 0; phase ^= 1; }
-            continue;
-          }
-          mbar_expect_tx(full, stage_tx);
-          if (A_MN) {
-            tma_load_3d(sa, &tmA, full, m0, k0, ba);
-            tma_load_3d(sa + BK * 128, &tmA, full, m0 + 64, k0, ba);
-          } else {
-            tma_load_3d(sa, &tmA, full, k0, m0, ba);
-          }
-          if (PAIR) {
-            if (B_MN) {   // 64-wide slabs alternate between the two CTAs
-              for (int i = crank; i < nb_boxes; i += 2) tma_load_3d_mc(sb + i * (BK * 128), &tmB, full, n0 + 64 * i, k0, bb, 3);
-            } else {      // rows [crank * BN/2, (crank + 1) * BN/2) of the tile
-              const int half_rows = p.BN >> 1;
-              tma_load_3d_mc(sb + crank * half_rows * 128, &tmBh, full, k0, n0 + crank * half_rows, bb, 3);
-            }
-          } else if (B_MN) {
-            for (int i = 0; i < nb_boxes; ++i) tma_load_3d(sb + i * (BK * 128), &tmB, full, n0 + 64 * i, k0, bb);
-          } else {
-            tma_load_3d(sb, &tmB, full, k0, n0, bb);
           }
           if (++stage == nstages) { stage = 0; phase ^= 1; }
         }
@@ -667,9 +676,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
   } else if (warp == WARP_MMA) {
     // ===================== MMA issuer (cta_group::2: the leader CTA only) =====================
-    if (lane == 0 && (PAIR != 2 || crank == 0)) {
+    if (PAIR != 2 || crank == 0) {
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)A_MN << 15) | ((uint32_t)B_MN << 16) |
                              ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)((PAIR == 2 ? 2 * BM : BM) >> 4) << 24);
+      // descriptors of ring stage 0, built once; a stage / k-step only moves the 14-bit address field (the ring lies below 256 KB)
+      const uint64_t a_desc0 = A_MN ? make_smem_desc(smem_u32(smem_a), BK * 128, 1024) : make_smem_desc(smem_u32(smem_a), 16, 1024);
+      const uint64_t b_desc0 = B_MN ? make_smem_desc(smem_u32(smem_b), BK * 128, 1024) : make_smem_desc(smem_u32(smem_b), 16, 1024);
+      constexpr uint32_t A_KSTEP = (A_MN ? 2048 : 32) >> 4, B_KSTEP = (B_MN ? 2048 : 32) >> 4;   // 16 k-elements further
+      const uint32_t b_stage_step = (uint32_t)B_STAGE_BYTES >> 4;
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
       for (int t = w_first; t < w_total; t += w_stride) {
@@ -682,22 +696,24 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         for (int ci = kb_begin; ci < kb_end; ++ci) {
           mbar_wait(smem_u32(&bars[stage]), phase, p.err_flag, 3);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem_a + stage * A_STAGE_BYTES);
-          const uint32_t sb = smem_u32(smem_b + stage * B_STAGE_BYTES);
+          if (elect_one()) {
+            const uint64_t ad = a_desc0 + (uint32_t)stage * (uint32_t)(A_STAGE_BYTES >> 4);
+            const uint64_t bd = b_desc0 + (uint32_t)stage * b_stage_step;
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            const uint64_t adesc = A_MN ? make_smem_desc(sa + k * 2048, BK * 128, 1024) : make_smem_desc(sa + k * 32, 16, 1024);
-            const uint64_t bdesc = B_MN ? make_smem_desc(sb + k * 2048, BK * 128, 1024) : make_smem_desc(sb + k * 32, 16, 1024);
-            if (PAIR == 2) tc_mma_bf16_2sm(tmem_d, adesc, bdesc, idesc, (ci > kb_begin || k > 0) ? 1u : 0u);
-            else tc_mma_bf16(tmem_d, adesc, bdesc, idesc, (ci > kb_begin || k > 0) ? 1u : 0u);
+            for (int k = 0; k < BK / 16; ++k) {
+              if (PAIR == 2) tc_mma_bf16_2sm(tmem_d, ad + k * A_KSTEP, bd + k * B_KSTEP, idesc, (ci > kb_begin || k > 0) ? 1u : 0u);
+              else tc_mma_bf16(tmem_d, ad + k * A_KSTEP, bd + k * B_KSTEP, idesc, (ci > kb_begin || k > 0) ? 1u : 0u);
+            }
+            if (PAIR == 2) tc_commit_2sm(smem_u32(&bars[STAGES + stage]), 3);      // frees the stage in BOTH CTAs
+            else if (PAIR) tc_commit_mc(smem_u32(&bars[STAGES + stage]), 3);       // both CTAs' producers wait for both consumers
+            else tc_commit(smem_u32(&bars[STAGES + stage]));                       // frees this smem stage when the MMAs above retire
           }
-          if (PAIR == 2) tc_commit_2sm(smem_u32(&bars[STAGES + stage]), 3);      // frees the stage in BOTH CTAs
-          else if (PAIR) tc_commit_mc(smem_u32(&bars[STAGES + stage]), 3);       // both CTAs' producers wait for both consumers
-          else tc_commit(smem_u32(&bars[STAGES + stage]));                       // frees this smem stage when the MMAs above retire
           if (++stage == nstages) { stage = 0; phase ^= 1; }
         }
-        if (PAIR == 2) tc_commit_2sm(smem_u32(&bars[2 * STAGES + acc]), 3);      // both CTAs' epilogues
-        else tc_commit(smem_u32(&bars[2 * STAGES + acc]));                       // accumulator ready for the epilogue
+        if (elect_one()) {
+          if (PAIR == 2) tc_commit_2sm(smem_u32(&bars[2 * STAGES + acc]), 3);      // both CTAs' epilogues
+          else tc_commit(smem_u32(&bars[2 * STAGES + acc]));                       // accumulator ready for the epilogue
+        }
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
@@ -985,11 +1001,11 @@ extern "C" int32_t calm_gemm(const calm_gemm_args* a, cudaStream_t stream) {
   const bool add_ok = !a->addend || (a->epilogue == CALM_EPI_NONE && (a->addend_dtype == CALM_F32) == (a->c_dtype == CALM_F32) &&
                                       a->stride_addend % 8 == 0);
   const bool act_ok = a->epilogue == CALM_EPI_NONE || (a->c_dtype == CALM_BF16 && !a->addend && a->stride_aux % 8 == 0);
-  // Measured (profiles/r01_gemm_epilogue_ab.txt): staging wins wherever a residual is read back (-8..-30 %) and on the many-wave
-  // cta_group::2 problems (-10..-20 %); on one-wave / short problems the 48 KB it takes from the operand ring and its longer
-  // per-tile latency cost 5-25 %, and fp32 split-K partials (one exposed epilogue per CTA) are better off writing directly.
-  const bool want_tma = (g_debug_flags & CALM_DEBUG_FORCE_STAGED_EPILOGUE) || ((a->addend || pair == 2) && !(a->c_dtype == CALM_F32 && !a->addend));
-  p.epi_tma = !(g_debug_flags & CALM_DEBUG_DIRECT_EPILOGUE) && want_tma && add_ok && act_ok && a->stride_split % 4 == 0;
+  // Measured with the two forms interleaved in one process (profiles/r01_gemm_epilogue_ab.txt): staging wins wherever a residual
+  // or a saved pre-activation is read back (-20..-40 %), on bf16 outputs of many-wave problems (-20 %), and by 0-15 % on the
+  // small / split-K shapes; the only losses are +2..4 % on the three largest split-K weight gradients. It is the default
+  // wherever the operand mix has an in-place form.
+  p.epi_tma = !(g_debug_flags & CALM_DEBUG_DIRECT_EPILOGUE) && add_ok && act_ok && a->stride_split % 4 == 0;
   // slots per epilogue warp: 3 in-flight stores; GELU stores two slots per unit; units with an input keep 3 loads in flight
   p.epi_slots = !p.epi_tma ? 0 : (a->addend || a->epilogue == CALM_EPI_DGELU) ? 5 : a->epilogue == CALM_EPI_GELU ? 4 : 3;
   {

@@ -188,13 +188,13 @@ def test_gemm_pair_mode(K, M, N, Kd, a_mn, b_mn):
 @pytest.mark.parametrize("M,N,Kd,nb", [(300, 264, 240, 1), (1000, 1344, 128, 1), (130, 8, 64, 1), (224, 224, 96, 5), (96, 40, 80, 3)])
 @pytest.mark.parametrize("form", ["bf16", "f32", "f32+add", "bf16+add_inplace", "gelu", "dgelu", "bf16<-f32add"])
 def test_gemm_epilogue_forms(K, M, N, Kd, nb, form):
-    """The TMA-staged epilogue (forced: flag 64) and the row-owner direct epilogue (flag 32) must agree bit for
+    """The TMA-staged epilogue (default) and the row-owner direct epilogue (flag 32) must agree bit for
     bit on every operand mix, ragged tiles and batches included; the last form has no staged variant and checks the fallback."""
     import calm_lib
     a, b = rnd(nb * M, Kd, seed=61), rnd(nb * N, Kd, scale=0.1, seed=62)
     bias = rnd(N, dtype=f32, seed=63)
     outs = []
-    for flags in (64, 32):                          # FORCE_STAGED_EPILOGUE, DIRECT_EPILOGUE
+    for flags in (0, 32):                           # default (TMA-staged), DIRECT_EPILOGUE
         calm_lib.load().calm_set_debug_flags(flags)
         try:
             cdt = f32 if form in ("f32", "f32+add") else bf16

@@ -28,20 +28,34 @@ except Exception:
 results = []
 
 
+AB = [int(x, 0) for x in os.environ["KB_AB"].split(",")] if os.environ.get("KB_AB") else None   # interleaved A/B of debug flags
+last_ab = {}
+
+
 def timeit(fn, nsets=3, iters=12):
+    import calm_lib
+    flags = AB or [None]
     for i in range(3):
-        fn(i % nsets)
+        for f in flags:
+            if f is not None:
+                calm_lib.load().calm_set_debug_flags(f)
+            fn(i % nsets)
     torch.cuda.synchronize()
-    ts = []
+    ts = {f: [] for f in flags}
     for i in range(iters):
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        fn(i % nsets)
-        b.record()
-        torch.cuda.synchronize()
-        ts.append(a.elapsed_time(b))
-    ts.sort()
-    return ts[len(ts) // 2]
+        for f in flags:
+            if f is not None:
+                calm_lib.load().calm_set_debug_flags(f)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn(i % nsets)
+            b.record()
+            torch.cuda.synchronize()
+            ts[f].append(a.elapsed_time(b))
+    med = {f: sorted(v)[len(v) // 2] for f, v in ts.items()}
+    last_ab.clear()
+    last_ab.update(med)
+    return med[flags[0]]
 
 
 def report(family, name, ms, flops=None, bytes_=None):
@@ -53,6 +67,9 @@ def report(family, name, ms, flops=None, bytes_=None):
         r["gbs"] = bytes_ / ms / 1e6
         r["frac_hbm_peak"] = r["gbs"] / PEAK_GB
     results.append(r)
+    if AB:
+        print("%-8s %-62s %s" % (family, name, "  ".join("[%#x] %.3f ms (%+.1f%%)" % (f, t, 100 * (t - ms) / ms) for f, t in last_ab.items())), flush=True)
+        return
     print("%-8s %-46s %8.3f ms %s %s" % (family, name, ms, ("%7.1f TF/s (%.2f)" % (r["tflops"], r["frac_tensor_peak"])) if flops else "",
                                           ("%7.0f GB/s (%.2f)" % (r["gbs"], r["frac_hbm_peak"])) if bytes_ else ""), flush=True)
 
