@@ -11,7 +11,9 @@ namespace {
 constexpr int LN_WARPS = 8;
 constexpr int LN_THREADS = LN_WARPS * 32;
 
-template <bool OUT_F32>
+// One warp per row. The row lives in registers (VPL float4 per lane, D <= 128 VPL): one pass over global memory, mean and the
+// centred second moment from the registers. VPL = 0 is the generic three-pass form (re-reads hit the L1).
+template <bool OUT_F32, int VPL>
 __global__ void __launch_bounds__(LN_THREADS)
 ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, void* __restrict__ y, float* __restrict__ mean,
               float* __restrict__ rstd, long long rows, int D, float eps) {
@@ -20,6 +22,42 @@ ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, void* __
   if (row >= rows) return;
   const float* xr = x + row * D;
   const int nv = D >> 2;  // D % 4 == 0
+  if (VPL > 0) {
+    float4 v[VPL > 0 ? VPL : 1];
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) {
+      const int i = lane + 32 * k;
+      v[k] = i < nv ? __ldcs(reinterpret_cast<const float4*>(xr) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+      s += v[k].x + v[k].y + v[k].z + v[k].w;
+    }
+    const float mu = warp_sum(s) / D;
+    float q = 0.f;
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) {
+      if (lane + 32 * k < nv) {
+        const float a = v[k].x - mu, b = v[k].y - mu, c = v[k].z - mu, d = v[k].w - mu;
+        q += a * a + b * b + c * c + d * d;
+      }
+    }
+    const float rs = rsqrtf(warp_sum(q) / D + eps);
+    if (lane == 0) { mean[row] = mu; rstd[row] = rs; }
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) {
+      const int i = lane + 32 * k;
+      if (i < nv) {
+        const float4 g = reinterpret_cast<const float4*>(w)[i];
+        const float a = (v[k].x - mu) * rs * g.x, b = (v[k].y - mu) * rs * g.y, c = (v[k].z - mu) * rs * g.z, d = (v[k].w - mu) * rs * g.w;
+        if (OUT_F32) {
+          reinterpret_cast<float4*>(reinterpret_cast<float*>(y) + row * D)[i] = make_float4(a, b, c, d);
+        } else {
+          uint2 o; o.x = pack_bf16x2(a, b); o.y = pack_bf16x2(c, d);
+          reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(y) + row * D)[i] = o;
+        }
+      }
+    }
+    return;
+  }
   float s = 0.f;
   for (int i = lane; i < nv; i += 32) {
     const float4 v = reinterpret_cast<const float4*>(xr)[i];
@@ -205,8 +243,16 @@ extern "C" int32_t calm_layernorm_fwd(const float* x, const float* w, void* y, i
                                       int64_t rows, int32_t D, float eps, cudaStream_t stream) {
   CALM_CHECK_ARG(rows > 0 && D > 0 && D % 4 == 0, "calm_layernorm_fwd: rows=%lld D=%d (D must be a multiple of 4)", (long long)rows, D);
   const unsigned grid = (unsigned)((rows + LN_WARPS - 1) / LN_WARPS);
-  if (y_dtype == CALM_F32) ln_fwd_kernel<true><<<grid, LN_THREADS, 0, stream>>>(x, w, y, mean, rstd, rows, D, eps);
-  else                     ln_fwd_kernel<false><<<grid, LN_THREADS, 0, stream>>>(x, w, y, mean, rstd, rows, D, eps);
+  const int vpl = (D / 4 + 31) / 32;  // float4 per lane and row
+#define LN_FWD_LAUNCH(F32, VPL) ln_fwd_kernel<F32, VPL><<<grid, LN_THREADS, 0, stream>>>(x, w, y, mean, rstd, rows, D, eps)
+  if (y_dtype == CALM_F32) {
+    if (vpl <= 2) LN_FWD_LAUNCH(true, 2); else if (vpl <= 4) LN_FWD_LAUNCH(true, 4); else if (vpl <= 6) LN_FWD_LAUNCH(true, 6);
+    else if (vpl <= 12) LN_FWD_LAUNCH(true, 12); else LN_FWD_LAUNCH(true, 0);
+  } else {
+    if (vpl <= 2) LN_FWD_LAUNCH(false, 2); else if (vpl <= 4) LN_FWD_LAUNCH(false, 4); else if (vpl <= 6) LN_FWD_LAUNCH(false, 6);
+    else if (vpl <= 12) LN_FWD_LAUNCH(false, 12); else LN_FWD_LAUNCH(false, 0);
+  }
+#undef LN_FWD_LAUNCH
   CALM_CHECK_LAUNCH("calm_layernorm_fwd");
   return CALM_OK;
 }

@@ -7,12 +7,44 @@ namespace {
 
 // out[b, j, i, :] = in[b, i, j, :] on (B, S, S, 3) fp32: the row<->column token swap of Block.forward
 // (Vi_Tools_CNN_less_V2.py:394-395,397-398). 32x32-pixel tiles staged through shared memory, 12 B pixels.
+// Global accesses are 16-byte (a row of 32 pixels = 96 floats = 24 float4; S * 3 floats per image row is a multiple of 4 whenever S is),
+// the transposition itself happens on scalar shared-memory reads (pitch 97: conflict-free both ways).
+template <bool VEC>
 __global__ void __launch_bounds__(256)
 token_transpose_kernel(const float* __restrict__ in, const float* __restrict__ addend, float* __restrict__ out, int S) {
   __shared__ float tile[32][32 * 3 + 1];
   const int b = blockIdx.z, i0 = blockIdx.y * 32, j0 = blockIdx.x * 32;
   const float* src = in + (long long)b * S * S * 3;
   float* dst = out + (long long)b * S * S * 3;
+  const float* add = addend ? addend + (long long)b * S * S * 3 : nullptr;
+  if (VEC) {
+    const int row_f = S * 3;
+    for (int idx = threadIdx.x; idx < 32 * 24; idx += 256) {
+      const int r = idx / 24, q4 = (idx - r * 24) * 4;
+      const int i = i0 + r, col = j0 * 3 + q4;
+      if (i < S && col < row_f) {
+        const float4 v = __ldcs(reinterpret_cast<const float4*>(src + (long long)i * row_f + col));
+        tile[r][q4] = v.x; tile[r][q4 + 1] = v.y; tile[r][q4 + 2] = v.z; tile[r][q4 + 3] = v.w;
+      }
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < 32 * 24; idx += 256) {
+      const int r = idx / 24, q4 = (idx - r * 24) * 4;   // output row j0 + r, output floats [q4, q4 + 4) of the segment starting at pixel i0
+      const int j = j0 + r, col = i0 * 3 + q4;
+      if (j < S && col < row_f) {
+        float v[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { const int e = q4 + k; v[k] = tile[e / 3][r * 3 + e % 3]; }
+        const long long o = (long long)j * row_f + col;
+        if (add) {
+          const float4 a = __ldcs(reinterpret_cast<const float4*>(add + o));
+          v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w;
+        }
+        *reinterpret_cast<float4*>(dst + o) = make_float4(v[0], v[1], v[2], v[3]);
+      }
+    }
+    return;
+  }
   for (int idx = threadIdx.x; idx < 32 * 96; idx += 256) {
     const int r = idx / 96, cc = idx - r * 96;
     const int i = i0 + r, j = j0 + cc / 3;
@@ -25,7 +57,7 @@ token_transpose_kernel(const float* __restrict__ in, const float* __restrict__ a
     if (i < S && j < S) {
       const long long o = ((long long)j * S + i0) * 3 + cc;
       float val = tile[cc / 3][r * 3 + cc % 3];
-      if (addend) val += addend[(long long)b * S * S * 3 + o];
+      if (add) val += add[o];
       dst[o] = val;
     }
   }
@@ -132,7 +164,9 @@ __global__ void seq_mean_bwd_kernel(const bf16* __restrict__ dout, float* __rest
 extern "C" int32_t calm_token_transpose(const float* in, const float* addend, float* out, int32_t B, int32_t S, cudaStream_t stream) {
   CALM_CHECK_ARG(B > 0 && S > 0 && in != out, "calm_token_transpose: B=%d S=%d (out of place only)", B, S);
   dim3 grid((S + 31) / 32, (S + 31) / 32, B);
-  token_transpose_kernel<<<grid, 256, 0, stream>>>(in, addend, out, S);
+  const bool vec = S % 4 == 0 && ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(addend)) & 15) == 0;
+  if (vec) token_transpose_kernel<true><<<grid, 256, 0, stream>>>(in, addend, out, S);
+  else token_transpose_kernel<false><<<grid, 256, 0, stream>>>(in, addend, out, S);
   CALM_CHECK_LAUNCH("calm_token_transpose");
   return CALM_OK;
 }

@@ -3,6 +3,7 @@
 // cos/sin are rebuilt from inv_freq every call (the parameter is learned, :70-72,86-91); backward returns d inv_freq.
 // All math fp32, storage bf16 — the reference promotes to fp32 against the fp32 cos table and SDPA/bmm re-round to bf16.
 #include "common.cuh"
+#include <initializer_list>
 #include "../../include/calm_b200.h"
 
 namespace {
@@ -20,86 +21,147 @@ __global__ void rope_table_kernel(const float* __restrict__ inv_freq, float* __r
   cs[2 * i + 1] = sn;
 }
 
-// One CTA per ROPE_TPC consecutive tokens; a thread resolves its (head, element) once and then walks the CTA's tokens, so the
-// index arithmetic is amortised and ROPE_TPC independent load chains are in flight per thread.
-constexpr int ROPE_TPC = 8;
+// V consecutive bf16 values moved as one 2V-byte access
+template <int V> struct BVec;
+template <> struct BVec<1> { using T = unsigned short; };
+template <> struct BVec<2> { using T = uint32_t; };
+template <> struct BVec<4> { using T = uint2; };
+template <> struct BVec<8> { using T = uint4; };
+template <int V>
+__device__ __forceinline__ void ld_bf16(const bf16* p, float* f) {
+  union { typename BVec<V>::T t; bf16 e[V]; } u;
+  u.t = *reinterpret_cast<const typename BVec<V>::T*>(p);
+#pragma unroll
+  for (int e = 0; e < V; ++e) f[e] = __bfloat162float(u.e[e]);
+}
+template <int V>
+__device__ __forceinline__ void st_bf16(bf16* p, const float* f) {
+  union { typename BVec<V>::T t; bf16 e[V]; } u;
+#pragma unroll
+  for (int e = 0; e < V; ++e) u.e[e] = __float2bfloat16(f[e]);
+  *reinterpret_cast<typename BVec<V>::T*>(p) = u.t;
+}
+
+// grid (S, ROPE_BCH): a CTA owns one sequence position and a slice of the batch. A thread owns V consecutive elements of one
+// head (a copied content chunk, or the rotation pair chunks [j, j+V) and [j+half, j+half+V)), loads its cos/sin once and walks
+// the images with several independent 2V-byte loads in flight. (The first version moved single bf16 elements: 21 % of the HBM
+// rate at 224^2; the index arithmetic and 2-byte accesses were the limit, not the memory system.)
+constexpr int ROPE_UNROLL = 4;
+template <int V>
 __global__ void __launch_bounds__(256)
 rope_fwd_kernel(const bf16* __restrict__ content, long long ld_content, const bf16* __restrict__ ropein, long long ld_rope,
-                bf16* __restrict__ out, long long ld_out, const float* __restrict__ cs, long long tokens, int S, int heads,
-                int dc, int dr) {
+                bf16* __restrict__ out, long long ld_out, const float* __restrict__ cs, int B, int S, int heads, int dc, int dr) {
   const int half = dr >> 1;
-  const int per_head = dc + half;  // work items per (token, head): dc copies + half rotations
-  const int per_tok = heads * per_head;
-  const long long t0 = (long long)blockIdx.x * ROPE_TPC;
-  const int nt = (int)min((long long)ROPE_TPC, tokens - t0);
-  const int p0 = (int)(t0 % S);
-  const float2* cs2 = reinterpret_cast<const float2*>(cs);
-  for (int w = threadIdx.x; w < per_tok; w += blockDim.x) {
-    const int h = w / per_head, i = w - h * per_head;
+  const int per_head = (dc + half) / V;
+  const int pos = blockIdx.x;
+  const int bpc = (B + (int)gridDim.y - 1) / (int)gridDim.y;
+  const int b0 = blockIdx.y * bpc, b1 = min(B, b0 + bpc);
+  const float2* cs2 = reinterpret_cast<const float2*>(cs) + (long long)pos * half;
+  for (int w = threadIdx.x; w < heads * per_head; w += blockDim.x) {
+    const int h = w / per_head, i = (w - h * per_head) * V;
     if (i < dc) {
-#pragma unroll
-      for (int k = 0; k < ROPE_TPC; ++k)
-        if (k < nt) out[(t0 + k) * ld_out + (long long)h * (dc + dr) + i] = content[(t0 + k) * ld_content + (long long)h * dc + i];
+      const bf16* src = content + (long long)h * dc + i;
+      bf16* dst = out + (long long)h * (dc + dr) + i;
+      for (int b = b0; b < b1; ++b) {
+        const long long t = (long long)b * S + pos;
+        *reinterpret_cast<typename BVec<V>::T*>(dst + t * ld_out) = *reinterpret_cast<const typename BVec<V>::T*>(src + t * ld_content);
+      }
     } else {
       const int j = i - dc;
-      float x1[ROPE_TPC], x2[ROPE_TPC];
-      float2 csv[ROPE_TPC];
+      float c[V], sn[V];
 #pragma unroll
-      for (int k = 0; k < ROPE_TPC; ++k) {
-        if (k < nt) {
-          int pos = p0 + k;
-          if (pos >= S) pos -= S;
-          const bf16* r = ropein + (t0 + k) * ld_rope + (long long)h * dr;
-          x1[k] = __bfloat162float(r[j]);
-          x2[k] = __bfloat162float(r[j + half]);
-          csv[k] = cs2[pos * half + j];
+      for (int e = 0; e < V; ++e) { const float2 v = cs2[j + e]; c[e] = v.x; sn[e] = v.y; }
+      const bf16* src = ropein + (long long)h * dr + j;
+      bf16* dst = out + (long long)h * (dc + dr) + dc + j;
+      for (int bb = b0; bb < b1; bb += ROPE_UNROLL) {
+        float x1[ROPE_UNROLL][V], x2[ROPE_UNROLL][V];
+#pragma unroll
+        for (int k = 0; k < ROPE_UNROLL; ++k) {
+          if (bb + k < b1) {
+            const long long t = (long long)(bb + k) * S + pos;
+            ld_bf16<V>(src + t * ld_rope, x1[k]);
+            ld_bf16<V>(src + t * ld_rope + half, x2[k]);
+          }
         }
-      }
 #pragma unroll
-      for (int k = 0; k < ROPE_TPC; ++k) {
-        if (k < nt) {
-          bf16* o = out + (t0 + k) * ld_out + (long long)h * (dc + dr) + dc;
-          o[j] = __float2bfloat16(x1[k] * csv[k].x - x2[k] * csv[k].y);
-          o[j + half] = __float2bfloat16(x2[k] * csv[k].x + x1[k] * csv[k].y);
+        for (int k = 0; k < ROPE_UNROLL; ++k) {
+          if (bb + k < b1) {
+            const long long t = (long long)(bb + k) * S + pos;
+            float y1[V], y2[V];
+#pragma unroll
+            for (int e = 0; e < V; ++e) {
+              y1[e] = x1[k][e] * c[e] - x2[k][e] * sn[e];
+              y2[e] = x2[k][e] * c[e] + x1[k][e] * sn[e];
+            }
+            st_bf16<V>(dst + t * ld_out, y1);
+            st_bf16<V>(dst + t * ld_out + half, y2);
+          }
         }
       }
     }
   }
 }
 
-// grid (S, ROPE_BCH); each CTA owns one position and a slice of the batch, threads own (head, j) pairs.
-__global__ void rope_bwd_kernel(const bf16* __restrict__ dout, long long ld_dout, const bf16* __restrict__ out, long long ld_out,
-                                bf16* __restrict__ dcontent, long long ld_dcontent, bf16* __restrict__ dropein, long long ld_drope,
-                                const float* __restrict__ cs, float* __restrict__ dtheta_part, int B, int S, int heads, int dc, int dr) {
+// same decomposition; d theta[pos, j] partial sums per (head, j) slot of shared memory, then over the heads (fixed order)
+template <int V>
+__global__ void __launch_bounds__(256)
+rope_bwd_kernel(const bf16* __restrict__ dout, long long ld_dout, const bf16* __restrict__ out, long long ld_out,
+                bf16* __restrict__ dcontent, long long ld_dcontent, bf16* __restrict__ dropein, long long ld_drope,
+                const float* __restrict__ cs, float* __restrict__ dtheta_part, int B, int S, int heads, int dc, int dr) {
   extern __shared__ float dth_s[];  // heads * half floats (one slot per (head, j): deterministic reduce)
   const int half = dr >> 1;
+  const int per_head = (dc + half) / V;
   const int pos = blockIdx.x, chunk = blockIdx.y;
   const int bpc = (B + ROPE_BCH - 1) / ROPE_BCH;
   const int b0 = chunk * bpc, b1 = min(B, b0 + bpc);
-  const int per_head = dc + half;
+  const float2* cs2 = reinterpret_cast<const float2*>(cs) + (long long)pos * half;
   for (int w = threadIdx.x; w < heads * per_head; w += blockDim.x) {
-    const int h = w / per_head, i = w - h * per_head;
+    const int h = w / per_head, i = (w - h * per_head) * V;
     if (i < dc) {
+      const bf16* src = dout + (long long)h * (dc + dr) + i;
+      bf16* dst = dcontent + (long long)h * dc + i;
       for (int b = b0; b < b1; ++b) {
         const long long t = (long long)b * S + pos;
-        dcontent[t * ld_dcontent + (long long)h * dc + i] = dout[t * ld_dout + (long long)h * (dc + dr) + i];
+        *reinterpret_cast<typename BVec<V>::T*>(dst + t * ld_dcontent) = *reinterpret_cast<const typename BVec<V>::T*>(src + t * ld_dout);
       }
     } else {
       const int j = i - dc;
-      const float c = cs[2 * (pos * half + j)], s = cs[2 * (pos * half + j) + 1];
-      float acc = 0.f;
-      for (int b = b0; b < b1; ++b) {
-        const long long t = (long long)b * S + pos;
-        const bf16* dyp = dout + t * ld_dout + (long long)h * (dc + dr) + dc;
-        const bf16* yp = out + t * ld_out + (long long)h * (dc + dr) + dc;
-        const float dy1 = __bfloat162float(dyp[j]), dy2 = __bfloat162float(dyp[j + half]);
-        const float y1 = __bfloat162float(yp[j]), y2 = __bfloat162float(yp[j + half]);
-        bf16* dxp = dropein + t * ld_drope + (long long)h * dr;
-        dxp[j] = __float2bfloat16(dy1 * c + dy2 * s);
-        dxp[j + half] = __float2bfloat16(dy2 * c - dy1 * s);
-        acc += y1 * dy2 - y2 * dy1;
+      float c[V], sn[V], acc[V];
+#pragma unroll
+      for (int e = 0; e < V; ++e) { const float2 v = cs2[j + e]; c[e] = v.x; sn[e] = v.y; acc[e] = 0.f; }
+      const bf16* dyp = dout + (long long)h * (dc + dr) + dc + j;
+      const bf16* yp = out + (long long)h * (dc + dr) + dc + j;
+      bf16* dxp = dropein + (long long)h * dr + j;
+      for (int bb = b0; bb < b1; bb += ROPE_UNROLL) {
+        float dy1[ROPE_UNROLL][V], dy2[ROPE_UNROLL][V], y1[ROPE_UNROLL][V], y2[ROPE_UNROLL][V];
+#pragma unroll
+        for (int k = 0; k < ROPE_UNROLL; ++k) {
+          if (bb + k < b1) {
+            const long long t = (long long)(bb + k) * S + pos;
+            ld_bf16<V>(dyp + t * ld_dout, dy1[k]);
+            ld_bf16<V>(dyp + t * ld_dout + half, dy2[k]);
+            ld_bf16<V>(yp + t * ld_out, y1[k]);
+            ld_bf16<V>(yp + t * ld_out + half, y2[k]);
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < ROPE_UNROLL; ++k) {
+          if (bb + k < b1) {
+            const long long t = (long long)(bb + k) * S + pos;
+            float dx1[V], dx2[V];
+#pragma unroll
+            for (int e = 0; e < V; ++e) {
+              dx1[e] = dy1[k][e] * c[e] + dy2[k][e] * sn[e];
+              dx2[e] = dy2[k][e] * c[e] - dy1[k][e] * sn[e];
+              acc[e] += y1[k][e] * dy2[k][e] - y2[k][e] * dy1[k][e];
+            }
+            st_bf16<V>(dxp + t * ld_drope, dx1);
+            st_bf16<V>(dxp + t * ld_drope + half, dx2);
+          }
+        }
       }
-      dth_s[h * half + j] = acc;
+#pragma unroll
+      for (int e = 0; e < V; ++e) dth_s[h * half + j + e] = acc[e];
     }
   }
   __syncthreads();
@@ -108,6 +170,22 @@ __global__ void rope_bwd_kernel(const bf16* __restrict__ dout, long long ld_dout
     for (int h = 0; h < heads; ++h) s += dth_s[h * half + j];
     dtheta_part[((size_t)chunk * S + pos) * half + j] = s;
   }
+}
+
+// widest vector (elements) all the operands of a call allow
+int rope_vec(int dc, int dr, std::initializer_list<long long> lds, std::initializer_list<const void*> ptrs) {
+  for (int v = 8; v > 1; v >>= 1) {
+    bool ok = (dr / 2) % v == 0 && dc % v == 0;
+    for (long long ld : lds) ok = ok && ld % v == 0;
+    for (const void* p : ptrs) ok = ok && (reinterpret_cast<uintptr_t>(p) % (2 * v)) == 0;
+    if (ok) return v;
+  }
+  return 1;
+}
+int rope_threads(int heads, int dc, int dr, int v) {
+  int t = heads * ((dc + dr / 2) / v);
+  t = ((t + 31) / 32) * 32;
+  return t > 256 ? 256 : t;
 }
 
 // d inv_freq[j] = sum_pos pos * sum_chunk dtheta_part[chunk,pos,j]
@@ -139,11 +217,17 @@ extern "C" int32_t calm_rope_fwd(const void* content, int64_t ld_content, const 
                                  int32_t dr, cudaStream_t stream) {
   CALM_CHECK_ARG(tokens > 0 && S > 0 && heads > 0 && dr > 0 && dr % 2 == 0 && dc >= 0, "calm_rope_fwd: bad dims");
   CALM_CHECK_ARG(dc == 0 || content != nullptr, "calm_rope_fwd: content missing");
-  CALM_CHECK_ARG(S >= ROPE_TPC, "calm_rope_fwd: S=%d too short", S);
-  const long long blocks = (tokens + ROPE_TPC - 1) / ROPE_TPC;
-  rope_fwd_kernel<<<(unsigned)blocks, 256, 0, stream>>>(reinterpret_cast<const bf16*>(content), ld_content,
-                                                         reinterpret_cast<const bf16*>(ropein), ld_rope,
-                                                         reinterpret_cast<bf16*>(out), ld_out, cos_sin, tokens, S, heads, dc, dr);
+  CALM_CHECK_ARG(tokens % S == 0, "calm_rope_fwd: tokens=%lld is not a multiple of S=%d", (long long)tokens, S);
+  const int B = (int)(tokens / S);
+  const int v = rope_vec(dc, dr, {(long long)ld_content, (long long)ld_rope, (long long)ld_out}, {content, ropein, out});
+  dim3 grid(S, B < ROPE_BCH ? B : ROPE_BCH);
+  const int threads = rope_threads(heads, dc, dr, v);
+#define CALM_ROPE_FWD(V)                                                                                                          \
+  rope_fwd_kernel<V><<<grid, threads, 0, stream>>>(reinterpret_cast<const bf16*>(content), ld_content,                            \
+                                                   reinterpret_cast<const bf16*>(ropein), ld_rope, reinterpret_cast<bf16*>(out), \
+                                                   ld_out, cos_sin, B, S, heads, dc, dr)
+  if (v == 8) CALM_ROPE_FWD(8); else if (v == 4) CALM_ROPE_FWD(4); else if (v == 2) CALM_ROPE_FWD(2); else CALM_ROPE_FWD(1);
+#undef CALM_ROPE_FWD
   CALM_CHECK_LAUNCH("calm_rope_fwd");
   return CALM_OK;
 }
@@ -157,13 +241,18 @@ extern "C" int32_t calm_rope_bwd(const void* dout, int64_t ld_dout, const void* 
   CALM_CHECK_ARG(tokens > 0 && S > 0 && tokens % S == 0 && heads > 0 && dr > 0 && dr % 2 == 0 && dc >= 0, "calm_rope_bwd: bad dims");
   CALM_CHECK_ARG(dc == 0 || dcontent != nullptr, "calm_rope_bwd: dcontent missing");
   const int B = (int)(tokens / S), half = dr / 2;
-  int threads = heads * (dc + half);
-  threads = ((threads + 31) / 32) * 32;
-  if (threads > 512) threads = 512;
+  const int v = rope_vec(dc, dr, {(long long)ld_dout, (long long)ld_out, (long long)ld_dcontent, (long long)ld_drope},
+                         {dout, out, dcontent, dropein});
+  const int threads = rope_threads(heads, dc, dr, v);
   dim3 grid(S, ROPE_BCH);
-  rope_bwd_kernel<<<grid, threads, (size_t)heads * half * sizeof(float), stream>>>(
-      reinterpret_cast<const bf16*>(dout), ld_dout, reinterpret_cast<const bf16*>(out), ld_out, reinterpret_cast<bf16*>(dcontent),
-      ld_dcontent, reinterpret_cast<bf16*>(dropein), ld_drope, cos_sin, dtheta_part, B, S, heads, dc, dr);
+  const size_t smem = (size_t)heads * half * sizeof(float);
+#define CALM_ROPE_BWD(V)                                                                                                       \
+  rope_bwd_kernel<V><<<grid, threads, smem, stream>>>(reinterpret_cast<const bf16*>(dout), ld_dout,                            \
+                                                      reinterpret_cast<const bf16*>(out), ld_out, reinterpret_cast<bf16*>(dcontent), \
+                                                      ld_dcontent, reinterpret_cast<bf16*>(dropein), ld_drope, cos_sin, dtheta_part, \
+                                                      B, S, heads, dc, dr)
+  if (v == 8) CALM_ROPE_BWD(8); else if (v == 4) CALM_ROPE_BWD(4); else if (v == 2) CALM_ROPE_BWD(2); else CALM_ROPE_BWD(1);
+#undef CALM_ROPE_BWD
   CALM_CHECK_LAUNCH("calm_rope_bwd");
   rope_dfreq_kernel<<<half, 128, 0, stream>>>(dtheta_part, dinv_freq, S, half);
   CALM_CHECK_LAUNCH("calm_rope_bwd(dfreq)");
