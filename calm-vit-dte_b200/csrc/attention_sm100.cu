@@ -145,14 +145,15 @@ struct FwdParams {
 
 __global__ void __launch_bounds__(NTHREADS, 1)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap mQ, const __grid_constant__ CUtensorMap mK, const __grid_constant__ CUtensorMap mV,
-                   const FwdParams p) {
+                   const __grid_constant__ CUtensorMap mB, const FwdParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sK = smem;
   uint8_t* sV = sK + KV_BYTES;
   uint8_t* sQ = sV + KV_BYTES;
   uint8_t* sP = sQ + QT_BYTES;
-  float* xchg = reinterpret_cast<float*>(sP + P_BYTES);          // [2][2][128]: row max / row sum halves of the two column groups
+  uint8_t* sB = sP + P_BYTES;                                    // bias rows of the query tile: [128][256] bf16 in 4 swizzled atoms
+  float* xchg = reinterpret_cast<float*>(sB + P_BYTES);          // [2][2][128]: row max / row sum halves of the two column groups
   uint64_t* bars = reinterpret_cast<uint64_t*>(xchg + 512);      // kv, q, mma, work
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
   const uint32_t bar_kv = smem_u32(&bars[0]), bar_q = smem_u32(&bars[1]), bar_mma = smem_u32(&bars[2]), bar_work = smem_u32(&bars[3]);
@@ -161,7 +162,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap mQ, const __grid_constant
   const int S = c.S, hd = c.hd;
 
   if (threadIdx.x == NWORKERS) {
-    prefetch_tensormap(&mQ); prefetch_tensormap(&mK); prefetch_tensormap(&mV);
+    prefetch_tensormap(&mQ); prefetch_tensormap(&mK); prefetch_tensormap(&mV); prefetch_tensormap(&mB);
     mbar_init(bar_kv, 1); mbar_init(bar_q, 1); mbar_init(bar_mma, 1); mbar_init(bar_work, NWORKERS);
     fence_barrier_init();
   }
@@ -171,60 +172,84 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap mQ, const __grid_constant
   fence_after();
   const uint32_t tmem = *tmem_slot;
   const int ntiles = (S + 127) >> 7;
+  const int natoms = (S + 63) >> 6;
   const int items = c.B * c.heads;
 
   if (warp == CTRL_WARP) {
     // ============================ controller: TMA + MMA issue ============================
-    {
-      // The whole warp walks the control flow (loop counters, descriptors and barrier addresses stay warp-uniform, so they live
-      // in uniform registers); only the instructions with side effects are issued by lane 0. Under `if (lane == 0) { loops }`
-      // ptxas moves every tcgen05.mma operand through an ELECT / R2UR.BROADCAST loop: ~20 instructions per MMA.
-      uint32_t ph_kv = 0, ph_q = 0, ph_work = 0;
-      const uint32_t id_s = idesc_bf16(128, S, 0, 0);      // S = Q K^T : both K-major
-      // descriptors of the (fixed) tiles, built once: per MMA only the low word advances by (byte offset >> 4)
-      const uint64_t dQk = smem_desc(smem_u32(sQ), 16, 1024), dKk = smem_desc(smem_u32(sK), 16, 1024);
-      const uint64_t dPk = smem_desc(smem_u32(sP), 16, 1024), dVmn = smem_desc(smem_u32(sV), 8192, 1024);
-      for (int it = blockIdx.x; it < items; it += gridDim.x) {
-        const int b = it / c.heads, h = it - b * c.heads;
-        const HeadCols hc = head_cols(h, hd);
-        const int hdp = hc.hdp;
-        const uint32_t id_o = idesc_bf16(128, hdp, 0, 1);  // O = P V   : A K-major, B (V: keys x hd) MN-major
-        if (leader) mbar_expect_tx(bar_kv, 2u * S * 128u);
-        if (leader) tma_load_2d(smem_u32(sK), &mK, bar_kv, hc.col0, b * S);
-        if (leader) tma_load_2d(smem_u32(sV), &mV, bar_kv, hc.col0, b * S);
-        for (int i = 0; i < ntiles; ++i) {
-          if (leader) mbar_expect_tx(bar_q, QT_BYTES);
-          if (leader) tma_load_2d(smem_u32(sQ), &mQ, bar_q, hc.col0, b * S + i * 128);
-          if (i == 0) { mbar_wait(bar_kv, ph_kv, c.err_flag, 11); ph_kv ^= 1; }
-          mbar_wait(bar_q, ph_q, c.err_flag, 12); ph_q ^= 1;
-          mbar_wait(bar_work, ph_work, c.err_flag, 13); ph_work ^= 1;   // A: Q tail zeroed
-          fence_after();
-          if (leader) {   // one branch per batch, immediates for the operand steps: ~4 instructions per MMA on the issuing lane
-#pragma unroll
-            for (int ks = 0; ks < 4; ++ks) if (ks < hdp / 16) mma_bf16(tmem, dQk + 2 * ks, dKk + 2 * ks, id_s, ks > 0);
-          }
-          if (leader) commit(bar_mma);
-          mbar_wait(bar_work, ph_work, c.err_flag, 14); ph_work ^= 1;   // B: P written
-          fence_after();
-          if (leader) {
-            const int nk16 = S / 16;
-            for (int a = 0; 4 * a < nk16; ++a) {    // 64 keys = one swizzle atom of P, 8 KB of MN-major V
-              const uint64_t da = dPk + (uint32_t)(a * 1024), db = dVmn + (uint32_t)(a * 512);
-#pragma unroll
-              for (int j = 0; j < 4; ++j)
-                if (4 * a + j < nk16) mma_bf16(tmem + 256, da + 2 * j, db + 128 * j, id_o, (a | j) != 0);
-            }
-          }
-          if (leader) commit(bar_mma);
-          mbar_wait(bar_work, ph_work, c.err_flag, 15); ph_work ^= 1;   // C: epilogue done, Q / P / TMEM free
+    // The whole warp walks the control flow (loop counters, descriptors and barrier addresses stay warp-uniform, so they live in
+    // uniform registers); the instructions with side effects are issued under `if (leader)` (elect.sync).
+    uint32_t ph_kv = 0, ph_q = 0, ph_work = 0;
+    const uint32_t id_s = idesc_bf16(128, S, 0, 0);      // S = Q K^T : both K-major
+    // descriptors of the (fixed) tiles, built once: per MMA only the low word advances by (byte offset >> 4)
+    const uint64_t dQk = smem_desc(smem_u32(sQ), 16, 1024), dKk = smem_desc(smem_u32(sK), 16, 1024);
+    const uint64_t dPk = smem_desc(smem_u32(sP), 16, 1024), dVmn = smem_desc(smem_u32(sV), 8192, 1024);
+    // Q tile + the tile's bias rows (one transaction barrier); K / V with the item's first tile
+    auto issue_q = [&](int it, int i) {
+      const int b = it / c.heads, h = it - b * c.heads;
+      const HeadCols lc = head_cols(h, hd);
+      if (leader) {
+        mbar_expect_tx(bar_q, QT_BYTES + natoms * 16384u);
+        tma_load_2d(smem_u32(sQ), &mQ, bar_q, lc.col0, b * S + i * 128);
+        for (int a = 0; a < natoms; ++a) tma_load_2d(smem_u32(sB) + a * 16384, &mB, bar_q, a * 64, b * S + i * 128);
+      }
+    };
+    auto issue_kv = [&](int it) {
+      const int b = it / c.heads, h = it - b * c.heads;
+      const HeadCols lc = head_cols(h, hd);
+      if (leader) {
+        mbar_expect_tx(bar_kv, 2u * S * 128u);
+        tma_load_2d(smem_u32(sK), &mK, bar_kv, lc.col0, b * S);
+        tma_load_2d(smem_u32(sV), &mV, bar_kv, lc.col0, b * S);
+      }
+    };
+    if ((int)blockIdx.x < items) { issue_kv(blockIdx.x); issue_q(blockIdx.x, 0); }
+    for (int it = blockIdx.x; it < items; it += gridDim.x) {
+      const int h = it % c.heads;
+      const HeadCols hc = head_cols(h, hd);
+      const int hdp = hc.hdp;
+      const uint32_t id_o = idesc_bf16(128, hdp, 0, 1);  // O = P V   : A K-major, B (V: keys x hd) MN-major
+      for (int i = 0; i < ntiles; ++i) {
+        if (i == 0) {
+          mbar_wait(bar_kv, ph_kv, c.err_flag, 11); ph_kv ^= 1;
+          mbar_wait(bar_work, ph_work, c.err_flag, 13); ph_work ^= 1;   // A: the workers zeroed the K column tail of this item
         }
+        mbar_wait(bar_q, ph_q, c.err_flag, 12); ph_q ^= 1;
+        fence_after();
+        if (leader) {   // one branch per batch, immediates for the operand steps: ~4 instructions per MMA on the issuing lane
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) if (ks < hdp / 16) mma_bf16(tmem, dQk + 2 * ks, dKk + 2 * ks, id_s, ks > 0);
+          commit(bar_mma);
+        }
+        mbar_wait(bar_work, ph_work, c.err_flag, 14); ph_work ^= 1;     // B: P written; S, Q and the bias tile consumed
+        fence_after();
+        if (leader) {
+          const int nk16 = S / 16;
+          for (int a = 0; 4 * a < nk16; ++a) {    // 64 keys = one swizzle atom of P, 8 KB of MN-major V
+            const uint64_t da = dPk + (uint32_t)(a * 1024), db = dVmn + (uint32_t)(a * 512);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              if (4 * a + j < nk16) mma_bf16(tmem + 256, da + 2 * j, db + 128 * j, id_o, (a | j) != 0);
+          }
+          commit(bar_mma);
+        }
+        // the next tile's Q and bias load under the P.V MMA and the store epilogue; a new item's K / V once P.V has retired
+        if (i + 1 < ntiles) {
+          issue_q(it, i + 1);
+        } else if (it + (int)gridDim.x < items) {
+          mbar_wait(bar_mma, 1, c.err_flag, 16);   // second completion of the tile (phases alternate S-ready / O-ready)
+          issue_kv(it + gridDim.x);
+          issue_q(it + gridDim.x, 0);
+        }
+        mbar_wait(bar_work, ph_work, c.err_flag, 15); ph_work ^= 1;     // C: epilogue done, P / TMEM free
       }
     }
   } else {
     // ============================ workers: a query row is shared by two threads (alternate 16-column chunks) ============================
     const int grp = warp >> 2;                    // 0: even chunks, 1: odd chunks
-    const int r = (warp & 3) * 32 + lane;         // query row within the tile == TMEM lane
-    const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+    const int quad = warp & 3;
+    const int r = quad * 32 + lane;               // query row within the tile == TMEM lane
+    const uint32_t trow = tmem + ((uint32_t)(quad * 32) << 16);
     uint32_t ph_kv = 0, ph_q = 0, ph_mma = 0;
     for (int it = blockIdx.x; it < items; it += gridDim.x) {
       const int b = it / c.heads, h = it - b * c.heads;
@@ -233,23 +258,16 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap mQ, const __grid_constant
       for (int i = 0; i < ntiles; ++i) {
         const int q = i * 128 + r;
         const bool valid = q < S;
-        if (i == 0) { mbar_wait(bar_kv, ph_kv, c.err_flag, 21); ph_kv ^= 1; }
-        mbar_wait(bar_q, ph_q, c.err_flag, 22); ph_q ^= 1;
-        if (grp == 0) zero_outside(sQ, r, hc, hd);
-        fence_proxy_async();
-        mbar_arrive(bar_work);                                            // A
-        // this thread's half of the row's bias (chunks grp, grp+2, ...) is requested now and lives in registers for both
-        // softmax passes: its latency overlaps the Q.K^T MMA, and the chunk loops below touch only TMEM and registers
-        const bf16* brow = c.bias + ((long long)b * S + (valid ? q : 0)) * S;
-        uint4 bb[16];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int kc = (2 * j + grp) * 16;
-          if (kc < S) {
-            bb[2 * j] = *reinterpret_cast<const uint4*>(brow + kc);
-            bb[2 * j + 1] = *reinterpret_cast<const uint4*>(brow + kc + 8);
-          }
+        if (i == 0) {
+          // the 64-column boxes also bring the neighbouring heads' columns: zeroing them in K (once per item) keeps them out of
+          // S = Q K^T; the tails of V only reach O columns nobody stores
+          mbar_wait(bar_kv, ph_kv, c.err_flag, 21); ph_kv ^= 1;
+          if (grp == 0) zero_outside(sK, r, hc, hd);
+          else if (r + 128 < S) zero_outside(sK, r + 128, hc, hd);
+          fence_proxy_async();
+          mbar_arrive(bar_work);                                          // A
         }
+        mbar_wait(bar_q, ph_q, c.err_flag, 22); ph_q ^= 1;               // the bias tile landed (with Q)
         mbar_wait(bar_mma, ph_mma, c.err_flag, 23); ph_mma ^= 1;
         fence_after();
         // pass 1: maximum of x = s * scale*log2e + bias*log2e over this thread's chunks, then over the row
@@ -260,9 +278,12 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap mQ, const __grid_constant
           if (kc < S) {
             uint32_t sr[16];
             tmem_ld16(trow + kc, sr);
-            tmem_ld_wait();
+            const uint8_t* ba = sB + (kc >> 6) * 16384;
+            const int g = (kc & 63) >> 3;
+            const uint4 b0 = *reinterpret_cast<const uint4*>(ba + swz128(r, g)), b1 = *reinterpret_cast<const uint4*>(ba + swz128(r, g + 1));
             float bf[16];
-            unpack16(bb[2 * j], bb[2 * j + 1], bf);
+            unpack16(b0, b1, bf);
+            tmem_ld_wait();
 #pragma unroll
             for (int jj = 0; jj < 16; ++jj) mx = fmaxf(mx, fmaf(__uint_as_float(sr[jj]), c.scale_log2, bf[jj] * LOG2E));
           }
@@ -278,9 +299,12 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap mQ, const __grid_constant
           if (kc < S) {
             uint32_t sr[16];
             tmem_ld16(trow + kc, sr);
-            tmem_ld_wait();
+            const uint8_t* ba = sB + (kc >> 6) * 16384;
+            const int g = (kc & 63) >> 3;
+            const uint4 b0 = *reinterpret_cast<const uint4*>(ba + swz128(r, g)), b1 = *reinterpret_cast<const uint4*>(ba + swz128(r, g + 1));
             float bf[16], pv[16];
-            unpack16(bb[2 * j], bb[2 * j + 1], bf);
+            unpack16(b0, b1, bf);
+            tmem_ld_wait();
 #pragma unroll
             for (int jj = 0; jj < 16; ++jj) {
               pv[jj] = ex2_approx(fmaf(__uint_as_float(sr[jj]), c.scale_log2, fmaf(bf[jj], LOG2E, -mx)));
@@ -297,14 +321,17 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap mQ, const __grid_constant
         fence_after();
         l += xchg[256 + (grp ^ 1) * 128 + r];
         const float inv = 1.0f / l;
-        bf16* orow = p.o + ((long long)b * S + q) * p.ld_o + (long long)h * hd;
+        // O rows: TMEM -> staging atom 0 of sP (P has been consumed) -> rows written with the lanes along the row
         for (int c0 = grp * 16; c0 < hdp; c0 += 32) {
           uint32_t orr[16];
           tmem_ld16(trow + 256 + c0, orr);
           tmem_ld_wait();
-          if (valid) store_cols16(orow, orr, c0, hc, hd, inv);
+          stage_cols16(sP, r, orr, c0, inv);
         }
         if (valid && grp == 0) p.lse[((long long)b * c.heads + h) * S + q] = (mx + log2f(l)) * LN2;
+        quad_sync(quad);
+        store_rows16(sP, p.o + (long long)h * hd, p.ld_o, quad * 32 + grp * 16, (long long)b * S + i * 128, (long long)b * S + S, hc, hd, lane);
+        quad_sync(quad);   // the partner warp rewrites these staging rows with the next tile's P
         fence_before();
         mbar_arrive(bar_work);                                            // C
       }
@@ -701,7 +728,7 @@ int make_map_ds(CUtensorMap* map, void* base, uint64_t S, uint64_t bh) {
   return CALM_OK;
 }
 
-constexpr size_t FWD_SMEM = 2 * KV_BYTES + QT_BYTES + P_BYTES + 2048 + 256 + 1024;
+constexpr size_t FWD_SMEM = 2 * KV_BYTES + QT_BYTES + 2 * P_BYTES + 2048 + 256 + 1024;
 constexpr size_t BWD_SMEM = 2 * KV_BYTES + 2 * QT_BYTES + 2 * P_BYTES + 256 + 1024;
 
 int fill_common(Common& c, const void* bias, int B, int S, int heads, int hd) {
@@ -730,12 +757,13 @@ int calm_attention_fwd_tc(const void* q, const void* k, const void* v, const voi
   FwdParams p;
   fill_common(p.c, bias, B, S, heads, hd);
   p.o = reinterpret_cast<bf16*>(o); p.ld_o = ld_o; p.lse = lse;
-  CUtensorMap mQ, mK, mV;
+  CUtensorMap mQ, mK, mV, mB;
   int rc;
   const uint64_t rows = (uint64_t)B * S, cols = (uint64_t)heads * hd;
   if ((rc = tc::make_map_2d(&mQ, q, cols, rows, ld_q, 128))) return rc;
   if ((rc = tc::make_map_2d(&mK, k, cols, rows, ld_k, S))) return rc;
   if ((rc = tc::make_map_2d(&mV, v, cols, rows, ld_v, S))) return rc;
+  if ((rc = tc::make_map_2d(&mB, bias, (uint64_t)S, rows, S, 128))) return rc;   // bias viewed as (B*S rows, S columns)
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FWD_SMEM);
@@ -744,7 +772,7 @@ int calm_attention_fwd_tc(const void* q, const void* k, const void* v, const voi
   }
   const int items = B * heads;
   const int grid = items < calm_num_sms() ? items : calm_num_sms();
-  attn_fwd_tc_kernel<<<grid, NTHREADS, FWD_SMEM, stream>>>(mQ, mK, mV, p);
+  attn_fwd_tc_kernel<<<grid, NTHREADS, FWD_SMEM, stream>>>(mQ, mK, mV, mB, p);
   CALM_CHECK_LAUNCH("calm_attention_fwd(tcgen05)");
   return CALM_OK;
 }
