@@ -150,20 +150,22 @@ ln_bwd_kernel(const void* __restrict__ dy, const float* __restrict__ x, const fl
 // the output pass), a lane owns fixed columns so the dw accumulators live in registers too (no shared-memory
 // read-modify-write per element); shared memory is only used to combine the 8 warps of a CTA at the very end.
 template <int VPL, bool DY_F32>
-__global__ void __launch_bounds__(LN_THREADS)
+__global__ void __launch_bounds__(LN_THREADS, VPL <= 3 ? 3 : VPL <= 6 ? 2 : 1)
 ln_bwd_reg_kernel(const void* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ w,
                   const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ dres,
                   float* __restrict__ dx, float* __restrict__ dw_partial, long long rows, int D) {
-  extern __shared__ float acc_s[];  // LN_WARPS * D
+  extern __shared__ float acc_s[];  // LN_WARPS * D, then D floats of w
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nv = D >> 2;
-  float4 wv[VPL], dwa[VPL];
+  // w is read from shared memory at every use: keeping it in registers next to x-hat, dy and the dw accumulators costs
+  // 128-138 registers per thread = one 8-warp CTA per SM, too few loads in flight for the HBM (44 % of peak at D = 672)
+  float* w_s = acc_s + (size_t)LN_WARPS * D;
+  for (int i = threadIdx.x; i < D; i += LN_THREADS) w_s[i] = w[i];
+  __syncthreads();
+  const float4* wv = reinterpret_cast<const float4*>(w_s) + lane;
+  float4 dwa[VPL];
 #pragma unroll
-  for (int i = 0; i < VPL; ++i) {
-    const int idx = lane + 32 * i;
-    wv[i] = idx < nv ? reinterpret_cast<const float4*>(w)[idx] : make_float4(0.f, 0.f, 0.f, 0.f);
-    dwa[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-  }
+  for (int i = 0; i < VPL; ++i) dwa[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   const float invD = 1.0f / D;
   for (long long row = (long long)blockIdx.x * LN_WARPS + warp; row < rows; row += (long long)gridDim.x * LN_WARPS) {
     const float mu = mean[row], rs = rstd[row];
@@ -180,7 +182,8 @@ ln_bwd_reg_kernel(const void* __restrict__ dy, const float* __restrict__ x, cons
         dv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         hv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
       }
-      const float g0 = dv[i].x * wv[i].x, g1 = dv[i].y * wv[i].y, g2 = dv[i].z * wv[i].z, g3 = dv[i].w * wv[i].w;
+      const float4 wq = idx < nv ? wv[32 * i] : make_float4(0.f, 0.f, 0.f, 0.f);
+      const float g0 = dv[i].x * wq.x, g1 = dv[i].y * wq.y, g2 = dv[i].z * wq.z, g3 = dv[i].w * wq.w;
       s1 += g0 + g1 + g2 + g3;
       s2 += g0 * hv[i].x + g1 * hv[i].y + g2 * hv[i].z + g3 * hv[i].w;
       dwa[i].x = fmaf(dv[i].x, hv[i].x, dwa[i].x); dwa[i].y = fmaf(dv[i].y, hv[i].y, dwa[i].y);
@@ -191,11 +194,12 @@ ln_bwd_reg_kernel(const void* __restrict__ dy, const float* __restrict__ x, cons
     for (int i = 0; i < VPL; ++i) {
       const int idx = lane + 32 * i;
       if (idx < nv) {
+        const float4 wq = wv[32 * i];
         float4 o;
-        o.x = rs * (dv[i].x * wv[i].x - c2 - hv[i].x * c1);
-        o.y = rs * (dv[i].y * wv[i].y - c2 - hv[i].y * c1);
-        o.z = rs * (dv[i].z * wv[i].z - c2 - hv[i].z * c1);
-        o.w = rs * (dv[i].w * wv[i].w - c2 - hv[i].w * c1);
+        o.x = rs * (dv[i].x * wq.x - c2 - hv[i].x * c1);
+        o.y = rs * (dv[i].y * wq.y - c2 - hv[i].y * c1);
+        o.z = rs * (dv[i].z * wq.z - c2 - hv[i].z * c1);
+        o.w = rs * (dv[i].w * wq.w - c2 - hv[i].w * c1);
         if (dres) {
           const float4 r = reinterpret_cast<const float4*>(dres + row * D)[idx];
           o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
@@ -269,7 +273,7 @@ extern "C" int32_t calm_layernorm_bwd(const void* dy, int32_t dy_dtype, const fl
                                       float* dw, int64_t rows, int32_t D, cudaStream_t stream) {
   CALM_CHECK_ARG(rows > 0 && D > 0 && D % 4 == 0, "calm_layernorm_bwd: rows=%lld D=%d", (long long)rows, D);
   CALM_CHECK_ARG(nparts == calm_layernorm_bwd_parts(rows, D), "calm_layernorm_bwd: nparts=%d, expected %d", nparts, calm_layernorm_bwd_parts(rows, D));
-  const size_t smem = (size_t)LN_WARPS * D * sizeof(float);
+  const size_t smem = (size_t)(LN_WARPS + 1) * D * sizeof(float);   // per-warp dw rows + w
   const bool f32 = dy_dtype == CALM_F32;
   const int vpl = (D / 4 + 31) / 32;  // float4 per lane and row
 #define LN_BWD_LAUNCH(KERNEL)                                                                                         \
