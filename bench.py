@@ -304,6 +304,10 @@ def main():
     if not args.no_profile:
         calm_lib.profile = []
         n1 = calm_lib.launch_count
+        # The eager launch path (Python + ctypes) is slower than the small kernels: without a head start every interval between
+        # two events would also contain the GPU waiting for the next launch. A ~0.3 s spin kernel lets the host enqueue the whole
+        # step first, so the events bracket back-to-back kernels, as in the captured graph.
+        torch.cuda._sleep(int(6e8))
         tr._step()
         torch.cuda.synchronize()
         launches_per_step = calm_lib.launch_count - n1
