@@ -26,11 +26,7 @@ constexpr int WSM = 644;  // w1b[32][4] | w2p[32][12] | w3t[32][4] | b3[4]
 
 struct CnnW { const float *w1, *b1, *w2, *b2, *w3, *b3; };
 
-__device__ __forceinline__ float gelu_fast(float x) {
-  float g, dg;
-  gelu_pair(x, g, dg);
-  return g;
-}
+__device__ __forceinline__ float gelu_fast(float x) { return gelu_erf(x); }
 
 
 // Sum N register values over the 32 lanes with N - 1 + log2(32/N)... shuffles instead of 5 N: at every butterfly step a lane

@@ -84,7 +84,16 @@ __device__ __forceinline__ void gelu_pair(float x, float& g, float& dg) {
   g = x * phi;
   dg = fmaf(x * 0.3989422804014327f, e, phi);
 }
-__device__ __forceinline__ float gelu_erf(float x) { float g, dg; gelu_pair(x, g, dg); return g; }
+// value only: x Phi(x) = max(x, 0) - |x| Phi(-|x|) saves the sign reconstruction of Phi (12 FP32 + 2 MUFU)
+__device__ __forceinline__ float gelu_erf(float x) {
+  const float t = rcp_approx(fmaf(fabsf(x), 0.3275911f * 0.70710678118654752f, 1.0f));
+  float p = fmaf(0.5f * 1.061405429f, t, 0.5f * -1.453152027f);
+  p = fmaf(p, t, 0.5f * 1.421413741f);
+  p = fmaf(p, t, 0.5f * -0.284496736f);
+  p = fmaf(p, t, 0.5f * 0.254829592f);
+  const float e = ex2_approx(x * x * (-0.5f * 1.4426950408889634f));
+  return fmaf(-fabsf(x), p * t * e, fmaxf(x, 0.0f));
+}
 __device__ __forceinline__ float dgelu_erf(float x) { float g, dg; gelu_pair(x, g, dg); return dg; }
 
 __device__ __forceinline__ float bf16_bits_to_float(uint16_t b) { return __uint_as_float(((uint32_t)b) << 16); }
