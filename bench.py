@@ -29,6 +29,7 @@ for p in (PKG, ROOT):
     if p not in sys.path:
         sys.path.insert(0, p)
 
+os.environ.setdefault("NCCL_DEBUG", "WARN")   # keep NCCL's version banner off stdout: the driver reads one JSON line
 import torch  # noqa: E402
 import torch.distributed as dist  # noqa: E402
 
@@ -237,7 +238,9 @@ def main():
     model = build_model(dev, args.task)
     model.train()
     B = args.batch
-    use_graph = not args.no_graph and world == 1
+    # N > 1: the bucketed NCCL all-reduces (calm_ddp.DataParallel, side stream + events) are captured with the step; the
+    # eager launch path (~90 ms of Python/ctypes per step) would otherwise bound every rank. CALM_BENCH_GRAPH_MULTI=0 forces eager.
+    use_graph = not args.no_graph and (world == 1 or os.environ.get("CALM_BENCH_GRAPH_MULTI", "1") == "1")
     wrapped = model
     if world > 1:
         from calm_ddp import DataParallel
@@ -365,6 +368,13 @@ def main():
             line["cpu_baseline"] = cpu_baseline(model)
         print(json.dumps(line), flush=True)
     if world > 1:
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush(); sys.stderr.flush()
+        if tr.graph is not None:
+            # The step graph holds captured NCCL kernels: tearing the communicator down while the graph object is alive hangs
+            # (observed on 2 x B200: the JSON line was out, the processes never exited). Everything is flushed: leave directly.
+            os._exit(0)
         dist.destroy_process_group()
 
 
