@@ -71,20 +71,6 @@ __device__ __forceinline__ void zero_outside(uint8_t* tile, int r, const HeadCol
   for (int c = hc.shift + hd; c < hc.hdp; c += 4)
     *reinterpret_cast<uint2*>(tile + swz128(r, c >> 3) + ((c & 4) << 1)) = make_uint2(0u, 0u);
 }
-// store TMEM columns [c0, c0+16) (already scaled) of a row whose head occupies TMEM columns [shift, shift+hd)
-__device__ __forceinline__ void store_cols16(bf16* row, const uint32_t* v, int c0, const HeadCols& hc, int hd, float mul) {
-#pragma unroll
-  for (int j = 0; j < 16; j += 4) {
-    const int g = c0 + j - hc.shift;
-    if (g >= 0 && g < hd) {
-      uint2 u;
-      u.x = pack_bf16x2(__uint_as_float(v[j]) * mul, __uint_as_float(v[j + 1]) * mul);
-      u.y = pack_bf16x2(__uint_as_float(v[j + 2]) * mul, __uint_as_float(v[j + 3]) * mul);
-      *reinterpret_cast<uint2*>(row + g) = u;
-    }
-  }
-}
-
 __device__ __forceinline__ void unpack16(const uint4& a, const uint4& b, float* f) {
   float2 t;
   t = unpack_bf16x2(a.x); f[0] = t.x; f[1] = t.y;   t = unpack_bf16x2(a.y); f[2] = t.x; f[3] = t.y;

@@ -43,22 +43,22 @@ token_transpose_kernel(const float* __restrict__ in, const float* __restrict__ a
         *reinterpret_cast<float4*>(dst + o) = make_float4(v[0], v[1], v[2], v[3]);
       }
     }
-    return;
-  }
-  for (int idx = threadIdx.x; idx < 32 * 96; idx += 256) {
-    const int r = idx / 96, cc = idx - r * 96;
-    const int i = i0 + r, j = j0 + cc / 3;
-    if (i < S && j < S) tile[r][cc] = src[((long long)i * S + j0) * 3 + cc];
-  }
-  __syncthreads();
-  for (int idx = threadIdx.x; idx < 32 * 96; idx += 256) {
-    const int r = idx / 96, cc = idx - r * 96;  // output row j0 + r, output pixel column i0 + cc/3
-    const int j = j0 + r, i = i0 + cc / 3;
-    if (i < S && j < S) {
-      const long long o = ((long long)j * S + i0) * 3 + cc;
-      float val = tile[cc / 3][r * 3 + cc % 3];
-      if (add) val += add[o];
-      dst[o] = val;
+  } else {
+    for (int idx = threadIdx.x; idx < 32 * 96; idx += 256) {
+      const int r = idx / 96, cc = idx - r * 96;
+      const int i = i0 + r, j = j0 + cc / 3;
+      if (i < S && j < S) tile[r][cc] = src[((long long)i * S + j0) * 3 + cc];
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < 32 * 96; idx += 256) {
+      const int r = idx / 96, cc = idx - r * 96;  // output row j0 + r, output pixel column i0 + cc/3
+      const int j = j0 + r, i = i0 + cc / 3;
+      if (i < S && j < S) {
+        const long long o = ((long long)j * S + i0) * 3 + cc;
+        float val = tile[cc / 3][r * 3 + cc % 3];
+        if (add) val += add[o];
+        dst[o] = val;
+      }
     }
   }
 }
