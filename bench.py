@@ -326,7 +326,7 @@ def main():
             d["work"] += work
             d["n"] += 1
         tot = sum(d["ms"] for d in fam.values())
-        top_shapes = sorted(shapes.items(), key=lambda t: -t[1]["ms"])[:60]
+        top_shapes = sorted(shapes.items(), key=lambda t: -t[1]["ms"])
         breakdown_shapes = [{"shape": k, "ms": round(v["ms"], 3), "n": v["n"], "tflops": round(v["work"] / (v["ms"] * 1e9), 1)} for k, v in top_shapes]
         breakdown = {k: {"ms": round(v["ms"], 3), "n": v["n"], "share": round(v["ms"] / tot, 4),
                          "rate": (v["work"] / (v["ms"] * 1e-3) if v["work"] and v["ms"] > 0 else None)} for k, v in fam.items()}

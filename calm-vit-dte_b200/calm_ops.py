@@ -321,7 +321,8 @@ class LinearFn(Function):
 
 
 def _mlp_forward(bank, g1, g2, x2, M, lda, b1, b2, addend2, ld_add, out):
-    """hidden = gelu(x W1^T + b1) ; out = hidden W2^T + b2 + addend. Returns (pre, hidden) for backward."""
+    """hidden = gelu(x W1^T + b1) ; out = hidden W2^T + b2 + addend. Returns (pre, hidden) for backward, where `pre` holds
+    gelu'(pre-activation): the GELU epilogue saves the derivative, the dgrad epilogue multiplies by it."""
     H = bank.groups[g1]["rows"]
     pre = torch.empty(M, H, dtype=bf16, device=x2.device)
     hid = torch.empty(M, H, dtype=bf16, device=x2.device)

@@ -292,13 +292,14 @@ __device__ __forceinline__ void epi_finish(const GemmParams& p, const EpiPre& e,
     uint4* up = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.aux) + (long long)b * p.stride_aux + row * p.ld_aux + col0);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const uint4 u = pack8(v + 8 * j);
-      if (8 * j < nvalid && !(p.dbg & 1)) up[j] = u;
-      // GELU is applied to the bf16-rounded pre-activation so that backward (which only sees aux) is consistent.
-      float f[8];
-      unpack8(u, f);
+      // GELU acts on the bf16-rounded pre-activation (the reference's autocast Linear output); what backward needs is the
+      // derivative at that point: it is evaluated here, next to the value (shared rcp / ex2), and saved instead of the
+      // pre-activation, so the dgrad epilogue is a plain multiply
+      float f[8], dg[8];
+      unpack8(pack8(v + 8 * j), f);
 #pragma unroll
-      for (int k = 0; k < 8; ++k) v[8 * j + k] = gelu_erf(f[k]);
+      for (int k = 0; k < 8; ++k) gelu_pair(f[k], v[8 * j + k], dg[k]);
+      if (8 * j < nvalid && !(p.dbg & 1)) up[j] = pack8(dg);
     }
   } else if (p.epi == CALM_EPI_DGELU) {
 #pragma unroll
@@ -306,7 +307,7 @@ __device__ __forceinline__ void epi_finish(const GemmParams& p, const EpiPre& e,
       float f[8];
       unpack8(e.aux[j], f);
 #pragma unroll
-      for (int k = 0; k < 8; ++k) v[8 * j + k] *= dgelu_erf(f[k]);
+      for (int k = 0; k < 8; ++k) v[8 * j + k] *= f[k];
     }
   }
   if (p.dbg & 1) { float acc = 0.f;
@@ -380,7 +381,7 @@ __device__ __forceinline__ void epilogue_tma(const GemmParams& p, const CUtensor
   const bool gelu = p.epi == CALM_EPI_GELU, dgelu = p.epi == CALM_EPI_DGELU;
   const bool has_load = p.addend != nullptr || dgelu;
   const CUtensorMap* tmL = dgelu ? tmAux : tmAdd;
-  const int per_unit = gelu ? 2 : 1;                   // GELU stores the pre-activation and the activation
+  const int per_unit = gelu ? 2 : 1;                   // GELU stores the activation and its derivative
   const uint32_t NU = (uint32_t)(p.epi_slots / per_unit);
   uint8_t* stage_ptr = smem + 1024 + warp * p.epi_slots * EPI_SLOT_BYTES;
   uint64_t* lbar = bars + EPI_BAR_OFFSET + warp * EPI_MAX_SLOTS;
@@ -482,19 +483,18 @@ __device__ __forceinline__ void epilogue_tma(const GemmParams& p, const CUtensor
               unpack8(*gp, f);
               if (dgelu) {
 #pragma unroll
-                for (int k = 0; k < 8; ++k) vj[k] *= dgelu_erf(f[k]);
+                for (int k = 0; k < 8; ++k) vj[k] *= f[k];   // aux = gelu'(pre-activation), saved by the forward epilogue
               } else {
 #pragma unroll
                 for (int k = 0; k < 8; ++k) vj[k] += f[k];
               }
               *gp = pack8(vj);
             } else if (gelu) {
-              const uint4 pre = pack8(vj);   // GELU acts on the bf16-rounded pre-activation, the only thing backward sees
-              *gp = pre;
-              float f[8];
-              unpack8(pre, f);
+              float f[8], dg[8];
+              unpack8(pack8(vj), f);         // GELU acts on the bf16-rounded pre-activation (the reference's bf16 Linear output)
 #pragma unroll
-              for (int k = 0; k < 8; ++k) f[k] = gelu_erf(f[k]);
+              for (int k = 0; k < 8; ++k) gelu_pair(f[k], f[k], dg[k]);
+              *gp = pack8(dg);               // aux <- gelu'(pre): the dgrad epilogue multiplies by it
               *reinterpret_cast<uint4*>(slot + EPI_SLOT_BYTES + ((j ^ sw) << 4)) = pack8(f);
             } else {
               *gp = pack8(vj);
@@ -819,11 +819,12 @@ __global__ void gemm_simt_debug_kernel(const bf16* A, const bf16* B, GemmParams 
     v += p.addend_f32 ? reinterpret_cast<const float*>(p.addend)[off] : __bfloat162float(reinterpret_cast<const bf16*>(p.addend)[off]);
   }
   if (p.epi == CALM_EPI_GELU) {
-    bf16 u = __float2bfloat16(v);
-    reinterpret_cast<bf16*>(p.aux)[(long long)bidx * p.stride_aux + (long long)m * p.ld_aux + n] = u;
-    v = gelu_erf(__bfloat162float(u));
+    float g, dg;
+    gelu_pair(__bfloat162float(__float2bfloat16(v)), g, dg);
+    reinterpret_cast<bf16*>(p.aux)[(long long)bidx * p.stride_aux + (long long)m * p.ld_aux + n] = __float2bfloat16(dg);
+    v = g;
   } else if (p.epi == CALM_EPI_DGELU) {
-    v *= dgelu_erf(__bfloat162float(reinterpret_cast<const bf16*>(p.aux)[(long long)bidx * p.stride_aux + (long long)m * p.ld_aux + n]));
+    v *= __bfloat162float(reinterpret_cast<const bf16*>(p.aux)[(long long)bidx * p.stride_aux + (long long)m * p.ld_aux + n]);
   }
   if (p.c_f32)
     reinterpret_cast<float*>(p.c)[(long long)split * p.stride_split + (long long)bidx * p.stride_c + (long long)m * p.ldc + n] = v;

@@ -49,8 +49,8 @@ int32_t calm_set_error_flag_buffer(int32_t* device_int); /* optional: receives t
  *   stride_* = batch strides in elements (0 = operand shared by all batch entries)
  *   reduce_batch=1: C = sum over b (the contraction runs over batch x K)
  *   splits>1: fp32 partial sums, partial s at c + s*stride_split (epilogue must be NONE; caller reduces)
- *   epilogue GELU : aux <- bf16(pre-activation), C <- gelu_erf(aux)      (mlp.0 / linear_mask.0 forward)
- *   epilogue DGELU: C <- acc * gelu_erf'(aux)                            (their dgrad)
+ *   epilogue GELU : u = bf16(pre-activation); C <- gelu_erf(u), aux <- bf16(gelu_erf'(u))   (mlp.0 / linear_mask.0 forward)
+ *   epilogue DGELU: C <- acc * aux      (their dgrad: aux is the derivative the forward epilogue saved)
  * ------------------------------------------------------------------------------------------------------------------ */
 typedef struct {
   const void* a; const void* b; void* c;

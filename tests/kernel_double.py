@@ -44,13 +44,13 @@ def gemm(a, b, c, M, N, K, *, lda, ldb, ldc, batch=1, stride_a=0, stride_b=0, st
         acc = acc + bias.float()
     if addend is not None:
         acc = acc + _view(addend, (batch, M, N), (stride_addend, ld_addend, 1)).float()
-    if epilogue == EPI_GELU:
-        pre = acc.to(bf16)
-        _view(aux, (batch, M, N), (stride_aux, ld_aux, 1)).copy_(pre)
-        acc = F.gelu(pre.float())
+    if epilogue == EPI_GELU:   # aux <- gelu'(pre), C <- gelu(pre), pre rounded like the Linear output
+        x = acc.to(bf16).float()
+        dg = 0.5 * (1 + torch.erf(x / math.sqrt(2))) + x * torch.exp(-0.5 * x * x) / math.sqrt(2 * math.pi)
+        _view(aux, (batch, M, N), (stride_aux, ld_aux, 1)).copy_(dg.to(aux.dtype))
+        acc = F.gelu(x)
     elif epilogue == EPI_DGELU:
-        x = _view(aux, (batch, M, N), (stride_aux, ld_aux, 1)).float()
-        acc = acc * (0.5 * (1 + torch.erf(x / math.sqrt(2))) + x * torch.exp(-0.5 * x * x) / math.sqrt(2 * math.pi))
+        acc = acc * _view(aux, (batch, M, N), (stride_aux, ld_aux, 1)).float()
     _view(c, (batch, M, N), (stride_c, ldc, 1)).copy_(acc.to(c.dtype))
     return c
 

@@ -63,20 +63,21 @@ def test_gemm_epilogues(K):
     addb = add.to(bf16)
     K.gemm(a, b, c, M, N, Kd, lda=Kd, ldb=Kd, ldc=N, addend=addb, ld_addend=N)
     assert rel(c, a.float() @ b.float().t() + addb.float()) < 1e-5
-    # GELU: aux <- bf16(pre), C <- gelu(aux)
+    # GELU: u = bf16(pre); C <- gelu(u), aux <- bf16(gelu'(u))   (the derivative is what the dgrad epilogue consumes)
     aux = torch.empty(M, N, dtype=bf16, device=dev())
     cg = torch.empty(M, N, dtype=bf16, device=dev())
     K.gemm(a, b, cg, M, N, Kd, lda=Kd, ldb=Kd, ldc=N, bias=bias, epilogue=K.EPI_GELU, aux=aux, ld_aux=N)
-    pre = (a.float() @ b.float().t() + bias)
-    assert rel(aux, pre) < 4e-3
-    assert rel(cg, torch.nn.functional.gelu(aux.float())) < 4e-3
-    # dGELU: C <- acc * gelu'(aux)
+    u = (a.float() @ b.float().t() + bias).to(bf16).float().requires_grad_(True)
+    act = torch.nn.functional.gelu(u)
+    act.sum().backward()
+    assert rel(cg, act.detach()) < 4e-3
+    assert rel(aux, u.grad) < 4e-3
+    # dGELU: C <- acc * aux
     g = rnd(M, Kd, seed=7)
     cd = torch.empty(M, N, dtype=bf16, device=dev())
     K.gemm(g, b, cd, M, N, Kd, lda=Kd, ldb=Kd, ldc=N, epilogue=K.EPI_DGELU, aux=aux, ld_aux=N)
-    x = aux.float().requires_grad_(True)
-    torch.nn.functional.gelu(x).backward(g.float() @ b.float().t())
-    assert rel(cd, x.grad) < 5e-3
+    assert rel(cd, (g.float() @ b.float().t()) * aux.float()) < 5e-3
+    assert rel(cd, (g.float() @ b.float().t()) * u.grad) < 8e-3   # end to end against the exact derivative
 
 
 def test_gemm_dgrad_b_mn(K):
@@ -178,9 +179,11 @@ def test_gemm_pair_mode(K, M, N, Kd, a_mn, b_mn):
             outs.append((c, aux))
         finally:
             calm_lib.load().calm_set_debug_flags(0)
-    pre = a.float() @ b.float().t() + bias
-    assert rel(outs[0][1], pre) < 4e-3
-    assert rel(outs[0][0], torch.nn.functional.gelu(outs[0][1].float())) < 4e-3
+    u = (a.float() @ b.float().t() + bias).to(bf16).float().requires_grad_(True)
+    act = torch.nn.functional.gelu(u)
+    act.sum().backward()
+    assert rel(outs[0][1], u.grad) < 4e-3
+    assert rel(outs[0][0], act.detach()) < 4e-3
     assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
     assert torch.equal(outs[2][0], outs[1][0]) and torch.equal(outs[2][1], outs[1][1])
 
