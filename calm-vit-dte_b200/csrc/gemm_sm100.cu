@@ -537,7 +537,7 @@ __device__ __forceinline__ void epilogue_tma(const GemmParams& p, const CUtensor
     if (!released) release_acc();
     if (++acc == 2) { acc = 0; acc_phase ^= 1; }
   }
-  if (lane == 0) bulk_wait_all();   // staging memory must outlive the last store's read
+  if (lane == 0) bulk_wait_read<0>();   // staging memory must outlive the last store's READ (the writes are complete at grid end)
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -575,17 +575,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
   }
-  if (warp == WARP_MMA && lane == 0) {
-    for (int i = 0; i < MAX_STAGES; ++i) {
-      mbar_init(smem_u32(&bars[i]), 1);
-      mbar_init(smem_u32(&bars[STAGES + i]), PAIR == 1 ? 2 : 1);
+  if (warp == WARP_MMA) {
+    // ~60 barriers: one per lane (a single thread initialising them all costs ~1 us of every launch's prologue)
+    for (int i = lane; i < 2 * MAX_STAGES + 4; i += 32) {
+      uint32_t count = 1;
+      if (i >= STAGES && i < 2 * STAGES) count = PAIR == 1 ? 2 : 1;                                  // empty: both consumers of a multicast pair
+      else if (i >= 2 * STAGES + 2) count = PAIR == 2 ? 2 * NUM_EPI_WARPS : NUM_EPI_WARPS;            // tmem_empty: one arrive per epilogue warp
+      mbar_init(smem_u32(&bars[i]), count);
     }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(smem_u32(&bars[2 * STAGES + i]), 1);
-      // one arrive per epilogue warp; with cta_group::2 the leader collects both CTAs' epilogue warps
-      mbar_init(smem_u32(&bars[2 * STAGES + 2 + i]), PAIR == 2 ? 2 * NUM_EPI_WARPS : NUM_EPI_WARPS);
-    }
-    for (int i = 0; i < NUM_EPI_WARPS * EPI_MAX_SLOTS; ++i) mbar_init(smem_u32(&bars[EPI_BAR_OFFSET + i]), 1);
+    for (int i = lane; i < NUM_EPI_WARPS * EPI_MAX_SLOTS; i += 32) mbar_init(smem_u32(&bars[EPI_BAR_OFFSET + i]), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == WARP_ALLOC) {
