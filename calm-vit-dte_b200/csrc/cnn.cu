@@ -261,6 +261,7 @@ cnn_bwd_body(const float* __restrict__ x, const float* __restrict__ dy, float* _
         cmask |= (valid ? 1u : 0u) << j | (owned ? 16u : 0u) << j;
       }
     }
+    asm volatile("" : "+r"(cmask));   // opaque from here on: ptxas otherwise re-derives the eight comparisons inside the channel loop
 
     for (int chunk = 0; chunk < CH / BCC; ++chunk) {
       float* g1b = g1s + (chunk & 1) * BCC * g1_plane;
