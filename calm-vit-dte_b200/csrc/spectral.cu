@@ -163,10 +163,19 @@ sn_bwd_a_kernel(const calm_sn_layer* __restrict__ table, const calm_sn_item* __r
     float rowdot = 0.f;
     if ((cols & 3) == 0) {
       for (int c4 = lane; c4 < (cols >> 2); c4 += 32) {
+        // split-K partials: up to 8 planes requested before the first add (a runtime-length loop of dependent
+        // load -> add steps ran one memory latency per split: 32 of them on the small layers); summed in split order
         float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int s = 0; s < L.g_splits; ++s) {
-          const float4 p = reinterpret_cast<const float4*>(L.g_eff + s * plane + rowoff)[c4];
-          g.x += p.x; g.y += p.y; g.z += p.z; g.w += p.w;
+        const float4* gp = reinterpret_cast<const float4*>(L.g_eff + rowoff) + c4;
+        const size_t plane4 = plane >> 2;
+        for (int s0 = 0; s0 < L.g_splits; s0 += 8) {
+          float4 p[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            if (s0 + k < L.g_splits) p[k] = __ldcs(gp + (size_t)(s0 + k) * plane4);
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            if (s0 + k < L.g_splits) { g.x += p[k].x; g.y += p[k].y; g.z += p[k].z; g.w += p[k].w; }
         }
         const float4 w = reinterpret_cast<const float4*>(L.w + rowoff)[c4];
         rowdot += g.x * w.x + g.y * w.y + g.z * w.z + g.w * w.w;
