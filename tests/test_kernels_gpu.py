@@ -270,7 +270,8 @@ def _rope_ref(x, inv_freq):
     return x * emb.cos() + torch.cat((-x2, x1), -1) * emb.sin()
 
 
-@pytest.mark.parametrize("B,S,h,dc,dr", [(3, 80, 12, 0, 20), (2, 176, 12, 22, 22), (2, 224, 12, 0, 56)])
+@pytest.mark.parametrize("B,S,h,dc,dr", [(3, 80, 12, 0, 20), (2, 176, 12, 22, 22), (2, 224, 12, 0, 56), (9, 176, 12, 0, 44),
+                                         (5, 224, 12, 28, 28), (2, 128, 12, 0, 32), (3, 48, 3, 2, 6)])
 def test_rope(K, B, S, h, dc, dr):
     tokens = B * S
     inv = (1.0 / (10000.0 ** (torch.arange(0, dr, 2).float() / dr))).to(dev())
