@@ -96,6 +96,38 @@ def synth_batch(B, task, seed):
     return x, y
 
 
+def bracket_overhead_us(n=64):
+    """What a (start event, launch, end event) bracket adds to a kernel compared with the same launch inside a CUDA graph,
+    measured on a trivial kernel (calm_cast_bf16 of 8 elements): median bracketed time - per-launch time of a graph of n launches."""
+    import calm_kernels as K
+    x = torch.zeros(8, device="cuda")
+    K.cast_bf16(x)
+    torch.cuda.synchronize()
+    torch.cuda._sleep(int(2e8))                       # same head start as the profiling step: the GPU never waits for the host
+    ev = []
+    for _ in range(n):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); K.cast_bf16(x); b.record()
+        ev.append((a, b))
+    torch.cuda.synchronize()
+    t = sorted(a.elapsed_time(b) for a, b in ev)
+    bracketed = t[len(t) // 2] * 1e3
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        K.cast_bf16(x)
+    torch.cuda.current_stream().wait_stream(side)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for _ in range(n):
+            K.cast_bf16(x)
+    g.replay(); torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record(); g.replay(); b.record(); torch.cuda.synchronize()
+    in_graph = a.elapsed_time(b) / n * 1e3
+    return max(0.0, bracketed - in_graph), bracketed, in_graph
+
+
 class Trainer:
     """The per-rank training step of the reference loop, optionally captured into one CUDA graph (static shapes)."""
 
@@ -337,7 +369,20 @@ def main():
             peak = (pk or {}).get("bf16_tflops_sustained", 1400.0)
             roof = {"bound": "tensor", "kernel": "gemm_tcgen05_kernel (calm_gemm, %d launches/step, %.1f%% of kernel time)" % (g["n"], 100 * g["ms"] / tot),
                     "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
-                    "peak_source": "measured (MEASURED_PEAKS.json bf16_tflops_sustained)" if pk else "fallback (B200_PROFILING.md)"}
+                    "peak_source": "measured (MEASURED_PEAKS.json bf16_tflops_sustained)" if pk else "fallback (B200_PROFILING.md)",
+                    "timing": "CUDA events around every launch of one eager step"}
+            # Events around a 10 us kernel add several us of their own (and an eager launch is not a graph node): the bracket
+            # overhead is measured on a trivial kernel and removed once per launch; both numbers are reported.
+            try:
+                ov, t_b, t_g = bracket_overhead_us()
+                ms_corr = max(g["ms"] - g["n"] * ov * 1e-3, 0.25 * g["ms"])
+                ach2 = g["work"] / (ms_corr * 1e-3) / 1e12
+                roof.update({"achieved_event_bracketed": ach, "achieved": ach2, "frac": ach2 / peak,
+                             "bracket_overhead_us": round(ov, 2), "family_ms_per_step": round(ms_corr, 3),
+                             "timing": "CUDA events around every launch of one eager step, minus the bracket overhead measured on a "
+                                       "trivial kernel (bracketed %.1f us vs %.1f us per launch inside a CUDA graph)" % (t_b, t_g)})
+            except Exception as e:
+                roof["calibration_error"] = repr(e)[:120]
     line = {
         "metric": "train images/sec at 224^2", "value": value, "unit": "images/sec", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
