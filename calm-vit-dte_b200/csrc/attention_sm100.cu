@@ -39,6 +39,12 @@ using namespace tc;
 constexpr int NWORKERS = 256;            // 8 worker warps: warps w and w+4 share TMEM lane quadrant w%4 and split the columns
 constexpr int NTHREADS = NWORKERS + 32;  // + controller warp (warp 8)
 constexpr int CTRL_WARP = NWORKERS / 32;
+// forward: 16 worker warps (4 per TMEM lane quadrant, each takes every 4th 16-column chunk): the two softmax passes are a serial
+// chain per thread, twice as many threads halve it
+constexpr int FWD_WORKERS = 512;
+constexpr int FWD_GROUPS = FWD_WORKERS / 128;
+constexpr int FWD_THREADS = FWD_WORKERS + 32;
+constexpr int FWD_CTRL_WARP = FWD_WORKERS / 32;
 constexpr float LOG2E = 1.4426950408889634f;
 constexpr float LN2 = 0.6931471805599453f;
 constexpr int KV_BYTES = 256 * 128;     // up to 256 keys x 64 columns bf16
@@ -104,13 +110,15 @@ __device__ __forceinline__ void stage_cols16(uint8_t* atom, int r, const uint32_
   *reinterpret_cast<uint4*>(atom + swz128(r, (c0 >> 3) + 1)) = pack8f(f + 8);
 }
 __device__ __forceinline__ void quad_sync(int quad) { asm volatile("bar.sync %0, 64;" ::"r"(2 + quad) : "memory"); }
+__device__ __forceinline__ void quad_sync128(int quad) { asm volatile("bar.sync %0, 128;" ::"r"(2 + quad) : "memory"); }
 // rows [row_begin, row_begin + 16) of the tile (tile-relative), global row g = g0 + row (valid while g < g_end)
+template <int NROWS = 16>
 __device__ __forceinline__ void store_rows16(const uint8_t* atom, bf16* base, long long ld, int row_begin, long long g0, long long g_end,
                                              const HeadCols& hc, int hd, int lane) {
   const int unit = lane & 15, sub = lane >> 4;    // 8-byte unit along the row, row of the pair
   const int c = hc.shift + 4 * unit;              // tile column of the unit
 #pragma unroll
-  for (int k = 0; k < 8; ++k) {
+  for (int k = 0; k < NROWS / 2; ++k) {
     const int row = row_begin + 2 * k + sub;
     const long long g = g0 + row;
     if (4 * unit < hd && g < g_end) {
@@ -129,7 +137,7 @@ struct FwdParams {
   float* lse;  // (B, heads, S), natural log
 };
 
-__global__ void __launch_bounds__(NTHREADS, 1)
+__global__ void __launch_bounds__(FWD_THREADS, 1)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap mQ, const __grid_constant__ CUtensorMap mK, const __grid_constant__ CUtensorMap mV,
                    const __grid_constant__ CUtensorMap mB, const FwdParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -139,20 +147,20 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap mQ, const __grid_constant
   uint8_t* sQ = sV + KV_BYTES;
   uint8_t* sP = sQ + QT_BYTES;
   uint8_t* sB = sP + P_BYTES;                                    // bias rows of the query tile: [128][256] bf16 in 4 swizzled atoms
-  float* xchg = reinterpret_cast<float*>(sB + P_BYTES);          // [2][2][128]: row max / row sum halves of the two column groups
-  uint64_t* bars = reinterpret_cast<uint64_t*>(xchg + 512);      // kv, q, mma, work
+  float* xchg = reinterpret_cast<float*>(sB + P_BYTES);          // [2][FWD_GROUPS][128]: row max / row sum parts of the column groups
+  uint64_t* bars = reinterpret_cast<uint64_t*>(xchg + 2 * FWD_GROUPS * 128);      // kv, q, mma, work
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
   const uint32_t bar_kv = smem_u32(&bars[0]), bar_q = smem_u32(&bars[1]), bar_mma = smem_u32(&bars[2]), bar_work = smem_u32(&bars[3]);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const Common& c = p.c;
   const int S = c.S, hd = c.hd;
 
-  if (threadIdx.x == NWORKERS) {
+  if (threadIdx.x == FWD_WORKERS) {
     prefetch_tensormap(&mQ); prefetch_tensormap(&mK); prefetch_tensormap(&mV); prefetch_tensormap(&mB);
-    mbar_init(bar_kv, 1); mbar_init(bar_q, 1); mbar_init(bar_mma, 1); mbar_init(bar_work, NWORKERS);
+    mbar_init(bar_kv, 1); mbar_init(bar_q, 1); mbar_init(bar_mma, 1); mbar_init(bar_work, FWD_WORKERS);
     fence_barrier_init();
   }
-  if (warp == CTRL_WARP) tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
+  if (warp == FWD_CTRL_WARP) tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
   fence_before();
   __syncthreads();
   fence_after();
@@ -161,7 +169,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap mQ, const __grid_constant
   const int natoms = (S + 63) >> 6;
   const int items = c.B * c.heads;
 
-  if (warp == CTRL_WARP) {
+  if (warp == FWD_CTRL_WARP) {
     // ============================ controller: TMA + MMA issue ============================
     // The whole warp walks the control flow (loop counters, descriptors and barrier addresses stay warp-uniform, so they live in
     // uniform registers); the instructions with side effects are issued under `if (leader)` (elect.sync).
@@ -231,8 +239,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap mQ, const __grid_constant
       }
     }
   } else {
-    // ============================ workers: a query row is shared by two threads (alternate 16-column chunks) ============================
-    const int grp = warp >> 2;                    // 0: even chunks, 1: odd chunks
+    // ============================ workers: a query row is shared by FWD_GROUPS threads (every 4th 16-column chunk each) ============================
+    const int grp = warp >> 2;                    // 0..3: chunks grp, grp + 4, ...
     const int quad = warp & 3;
     const int r = quad * 32 + lane;               // query row within the tile == TMEM lane
     const uint32_t trow = tmem + ((uint32_t)(quad * 32) << 16);
@@ -249,7 +257,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap mQ, const __grid_constant
           // S = Q K^T; the tails of V only reach O columns nobody stores
           mbar_wait(bar_kv, ph_kv, c.err_flag, 21); ph_kv ^= 1;
           if (grp == 0) zero_outside(sK, r, hc, hd);
-          else if (r + 128 < S) zero_outside(sK, r + 128, hc, hd);
+          else if (grp == 1 && r + 128 < S) zero_outside(sK, r + 128, hc, hd);
           fence_proxy_async();
           mbar_arrive(bar_work);                                          // A
         }
@@ -259,8 +267,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap mQ, const __grid_constant
         // pass 1: maximum of x = s * scale*log2e + bias*log2e over this thread's chunks, then over the row
         float mx = -INFINITY;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int kc = (2 * j + grp) * 16;
+        for (int j = 0; j < 4; ++j) {
+          const int kc = (FWD_GROUPS * j + grp) * 16;
           if (kc < S) {
             uint32_t sr[16];
             tmem_ld16(trow + kc, sr);
@@ -275,13 +283,14 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap mQ, const __grid_constant
           }
         }
         xchg[grp * 128 + r] = mx;
-        asm volatile("bar.sync 1, %0;" ::"n"(NWORKERS) : "memory");
-        mx = fmaxf(mx, xchg[(grp ^ 1) * 128 + r]);
+        asm volatile("bar.sync 1, %0;" ::"n"(FWD_WORKERS) : "memory");
+#pragma unroll
+        for (int gq = 0; gq < FWD_GROUPS; ++gq) mx = fmaxf(mx, xchg[gq * 128 + r]);
         // pass 2: P = exp2(x - max), partial row sum, bf16 P into the swizzled A-operand tile
         float l = 0.f;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int kc = (2 * j + grp) * 16;
+        for (int j = 0; j < 4; ++j) {
+          const int kc = (FWD_GROUPS * j + grp) * 16;
           if (kc < S) {
             uint32_t sr[16];
             tmem_ld16(trow + kc, sr);
@@ -299,25 +308,27 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap mQ, const __grid_constant
             store_row16(sP, r, kc, pv);
           }
         }
-        xchg[256 + grp * 128 + r] = l;
+        xchg[(FWD_GROUPS + grp) * 128 + r] = l;
         fence_proxy_async();
         fence_before();
         mbar_arrive(bar_work);                                            // B
         mbar_wait(bar_mma, ph_mma, c.err_flag, 24); ph_mma ^= 1;           // (all 256 workers arrived at B before the MMA ran)
         fence_after();
-        l += xchg[256 + (grp ^ 1) * 128 + r];
+        l = 0.f;
+#pragma unroll
+        for (int gq = 0; gq < FWD_GROUPS; ++gq) l += xchg[(FWD_GROUPS + gq) * 128 + r];   // same order in every thread of the row
         const float inv = 1.0f / l;
         // O rows: TMEM -> staging atom 0 of sP (P has been consumed) -> rows written with the lanes along the row
-        for (int c0 = grp * 16; c0 < hdp; c0 += 32) {
+        for (int c0 = grp * 16; c0 < hdp; c0 += 16 * FWD_GROUPS) {
           uint32_t orr[16];
           tmem_ld16(trow + 256 + c0, orr);
           tmem_ld_wait();
           stage_cols16(sP, r, orr, c0, inv);
         }
         if (valid && grp == 0) p.lse[((long long)b * c.heads + h) * S + q] = (mx + log2f(l)) * LN2;
-        quad_sync(quad);
-        store_rows16(sP, p.o + (long long)h * hd, p.ld_o, quad * 32 + grp * 16, (long long)b * S + i * 128, (long long)b * S + S, hc, hd, lane);
-        quad_sync(quad);   // the partner warp rewrites these staging rows with the next tile's P
+        quad_sync128(quad);
+        store_rows16<8>(sP, p.o + (long long)h * hd, p.ld_o, quad * 32 + grp * 8, (long long)b * S + i * 128, (long long)b * S + S, hc, hd, lane);
+        quad_sync128(quad);   // the partner warps rewrite these staging rows with the next tile's P
         fence_before();
         mbar_arrive(bar_work);                                            // C
       }
@@ -325,7 +336,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap mQ, const __grid_constant
   }
   fence_before();
   __syncthreads();
-  if (warp == CTRL_WARP) {
+  if (warp == FWD_CTRL_WARP) {
     fence_after();
     tmem_dealloc(tmem, TMEM_COLS);
   }
@@ -714,7 +725,7 @@ int make_map_ds(CUtensorMap* map, void* base, uint64_t S, uint64_t bh) {
   return CALM_OK;
 }
 
-constexpr size_t FWD_SMEM = 2 * KV_BYTES + QT_BYTES + 2 * P_BYTES + 2048 + 256 + 1024;
+constexpr size_t FWD_SMEM = 2 * KV_BYTES + QT_BYTES + 2 * P_BYTES + 2 * FWD_GROUPS * 128 * 4 + 256 + 1024;
 constexpr size_t BWD_SMEM = 2 * KV_BYTES + 2 * QT_BYTES + 2 * P_BYTES + 256 + 1024;
 
 int fill_common(Common& c, const void* bias, int B, int S, int heads, int hd) {
@@ -758,7 +769,7 @@ int calm_attention_fwd_tc(const void* q, const void* k, const void* v, const voi
   }
   const int items = B * heads;
   const int grid = items < calm_num_sms() ? items : calm_num_sms();
-  attn_fwd_tc_kernel<<<grid, NTHREADS, FWD_SMEM, stream>>>(mQ, mK, mV, mB, p);
+  attn_fwd_tc_kernel<<<grid, FWD_THREADS, FWD_SMEM, stream>>>(mQ, mK, mV, mB, p);
   CALM_CHECK_LAUNCH("calm_attention_fwd(tcgen05)");
   return CALM_OK;
 }
