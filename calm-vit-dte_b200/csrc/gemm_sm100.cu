@@ -992,7 +992,12 @@ extern "C" int32_t calm_gemm(const calm_gemm_args* a, cudaStream_t stream) {
   p.total_pairs = p.tiles_mp * p.tiles_n * p.splits * (p.reduce_batch ? 1 : a->batch);
   // pair (cluster + multicast) mode pays off on many-wave problems (measured: +9 % on the 57344 x 2016 x 672 GEMM, nothing on
   // one-wave problems, where the coarser work unit and the phantom tile of an odd M-tile count cost more than they save)
-  const bool want_pair = !(g_debug_flags & CALM_DEBUG_NO_CLUSTER) && (g_debug_flags & CALM_DEBUG_FORCE_CLUSTER || (p.total_pairs >= 2 * calm_num_sms() && (p.tiles_m % 2 == 0 || p.tiles_m >= 32))) && p.tiles_m >= 2;
+  // ... and on one-wave problems with a long contraction and an even M-tile count (the big weight gradients: -24 % at
+  // M = 2016 / 672, K = 57344 / 3-4 splits): the pair halves the B traffic per CTA and nothing is lost to a phantom tile.
+  // Odd tile counts and short contractions measured 10-40 % slower in pair mode and stay single-CTA.
+  const bool many_wave = p.total_pairs >= 2 * calm_num_sms() && (p.tiles_m % 2 == 0 || p.tiles_m >= 32);
+  const bool long_k_even = p.tiles_m % 2 == 0 && p.kb_per_split >= 128;
+  const bool want_pair = !(g_debug_flags & CALM_DEBUG_NO_CLUSTER) && (g_debug_flags & CALM_DEBUG_FORCE_CLUSTER || many_wave || long_k_even) && p.tiles_m >= 2;
   // mode 2 = tcgen05.mma.cta_group::2 (each CTA of the pair holds half of B), mode 1 = cta_group::1 + multicast B
   const int pair = !want_pair ? 0 : (g_debug_flags & CALM_DEBUG_PAIR_MULTICAST) ? 1 : 2;
   // TMA-staged epilogue unless the operand mix has no in-place form (addend of another dtype than C, GELU into fp32, ...)
