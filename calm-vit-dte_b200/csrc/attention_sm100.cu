@@ -19,7 +19,7 @@
 // V (keys x hd) serves as the MN-major B operand of P.V; in backward the same P / dS tiles serve K-major (dQ = dS K) and
 // MN-major (dK = dS^T Q, dV = P^T dO) without a second copy.
 //
-// Backward: per image the CTA walks the 12 heads; per head and 128-query tile
+// Backward: (image, head) work items; per item and 128-query tile
 //   S = Q K^T and dP = dO V^T in key parts of <= 64 columns, two parts in flight  ->  P = exp2(S c + bias - lse), dS = P (dP - delta)
 //   dQ = dS K (complete per tile), dK += dS^T Q, dV += P^T dO (accumulated in TMEM over the query tiles)
 // TMEM budget (512 columns): 2 x (S part 64 | dP part 64), dQ reuses the first S part | dK 2 x 64 | dV 2 x 64.
@@ -452,8 +452,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap mQ, const __grid_constant
           if (leader) tma_prefetch_2d(&mQ, lc.col0, bb * S + (ii + 1) * 128);
           if (leader) tma_prefetch_2d(&mDO, lc.col0, bb * S + (ii + 1) * 128);
         } else {
-          int nb = bb, nh = hh + 1;
-          if (nh == heads) { nh = 0; nb = bb + (int)gridDim.x; }
+          const int nit = bb * heads + hh + (int)gridDim.x;   // this CTA's next (image, head) item
+          const int nb = nit / heads, nh = nit - nb * heads;
           if (nb < c.B) {
             const HeadCols nc = head_cols(nh, hd);
             if (leader) tma_prefetch_2d(&mK, nc.col0, nb * S);
@@ -463,9 +463,13 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap mQ, const __grid_constant
           }
         }
       };
-      if ((int)blockIdx.x < c.B) issue_loads(blockIdx.x, 0, 0);
-      for (int b = blockIdx.x; b < c.B; b += gridDim.x) {
-        for (int h = 0; h < heads; ++h) {
+      // work items are (image, head) pairs, head fastest: the heads of an image run on neighbouring CTAs at the same time (its bias
+      // rows are shared through the L2) and B * heads items spread over the SMs without the 2-wave tail B = 256 images left
+      const int items = c.B * heads;
+      if ((int)blockIdx.x < items) issue_loads((int)blockIdx.x / heads, (int)blockIdx.x % heads, 0);
+      for (int it = blockIdx.x; it < items; it += gridDim.x) {
+        {
+          const int b = it / heads, h = it - b * heads;
           const HeadCols hc = head_cols(h, hd);
           const int hdp = hc.hdp;
           const int nks = hdp / 16;
@@ -535,9 +539,9 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap mQ, const __grid_constant
             // the workers' store epilogue
             mbar_wait(bar_fin, ph_fin, c.err_flag, 37); ph_fin ^= 1;
             {
-              int nb = b, nh = h, ni = i + 1;
-              if (ni == ntiles) { ni = 0; if (++nh == heads) { nh = 0; nb = b + (int)gridDim.x; } }
-              if (nb < c.B) issue_loads(nb, nh, ni);
+              int nit = it, ni = i + 1;
+              if (ni == ntiles) { ni = 0; nit = it + (int)gridDim.x; }
+              if (nit < items) issue_loads(nit / heads, nit % heads, ni);
             }
             mbar_wait(bar_tile, ph_tile, c.err_flag, 36); ph_tile ^= 1;         // epilogues done: P / dS tiles and TMEM free
             if (leader) trace_evt(p, 1050);
@@ -566,12 +570,13 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap mQ, const __grid_constant
         }
       }
     };
-    if ((int)blockIdx.x < c.B) load_bias(bcur, blockIdx.x, 0, 0);
-    for (int b = blockIdx.x; b < c.B; b += gridDim.x) {
-      for (int h = 0; h < heads; ++h) {
+    const int items = c.B * heads;
+    if ((int)blockIdx.x < items) load_bias(bcur, (int)blockIdx.x / heads, 0, 0);
+    for (int it = blockIdx.x; it < items; it += gridDim.x) {
+      {
+        const int b = it / heads, h = it - b * heads;
         const HeadCols hc = head_cols(h, hd);
         const int hdp = hc.hdp;
-        const bool last = h == heads - 1;
         for (int i = 0; i < ntiles; ++i) {
           const int q = i * 128 + r;
           const bool valid = q < S;
@@ -593,12 +598,12 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap mQ, const __grid_constant
             const int k0 = part * KPART, w = min(KPART, S - k0);
             // next part's bias (next tile / head / image after the tile's last part)
             {
-              int nb = b, ni = i, np = part + 1;
+              int nit = it, ni = i, np = part + 1;
               if (np == nparts) {
                 np = 0;
-                if (++ni == ntiles) { ni = 0; if (last) nb = b + (int)gridDim.x; }
+                if (++ni == ntiles) { ni = 0; nit = it + (int)gridDim.x; }
               }
-              if (nb < c.B) load_bias(bnxt, nb, ni, np);
+              if (nit < items) load_bias(bnxt, nit / heads, ni, np);
             }
             if (threadIdx.x == 0) trace_evt(p, 2020 + part);
             mbar_wait(bar_sd0 + 8 * buf, ph_sd[buf], c.err_flag, 43); ph_sd[buf] ^= 1;
@@ -807,7 +812,8 @@ int calm_attention_bwd_tc(const void* q, const void* k, const void* v, const voi
     if (e != cudaSuccess) { calm_set_error("calm_attention_bwd(tcgen05): smem: %s", cudaGetErrorString(e)); return CALM_ERR_CUDA; }
     configured = true;
   }
-  const int grid = B < calm_num_sms() ? B : calm_num_sms();
+  const int bwd_items = B * heads;
+  const int grid = bwd_items < calm_num_sms() ? bwd_items : calm_num_sms();
   attn_bwd_tc_kernel<<<grid, NTHREADS, BWD_SMEM, stream>>>(mQ, mK, mV, mDO, mDS, p);
   CALM_CHECK_LAUNCH("calm_attention_bwd(tcgen05)");
   const long long ss8 = (long long)S * S / 8, total8 = ss8 * B;
