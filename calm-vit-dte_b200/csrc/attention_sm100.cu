@@ -598,12 +598,16 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap mQ, const __grid_constant
             const int k0 = part * KPART, w = min(KPART, S - k0);
             // next part's bias (next tile / head / image after the tile's last part)
             {
-              int nit = it, ni = i, np = part + 1;
+              int nb = b, ni = i, np = part + 1;   // (the division by `heads` only when the item changes)
               if (np == nparts) {
                 np = 0;
-                if (++ni == ntiles) { ni = 0; nit = it + (int)gridDim.x; }
+                if (++ni == ntiles) {
+                  ni = 0;
+                  const int nit = it + (int)gridDim.x;
+                  nb = nit < items ? nit / heads : -1;
+                }
               }
-              if (nit < items) load_bias(bnxt, nit / heads, ni, np);
+              if (nb >= 0) load_bias(bnxt, nb, ni, np);
             }
             if (threadIdx.x == 0) trace_evt(p, 2020 + part);
             mbar_wait(bar_sd0 + 8 * buf, ph_sd[buf], c.err_flag, 43); ph_sd[buf] ^= 1;
