@@ -264,7 +264,19 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group(backend="nccl", device_id=dev)
+        # NCCL writes its version banner to stdout when the communicator is created; the driver reads ONE JSON line from
+        # stdout, so fd 1 points at stderr until the communicator exists (first collective)
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group(backend="nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
     import calm_lib
     torch.manual_seed(0)                      # identical initial weights on every rank (then broadcast from rank 0 anyway)
     model = build_model(dev, args.task)
