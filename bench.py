@@ -131,12 +131,18 @@ def bracket_overhead_us(n=64):
 class Trainer:
     """The per-rank training step of the reference loop, optionally captured into one CUDA graph (static shapes)."""
 
-    def __init__(self, model, task, dev, B, use_graph):
-        from torch.amp import GradScaler
+    def __init__(self, model, task, dev, B, use_graph, torch_glue=False):
         self.model, self.task, self.dev = model, task, dev
         self.params = [p for p in model.parameters()]
-        self.opt = torch.optim.AdamW(self.params, lr=3.1e-3, weight_decay=0.02, betas=(0.9, 0.98), fused=True, capturable=True)
-        self.scaler = GradScaler(enabled=True)
+        self.torch_glue = torch_glue
+        if torch_glue:      # A/B arm: the reference loop's own torch objects (GradScaler, clip_grad_norm_, fused AdamW, F.* losses)
+            from torch.amp import GradScaler
+            self.opt = torch.optim.AdamW(self.params, lr=3.1e-3, weight_decay=0.02, betas=(0.9, 0.98), fused=True, capturable=True)
+            self.scaler = GradScaler(enabled=True)
+        else:               # product: calm_trainer (loss heads + unscale/clip/AdamW/scale-update kernels of libcalm_b200.so)
+            import calm_trainer
+            self.ct = calm_trainer
+            self.glue = calm_trainer.TrainerStep(self.params, lr=3.1e-3, weight_decay=0.02, betas=(0.9, 0.98), max_norm=1.0)
         self.x = torch.zeros(B, 3, 224, 224, device=dev)
         self.y = torch.zeros(B, 1000, device=dev) if task == "cls" else None
         self.loss = torch.zeros((), device=dev)
@@ -144,6 +150,18 @@ class Trainer:
         self.use_graph = use_graph
 
     def _step(self):
+        if not self.torch_glue:
+            with torch.autocast(device_type="cuda", dtype=torch.bfloat16):
+                y_hat, kl = self.model(self.x)
+            if self.task == "cls":
+                loss, _acc = self.ct.soft_target_cross_entropy(y_hat.squeeze(), self.y)
+            else:
+                loss, _h = self.ct.huber_kl_loss(y_hat, self.x, kl, 0.1, 1.0)
+            self.glue.backward(loss)
+            self.glue.step()
+            self.glue.zero_grad()
+            self.loss.copy_(loss.detach())
+            return
         with torch.autocast(device_type="cuda", dtype=torch.bfloat16):
             y_hat, kl = self.model(self.x)
             if self.task == "cls":
@@ -252,6 +270,7 @@ def main():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-profile", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--torch-glue", action="store_true", help="A/B: torch GradScaler/clip/AdamW/loss instead of calm_trainer")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
@@ -289,7 +308,7 @@ def main():
     if world > 1:
         from calm_ddp import DataParallel
         wrapped = DataParallel(model)
-    tr = Trainer(wrapped, args.task, dev, B, use_graph)
+    tr = Trainer(wrapped, args.task, dev, B, use_graph, torch_glue=args.torch_glue)
     xh, yh = synth_batch(B, args.task, 2006 + rank)
     xh, yh = xh.pin_memory(), (yh.pin_memory() if yh is not None else None)
     tr.x.copy_(xh)

@@ -15,7 +15,7 @@ CSRC = os.path.join(HERE, "csrc")
 ROOT = os.path.dirname(HERE)
 OUT = os.path.join(HERE, "libcalm_b200.so")
 OBJ = os.path.join(HERE, "build")
-SOURCES = ["core.cu", "gemm_sm100.cu", "attention.cu", "attention_sm100.cu", "spectral.cu", "layernorm.cu", "rope.cu", "latent.cu", "cnn.cu", "misc.cu"]
+SOURCES = ["core.cu", "gemm_sm100.cu", "attention.cu", "attention_sm100.cu", "spectral.cu", "layernorm.cu", "rope.cu", "latent.cu", "cnn.cu", "misc.cu", "trainer.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC"]
 
 

@@ -40,11 +40,12 @@ class DataParallel(torch.nn.Module):
             self.buckets.append(cur)
         self.flat, self.views, self.bucket_of = [], [], {}
         for bi, bucket in enumerate(self.buckets):
-            flat = torch.zeros(sum(p.numel() for p in bucket), dtype=torch.float32, device=self.device)
+            # slices start on 16-byte boundaries (4 floats) so that the optimizer kernels keep their 128-bit accesses
+            flat = torch.zeros(sum(-(-p.numel() // 4) * 4 for p in bucket), dtype=torch.float32, device=self.device)
             views, off = [], 0
             for p in bucket:
                 views.append(flat[off: off + p.numel()].view_as(p))
-                off += p.numel()
+                off += -(-p.numel() // 4) * 4
                 self.bucket_of[p] = bi
             self.flat.append(flat)
             self.views.append(views)

@@ -17,6 +17,9 @@ BF16, F32 = 0, 1
 MAJOR_K, MAJOR_MN = 0, 1
 EPI_NONE, EPI_GELU, EPI_DGELU = 0, 1, 2
 CNN_NPARAM = 547
+OPT_CHUNK = 8192
+OPT_SCALE, OPT_GROWTH_TRACKER, OPT_STEP, OPT_LR, OPT_GRAD_NORM, OPT_FOUND_INF, OPT_MULT, OPT_BIAS1, OPT_BIAS2_SQRT = range(9)
+OPT_STATE_FLOATS = 16
 
 i32, i64, f32, vp = C.c_int32, C.c_int64, C.c_float, C.c_void_p
 
@@ -45,6 +48,17 @@ class SnLayer(C.Structure):
         ("g_split_stride", i64),
         ("rows", i32), ("cols", i32), ("g_splits", i32), ("eff_f32", i32),
         ("item_count", i32), ("_pad", i32),
+    ]
+
+
+class TrainerStepArgs(C.Structure):
+    """Mirror of calm_trainer_step_args."""
+    _fields_ = [
+        ("params", vp), ("grads", vp), ("grads_host", vp), ("elem_off", vp), ("chunk_tensor", vp), ("chunk_start", vp),
+        ("exp_avg", vp), ("exp_avg_sq", vp), ("partial", vp), ("state", vp),
+        ("n_tensors", i32), ("n_chunks", i32),
+        ("beta1", f32), ("beta2", f32), ("eps", f32), ("weight_decay", f32), ("max_norm", f32),
+        ("growth_factor", f32), ("backoff_factor", f32), ("growth_interval", i32), ("use_scaler", i32), ("_pad", i32),
     ]
 
 
@@ -92,6 +106,12 @@ PROTOTYPES = {
     "calm_cast_f32": (i32, [vp, vp, i64, vp]),
     "calm_seq_mean_fwd": (i32, [vp, vp, i32, i32, i32, vp]),
     "calm_seq_mean_bwd": (i32, [vp, vp, i32, i32, i32, vp]),
+    "calm_soft_ce_fwd": (i32, [vp, i64, vp, i64, vp, vp, vp, i32, i32, vp]),
+    "calm_soft_ce_bwd": (i32, [vp, i64, vp, i64, vp, vp, vp, vp, i64, i32, i32, vp]),
+    "calm_huber_parts": (i32, [i32, i32]),
+    "calm_huber_tokens_fwd": (i32, [vp, vp, vp, f32, f32, vp, i32, vp, i32, i32, vp]),
+    "calm_huber_tokens_bwd": (i32, [vp, vp, vp, f32, f32, vp, vp, i32, i32, vp]),
+    "calm_trainer_step": (i32, [C.POINTER(TrainerStepArgs), vp]),
 }
 
 _lib = None

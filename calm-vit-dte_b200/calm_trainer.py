@@ -1,0 +1,314 @@
+"""Device-side training-step glue of the reference's per-rank loop.
+
+The reference loop (distributed_trainer_cls.py:84-102, distributed_trainer_reg.py:76-98) is
+
+    loss = criterion(y_hat.squeeze(), y)            |  loss = huber(img, x) + kl_loss * 0.1
+    scaler.scale(loss).backward()
+    scaler.unscale_(optimizer)
+    torch.nn.utils.clip_grad_norm_(model.parameters(), max_norm=1, error_if_nonfinite=False)
+    scaler.step(optimizer); scaler.update(); optimizer.zero_grad()
+    epoch_loss += loss.item(); ... accuracy via two torch.max + .item()
+
+Here the same arithmetic runs as a handful of kernels of libcalm_b200.so with every scalar (loss scale, step count,
+learning rate, gradient norm, skip flag, loss, accuracy) resident on the device:
+
+    step = TrainerStep(model.parameters(), lr=3.1e-3, weight_decay=0.02, betas=(0.9, 0.98))
+    loss, acc = soft_target_cross_entropy(y_hat.squeeze(), y)        # or huber_kl_loss(y_hat, x, kl_loss, 0.1)
+    step.backward(loss)                                               # = scaler.scale(loss).backward()
+    step.step()                                                       # unscale + clip + AdamW + scale update, 3 launches
+    step.zero_grad()
+
+No `.item()` is needed inside the loop; `float(loss)` when the loop wants to print. Plumbing only (tensors, pointer
+tables); there is no PyTorch fallback for any of it.
+"""
+import ctypes as C
+import math
+
+import torch
+from torch.autograd import Function
+
+import calm_lib as L
+from calm_lib import ptr
+
+f32 = torch.float32
+
+
+# ---------------------------------------------------------------------------------------------------- loss heads
+class _SoftCeFn(Function):
+    @staticmethod
+    def forward(ctx, logits, target):
+        if logits.dim() != 2:
+            raise L.CalmError("soft_target_cross_entropy expects (B, C) logits, got %s" % (tuple(logits.shape),))
+        x = logits.float()
+        if x.stride(1) != 1:
+            x = x.contiguous()
+        B, Cn = x.shape
+        if target.dtype == torch.int64:
+            if target.shape != (B,):
+                raise L.CalmError("class-index target must have shape (B,)")
+            t, lab, ld_t = None, target.contiguous(), 0
+        else:
+            if target.shape != x.shape:
+                raise L.CalmError("probability target must have the logits' shape")
+            t = target.float()
+            if t.stride(1) != 1:
+                t = t.contiguous()
+            lab, ld_t = None, t.stride(0)
+        stats = torch.empty(B, 4, dtype=f32, device=x.device)
+        out = torch.empty(2, dtype=f32, device=x.device)
+        L.call("calm_soft_ce_fwd", ptr(x), x.stride(0), ptr(t), ld_t, ptr(lab), ptr(stats), ptr(out), B, Cn,
+               work=8.0 * B * Cn)
+        ctx.save_for_backward(x, t if t is not None else lab, stats)
+        ctx.index_target = t is None
+        ctx.in_dtype = logits.dtype
+        ctx.mark_non_differentiable(out)
+        return out[0], out
+
+    @staticmethod
+    def backward(ctx, dloss, _dout):
+        x, tgt, stats = ctx.saved_tensors
+        B, Cn = x.shape
+        t, lab = (None, tgt) if ctx.index_target else (tgt, None)
+        d = torch.empty(B, Cn, dtype=f32, device=x.device)
+        g = dloss.float().contiguous()
+        L.call("calm_soft_ce_bwd", ptr(x), x.stride(0), ptr(t), t.stride(0) if t is not None else 0, ptr(lab), ptr(stats),
+               ptr(g), ptr(d), Cn, B, Cn, work=12.0 * B * Cn)
+        return (d if ctx.in_dtype == f32 else d.to(ctx.in_dtype)), None
+
+
+def soft_target_cross_entropy(logits, target):
+    """`torch.nn.CrossEntropyLoss()(logits, target)` for probability targets (CutMix / MixUp labels) or int64 class indices
+    (distributed_trainer_cls.py:63,86), fp32 like autocast's policy for cross_entropy. Returns (loss, accuracy): 0-dim
+    tensors on the device; accuracy is the dominant-class accuracy the loop prints (:97-100)."""
+    loss, out = _SoftCeFn.apply(logits, target)
+    return loss, out[1]
+
+
+class _HuberKlFn(Function):
+    @staticmethod
+    def forward(ctx, tokens, image, kl, kl_weight, delta):
+        B = image.shape[0]
+        S = image.shape[-1]
+        if image.shape != (B, 3, S, S) or tokens.numel() != image.numel():
+            raise L.CalmError("huber_kl_loss: tokens %s do not match the image %s" % (tuple(tokens.shape), tuple(image.shape)))
+        t = tokens.float().contiguous()
+        img = image.float().contiguous()
+        nparts = L.load().calm_huber_parts(B, S)
+        partial = torch.empty(nparts, dtype=f32, device=t.device)
+        out = torch.empty(2, dtype=f32, device=t.device)
+        klf = kl.float().contiguous() if kl is not None else None
+        L.call("calm_huber_tokens_fwd", ptr(t), ptr(img), ptr(klf), float(kl_weight), float(delta), ptr(partial), nparts,
+               ptr(out), B, S, work=8.0 * t.numel())
+        ctx.save_for_backward(t, img)
+        ctx.meta = (B, S, float(kl_weight), float(delta), tokens.shape, tokens.dtype, kl is not None, kl.dtype if kl is not None else None)
+        ctx.mark_non_differentiable(out)
+        return out[0], out
+
+    @staticmethod
+    def backward(ctx, dloss, _dout):
+        t, img = ctx.saved_tensors
+        B, S, klw, delta, shape, dtype, has_kl, kl_dtype = ctx.meta
+        d = torch.empty_like(t)
+        dkl = torch.empty((), dtype=f32, device=t.device) if has_kl else None
+        g = dloss.float().contiguous()
+        L.call("calm_huber_tokens_bwd", ptr(t), ptr(img), ptr(g), klw, delta, ptr(d), ptr(dkl), B, S, work=12.0 * t.numel())
+        d = d.view(shape)
+        if dtype != f32:
+            d = d.to(dtype)
+        if has_kl and kl_dtype != f32:
+            dkl = dkl.to(kl_dtype)
+        return d, None, dkl, None, None
+
+
+def huber_kl_loss(tokens, image, kl=None, kl_weight=0.1, delta=1.0):
+    """`HuberLoss(delta)(y_hat.reshape(-1,S,S,3).permute(0,3,1,2), x) + kl_loss * kl_weight`
+    (distributed_trainer_reg.py:76-88) without materialising the NCHW permute. Returns (loss, huber_term)."""
+    loss, out = _HuberKlFn.apply(tokens, image, kl, kl_weight, delta)
+    return loss, out[1]
+
+
+# ---------------------------------------------------------------------------------------------------- optimizer step
+class TrainerStep:
+    """GradScaler + clip_grad_norm_ + AdamW of the reference loop as one object (distributed_trainer_cls.py:64,88-96,158).
+
+    state (device, fp32): loss scale, growth tracker, step count, learning rate, last gradient norm, last skip flag.
+    `step()` launches three kernels and never synchronises; it can be captured in a CUDA graph — the gradient pointer table
+    is re-uploaded (one small async copy) only when a `.grad` tensor changed its address.
+    """
+
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2, max_norm=1.0, use_scaler=True,
+                 init_scale=65536.0, growth_factor=2.0, backoff_factor=0.5, growth_interval=2000):
+        self.params = [p for p in params if p.requires_grad]
+        if not self.params:
+            raise L.CalmError("TrainerStep: no parameters")
+        dev = self.params[0].device
+        if dev.type != "cuda":
+            raise L.CalmError("TrainerStep needs CUDA parameters (got %s); there is no CPU fallback" % dev)
+        for p in self.params:
+            if p.dtype != f32 or not p.is_contiguous() or p.device != dev:
+                raise L.CalmError("TrainerStep: parameters must be contiguous fp32 tensors on one device")
+        L.load()
+        self.device = dev
+        self.hyper = dict(beta1=float(betas[0]), beta2=float(betas[1]), eps=float(eps), weight_decay=float(weight_decay),
+                          max_norm=float(max_norm) if max_norm else 0.0, growth_factor=float(growth_factor),
+                          backoff_factor=float(backoff_factor), growth_interval=int(growth_interval), use_scaler=int(bool(use_scaler)))
+        numels = [p.numel() for p in self.params]
+        off = [0]
+        for n in numels:
+            off.append(off[-1] + n)
+        chunk_tensor, chunk_start = [], []
+        for i, n in enumerate(numels):
+            for j in range(-(-n // L.OPT_CHUNK)):
+                chunk_tensor.append(i)
+                chunk_start.append(j)
+        self.n_tensors, self.n_chunks, self.total = len(numels), len(chunk_tensor), off[-1]
+        i64, i32 = torch.int64, torch.int32
+        self.elem_off = torch.tensor(off, dtype=i64, device=dev)
+        self.chunk_tensor = torch.tensor(chunk_tensor, dtype=i32, device=dev)
+        self.chunk_start = torch.tensor(chunk_start, dtype=i32, device=dev)
+        self.param_ptrs = torch.tensor([p.data_ptr() for p in self.params], dtype=i64, device=dev)
+        self.grad_ptrs = torch.zeros(self.n_tensors, dtype=i64, device=dev)
+        self._grad_ptr_list = None
+        # pinned staging for the gradient pointer table: two alternate in eager mode (each guarded by an event), a third is
+        # dedicated to CUDA-graph capture (the captured copy node re-reads it at every replay, so it is never rewritten)
+        self._stage = [torch.zeros(self.n_tensors, dtype=i64).pin_memory() for _ in range(3)]
+        self._stage_event = [None, None]
+        self._stage_next = 0
+        self._graph_stage_used = False
+        self.exp_avg = torch.zeros(self.total, dtype=f32, device=dev)
+        self.exp_avg_sq = torch.zeros(self.total, dtype=f32, device=dev)
+        self.partial = torch.empty(self.n_chunks, dtype=f32, device=dev)
+        st = torch.zeros(L.OPT_STATE_FLOATS, dtype=f32)
+        st[L.OPT_SCALE] = float(init_scale) if use_scaler else 1.0
+        st[L.OPT_LR] = float(lr)
+        st[L.OPT_BIAS1] = 1.0
+        st[L.OPT_BIAS2_SQRT] = 1.0
+        self.state = st.to(dev)
+
+    # -- GradScaler surface ----------------------------------------------------------------------------------------------
+    def scale(self, loss):
+        """`scaler.scale(loss)`: the loss times the current loss scale (read on the device)."""
+        if not self.hyper["use_scaler"]:
+            return loss
+        return loss * self.state[L.OPT_SCALE]
+
+    def backward(self, loss):
+        """`scaler.scale(loss).backward()` without the multiply: the loss scale is handed to autograd as the upstream gradient."""
+        if not self.hyper["use_scaler"]:
+            loss.backward()
+        else:
+            loss.backward(gradient=self.state[L.OPT_SCALE].to(loss.dtype))
+
+    def get_scale(self):
+        return float(self.state[L.OPT_SCALE].item())
+
+    # -- scheduler surface -----------------------------------------------------------------------------------------------
+    def set_lr(self, lr):
+        """What a scheduler (CosineAnnealingLR in the reference, distributed_trainer_cls.py:160) does to param_groups: one
+        scalar written to the device state; a captured graph picks it up at the next replay."""
+        self.state[L.OPT_LR:L.OPT_LR + 1].fill_(float(lr))
+
+    def get_lr(self):
+        return float(self.state[L.OPT_LR].item())
+
+    # -- results of the last step (device scalars; reading them as floats synchronises) -------------------------------------
+    @property
+    def grad_norm(self):
+        return self.state[L.OPT_GRAD_NORM]
+
+    @property
+    def found_inf(self):
+        return self.state[L.OPT_FOUND_INF]
+
+    @property
+    def step_count(self):
+        return self.state[L.OPT_STEP]
+
+    def moments(self, i):
+        """(exp_avg, exp_avg_sq) views of parameter i, shaped like it (torch.optim.AdamW's per-parameter state)."""
+        a, b = int(self.elem_off[i].item()), int(self.elem_off[i + 1].item())
+        return self.exp_avg[a:b].view_as(self.params[i]), self.exp_avg_sq[a:b].view_as(self.params[i])
+
+    # -- the step --------------------------------------------------------------------------------------------------------
+    def _stage_grad_ptrs(self):
+        """Returns the pinned host table to upload (or None when no .grad moved since the last upload)."""
+        ptrs = []
+        for p in self.params:
+            g = p.grad
+            if g is None:
+                raise L.CalmError("TrainerStep.step: a parameter has no gradient (the reference runs DDP without "
+                                  "find_unused_parameters: every parameter takes part in every step)")
+            if g.dtype != f32 or not g.is_contiguous() or g.device != self.device:
+                raise L.CalmError("TrainerStep.step: gradients must be contiguous fp32 tensors on the parameters' device")
+            ptrs.append(g.data_ptr())
+        if ptrs == self._grad_ptr_list:
+            return None, None
+        if torch.cuda.is_current_stream_capturing():
+            if self._graph_stage_used:
+                raise L.CalmError("TrainerStep: a second CUDA-graph capture needs a second TrainerStep (pointer staging is baked in)")
+            self._graph_stage_used = True
+            self._grad_ptr_list = None   # addresses inside the capture pool say nothing about the next eager step
+            k = 2
+        else:
+            k = self._stage_next
+            self._stage_next ^= 1
+            if self._stage_event[k] is not None:
+                self._stage_event[k].synchronize()   # the upload that last read this buffer has run (two steps ago)
+            self._grad_ptr_list = ptrs
+        self._stage[k].copy_(torch.tensor(ptrs, dtype=torch.int64))
+        return self._stage[k], k
+
+    def step(self):
+        """unscale_ + clip_grad_norm_ + scaler.step(AdamW) + scaler.update(), no host synchronisation."""
+        stage, k = self._stage_grad_ptrs()
+        a = L.TrainerStepArgs()
+        a.params, a.grads = ptr(self.param_ptrs), ptr(self.grad_ptrs)
+        a.grads_host = stage.data_ptr() if stage is not None else None
+        a.elem_off, a.chunk_tensor, a.chunk_start = ptr(self.elem_off), ptr(self.chunk_tensor), ptr(self.chunk_start)
+        a.exp_avg, a.exp_avg_sq, a.partial, a.state = ptr(self.exp_avg), ptr(self.exp_avg_sq), ptr(self.partial), ptr(self.state)
+        a.n_tensors, a.n_chunks = self.n_tensors, self.n_chunks
+        for key, v in self.hyper.items():
+            setattr(a, key, v)
+        L.call("calm_trainer_step", C.byref(a), work=32.0 * self.total)
+        if stage is not None and k < 2:
+            ev = torch.cuda.Event()
+            ev.record()
+            self._stage_event[k] = ev
+
+    def zero_grad(self, set_to_none=True):
+        """`optimizer.zero_grad()` (default set_to_none=True, distributed_trainer_cls.py:96)."""
+        for p in self.params:
+            if set_to_none:
+                p.grad = None
+            elif p.grad is not None:
+                p.grad.zero_()
+
+    # -- checkpoint surface (torch.optim.AdamW-shaped, so reference-side tooling can read it) --------------------------------
+    def state_dict(self):
+        st = self.state.cpu()
+        per = {}
+        for i in range(self.n_tensors):
+            m, v = self.moments(i)
+            per[i] = {"step": st[L.OPT_STEP].clone(), "exp_avg": m.clone(), "exp_avg_sq": v.clone()}
+        group = {"lr": float(st[L.OPT_LR]), "betas": (self.hyper["beta1"], self.hyper["beta2"]), "eps": self.hyper["eps"],
+                 "weight_decay": self.hyper["weight_decay"], "params": list(range(self.n_tensors))}
+        scaler = {"scale": float(st[L.OPT_SCALE]), "growth_factor": self.hyper["growth_factor"],
+                  "backoff_factor": self.hyper["backoff_factor"], "growth_interval": self.hyper["growth_interval"],
+                  "_growth_tracker": int(st[L.OPT_GROWTH_TRACKER])}
+        return {"state": per, "param_groups": [group], "scaler": scaler}
+
+    def load_state_dict(self, sd):
+        st = self.state.cpu()
+        for i, s in sd["state"].items():
+            m, v = self.moments(int(i))
+            m.copy_(s["exp_avg"])
+            v.copy_(s["exp_avg_sq"])
+            st[L.OPT_STEP] = float(s["step"])
+        st[L.OPT_LR] = float(sd["param_groups"][0]["lr"])
+        if "scaler" in sd:
+            st[L.OPT_SCALE] = float(sd["scaler"]["scale"])
+            st[L.OPT_GROWTH_TRACKER] = float(sd["scaler"]["_growth_tracker"])
+        step = float(st[L.OPT_STEP])
+        st[L.OPT_BIAS1] = 1.0 - math.pow(self.hyper["beta1"], step) if step > 0 else 1.0
+        st[L.OPT_BIAS2_SQRT] = math.sqrt(1.0 - math.pow(self.hyper["beta2"], step)) if step > 0 else 1.0
+        self.state.copy_(st)

@@ -196,6 +196,63 @@ int32_t calm_seq_mean_fwd(const float* x, void* out_bf16, int32_t B, int32_t S, 
 int32_t calm_seq_mean_bwd(const void* dout_bf16, float* dx, int32_t B, int32_t S, int32_t D, cudaStream_t stream);
 /* plain GELU(erf) forward on bf16 (head activation, CALM_ViT_V2.py:51) is covered by the GEMM epilogue. */
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * Training-step glue of the per-rank loop: loss heads and the fused optimizer step.
+ * ------------------------------------------------------------------------------------------------------------------ */
+/* torch.nn.CrossEntropyLoss() on f32 logits (B,C) with probability targets (CutMix/MixUp soft labels,
+ * distributed_trainer_cls.py:58-63,86) or, alternatively, int64 class labels (exactly one of target / labels non-NULL).
+ * row_stats (B,4) f32 = {loss_b, logsumexp_b, sum_c t_bc, [argmax x_b == argmax t_b]} (saved for backward);
+ * loss_out[0] = mean_b loss_b, loss_out[1] = dominant-class accuracy of the batch (:97-100, no host sync). */
+int32_t calm_soft_ce_fwd(const float* logits, int64_t ld, const float* target, int64_t ld_t, const int64_t* labels,
+                         float* row_stats, float* loss_out, int32_t B, int32_t C, cudaStream_t stream);
+/* dlogits = (softmax(x) * sum_c t - t) * dloss / B ; dloss = device scalar (the scaled upstream gradient) or NULL (=1) */
+int32_t calm_soft_ce_bwd(const float* logits, int64_t ld, const float* target, int64_t ld_t, const int64_t* labels,
+                         const float* row_stats, const float* dloss, float* dlogits, int64_t ld_d, int32_t B, int32_t C,
+                         cudaStream_t stream);
+/* torch.nn.HuberLoss(delta)(img, x) + kl_weight * kl (distributed_trainer_reg.py:76-88) where img is the generated token
+ * image (B,S,S,3) f32 read in place of its reshape/permute to NCHW and x the (B,3,S,S) f32 input image.
+ * loss_out[0] = total, loss_out[1] = the Huber term; partial: calm_huber_parts(B,S) floats of scratch */
+int32_t calm_huber_parts(int32_t B, int32_t S);
+int32_t calm_huber_tokens_fwd(const float* tokens, const float* target_nchw, const float* kl /* device scalar or NULL */,
+                              float kl_weight, float delta, float* partial, int32_t nparts, float* loss_out, int32_t B, int32_t S,
+                              cudaStream_t stream);
+/* dtokens = clamp(tokens - target, -delta, delta) * dloss / (3 B S^2) ; dkl[0] = kl_weight * dloss (dkl may be NULL) */
+int32_t calm_huber_tokens_bwd(const float* tokens, const float* target_nchw, const float* dloss, float kl_weight, float delta,
+                              float* dtokens, float* dkl, int32_t B, int32_t S, cudaStream_t stream);
+
+/* GradScaler.unscale_ + clip_grad_norm_(max_norm) + GradScaler.step(AdamW) + GradScaler.update
+ * (distributed_trainer_cls.py:88-96, distributed_trainer_reg.py:90-97) as three launches over all parameter tensors:
+ * (1) per-chunk sum of squares of the unscaled gradients, (2) one CTA: total norm, inf/nan check, clip coefficient, step
+ * count and bias corrections, loss-scale update, (3) AdamW on p / exp_avg / exp_avg_sq with the gradient multiplied by
+ * clip/scale on the fly (torch's fused AdamW arithmetic order). A non-finite gradient skips the update and backs the
+ * scale off, like GradScaler. The .grad tensors are read, not modified. All state lives in `state` on the device, so the
+ * step needs no host synchronisation and can be captured in a CUDA graph (the host changes the learning rate by writing
+ * state[CALM_OPT_LR]). */
+#define CALM_OPT_CHUNK 8192   /* elements per CTA; chunk c covers elements [chunk_start[c]*CHUNK, +CHUNK) of tensor chunk_tensor[c] */
+enum { CALM_OPT_SCALE = 0, CALM_OPT_GROWTH_TRACKER = 1, CALM_OPT_STEP = 2, CALM_OPT_LR = 3, CALM_OPT_GRAD_NORM = 4,
+       CALM_OPT_FOUND_INF = 5, CALM_OPT_MULT = 6, CALM_OPT_BIAS1 = 7, CALM_OPT_BIAS2_SQRT = 8, CALM_OPT_STATE_FLOATS = 16 };
+typedef struct {
+  const void* params;        /* device array of n_tensors float*  (parameter data, updated in place)            */
+  const void* grads;         /* device array of n_tensors const float* (their .grad, f32, contiguous)           */
+  const void* grads_host;    /* optional pinned HOST copy of that array: when non-NULL it is uploaded into `grads` on
+                                the stream first (autograd re-allocates .grad every step; inside a CUDA graph the copy
+                                becomes a memcpy node that re-reads this buffer at every replay)                   */
+  const int64_t* elem_off;   /* device (n_tensors + 1): prefix sum of numel = offsets into exp_avg / exp_avg_sq */
+  const int32_t* chunk_tensor; /* device (n_chunks) */
+  const int32_t* chunk_start;  /* device (n_chunks), in units of CALM_OPT_CHUNK elements                         */
+  float* exp_avg;            /* flat f32 first moments  (elem_off[n_tensors] floats)                            */
+  float* exp_avg_sq;         /* flat f32 second moments                                                         */
+  float* partial;            /* scratch, n_chunks floats                                                        */
+  float* state;              /* CALM_OPT_STATE_FLOATS floats, see the enum                                      */
+  int32_t n_tensors, n_chunks;
+  float beta1, beta2, eps, weight_decay;
+  float max_norm;            /* <= 0: no clipping                                                               */
+  float growth_factor, backoff_factor; int32_t growth_interval;
+  int32_t use_scaler;        /* 0: gradients are not scaled, never skip                                         */
+  int32_t _pad;
+} calm_trainer_step_args;
+int32_t calm_trainer_step(const calm_trainer_step_args* args, cudaStream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
