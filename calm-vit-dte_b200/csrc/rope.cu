@@ -172,6 +172,255 @@ rope_bwd_kernel(const bf16* __restrict__ dout, long long ld_dout, const bf16* __
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Row-staged kernels (v3, the default whenever every row starts on a 16-byte boundary): the head width is rarely a multiple
+// of 16 bytes (hd = 56, 44, 20 -> rotation halves of 28, 22, 10 elements), which held the kernels above to 8-, 4- or 2-byte
+// accesses (30-39 % of the HBM rate at 224^2 / 176^2). Here a thread owns one aligned 16-byte chunk of the ROW, whatever heads
+// or halves it straddles: rows go through shared memory so that the rotation partner (half a head away) can be fetched from
+// there, all global accesses are 128-bit and fully coalesced. A CTA still owns one position (cos/sin per thread in registers)
+// and a slice of the batch; R = 256 / chunks rows are processed side by side, U such groups are in flight per iteration,
+// and the staging buffer is double-buffered (one __syncthreads per iteration).
+// Staging coordinates of a row: [content row (heads*dc) | rope row (heads*dr)]; out coordinates: h*(dc+dr) + i.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int RS_NT = 256;
+constexpr int RS_UF = 4;   // forward: row groups in flight
+constexpr int RS_UB = 2;   // backward (two operands per row)
+
+__device__ __forceinline__ void unpack8(const uint4& v, float* f) {
+  f[0] = __uint_as_float(v.x << 16); f[1] = __uint_as_float(v.x & 0xffff0000u);
+  f[2] = __uint_as_float(v.y << 16); f[3] = __uint_as_float(v.y & 0xffff0000u);
+  f[4] = __uint_as_float(v.z << 16); f[5] = __uint_as_float(v.z & 0xffff0000u);
+  f[6] = __uint_as_float(v.w << 16); f[7] = __uint_as_float(v.w & 0xffff0000u);
+}
+__device__ __forceinline__ uint4 pack8(const float* f) {
+  return make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+}
+// staging layout: 4 bytes of padding after every 128 bytes, so that the 32 lanes' scalar partner reads (16 bytes apart) and the
+// word-wise chunk writes fall into 32 different banks. sidx(i) = position of row element i.
+__host__ __device__ __forceinline__ int sidx(int i) { return i + ((i >> 6) << 1); }
+__host__ __device__ __forceinline__ int rope_pitch(int rowlen) { return rowlen + 2 * ((rowlen + 63) / 64); }
+__device__ __forceinline__ void sts_chunk(bf16* row, int k, const uint4& v) {
+  uint32_t* w = reinterpret_cast<uint32_t*>(row + sidx(8 * k));
+  w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
+}
+__device__ __forceinline__ uint4 lds_chunk(const bf16* row, int k) {
+  const uint32_t* w = reinterpret_cast<const uint32_t*>(row + sidx(8 * k));
+  return make_uint4(w[0], w[1], w[2], w[3]);
+}
+__device__ __forceinline__ float lds_bf16(const bf16* p) {
+  return __uint_as_float(((uint32_t)*reinterpret_cast<const unsigned short*>(p)) << 16);
+}
+
+// per-thread description of the 8 out-coordinate columns [8k, 8k+8): cos, signed sin, own / partner position (sidx applied)
+template <bool BWD>
+__device__ __forceinline__ void rope_row_map(int k, int heads, int dc, int dr, const float2* __restrict__ cs2, float* c, float* s,
+                                             unsigned short* self_stage, unsigned short* partner) {
+  const int half = dr >> 1, hd = dc + dr, HC = heads * dc;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int col = 8 * k + e;
+    const int h = col / hd, i = col - h * hd;
+    if (i < dc) {
+      c[e] = 1.f; s[e] = 0.f;
+      self_stage[e] = (unsigned short)sidx(h * dc + i);
+      partner[e] = BWD ? (unsigned short)sidx(col) : self_stage[e];
+    } else {
+      const int j = i - dc;
+      const bool first = j < half;
+      const float2 v = cs2[first ? j : j - half];
+      c[e] = v.x;
+      // forward: y1 = x1 c - x2 s, y2 = x2 c + x1 s ; backward: dx1 = dy1 c + dy2 s, dx2 = dy2 c - dy1 s
+      s[e] = (first != BWD) ? -v.y : v.y;
+      self_stage[e] = (unsigned short)sidx(HC + h * dr + j);
+      const int pofs = first ? half : -half;
+      partner[e] = (unsigned short)sidx((BWD ? col : HC + h * dr + j) + pofs);   // backward stages the dout row in out coordinates
+    }
+  }
+}
+
+template <bool DC0, bool PAIR>
+__global__ void __launch_bounds__(RS_NT, 4)
+rope_rows_fwd_kernel(const bf16* __restrict__ content, long long ld_content, const bf16* __restrict__ ropein, long long ld_rope,
+                     bf16* __restrict__ out, long long ld_out, const float* __restrict__ cs, int B, int S, int heads, int dc, int dr,
+                     int R, int chunks) {
+  extern __shared__ __align__(16) unsigned char rs_smem[];
+  bf16* stage = reinterpret_cast<bf16*>(rs_smem);
+  const int rowlen = heads * (dc + dr), HC = heads * dc, half = dr >> 1;
+  const int tid = threadIdx.x, r = tid / chunks, k = tid - r * chunks;
+  const bool active = r < R;
+  const int pos = blockIdx.x;
+  const int bpc = (B + (int)gridDim.y - 1) / (int)gridDim.y;
+  const int b0 = blockIdx.y * bpc, b1 = min(B, b0 + bpc);
+  float c[8], sn[8];
+  unsigned short self[8], partner[8];
+  rope_row_map<false>(active ? k : 0, heads, dc, dr, reinterpret_cast<const float2*>(cs) + (long long)pos * half, c, sn, self, partner);
+  const bool from_content = 8 * k < HC;
+  const bf16* src = from_content ? content + 8 * k : ropein + (8 * k - HC);
+  const long long src_ld = from_content ? ld_content : ld_rope;
+  const int pitch = rope_pitch(rowlen), set = RS_UF * R * pitch;
+  int it = 0;
+  for (int bb = b0; bb < b1; bb += RS_UF * R, ++it) {
+    bf16* st = stage + (it & 1) * set;
+    uint4 v[RS_UF];
+    bool ok[RS_UF];
+#pragma unroll
+    for (int u = 0; u < RS_UF; ++u) {
+      const int b = bb + u * R + r;
+      ok[u] = active && b < b1;
+      if (ok[u]) v[u] = __ldcs(reinterpret_cast<const uint4*>(src + ((long long)b * S + pos) * src_ld));
+    }
+#pragma unroll
+    for (int u = 0; u < RS_UF; ++u)
+      if (ok[u]) sts_chunk(st + (u * R + r) * pitch, k, v[u]);
+    __syncthreads();
+#pragma unroll
+    for (int u = 0; u < RS_UF; ++u) {
+      if (!ok[u]) continue;
+      const bf16* row = st + (u * R + r) * pitch;
+      float x[8], xp[8], y[8];
+      if (DC0) unpack8(v[u], x);
+      if (PAIR) {   // even half / content widths: the partners of (e, e+1) are one aligned 32-bit word
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const uint32_t w = *reinterpret_cast<const uint32_t*>(row + partner[2 * q]);
+          xp[2 * q] = __uint_as_float(w << 16); xp[2 * q + 1] = __uint_as_float(w & 0xffff0000u);
+          if (!DC0) {
+            const uint32_t ws = *reinterpret_cast<const uint32_t*>(row + self[2 * q]);
+            x[2 * q] = __uint_as_float(ws << 16); x[2 * q + 1] = __uint_as_float(ws & 0xffff0000u);
+          }
+        }
+      } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          if (!DC0) x[e] = lds_bf16(row + self[e]);
+          xp[e] = lds_bf16(row + partner[e]);
+        }
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) y[e] = fmaf(xp[e], sn[e], x[e] * c[e]);
+      const int b = bb + u * R + r;
+      *reinterpret_cast<uint4*>(out + ((long long)b * S + pos) * ld_out + 8 * k) = pack8(y);
+    }
+  }
+}
+
+template <bool DC0, bool PAIR>
+__global__ void __launch_bounds__(RS_NT, 4)
+rope_rows_bwd_kernel(const bf16* __restrict__ dout, long long ld_dout, const bf16* __restrict__ out, long long ld_out,
+                     bf16* __restrict__ dcontent, long long ld_dcontent, bf16* __restrict__ dropein, long long ld_drope,
+                     const float* __restrict__ cs, float* __restrict__ dtheta_part, int B, int S, int heads, int dc, int dr,
+                     int R, int chunks) {
+  extern __shared__ __align__(16) unsigned char rs_smem[];
+  const int rowlen = heads * (dc + dr), HC = heads * dc, half = dr >> 1, hd = dc + dr;
+  const int pitch = rope_pitch(rowlen), set = RS_UB * R * pitch;
+  bf16* stage = reinterpret_cast<bf16*>(rs_smem);            // 2 sets: dout rows, out coordinates
+  bf16* result = stage + 2 * set;                              // 1 set (dc > 0 only): results, staging coordinates
+  float* accs = reinterpret_cast<float*>(result + (DC0 ? 0 : set));   // R * rowlen floats
+  const int tid = threadIdx.x, r = tid / chunks, k = tid - r * chunks;
+  const bool active = r < R;
+  const int pos = blockIdx.x, chunk = blockIdx.y;
+  const int bpc = (B + ROPE_BCH - 1) / ROPE_BCH;
+  const int b0 = chunk * bpc, b1 = min(B, b0 + bpc);
+  float c[8], sn[8], acc[8];
+  unsigned short dest[8], partner[8];
+  rope_row_map<true>(active ? k : 0, heads, dc, dr, reinterpret_cast<const float2*>(cs) + (long long)pos * half, c, sn, dest, partner);
+#pragma unroll
+  for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+  const bool to_content = 8 * k < HC;
+  bf16* dst = to_content ? dcontent + 8 * k : dropein + (8 * k - HC);
+  const long long dst_ld = to_content ? ld_dcontent : ld_drope;
+  int it = 0;
+  for (int bb = b0; bb < b1; bb += RS_UB * R, ++it) {
+    bf16* st = stage + (it & 1) * set;
+    uint4 vdy[RS_UB], vy[RS_UB];
+    bool ok[RS_UB];
+#pragma unroll
+    for (int u = 0; u < RS_UB; ++u) {
+      const int b = bb + u * R + r;
+      ok[u] = active && b < b1;
+      if (ok[u]) {
+        const long long t = (long long)b * S + pos;
+        vdy[u] = __ldcs(reinterpret_cast<const uint4*>(dout + t * ld_dout + 8 * k));
+        vy[u] = __ldcs(reinterpret_cast<const uint4*>(out + t * ld_out + 8 * k));
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < RS_UB; ++u)
+      if (ok[u]) sts_chunk(st + (u * R + r) * pitch, k, vdy[u]);
+    __syncthreads();
+#pragma unroll
+    for (int u = 0; u < RS_UB; ++u) {
+      if (!ok[u]) continue;
+      const bf16* row = st + (u * R + r) * pitch;
+      float dy[8], y[8], dx[8], dyp[8];
+      unpack8(vdy[u], dy);
+      unpack8(vy[u], y);
+      if (PAIR) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const uint32_t w = *reinterpret_cast<const uint32_t*>(row + partner[2 * q]);
+          dyp[2 * q] = __uint_as_float(w << 16); dyp[2 * q + 1] = __uint_as_float(w & 0xffff0000u);
+        }
+      } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) dyp[e] = lds_bf16(row + partner[e]);
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        dx[e] = fmaf(dyp[e], sn[e], dy[e] * c[e]);
+        acc[e] = fmaf(y[e], dyp[e], acc[e]);
+      }
+      if (DC0) {
+        const int b = bb + u * R + r;
+        *reinterpret_cast<uint4*>(dropein + ((long long)b * S + pos) * ld_drope + 8 * k) = pack8(dx);
+      } else {
+        bf16* res = result + (u * R + r) * pitch;
+        if (PAIR) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) *reinterpret_cast<uint32_t*>(res + dest[2 * q]) = pack_bf16x2(dx[2 * q], dx[2 * q + 1]);
+        } else {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) res[dest[e]] = __float2bfloat16(dx[e]);
+        }
+      }
+    }
+    if (!DC0) {
+      __syncthreads();
+#pragma unroll
+      for (int u = 0; u < RS_UB; ++u) {
+        if (!ok[u]) continue;
+        const int b = bb + u * R + r;
+        *reinterpret_cast<uint4*>(dst + ((long long)b * S + pos) * dst_ld) = lds_chunk(result + (u * R + r) * pitch, k);
+      }
+    }
+  }
+  // d theta[pos, j] = sum over rows, heads of (y1 dy2 - y2 dy1): per-thread partial sums meet in shared memory (fixed order)
+  __syncthreads();
+  if (active) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) accs[r * rowlen + 8 * k + e] = acc[e];
+  }
+  __syncthreads();
+  for (int j = tid; j < half; j += blockDim.x) {
+    float s = 0.f;
+    for (int rr = 0; rr < R; ++rr)
+      for (int h = 0; h < heads; ++h) {
+        const float* a = accs + rr * rowlen + h * hd + dc;
+        s += a[j] - a[j + half];
+      }
+    dtheta_part[((size_t)chunk * S + pos) * half + j] = s;
+  }
+}
+
+// can the row-staged kernels run? every row of every operand must be 16-byte aligned and a row must fit one CTA pass
+bool rope_rows_ok(int heads, int dc, int dr, std::initializer_list<long long> lds, std::initializer_list<const void*> ptrs) {
+  const int rowlen = heads * (dc + dr);
+  bool ok = (heads * dc) % 8 == 0 && (heads * dr) % 8 == 0 && rowlen / 8 <= RS_NT && rope_pitch(rowlen) <= 65535;
+  for (long long ld : lds) ok = ok && ld % 8 == 0;
+  for (const void* p : ptrs) ok = ok && (reinterpret_cast<uintptr_t>(p) % 16) == 0;
+  return ok;
+}
+
 // widest vector (elements) all the operands of a call allow
 int rope_vec(int dc, int dr, std::initializer_list<long long> lds, std::initializer_list<const void*> ptrs) {
   for (int v = 8; v > 1; v >>= 1) {
@@ -219,8 +468,28 @@ extern "C" int32_t calm_rope_fwd(const void* content, int64_t ld_content, const 
   CALM_CHECK_ARG(dc == 0 || content != nullptr, "calm_rope_fwd: content missing");
   CALM_CHECK_ARG(tokens % S == 0, "calm_rope_fwd: tokens=%lld is not a multiple of S=%d", (long long)tokens, S);
   const int B = (int)(tokens / S);
-  const int v = rope_vec(dc, dr, {(long long)ld_content, (long long)ld_rope, (long long)ld_out}, {content, ropein, out});
   dim3 grid(S, B < ROPE_BCH ? B : ROPE_BCH);
+  if (rope_rows_ok(heads, dc, dr, {(long long)(dc ? ld_content : 8), (long long)ld_rope, (long long)ld_out}, {content, ropein, out})) {
+    const int rowlen = heads * (dc + dr), chunks = rowlen / 8, R = RS_NT / chunks;
+    const int nthreads = ((R * chunks + 31) / 32) * 32;
+    const size_t smem = (size_t)2 * RS_UF * R * rope_pitch(rowlen) * sizeof(bf16);
+    if (smem <= 48 * 1024) {
+      const bool pair = (dr / 2) % 2 == 0 && dc % 2 == 0;
+#define CALM_ROPE_ROWS_FWD(DC0, PAIR)                                                                                            \
+  do {                                                                                                                           \
+    static bool carve = false;                                                                                                   \
+    if (!carve) { cudaFuncSetAttribute(rope_rows_fwd_kernel<DC0, PAIR>, cudaFuncAttributePreferredSharedMemoryCarveout, 100); carve = true; } \
+    rope_rows_fwd_kernel<DC0, PAIR><<<grid, nthreads, smem, stream>>>(reinterpret_cast<const bf16*>(content), ld_content,        \
+        reinterpret_cast<const bf16*>(ropein), ld_rope, reinterpret_cast<bf16*>(out), ld_out, cos_sin, B, S, heads, dc, dr, R, chunks); \
+  } while (0)
+      if (dc == 0) { if (pair) CALM_ROPE_ROWS_FWD(true, true); else CALM_ROPE_ROWS_FWD(true, false); }
+      else { if (pair) CALM_ROPE_ROWS_FWD(false, true); else CALM_ROPE_ROWS_FWD(false, false); }
+#undef CALM_ROPE_ROWS_FWD
+      CALM_CHECK_LAUNCH("calm_rope_fwd(rows)");
+      return CALM_OK;
+    }
+  }
+  const int v = rope_vec(dc, dr, {(long long)ld_content, (long long)ld_rope, (long long)ld_out}, {content, ropein, out});
   const int threads = rope_threads(heads, dc, dr, v);
 #define CALM_ROPE_FWD(V)                                                                                                          \
   rope_fwd_kernel<V><<<grid, threads, 0, stream>>>(reinterpret_cast<const bf16*>(content), ld_content,                            \
@@ -241,10 +510,34 @@ extern "C" int32_t calm_rope_bwd(const void* dout, int64_t ld_dout, const void* 
   CALM_CHECK_ARG(tokens > 0 && S > 0 && tokens % S == 0 && heads > 0 && dr > 0 && dr % 2 == 0 && dc >= 0, "calm_rope_bwd: bad dims");
   CALM_CHECK_ARG(dc == 0 || dcontent != nullptr, "calm_rope_bwd: dcontent missing");
   const int B = (int)(tokens / S), half = dr / 2;
+  dim3 grid(S, ROPE_BCH);
+  if (rope_rows_ok(heads, dc, dr, {(long long)ld_dout, (long long)ld_out, (long long)(dc ? ld_dcontent : 8), (long long)ld_drope},
+                   {dout, out, dcontent, dropein})) {
+    const int rowlen = heads * (dc + dr), chunks = rowlen / 8, R = RS_NT / chunks;
+    const int nthreads = ((R * chunks + 31) / 32) * 32;
+    const size_t rs_smem = (size_t)(dc ? 3 : 2) * RS_UB * R * rope_pitch(rowlen) * sizeof(bf16) + (size_t)R * rowlen * sizeof(float);
+    if (rs_smem <= 48 * 1024) {
+      const bool pair = half % 2 == 0 && dc % 2 == 0;
+#define CALM_ROPE_ROWS_BWD(DC0, PAIR)                                                                                            \
+  do {                                                                                                                           \
+    static bool carve = false;                                                                                                   \
+    if (!carve) { cudaFuncSetAttribute(rope_rows_bwd_kernel<DC0, PAIR>, cudaFuncAttributePreferredSharedMemoryCarveout, 100); carve = true; } \
+    rope_rows_bwd_kernel<DC0, PAIR><<<grid, nthreads, rs_smem, stream>>>(                                                        \
+        reinterpret_cast<const bf16*>(dout), ld_dout, reinterpret_cast<const bf16*>(out), ld_out, reinterpret_cast<bf16*>(dcontent), \
+        ld_dcontent, reinterpret_cast<bf16*>(dropein), ld_drope, cos_sin, dtheta_part, B, S, heads, dc, dr, R, chunks);          \
+  } while (0)
+      if (dc == 0) { if (pair) CALM_ROPE_ROWS_BWD(true, true); else CALM_ROPE_ROWS_BWD(true, false); }
+      else { if (pair) CALM_ROPE_ROWS_BWD(false, true); else CALM_ROPE_ROWS_BWD(false, false); }
+#undef CALM_ROPE_ROWS_BWD
+      CALM_CHECK_LAUNCH("calm_rope_bwd(rows)");
+      rope_dfreq_kernel<<<half, 128, 0, stream>>>(dtheta_part, dinv_freq, S, half);
+      CALM_CHECK_LAUNCH("calm_rope_bwd(dfreq)");
+      return CALM_OK;
+    }
+  }
   const int v = rope_vec(dc, dr, {(long long)ld_dout, (long long)ld_out, (long long)ld_dcontent, (long long)ld_drope},
                          {dout, out, dcontent, dropein});
   const int threads = rope_threads(heads, dc, dr, v);
-  dim3 grid(S, ROPE_BCH);
   const size_t smem = (size_t)heads * half * sizeof(float);
 #define CALM_ROPE_BWD(V)                                                                                                       \
   rope_bwd_kernel<V><<<grid, threads, smem, stream>>>(reinterpret_cast<const bf16*>(dout), ld_dout,                            \
