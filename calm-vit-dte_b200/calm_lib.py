@@ -146,6 +146,8 @@ def load(build_if_missing=True):
             fn.argtypes = args
         if lib.calm_abi_version() != 1:
             raise CalmError("libcalm_b200.so ABI version %d, expected 1" % lib.calm_abi_version())
+        if os.environ.get("CALM_DEBUG_FLAGS"):      # A/B switches of include/calm_b200.h (CALM_DEBUG_*), e.g. 64 = legacy RoPE kernels
+            lib.calm_set_debug_flags(int(os.environ["CALM_DEBUG_FLAGS"], 0))
         _lib = lib
     return _lib
 

@@ -469,7 +469,7 @@ extern "C" int32_t calm_rope_fwd(const void* content, int64_t ld_content, const 
   CALM_CHECK_ARG(tokens % S == 0, "calm_rope_fwd: tokens=%lld is not a multiple of S=%d", (long long)tokens, S);
   const int B = (int)(tokens / S);
   dim3 grid(S, B < ROPE_BCH ? B : ROPE_BCH);
-  if (rope_rows_ok(heads, dc, dr, {(long long)(dc ? ld_content : 8), (long long)ld_rope, (long long)ld_out}, {content, ropein, out})) {
+  if (!(calm_get_debug_flags() & CALM_DEBUG_LEGACY_ROPE) && rope_rows_ok(heads, dc, dr, {(long long)(dc ? ld_content : 8), (long long)ld_rope, (long long)ld_out}, {content, ropein, out})) {
     const int rowlen = heads * (dc + dr), chunks = rowlen / 8, R = RS_NT / chunks;
     const int nthreads = ((R * chunks + 31) / 32) * 32;
     const size_t smem = (size_t)2 * RS_UF * R * rope_pitch(rowlen) * sizeof(bf16);
@@ -511,7 +511,7 @@ extern "C" int32_t calm_rope_bwd(const void* dout, int64_t ld_dout, const void* 
   CALM_CHECK_ARG(dc == 0 || dcontent != nullptr, "calm_rope_bwd: dcontent missing");
   const int B = (int)(tokens / S), half = dr / 2;
   dim3 grid(S, ROPE_BCH);
-  if (rope_rows_ok(heads, dc, dr, {(long long)ld_dout, (long long)ld_out, (long long)(dc ? ld_dcontent : 8), (long long)ld_drope},
+  if (!(calm_get_debug_flags() & CALM_DEBUG_LEGACY_ROPE) && rope_rows_ok(heads, dc, dr, {(long long)ld_dout, (long long)ld_out, (long long)(dc ? ld_dcontent : 8), (long long)ld_drope},
                    {dout, out, dcontent, dropein})) {
     const int rowlen = heads * (dc + dr), chunks = rowlen / 8, R = RS_NT / chunks;
     const int nthreads = ((R * chunks + 31) / 32) * 32;

@@ -30,7 +30,8 @@ enum { CALM_MAJOR_K = 0, CALM_MAJOR_MN = 1 };
 enum { CALM_EPI_NONE = 0, CALM_EPI_GELU = 1, CALM_EPI_DGELU = 2 };
 enum { CALM_DEBUG_SIMT_GEMM = 1, CALM_DEBUG_LEGACY_ATTENTION = 2, CALM_DEBUG_NO_CLUSTER = 4, CALM_DEBUG_FORCE_CLUSTER = 8,
        CALM_DEBUG_PAIR_MULTICAST = 16 /* clusters use cta_group::1 + multicast B instead of cta_group::2 */,
-       CALM_DEBUG_DIRECT_EPILOGUE = 32 /* GEMM epilogue: per-thread global loads/stores instead of TMA-staged */ };
+       CALM_DEBUG_DIRECT_EPILOGUE = 32 /* GEMM epilogue: per-thread global loads/stores instead of TMA-staged */,
+       CALM_DEBUG_LEGACY_ROPE = 64 /* RoPE: per-head vector kernels instead of the row-staged 128-bit kernels */ };
 
 int32_t calm_abi_version(void);
 const char* calm_last_error(void); /* thread-local, valid until the next failing call on this thread */

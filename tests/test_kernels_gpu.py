@@ -411,6 +411,14 @@ def test_token_helpers(K):
     assert rel(K.colsum(xb, 1000, 448, 448), xb.float().sum(0)) < 1e-5
 
 
+@pytest.mark.parametrize("rows,N,ld", [(20480, 160, 160), (4099, 80, 240), (57344, 448, 448), (300, 352, 360), (777, 6, 10), (5, 224, 224)])
+def test_colsum_shapes(K, rows, N, ld):
+    # linear_mask bias gradients: the 128-bit kernel (N, ld multiples of 8) and the 4-byte fallback, strided views included
+    buf = rnd(rows, ld, seed=rows % 97)
+    got = K.colsum(buf, rows, N, ld)
+    assert rel(got, buf[:, :N].float().sum(0)) < 2e-5
+
+
 # ------------------------------------------------------------------------------------------------------ spectral norm
 def _sn_ref(w, u, v, eps=1e-12):
     # torch/nn/utils/spectral_norm.py:97-112, one power iteration
