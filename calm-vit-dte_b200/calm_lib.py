@@ -112,6 +112,7 @@ PROTOTYPES = {
     "calm_huber_tokens_fwd": (i32, [vp, vp, vp, f32, f32, vp, i32, vp, i32, i32, vp]),
     "calm_huber_tokens_bwd": (i32, [vp, vp, vp, f32, f32, vp, vp, i32, i32, vp]),
     "calm_trainer_step": (i32, [C.POINTER(TrainerStepArgs), vp]),
+    "calm_mix_batch": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, f32, f32, i32, i32, i32, i32, f32, f32, vp]),
 }
 
 _lib = None

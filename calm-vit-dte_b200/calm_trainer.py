@@ -127,6 +127,55 @@ def huber_kl_loss(tokens, image, kl=None, kl_weight=0.1, delta=1.0):
     return loss, out[1]
 
 
+# ---------------------------------------------------------------------------------------------------- input side
+class MixBatch:
+    """`transforms.RandomChoice([CutMix(num_classes=1000, alpha=1.0), MixUp(num_classes=1000, alpha=0.8)])` of the reference's
+    collate function (distributed_trainer_cls.py:58-61) applied to a batch that already lives on the device: one kernel
+    mixes the images (no `roll` / `clone` copies), one writes the (B, num_classes) soft labels.
+
+    `draw(H, W)` samples the parameters on the host with the torch CPU generator in torchvision's own order (multinomial for
+    the choice, Beta for lam, then two randint for the CutMix box centre), so a seeded run picks what torchvision would pick.
+    """
+
+    def __init__(self, num_classes=1000, cutmix_alpha=1.0, mixup_alpha=0.8):
+        self.num_classes = int(num_classes)
+        beta = torch.distributions.Beta
+        self._dist = [beta(torch.tensor([float(cutmix_alpha)]), torch.tensor([float(cutmix_alpha)])),
+                      beta(torch.tensor([float(mixup_alpha)]), torch.tensor([float(mixup_alpha)]))]
+
+    def draw(self, H, W):
+        idx = int(torch.multinomial(torch.tensor([0.5, 0.5]), 1))            # RandomChoice.forward
+        lam = float(self._dist[idx].sample(()))
+        if idx == 1:                                                          # MixUp.make_params
+            return {"mode": 0, "lam": lam, "box": (0, 0, 0, 0), "lam_labels": lam}
+        r_x = torch.randint(W, size=(1,))                                     # CutMix.make_params
+        r_y = torch.randint(H, size=(1,))
+        r = 0.5 * math.sqrt(1.0 - lam)
+        r_w_half, r_h_half = int(r * W), int(r * H)
+        x1 = int(torch.clamp(r_x - r_w_half, min=0))
+        y1 = int(torch.clamp(r_y - r_h_half, min=0))
+        x2 = int(torch.clamp(r_x + r_w_half, max=W))
+        y2 = int(torch.clamp(r_y + r_h_half, max=H))
+        return {"mode": 1, "lam": lam, "box": (x1, y1, x2, y2), "lam_labels": float(1.0 - (x2 - x1) * (y2 - y1) / (W * H))}
+
+    def __call__(self, images, labels, params=None):
+        """images f32 (B, C, H, W) and int64 labels (B,) on the device -> (mixed images, soft labels (B, num_classes))."""
+        if images.dim() != 4 or images.dtype != f32:
+            raise L.CalmError("MixBatch expects a float32 (B, C, H, W) batch")
+        if labels.dtype != torch.int64 or labels.shape != (images.shape[0],):
+            raise L.CalmError("MixBatch expects int64 class indices of shape (B,)")
+        B, Cc, H, W = images.shape
+        p = params if params is not None else self.draw(H, W)
+        x = images.contiguous()
+        out = torch.empty_like(x)
+        soft = torch.empty(B, self.num_classes, dtype=f32, device=x.device)
+        x1, y1, x2, y2 = p["box"]
+        L.call("calm_mix_batch", ptr(x), ptr(labels.contiguous()), ptr(out), ptr(soft), B, Cc, H, W, self.num_classes, int(p["mode"]),
+               float(p["lam"]), 1.0 - float(p["lam"]), x1, y1, x2, y2, float(p["lam_labels"]), 1.0 - float(p["lam_labels"]),
+               work=8.0 * x.numel())
+        return out, soft
+
+
 # ---------------------------------------------------------------------------------------------------- optimizer step
 class TrainerStep:
     """GradScaler + clip_grad_norm_ + AdamW of the reference loop as one object (distributed_trainer_cls.py:64,88-96,158).

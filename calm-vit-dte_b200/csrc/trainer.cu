@@ -292,9 +292,85 @@ opt_adamw_kernel(OptArgs a) {
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// input side: MixUp / CutMix of a device-resident batch + the soft labels they produce
+// ------------------------------------------------------------------------------------------------------------------
+template <bool VEC>
+__global__ void __launch_bounds__(256)
+mix_batch_kernel(const float* __restrict__ x, float* __restrict__ out, long long per_image, int H, int W, int B, int mode, float lam,
+                 float m, int bx1, int by1, int bx2, int by2) {
+  constexpr int V = VEC ? 4 : 1;
+  const long long n = (long long)B * per_image / V;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
+    const long long e = i * V;
+    const long long b = e / per_image, r = e - b * per_image;
+    const long long prev = (b == 0 ? (long long)B - 1 : b - 1) * per_image + r;     // images.roll(1, 0)
+    if (mode == 0) {
+      // torchvision: inpt.roll(1, 0).mul_(1.0 - lam).add_(inpt.mul(lam)) — two rounded products, one rounded sum (no FMA);
+      // m = 1.0 - lam comes from the host, evaluated in double before it becomes the fp32 scalar (like the Python expression)
+      if (VEC) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(x + e)), p = __ldg(reinterpret_cast<const float4*>(x + prev));
+        *reinterpret_cast<float4*>(out + e) = make_float4(__fadd_rn(__fmul_rn(p.x, m), __fmul_rn(a.x, lam)), __fadd_rn(__fmul_rn(p.y, m), __fmul_rn(a.y, lam)),
+                                                          __fadd_rn(__fmul_rn(p.z, m), __fmul_rn(a.z, lam)), __fadd_rn(__fmul_rn(p.w, m), __fmul_rn(a.w, lam)));
+      } else {
+        out[e] = __fadd_rn(__fmul_rn(x[prev], m), __fmul_rn(x[e], lam));
+      }
+    } else {
+      const int pix = (int)(r % ((long long)H * W));
+      const int yy = pix / W, xx = pix - yy * W;
+      const bool row_in = yy >= by1 && yy < by2;
+      if (VEC) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(x + e));
+        float4 o = a;
+        if (row_in && xx + 3 >= bx1 && xx < bx2) {
+          const float4 p = __ldg(reinterpret_cast<const float4*>(x + prev));
+          if (xx >= bx1 && xx < bx2) o.x = p.x;
+          if (xx + 1 >= bx1 && xx + 1 < bx2) o.y = p.y;
+          if (xx + 2 >= bx1 && xx + 2 < bx2) o.z = p.z;
+          if (xx + 3 >= bx1 && xx + 3 < bx2) o.w = p.w;
+        }
+        *reinterpret_cast<float4*>(out + e) = o;
+      } else {
+        out[e] = (row_in && xx >= bx1 && xx < bx2) ? x[prev] : x[e];
+      }
+    }
+  }
+}
+
+// soft[b, c] = lam [c == label_b] + (1 - lam) [c == label_{b-1}]  (one-hot labels mixed like the images)
+__global__ void __launch_bounds__(256)
+mix_labels_kernel(const long long* __restrict__ labels, float* __restrict__ soft, int B, int num_classes, float lam, float m) {
+  const int b = blockIdx.x;
+  const long long cur = labels[b], prev = labels[b == 0 ? B - 1 : b - 1];
+  for (int c = threadIdx.x; c < num_classes; c += 256)
+    soft[(long long)b * num_classes + c] = (c == cur ? lam : 0.0f) + (c == prev ? m : 0.0f);
+}
+
 }  // namespace
 
 extern "C" {
+
+int32_t calm_mix_batch(const float* x, const int64_t* labels, float* out, float* soft, int32_t B, int32_t channels, int32_t H,
+                       int32_t W, int32_t num_classes, int32_t mode, float lam, float one_minus_lam, int32_t x1, int32_t y1, int32_t x2,
+                       int32_t y2, float lam_labels, float one_minus_lam_labels, cudaStream_t stream) {
+  CALM_CHECK_ARG(x && out && x != out && B > 0 && channels > 0 && H > 0 && W > 0, "calm_mix_batch: bad arguments (out must not alias x)");
+  CALM_CHECK_ARG(mode == 0 || mode == 1, "calm_mix_batch: mode %d (0 = MixUp, 1 = CutMix)", mode);
+  CALM_CHECK_ARG((labels == nullptr) == (soft == nullptr) && (!labels || num_classes > 0), "calm_mix_batch: labels and soft go together");
+  const long long per_image = (long long)channels * H * W;
+  const bool vec = W % 4 == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
+  const long long n = (long long)B * per_image / (vec ? 4 : 1);
+  long long blocks = (n + 255) / 256;
+  const long long cap = 16LL * calm_num_sms();
+  if (blocks > cap) blocks = cap;
+  if (vec) mix_batch_kernel<true><<<(unsigned)blocks, 256, 0, stream>>>(x, out, per_image, H, W, B, mode, lam, one_minus_lam, x1, y1, x2, y2);
+  else mix_batch_kernel<false><<<(unsigned)blocks, 256, 0, stream>>>(x, out, per_image, H, W, B, mode, lam, one_minus_lam, x1, y1, x2, y2);
+  CALM_CHECK_LAUNCH("mix_batch_kernel");
+  if (labels) {
+    mix_labels_kernel<<<B, 256, 0, stream>>>(reinterpret_cast<const long long*>(labels), soft, B, num_classes, lam_labels, one_minus_lam_labels);
+    CALM_CHECK_LAUNCH("mix_labels_kernel");
+  }
+  return CALM_OK;
+}
 
 int32_t calm_soft_ce_fwd(const float* logits, int64_t ld, const float* target, int64_t ld_t, const int64_t* labels,
                          float* row_stats, float* loss_out, int32_t B, int32_t C, cudaStream_t stream) {

@@ -221,6 +221,17 @@ int32_t calm_huber_tokens_fwd(const float* tokens, const float* target_nchw, con
 int32_t calm_huber_tokens_bwd(const float* tokens, const float* target_nchw, const float* dloss, float kl_weight, float delta,
                               float* dtokens, float* dkl, int32_t B, int32_t S, cudaStream_t stream);
 
+/* Input side: torchvision.transforms.v2 MixUp / CutMix (distributed_trainer_cls.py:58-61, applied there by the
+ * collate function on the CPU) on a batch that is already on the device. x, out f32 (B, channels, H, W), out != x.
+ *   mode 0 (MixUp):  out[b] = lam * x[b] + (1 - lam) * x[b-1]                      (b-1 wraps: images.roll(1, 0))
+ *   mode 1 (CutMix): out[b] = x[b] with rows [y1,y2) x columns [x1,x2) taken from x[b-1]
+ *   soft (B, num_classes) f32 = lam_labels * onehot(labels[b]) + (1 - lam_labels) * onehot(labels[b-1])   (labels/soft may be NULL)
+ * one_minus_* = the Python expression 1.0 - lam evaluated in double by the caller (torchvision's scalar), then rounded to f32.
+ * The host draws lam / the box exactly like torchvision does (calm_trainer.MixBatch). */
+int32_t calm_mix_batch(const float* x, const int64_t* labels, float* out, float* soft, int32_t B, int32_t channels, int32_t H,
+                       int32_t W, int32_t num_classes, int32_t mode, float lam, float one_minus_lam, int32_t x1, int32_t y1, int32_t x2,
+                       int32_t y2, float lam_labels, float one_minus_lam_labels, cudaStream_t stream);
+
 /* GradScaler.unscale_ + clip_grad_norm_(max_norm) + GradScaler.step(AdamW) + GradScaler.update
  * (distributed_trainer_cls.py:88-96, distributed_trainer_reg.py:90-97) as three launches over all parameter tensors:
  * (1) per-chunk sum of squares of the unscaled gradients, (2) one CTA: total norm, inf/nan check, clip coefficient, step

@@ -2,8 +2,13 @@
 CrossEntropyLoss with soft targets, HuberLoss + 0.1 kl, GradScaler + clip_grad_norm_ + AdamW
 (distributed_trainer_cls.py:63-64,84-102,158; distributed_trainer_reg.py:76-98). fp32 arithmetic: tolerance 1e-5 relative
 (different summation orders), skip/scale bookkeeping exact."""
+import os
+import sys
+
 import pytest
 import torch
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 
 pytestmark = pytest.mark.gpu
 
@@ -166,3 +171,21 @@ def test_state_dict_round_trip():
     other.load_state_dict(sd)
     assert torch.equal(other.exp_avg, ts.exp_avg) and torch.equal(other.exp_avg_sq, ts.exp_avg_sq)
     assert other.get_lr() == pytest.approx(1e-3) and other.step_count.item() == 1.0 and other.get_scale() == ts.get_scale()
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2, 3, 5, 8])
+@pytest.mark.parametrize("shape", [(6, 3, 224, 224), (3, 3, 30, 42)])
+def test_mix_batch_matches_torchvision_semantics(seed, shape):
+    """Device CutMix / MixUp vs the restatement that tests/test_input_mix.py pins on torchvision itself (bit-exact)."""
+    import calm_trainer
+    from test_input_mix import mix_reference
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(*shape, generator=g)
+    y = torch.randint(0, 1000, (shape[0],), generator=g)
+    mb = calm_trainer.MixBatch(num_classes=1000)
+    torch.manual_seed(seed)
+    params = mb.draw(shape[2], shape[3])
+    want_x, want_y = mix_reference(x, y, params, 1000)
+    got_x, got_y = mb(x.cuda(), y.cuda(), params)
+    assert torch.equal(got_x.cpu(), want_x)
+    assert torch.equal(got_y.cpu(), want_y)
