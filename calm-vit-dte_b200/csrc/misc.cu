@@ -222,7 +222,7 @@ extern "C" int32_t calm_nchw_to_tokens(const float* in, float* out, int32_t B, i
 
 extern "C" int32_t calm_colsum_parts(int64_t rows, int32_t N) {
   (void)N;
-  const long long cap = 4LL * calm_num_sms();
+  const long long cap = 2LL * calm_num_sms();   // 2 CTAs x 256 threads x 8 loads of 16 bytes = 64 KB in flight per SM
   return (int32_t)(rows < cap ? rows : cap);
 }
 
