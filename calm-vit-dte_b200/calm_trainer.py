@@ -211,6 +211,7 @@ class TrainerStep:
                 chunk_tensor.append(i)
                 chunk_start.append(j)
         self.n_tensors, self.n_chunks, self.total = len(numels), len(chunk_tensor), off[-1]
+        self._off = off
         i64, i32 = torch.int64, torch.int32
         self.elem_off = torch.tensor(off, dtype=i64, device=dev)
         self.chunk_tensor = torch.tensor(chunk_tensor, dtype=i32, device=dev)
@@ -275,7 +276,7 @@ class TrainerStep:
 
     def moments(self, i):
         """(exp_avg, exp_avg_sq) views of parameter i, shaped like it (torch.optim.AdamW's per-parameter state)."""
-        a, b = int(self.elem_off[i].item()), int(self.elem_off[i + 1].item())
+        a, b = self._off[i], self._off[i + 1]
         return self.exp_avg[a:b].view_as(self.params[i]), self.exp_avg_sq[a:b].view_as(self.params[i])
 
     # -- the step --------------------------------------------------------------------------------------------------------
