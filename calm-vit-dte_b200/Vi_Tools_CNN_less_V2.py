@@ -249,7 +249,7 @@ class VMLA_Block(torch.nn.Module):
         x = lin(att, self.out_proj, addend=res, out_f32=True)                    # (attn Wo^T) * ls_att + residual, fp32
         if self.mlp is None:
             return ops.LayerNormFn.apply(x, self.ln_2.weight, True)[0]
-        y, res2 = ops.LayerNormFn.apply(x, self.ln_2.weight, False)
+        y, res2 = ops.LayerNormFn.apply(x, self.ln_2.weight, False, True)   # d x feeds out_proj's backward GEMMs
         return ops.MlpFn.apply(y, tok, res2, bank, gid(self.mlp[0]), gid(self.mlp[3]), True)   # x + mlp(y) * ls_mlp
 
 

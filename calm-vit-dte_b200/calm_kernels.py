@@ -67,17 +67,18 @@ def layernorm_fwd(x, w, eps=1e-6, out_dtype=bf16):
     return y, mean, rstd
 
 
-def layernorm_bwd(dy, x, w, mean, rstd, dres=None):
-    """dx f32 = LN'(dy) (+ dres), dw f32 (D)."""
+def layernorm_bwd(dy, x, w, mean, rstd, dres=None, want_bf16=False):
+    """dx f32 = LN'(dy) (+ dres), dw f32 (D); with want_bf16 also the bf16 copy of dx (third result)."""
     D = x.shape[-1]
     rows = x.numel() // D
     nparts = L.load().calm_layernorm_bwd_parts(rows, D)
     dx = torch.empty(x.shape, dtype=f32, device=x.device)
     part = torch.empty(nparts * D, dtype=f32, device=x.device)
     dw = torch.empty(D, dtype=f32, device=x.device)
-    L.call("calm_layernorm_bwd", ptr(dy), _dt(dy), ptr(x), ptr(w), ptr(mean), ptr(rstd), ptr(dres), ptr(dx), ptr(part),
+    dx16 = torch.empty(x.shape, dtype=bf16, device=x.device) if want_bf16 else None
+    L.call("calm_layernorm_bwd", ptr(dy), _dt(dy), ptr(x), ptr(w), ptr(mean), ptr(rstd), ptr(dres), ptr(dx), ptr(dx16), ptr(part),
            nparts, ptr(dw), rows, D)
-    return dx, dw
+    return (dx, dw, dx16) if want_bf16 else (dx, dw)
 
 
 # ------------------------------------------------------------------------------------------------ RoPE
@@ -178,23 +179,25 @@ def cnn_fwd(x, w1, b1, w2, b2, w3, b3, B, S):
     return y
 
 
-def cnn_bwd(x, dy, w1, b1, w2, b2, w3, b3, B, S, gp=None):
-    """Returns dx f32 and gparams f32 (547): w1[96] b1[32] w2[288] b2[32] w3[96] b3[3]."""
+def cnn_bwd(x, dy, w1, b1, w2, b2, w3, b3, B, S, gp=None, want_bf16=False):
+    """Returns dx f32 and gparams f32 (547): w1[96] b1[32] w2[288] b2[32] w3[96] b3[3] (+ the bf16 copy of dx with want_bf16)."""
     nblocks = L.load().calm_cnn_bwd_blocks(B, S)
     dx = torch.empty_like(x)
     part = torch.empty(nblocks * L.CNN_NPARAM, dtype=f32, device=x.device)
     if gp is None:
         gp = torch.empty(L.CNN_NPARAM, dtype=f32, device=x.device)
-    L.call("calm_cnn_bwd", ptr(x), ptr(dy), ptr(dx), ptr(w1), ptr(b1), ptr(w2), ptr(b2), ptr(w3), ptr(b3), ptr(part), nblocks,
+    dx16 = torch.empty(x.shape, dtype=bf16, device=x.device) if want_bf16 else None
+    L.call("calm_cnn_bwd", ptr(x), ptr(dy), ptr(dx), ptr(dx16), ptr(w1), ptr(b1), ptr(w2), ptr(b2), ptr(w3), ptr(b3), ptr(part), nblocks,
            ptr(gp), B, S)
-    return dx, gp
+    return (dx, gp, dx16) if want_bf16 else (dx, gp)
 
 
 # ------------------------------------------------------------------------------------------------ helpers
-def token_transpose(x, B, S, addend=None):
+def token_transpose(x, B, S, addend=None, want_bf16=False):
     out = torch.empty_like(x)
-    L.call("calm_token_transpose", ptr(x), ptr(addend), ptr(out), B, S)
-    return out
+    out16 = torch.empty(x.shape, dtype=bf16, device=x.device) if want_bf16 else None
+    L.call("calm_token_transpose", ptr(x), ptr(addend), ptr(out), ptr(out16), B, S)
+    return (out, out16) if want_bf16 else out
 
 
 def nchw_to_tokens(x):

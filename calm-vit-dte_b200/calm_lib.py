@@ -81,7 +81,7 @@ PROTOTYPES = {
     "calm_sn_forward": (i32, [vp, i32, vp, i32, i32, f32, vp]),
     "calm_sn_backward": (i32, [vp, i32, vp, i32, vp]),
     "calm_layernorm_fwd": (i32, [vp, vp, vp, i32, vp, vp, i64, i32, f32, vp]),
-    "calm_layernorm_bwd": (i32, [vp, i32, vp, vp, vp, vp, vp, vp, vp, i32, vp, i64, i32, vp]),
+    "calm_layernorm_bwd": (i32, [vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp, i64, i32, vp]),
     "calm_layernorm_bwd_parts": (i32, [i64, i32]),
     "calm_rope_table": (i32, [vp, vp, i32, i32, vp]),
     "calm_rope_fwd": (i32, [vp, i64, vp, i64, vp, i64, vp, i64, i32, i32, i32, i32, vp]),
@@ -95,9 +95,9 @@ PROTOTYPES = {
     "calm_latent_bwd": (i32, [vp, vp, vp, vp, f32, vp, vp, vp, i64, i32, vp]),
     "calm_latent_blocks": (i32, [i64, i32]),
     "calm_cnn_fwd": (i32, [vp] * 8 + [i32, i32, vp]),
-    "calm_cnn_bwd": (i32, [vp] * 10 + [i32, vp, i32, i32, vp]),
+    "calm_cnn_bwd": (i32, [vp] * 11 + [i32, vp, i32, i32, vp]),
     "calm_cnn_bwd_blocks": (i32, [i32, i32]),
-    "calm_token_transpose": (i32, [vp, vp, vp, i32, i32, vp]),
+    "calm_token_transpose": (i32, [vp, vp, vp, vp, i32, i32, vp]),
     "calm_nchw_to_tokens": (i32, [vp, vp, i32, i32, vp]),
     "calm_colsum": (i32, [vp, i64, vp, i32, vp, i64, i32, vp]),
     "calm_colsum_parts": (i32, [i64, i32]),

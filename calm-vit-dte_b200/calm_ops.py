@@ -12,6 +12,7 @@ per backward turns them into dL/dW_orig. The bank's autograd
 consumers by a 1-element `token` tensor every consumer takes as an input.
 """
 import functools
+import os
 import threading
 import weakref
 
@@ -254,8 +255,25 @@ def _lin_wgrad(bank, gid, dy2, ld_dy, x2, ld_x, M):
            splits=s, stride_split=g["rows"] * g["cols"])
 
 
+# bf16 copies of fp32 gradients that their producer (LayerNorm backward) already wrote: id(tensor) -> (weakref, bf16 tensor).
+# A hit requires the very same tensor object autograd hands on (identity through the weak reference), so a gradient that was
+# accumulated, copied or whose memory was recycled can never pick up a stale copy; entries die with their fp32 tensor.
+_BF16_SIDE = {}
+_SIDE_ON = os.environ.get("CALM_BF16_SIDE", "1") != "0"     # A/B switch: 0 = every fp32 gradient is cast by its consumer
+
+
+def _offer_bf16(g, g16):
+    key = id(g)
+    _BF16_SIDE[key] = (weakref.ref(g, lambda _r, k=key: _BF16_SIDE.pop(k, None)), g16)
+
+
 def _bf16_grad(g):
-    return g if g.dtype == bf16 else K.cast_bf16(g.contiguous())
+    if g.dtype == bf16:
+        return g
+    e = _BF16_SIDE.get(id(g))
+    if e is not None and e[0]() is g and e[1].shape == g.shape:
+        return e[1]
+    return K.cast_bf16(g.contiguous())
 
 
 # =====================================================================================================================
@@ -265,20 +283,28 @@ class LayerNormFn(Function):
     """y = LN(x)*w in bf16 (or fp32), plus an alias of x so that the residual consumer's gradient is fused into dx."""
 
     @staticmethod
-    def forward(ctx, x, w, out_f32):
+    def forward(ctx, x, w, out_f32, grad_feeds_gemm=False):
+        """grad_feeds_gemm: the gradient of x goes straight into a Linear's backward (ln_2 -> out_proj): LayerNorm backward then
+        also writes it as bf16, the form that GEMM reads."""
         x = x.contiguous()
         y, mean, rstd = K.layernorm_fwd(x, w, 1e-6, f32 if out_f32 else bf16)
         ctx.save_for_backward(x, w, mean, rstd)
         ctx.set_materialize_grads(False)
+        ctx.side = bool(grad_feeds_gemm) and _SIDE_ON
         return y, x.view_as(x)
 
     @staticmethod
     def backward(ctx, dy, dres):
         x, w, mean, rstd = ctx.saved_tensors
         if dy is None:
-            return dres, None, None
-        dx, dw = K.layernorm_bwd(dy.contiguous(), x, w, mean, rstd, dres.contiguous() if dres is not None else None)
-        return dx, dw, None
+            return dres, None, None, None
+        dres = dres.contiguous() if dres is not None else None
+        if not ctx.side:
+            dx, dw = K.layernorm_bwd(dy.contiguous(), x, w, mean, rstd, dres)
+            return dx, dw, None, None
+        dx, dw, dx16 = K.layernorm_bwd(dy.contiguous(), x, w, mean, rstd, dres, want_bf16=True)
+        _offer_bf16(dx, dx16)       # the producing Linear's backward takes this gradient as a bf16 GEMM operand
+        return dx, dw, None, None
 
 
 class LinearFn(Function):
@@ -566,7 +592,12 @@ class CnnFn(Function):
         B, S = x.shape[0], x.shape[1]
         # weight gradients wrt the effective conv weights land in the bank: w1[0:96] w2[128:416] w3[448:544]
         gp = bank.cnn_grad_buffer(g1, g2, g3)
-        dx, gp = K.cnn_bwd(x, dy.contiguous(), bank.weight(g1), b1, bank.weight(g2), b2, bank.weight(g3), b3, B, S, gp=gp)
+        if _SIDE_ON:
+            dx, gp, dx16 = K.cnn_bwd(x, dy.contiguous(), bank.weight(g1), b1, bank.weight(g2), b2, bank.weight(g3), b3, B, S, gp=gp,
+                                     want_bf16=True)
+            _offer_bf16(dx, dx16)   # next consumer: the cross block's MLP backward (bf16 GEMM operands)
+        else:
+            dx, gp = K.cnn_bwd(x, dy.contiguous(), bank.weight(g1), b1, bank.weight(g2), b2, bank.weight(g3), b3, B, S, gp=gp)
         return dx, None, gp[96:128].clone(), gp[416:448].clone(), gp[544:547].clone(), None, None, None, None
 
 
@@ -585,7 +616,12 @@ class TokenSwapFn(Function):
         if dt is None:
             return dalias
         dt = dt.contiguous()
-        return K.token_transpose(dt, dt.shape[0], dt.shape[1], addend=dalias.contiguous() if dalias is not None else None)
+        add = dalias.contiguous() if dalias is not None else None
+        if not _SIDE_ON:
+            return K.token_transpose(dt, dt.shape[0], dt.shape[1], addend=add)
+        d, d16 = K.token_transpose(dt, dt.shape[0], dt.shape[1], addend=add, want_bf16=True)
+        _offer_bf16(d, d16)         # next consumer: the previous attention block's MLP backward (bf16 GEMM operands)
+        return d
 
 
 class ImageToTokensFn(Function):

@@ -199,7 +199,7 @@ constexpr int WACC = 548;                          // per-warp accumulators: 32 
 constexpr int BWD_SMEM_FLOATS = B_XS + B_DYS + B_H1 + B_G1 + B_DP2 + WSM + NW * WACC;
 
 __device__ __forceinline__ void
-cnn_bwd_body(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dx, const CnnW& W,
+cnn_bwd_body(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dx, bf16* __restrict__ dx16, const CnnW& W,
              float* __restrict__ gpartial, int B, int S, int tiles_x, int tiles_y, int th) {
   extern __shared__ __align__(16) float sm[];
   float* xs = sm;
@@ -392,6 +392,7 @@ cnn_bwd_body(const float* __restrict__ x, const float* __restrict__ dy, float* _
       const int gy = ty0 + d_r;
       if (gy < S) {
         float* dxrow = dx + ((long long)b * S * S + (long long)gy * S) * 3;
+        bf16* dxrow16 = dx16 ? dx16 + ((long long)b * S * S + (long long)gy * S) * 3 : nullptr;   // optional bf16 copy of dx
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const int gx = tx0 + 4 * d_g + j;
@@ -400,6 +401,11 @@ cnn_bwd_body(const float* __restrict__ x, const float* __restrict__ dy, float* _
             dxrow[gx * 3 + 0] = dxa[j][0] + dc[0];
             dxrow[gx * 3 + 1] = dxa[j][1] + dc[1];
             dxrow[gx * 3 + 2] = dxa[j][2] + dc[2];
+            if (dxrow16) {
+              dxrow16[gx * 3 + 0] = __float2bfloat16(dxa[j][0] + dc[0]);
+              dxrow16[gx * 3 + 1] = __float2bfloat16(dxa[j][1] + dc[1]);
+              dxrow16[gx * 3 + 2] = __float2bfloat16(dxa[j][2] + dc[2]);
+            }
             gb3[0] += dc[0]; gb3[1] += dc[1]; gb3[2] += dc[2];
           }
         }
@@ -435,14 +441,14 @@ cnn_bwd_body(const float* __restrict__ x, const float* __restrict__ dy, float* _
 
 // two register budgets of the same body: 3 CTAs/SM (80 registers, a few spills) or 2 CTAs/SM (no spills)
 __global__ void __launch_bounds__(NT, 3)
-cnn_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dx, CnnW W,
+cnn_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dx, bf16* __restrict__ dx16, CnnW W,
                float* __restrict__ gpartial, int B, int S, int tiles_x, int tiles_y, int th) {
-  cnn_bwd_body(x, dy, dx, W, gpartial, B, S, tiles_x, tiles_y, th);
+  cnn_bwd_body(x, dy, dx, dx16, W, gpartial, B, S, tiles_x, tiles_y, th);
 }
 __global__ void __launch_bounds__(NT, 2)
-cnn_bwd_kernel_occ2(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dx, CnnW W,
+cnn_bwd_kernel_occ2(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dx, bf16* __restrict__ dx16, CnnW W,
                     float* __restrict__ gpartial, int B, int S, int tiles_x, int tiles_y, int th) {
-  cnn_bwd_body(x, dy, dx, W, gpartial, B, S, tiles_x, tiles_y, th);
+  cnn_bwd_body(x, dy, dx, dx16, W, gpartial, B, S, tiles_x, tiles_y, th);
 }
 
 __global__ void cnn_reduce_kernel(const float* __restrict__ partial, float* __restrict__ out, int nparts, int n) {
@@ -495,7 +501,7 @@ extern "C" int32_t calm_cnn_bwd_blocks(int32_t B, int32_t S) {
   return (int32_t)(total < cap ? total : cap);
 }
 
-extern "C" int32_t calm_cnn_bwd(const float* x, const float* dy, float* dx, const float* w1, const float* b1, const float* w2,
+extern "C" int32_t calm_cnn_bwd(const float* x, const float* dy, float* dx, void* dx_bf16, const float* w1, const float* b1, const float* w2,
                                 const float* b2, const float* w3, const float* b3, float* gpartial, int32_t nblocks, float* gparams,
                                 int32_t B, int32_t S, cudaStream_t stream) {
   CALM_CHECK_ARG(B > 0 && S > 0, "calm_cnn_bwd: B=%d S=%d", B, S);
@@ -511,8 +517,9 @@ extern "C" int32_t calm_cnn_bwd(const float* x, const float* dy, float* dx, cons
     configured = true;
   }
   CnnW W{w1, b1, w2, b2, w3, b3};
-  if (bwd_ctas_per_sm() == 2) cnn_bwd_kernel_occ2<<<nblocks, NT, smem, stream>>>(x, dy, dx, W, gpartial, B, S, tiles_x, tiles_y, th);
-  else cnn_bwd_kernel<<<nblocks, NT, smem, stream>>>(x, dy, dx, W, gpartial, B, S, tiles_x, tiles_y, th);
+  bf16* dx16 = reinterpret_cast<bf16*>(dx_bf16);
+  if (bwd_ctas_per_sm() == 2) cnn_bwd_kernel_occ2<<<nblocks, NT, smem, stream>>>(x, dy, dx, dx16, W, gpartial, B, S, tiles_x, tiles_y, th);
+  else cnn_bwd_kernel<<<nblocks, NT, smem, stream>>>(x, dy, dx, dx16, W, gpartial, B, S, tiles_x, tiles_y, th);
   CALM_CHECK_LAUNCH("calm_cnn_bwd");
   cnn_reduce_kernel<<<(CALM_CNN_NPARAM + 127) / 128, 128, 0, stream>>>(gpartial, gparams, nblocks, CALM_CNN_NPARAM);
   CALM_CHECK_LAUNCH("calm_cnn_bwd(reduce)");

@@ -98,7 +98,7 @@ template <bool DY_F32>
 __global__ void __launch_bounds__(LN_THREADS)
 ln_bwd_kernel(const void* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ w,
               const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ dres,
-              float* __restrict__ dx, float* __restrict__ dw_partial, long long rows, int D) {
+              float* __restrict__ dx, bf16* __restrict__ dx16, float* __restrict__ dw_partial, long long rows, int D) {
   extern __shared__ float acc_s[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float* my = acc_s + (size_t)warp * D;
@@ -135,6 +135,7 @@ ln_bwd_kernel(const void* __restrict__ dy, const float* __restrict__ x, const fl
         o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
       }
       reinterpret_cast<float4*>(dx + row * D)[i] = o;
+      if (dx16) reinterpret_cast<uint2*>(dx16 + row * D)[i] = make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
     }
   }
   __syncthreads();
@@ -153,7 +154,7 @@ template <int VPL, bool DY_F32>
 __global__ void __launch_bounds__(LN_THREADS, VPL <= 3 ? 3 : VPL <= 6 ? 2 : 1)
 ln_bwd_reg_kernel(const void* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ w,
                   const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ dres,
-                  float* __restrict__ dx, float* __restrict__ dw_partial, long long rows, int D) {
+                  float* __restrict__ dx, bf16* __restrict__ dx16, float* __restrict__ dw_partial, long long rows, int D) {
   extern __shared__ float acc_s[];  // LN_WARPS * D, then D floats of w
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nv = D >> 2;
@@ -205,6 +206,9 @@ ln_bwd_reg_kernel(const void* __restrict__ dy, const float* __restrict__ x, cons
           o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
         }
         reinterpret_cast<float4*>(dx + row * D)[idx] = o;
+        // optional bf16 copy: the GEMMs that consume this gradient next (dgrad / wgrad of the producing Linear) take bf16
+        // operands; writing it here replaces a separate 4-byte-read + 2-byte-write cast pass over the tensor
+        if (dx16) reinterpret_cast<uint2*>(dx16 + row * D)[idx] = make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
       }
     }
   }
@@ -269,8 +273,8 @@ extern "C" int32_t calm_layernorm_bwd_parts(int64_t rows, int32_t D) {
 }
 
 extern "C" int32_t calm_layernorm_bwd(const void* dy, int32_t dy_dtype, const float* x, const float* w, const float* mean,
-                                      const float* rstd, const float* dres, float* dx, float* dw_partial, int32_t nparts,
-                                      float* dw, int64_t rows, int32_t D, cudaStream_t stream) {
+                                      const float* rstd, const float* dres, float* dx, void* dx_bf16, float* dw_partial,
+                                      int32_t nparts, float* dw, int64_t rows, int32_t D, cudaStream_t stream) {
   CALM_CHECK_ARG(rows > 0 && D > 0 && D % 4 == 0, "calm_layernorm_bwd: rows=%lld D=%d", (long long)rows, D);
   CALM_CHECK_ARG(nparts == calm_layernorm_bwd_parts(rows, D), "calm_layernorm_bwd: nparts=%d, expected %d", nparts, calm_layernorm_bwd_parts(rows, D));
   const size_t smem = (size_t)(LN_WARPS + 1) * D * sizeof(float);   // per-warp dw rows + w
@@ -282,7 +286,7 @@ extern "C" int32_t calm_layernorm_bwd(const void* dy, int32_t dy_dtype, const fl
       cudaError_t e = cudaFuncSetAttribute(KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);           \
       if (e != cudaSuccess) { calm_set_error("calm_layernorm_bwd: smem %zu: %s", smem, cudaGetErrorString(e)); return CALM_ERR_CUDA; } \
     }                                                                                                                 \
-    KERNEL<<<nparts, LN_THREADS, smem, stream>>>(dy, x, w, mean, rstd, dres, dx, dw_partial, rows, D);                 \
+    KERNEL<<<nparts, LN_THREADS, smem, stream>>>(dy, x, w, mean, rstd, dres, dx, reinterpret_cast<bf16*>(dx_bf16), dw_partial, rows, D);                  \
   } while (0)
   if (vpl <= 3) { if (f32) LN_BWD_LAUNCH((ln_bwd_reg_kernel<3, true>)); else LN_BWD_LAUNCH((ln_bwd_reg_kernel<3, false>)); }
   else if (vpl <= 6) { if (f32) LN_BWD_LAUNCH((ln_bwd_reg_kernel<6, true>)); else LN_BWD_LAUNCH((ln_bwd_reg_kernel<6, false>)); }

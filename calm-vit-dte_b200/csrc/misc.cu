@@ -11,11 +11,13 @@ namespace {
 // the transposition itself happens on scalar shared-memory reads (pitch 97: conflict-free both ways).
 template <bool VEC>
 __global__ void __launch_bounds__(256)
-token_transpose_kernel(const float* __restrict__ in, const float* __restrict__ addend, float* __restrict__ out, int S) {
+token_transpose_kernel(const float* __restrict__ in, const float* __restrict__ addend, float* __restrict__ out,
+                       bf16* __restrict__ out16, int S) {
   __shared__ float tile[32][32 * 3 + 1];
   const int b = blockIdx.z, i0 = blockIdx.y * 32, j0 = blockIdx.x * 32;
   const float* src = in + (long long)b * S * S * 3;
   float* dst = out + (long long)b * S * S * 3;
+  bf16* dst16 = out16 ? out16 + (long long)b * S * S * 3 : nullptr;   // optional bf16 copy (the next GEMM's operand form)
   const float* add = addend ? addend + (long long)b * S * S * 3 : nullptr;
   if (VEC) {
     const int row_f = S * 3;
@@ -41,6 +43,7 @@ token_transpose_kernel(const float* __restrict__ in, const float* __restrict__ a
           v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w;
         }
         *reinterpret_cast<float4*>(dst + o) = make_float4(v[0], v[1], v[2], v[3]);
+        if (dst16) *reinterpret_cast<uint2*>(dst16 + o) = make_uint2(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]));
       }
     }
   } else {
@@ -58,6 +61,7 @@ token_transpose_kernel(const float* __restrict__ in, const float* __restrict__ a
         float val = tile[cc / 3][r * 3 + cc % 3];
         if (add) val += add[o];
         dst[o] = val;
+        if (dst16) dst16[o] = __float2bfloat16(val);
       }
     }
   }
@@ -202,12 +206,14 @@ __global__ void seq_mean_bwd_kernel(const bf16* __restrict__ dout, float* __rest
 
 }  // namespace
 
-extern "C" int32_t calm_token_transpose(const float* in, const float* addend, float* out, int32_t B, int32_t S, cudaStream_t stream) {
+extern "C" int32_t calm_token_transpose(const float* in, const float* addend, float* out, void* out_bf16, int32_t B, int32_t S,
+                                        cudaStream_t stream) {
   CALM_CHECK_ARG(B > 0 && S > 0 && in != out, "calm_token_transpose: B=%d S=%d (out of place only)", B, S);
   dim3 grid((S + 31) / 32, (S + 31) / 32, B);
-  const bool vec = S % 4 == 0 && ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(addend)) & 15) == 0;
-  if (vec) token_transpose_kernel<true><<<grid, 256, 0, stream>>>(in, addend, out, S);
-  else token_transpose_kernel<false><<<grid, 256, 0, stream>>>(in, addend, out, S);
+  const bool vec = S % 4 == 0 && ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(addend) |
+                                   reinterpret_cast<uintptr_t>(out_bf16)) & 15) == 0;
+  if (vec) token_transpose_kernel<true><<<grid, 256, 0, stream>>>(in, addend, out, reinterpret_cast<bf16*>(out_bf16), S);
+  else token_transpose_kernel<false><<<grid, 256, 0, stream>>>(in, addend, out, reinterpret_cast<bf16*>(out_bf16), S);
   CALM_CHECK_LAUNCH("calm_token_transpose");
   return CALM_OK;
 }

@@ -102,12 +102,13 @@ int32_t calm_sn_backward(const calm_sn_layer* table_dev, int32_t n_layers, const
 /* ------------------------------------------------------------------------------------------------------------------
  * Weight-only LayerNorm (eps 1e-6, no bias): ln_q / ln_kv / ln_2 / ln_final (Vi_Tools_CNN_less_V2.py:131-132,197,494)
  *   fwd: x f32 (rows, D) -> y bf16 (rows, D) [+ y_f32 optional], mean/rstd f32 (rows)
- *   bwd: dx f32 = LN'(dy) (+ dres), dw partials (nparts, D) to be summed by the caller-visible finalize
+ *   bwd: dx f32 = LN'(dy) (+ dres) [+ the same values as bf16 in dx_bf16 when non-NULL: the operand form the next
+ *        dgrad / wgrad GEMM reads], dw partials (nparts, D) to be summed by the caller-visible finalize
  * ------------------------------------------------------------------------------------------------------------------ */
 int32_t calm_layernorm_fwd(const float* x, const float* w, void* y, int32_t y_dtype, float* mean, float* rstd,
                            int64_t rows, int32_t D, float eps, cudaStream_t stream);
 int32_t calm_layernorm_bwd(const void* dy, int32_t dy_dtype, const float* x, const float* w, const float* mean,
-                           const float* rstd, const float* dres, float* dx, float* dw_partial, int32_t nparts,
+                           const float* rstd, const float* dres, float* dx, void* dx_bf16, float* dw_partial, int32_t nparts,
                            float* dw, int64_t rows, int32_t D, cudaStream_t stream);
 int32_t calm_layernorm_bwd_parts(int64_t rows, int32_t D);
 
@@ -171,7 +172,8 @@ int32_t calm_cnn_fwd(const float* x, float* y, const float* w1, const float* b1,
                      const float* w3, const float* b3, int32_t B, int32_t S, cudaStream_t stream);
 /* grads: dx f32 (B,S,S,3); parameter-gradient partials gp (nblocks, CALM_CNN_NPARAM) then reduced into gparams */
 #define CALM_CNN_NPARAM 547 /* 96 + 32 + 288 + 32 + 96 + 3 */
-int32_t calm_cnn_bwd(const float* x, const float* dy, float* dx, const float* w1, const float* b1, const float* w2,
+int32_t calm_cnn_bwd(const float* x, const float* dy, float* dx, void* dx_bf16 /* optional bf16 copy of dx, or NULL */,
+                     const float* w1, const float* b1, const float* w2,
                      const float* b2, const float* w3, const float* b3, float* gpartial, int32_t nblocks, float* gparams,
                      int32_t B, int32_t S, cudaStream_t stream);
 int32_t calm_cnn_bwd_blocks(int32_t B, int32_t S);
@@ -181,7 +183,8 @@ int32_t calm_cnn_bwd_blocks(int32_t B, int32_t S);
  * ------------------------------------------------------------------------------------------------------------------ */
 /* row<->column re-tokenisation (Vi_Tools_CNN_less_V2.py:394-395,397-398): out[b,j,i,:] = in[b,i,j,:] (+ addend[b,j,i,:])
  * on (B,S,S,3) f32; the optional addend fuses the gradient accumulation of the un-transposed consumer in backward */
-int32_t calm_token_transpose(const float* in, const float* addend, float* out, int32_t B, int32_t S, cudaStream_t stream);
+int32_t calm_token_transpose(const float* in, const float* addend, float* out, void* out_bf16 /* optional bf16 copy, or NULL */,
+                             int32_t B, int32_t S, cudaStream_t stream);
 /* first-block row tokenisation (:389-391): (B,3,S,S) NCHW f32 -> (B,S,S,3) ; and its inverse */
 int32_t calm_nchw_to_tokens(const float* in, float* out, int32_t B, int32_t S, cudaStream_t stream);
 /* column sums of a bf16 (rows, N) matrix -> f32 (N): linear_mask bias gradients */

@@ -67,14 +67,15 @@ def layernorm_fwd(x, w, eps=1e-6, out_dtype=bf16):
     return y, mean.reshape(-1), rstd.reshape(-1)
 
 
-def layernorm_bwd(dy, x, w, mean, rstd, dres=None):
+def layernorm_bwd(dy, x, w, mean, rstd, dres=None, want_bf16=False):
     D = x.shape[-1]
     xh = (x - mean.view(*x.shape[:-1], 1)) * rstd.view(*x.shape[:-1], 1)
     g = dy.float() * w
     dx = rstd.view(*x.shape[:-1], 1) * (g - g.mean(-1, keepdim=True) - xh * (g * xh).mean(-1, keepdim=True))
     if dres is not None:
         dx = dx + dres
-    return dx, (dy.float() * xh).reshape(-1, D).sum(0)
+    dw = (dy.float() * xh).reshape(-1, D).sum(0)
+    return (dx, dw, dx.to(torch.bfloat16)) if want_bf16 else (dx, dw)
 
 
 def rope_table(inv_freq, S):
@@ -199,7 +200,7 @@ def cnn_fwd(x, w1, b1, w2, b2, w3, b3, B, S):
     return _cnn_ref(x, w1, b1, w2, b2, w3, b3, B, S)
 
 
-def cnn_bwd(x, dy, w1, b1, w2, b2, w3, b3, B, S, gp=None):
+def cnn_bwd(x, dy, w1, b1, w2, b2, w3, b3, B, S, gp=None, want_bf16=False):
     ps = [t.detach().clone().requires_grad_(True) for t in (x, w1, b1, w2, b2, w3, b3)]
     with torch.enable_grad():
         _cnn_ref(*ps, B, S).backward(dy)
@@ -207,12 +208,13 @@ def cnn_bwd(x, dy, w1, b1, w2, b2, w3, b3, B, S, gp=None):
     if gp is None:
         gp = torch.empty(547)
     gp.copy_(g)
-    return ps[0].grad, gp
+    return (ps[0].grad, gp, ps[0].grad.to(torch.bfloat16)) if want_bf16 else (ps[0].grad, gp)
 
 
-def token_transpose(x, B, S, addend=None):
+def token_transpose(x, B, S, addend=None, want_bf16=False):
     out = x.reshape(B, S, S, 3).permute(0, 2, 1, 3).reshape(x.shape).contiguous()
-    return out + addend if addend is not None else out
+    out = out + addend if addend is not None else out
+    return (out, out.to(torch.bfloat16)) if want_bf16 else out
 
 
 def nchw_to_tokens(x):

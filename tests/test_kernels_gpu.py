@@ -253,6 +253,8 @@ def test_layernorm(K, rows, D):
     dy = rnd(rows, D, seed=23)
     dres = rnd(rows, D, dtype=f32, seed=24)
     dx, dw = K.layernorm_bwd(dy, x, w, mean, rstd, dres)
+    dx_b, dw_b, dx16 = K.layernorm_bwd(dy, x, w, mean, rstd, dres, want_bf16=True)     # optional bf16 copy for the next GEMM
+    assert torch.equal(dx_b, dx) and torch.equal(dw_b, dw) and torch.equal(dx16, dx.to(bf16))
     xr = x.clone().requires_grad_(True)
     wr = w.clone().requires_grad_(True)
     torch.nn.functional.layer_norm(xr, (D,), wr, None, 1e-6).backward(dy.float())
@@ -383,6 +385,8 @@ def test_cnn(K, B, S):
     assert rel(y, ref) < 1e-5
     dy = rnd(B, S, S, 3, dtype=f32, seed=42)
     dx, gp = K.cnn_bwd(x, dy, w1, b1, w2, b2, w3, b3, B, S)
+    dx_b, gp_b, dx16 = K.cnn_bwd(x, dy, w1, b1, w2, b2, w3, b3, B, S, want_bf16=True)
+    assert torch.equal(dx_b, dx) and torch.equal(gp_b, gp) and torch.equal(dx16, dx.to(bf16))
     ref.backward(dy)
     assert rel(dx, xr.grad) < 1e-4
     refg = torch.cat([w1r.grad.flatten(), b1r.grad, w2r.grad.flatten(), b2r.grad, w3r.grad.flatten(), b3r.grad])
@@ -403,6 +407,8 @@ def test_token_helpers(K):
     assert torch.equal(K.cast_bf16(a), a.to(bf16))
     assert torch.equal(K.cast_f32(a.to(bf16)), a.to(bf16).float())
     assert rel(K.token_transpose(x, B, S, addend=a), t + a) < 1e-7
+    t_b, t16 = K.token_transpose(x, B, S, addend=a, want_bf16=True)
+    assert torch.equal(t_b, K.token_transpose(x, B, S, addend=a)) and torch.equal(t16, t_b.to(bf16))
     m = K.seq_mean_fwd(x)
     assert rel(m, x.mean(1)) < 4e-3
     dm = rnd(B, 3 * S, seed=48)
