@@ -335,8 +335,8 @@ def _attention_case(K, B, S, h, hd):
 
 
 # ------------------------------------------------------------------------------------------------------ latent
-def test_latent(K):
-    rows, Mh = 2 * 80, 240
+@pytest.mark.parametrize("rows,Mh", [(2 * 80, 240), (48, 10), (33, 16)])   # 4-column kernels and the scalar fallback (Mh % 4 != 0)
+def test_latent(K, rows, Mh):
     mv = rnd(rows, 2 * Mh, seed=31)
     eps = rnd(rows, Mh, dtype=f32, seed=32)
     prev = rnd(rows, Mh, dtype=f32, seed=33)
