@@ -420,6 +420,10 @@ def main():
             peak = (pk or {}).get("bf16_tflops_sustained", 1400.0)
             roof = {"bound": "tensor", "kernel": "gemm_tcgen05_kernel (calm_gemm, %d launches/step, %.1f%% of kernel time)" % (g["n"], 100 * g["ms"] / tot),
                     "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
+                    # achieved is the family aggregate over 786 launches of ~190 shapes, so there is no single per-launch traffic
+                    # figure; the ncu --set full capture of the largest shape is committed and cited here
+                    "traffic_note": "per-launch dram bytes of the 57344x2016x672 launch (ncu --set full): 80 MB read + 182 MB written "
+                                    "for 77 MB + 231 MB algorithmic (profiles/r01_ncu_full_gemm_cta2_qkv_fwd_metrics.txt)",
                     "peak_source": "measured (MEASURED_PEAKS.json bf16_tflops_sustained)" if pk else "fallback (B200_PROFILING.md)",
                     "timing": "CUDA events around every launch of one eager step"}
             # Events around a 10 us kernel add several us of their own (and an eager launch is not a graph node): the bracket
