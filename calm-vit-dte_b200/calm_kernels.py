@@ -5,6 +5,7 @@ allocates nothing), passes raw pointers / sizes through ctypes and launches on t
 The autograd layer (calm_ops.py) and the GPU parity tests both go through these functions, i.e. through the C ABI.
 """
 import ctypes as C
+import os
 
 import torch
 
@@ -13,6 +14,7 @@ from calm_lib import BF16, F32, MAJOR_K, MAJOR_MN, EPI_NONE, EPI_GELU, EPI_DGELU
 
 bf16 = torch.bfloat16
 f32 = torch.float32
+SN_ITEM_WEIGHTS = int(os.environ.get("CALM_SN_ITEM_WEIGHTS", "4096"))   # tuning hook: work-item size of the spectral-norm kernels
 
 
 def _dt(t):
@@ -258,7 +260,7 @@ class SnTable:
         self.keep = [entries]
         for i, e in enumerate(entries):
             rows, cols = e["rows"], e["cols"]
-            chunk = max(4, min(rows, -(-16384 // cols)))          # ~16 K weights per item: a few hundred CTAs per scope
+            chunk = max(4, min(rows, -(-SN_ITEM_WEIGHTS // cols)))  # ~4 K weights per item: ~3 k CTAs per scope (same-box sweep: 16 K 59.3, 8 K 59.1, 4 K 58.9 ms/step)
             nit = -(-rows // chunk)
             for j in range(nit):
                 items.append((i, j * chunk, min(rows, (j + 1) * chunk), j))
