@@ -154,3 +154,31 @@ def test_mask_false_raises_like_reference(product):
     blk = model.autoencoder.block_bottle_neck_1.encoder
     with pytest.raises(AttributeError):
         blk(torch.zeros(1, blk.seq_length, blk.dim1))
+
+
+def test_gradient_operand_copies_change_nothing(product, monkeypatch):
+    """The bf16 copies that LayerNorm backward / the backward token transpose / the CNN backward hand to the next GEMM through
+    calm_ops' weak-reference side table must be a pure launch-count optimisation: with the table switched off (every consumer
+    casts its own operand) every gradient is bit-identical, and the table is empty after the step (no tensor kept alive)."""
+    import calm_ops
+    hits = {"n": 0}
+    real = calm_ops._bf16_grad
+
+    def counting(g):
+        e = calm_ops._BF16_SIDE.get(id(g))
+        if g.dtype != torch.bfloat16 and e is not None and e[0]() is g:
+            hits["n"] += 1
+        return real(g)
+
+    monkeypatch.setattr(calm_ops, "_bf16_grad", counting)
+    monkeypatch.setattr(calm_ops, "_SIDE_ON", True)
+    _, _, model_on, *_ = run_step(product, monkeypatch, "small_cls")
+    g_on = {k: p.grad.clone() for k, p in model_on.named_parameters()}
+    assert hits["n"] >= 40, hits            # 24 (ln_2 -> out_proj) + 16 (token transposes) + 8 (CNN) on this 8-Block model
+    assert len(calm_ops._BF16_SIDE) == 0
+    monkeypatch.setattr(calm_ops, "_SIDE_ON", False)
+    hits["n"] = 0
+    _, _, model_off, *_ = run_step(product, monkeypatch, "small_cls")
+    assert hits["n"] == 0
+    for k, p in model_off.named_parameters():
+        assert torch.equal(p.grad, g_on[k]), k
