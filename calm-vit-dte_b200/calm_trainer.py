@@ -176,6 +176,13 @@ class MixBatch:
         return out, soft
 
 
+def cosine_annealing_lr(epoch, base_lr, T_max, eta_min=1e-6):
+    """Learning rate after `epoch` calls of `CosineAnnealingLR(optimizer, T_max, eta_min).step()` (closed form of
+    torch.optim.lr_scheduler.CosineAnnealingLR; the reference builds it with T_max=epochs, eta_min=1e-6 and steps it once per
+    epoch, distributed_trainer_cls.py:52,108-109)."""
+    return eta_min + (base_lr - eta_min) * (1.0 + math.cos(math.pi * epoch / T_max)) / 2.0
+
+
 # ---------------------------------------------------------------------------------------------------- optimizer step
 class TrainerStep:
     """GradScaler + clip_grad_norm_ + AdamW of the reference loop as one object (distributed_trainer_cls.py:64,88-96,158).
@@ -254,8 +261,9 @@ class TrainerStep:
 
     # -- scheduler surface -----------------------------------------------------------------------------------------------
     def set_lr(self, lr):
-        """What a scheduler (CosineAnnealingLR in the reference, distributed_trainer_cls.py:160) does to param_groups: one
-        scalar written to the device state; a captured graph picks it up at the next replay."""
+        """What `scheduler.step()` (CosineAnnealingLR(T_max=epochs, eta_min=1e-6), distributed_trainer_cls.py:52,108-109) does to
+        param_groups, once per epoch: one scalar written to the device state; a captured graph picks it up at the next replay.
+        `cosine_annealing_lr` below gives the value."""
         self.state[L.OPT_LR:L.OPT_LR + 1].fill_(float(lr))
 
     def get_lr(self):

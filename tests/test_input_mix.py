@@ -44,3 +44,15 @@ def test_both_modes_are_drawn():
     torch.manual_seed(0)
     modes = {mb.draw(32, 32)["mode"] for _ in range(40)}
     assert modes == {0, 1}
+
+
+def test_cosine_annealing_lr_matches_torch_scheduler():
+    """calm_trainer.cosine_annealing_lr vs torch's CosineAnnealingLR stepped once per epoch (distributed_trainer_cls.py:52,108-109)."""
+    p = torch.nn.Parameter(torch.zeros(1))
+    opt = torch.optim.AdamW([p], lr=3.1e-3)
+    sched = torch.optim.lr_scheduler.CosineAnnealingLR(opt, T_max=65, eta_min=1e-6)
+    for epoch in range(65):
+        assert calm_trainer.cosine_annealing_lr(epoch, 3.1e-3, 65, 1e-6) == pytest.approx(opt.param_groups[0]["lr"], rel=1e-9)
+        opt.step()
+        sched.step()
+    assert calm_trainer.cosine_annealing_lr(65, 3.1e-3, 65, 1e-6) == pytest.approx(1e-6, rel=1e-9)
