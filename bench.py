@@ -178,20 +178,10 @@ class Trainer:
         self.loss.copy_(loss.detach())
 
     def capture(self):
-        """3 eager steps on a side stream (allocator + lazy state warm-up), then capture one step."""
-        s = torch.cuda.Stream()
-        s.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(s):
-            for _ in range(3):
-                self._step()
-        torch.cuda.current_stream().wait_stream(s)
-        torch.cuda.synchronize()
-        if not self.use_graph:
-            return
-        g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
-            self._step()
-        self.graph = g
+        """3 eager steps on a side stream (allocator + lazy state warm-up), then one step captured into a CUDA graph: the
+        product's own helper (calm_trainer.GraphedStep), which is what a user of the drop-in loop calls."""
+        import calm_trainer
+        self.graph = calm_trainer.GraphedStep(self._step, warmup=3, capture=self.use_graph).graph
 
     def step(self):
         if self.graph is not None:
