@@ -280,6 +280,7 @@ class SnTable:
         it = (L.SnItem * len(items))()
         for j, (li, rb, re, loc) in enumerate(items):
             it[j].layer, it[j].row_begin, it[j].row_end, it[j].local_index = li, rb, re, loc
+        L._tls.dev = None      # the pointers above were baked into a table, not handed to a launch
         self.n_layers, self.n_items = n, len(items)
         self.table = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(device)
         self.items = torch.frombuffer(bytearray(bytes(it)), dtype=torch.uint8).to(device)

@@ -162,12 +162,23 @@ def check(rc, what):
         raise CalmError("%s failed (rc=%d): %s" % (what, rc, last_error()))
 
 
+_tls = threading.local()   # device ordinal of the tensors handed to ptr() since the last call() on this thread
+
+
 def ptr(t):
-    """Raw device pointer of a tensor (None -> NULL). The tensor must live on a CUDA device."""
+    """Raw device pointer of a tensor (None -> NULL). The tensor must live on a CUDA device; all tensors of one call must
+    live on the same device (call() launches on that device's current stream, whatever the thread's current device is)."""
     if t is None:
         return None
     if not t.is_cuda:
         raise CalmError("calm_b200 kernels need CUDA tensors (got %s); there is no CPU fallback" % t.device)
+    idx = t.device.index
+    seen = getattr(_tls, "dev", None)
+    if seen is None:
+        _tls.dev = idx
+    elif seen != idx:
+        _tls.dev = None
+        raise CalmError("calm_b200: tensors of one kernel call live on different devices (cuda:%d and cuda:%d)" % (seen, idx))
     return t.data_ptr()
 
 
@@ -178,20 +189,34 @@ def stream():
 profile = None   # bench.py's per-kernel timing pass sets this to a list; entries: (name, work, start_event, end_event)
 
 
+def _launch(fn, name, args, work, tag):
+    if profile is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = fn(*args, stream())
+        e1.record()
+        profile.append((name, work, e0, e1, tag))
+        return rc
+    return fn(*args, stream())
+
+
 def call(name, *args, work=0.0, tag=None):
-    """Invoke an int32-returning entry point on the current torch stream (appended as last argument).
+    """Invoke an int32-returning entry point on the current torch stream OF THE TENSORS' DEVICE (appended as last argument).
+    The reference trainers only do `model.to(cuda:local_rank)` and never call torch.cuda.set_device, and autograd's worker
+    threads pick their own device: the launch is therefore wrapped in a device guard whenever the tensors' device (recorded by
+    ptr()) is not the thread's current one, so forward and backward always run on the device that owns the memory.
     `work` = algorithmic FLOPs (contractions) or bytes (memory-bound kernels) of this launch, used only by the
     optional CUDA-event profiling pass."""
     global launch_count
     lib = load()
-    if profile is not None:
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        rc = getattr(lib, name)(*args, stream())
-        e1.record()
-        profile.append((name, work, e0, e1, tag))
+    fn = getattr(lib, name)
+    dev = getattr(_tls, "dev", None)
+    _tls.dev = None
+    if dev is not None and dev != torch.cuda.current_device():
+        with torch.cuda.device(dev):
+            rc = _launch(fn, name, args, work, tag)
     else:
-        rc = getattr(lib, name)(*args, stream())
+        rc = _launch(fn, name, args, work, tag)
     launch_count += 1
     if rc != 0:
         raise CalmError("%s failed (rc=%d): %s" % (name, rc, last_error()))

@@ -23,6 +23,7 @@ tables); there is no PyTorch fallback for any of it.
 """
 import ctypes as C
 import math
+import weakref
 
 import torch
 from torch.autograd import Function
@@ -157,6 +158,7 @@ class GraphedStep:
             raise L.CalmError("GraphedStep needs a CUDA device; there is no CPU fallback")
         self.step_fn = step_fn
         self.graph = None
+        _live_graphs.add(self)
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
@@ -175,6 +177,24 @@ class GraphedStep:
             self.graph.replay()
         else:
             self.step_fn()
+
+    def release(self):
+        """Destroys the captured graph (the step function stays callable eagerly). A graph that captured NCCL all-reduces
+        (calm_ddp.DataParallel) keeps the communicator referenced: `dist.destroy_process_group()` waits for every such graph to
+        be destroyed, so call this (or `release_graphs()`) first — otherwise the teardown never returns."""
+        if self.graph is not None:
+            torch.cuda.synchronize()
+            self.graph.reset()
+            self.graph = None
+
+
+_live_graphs = weakref.WeakSet()
+
+
+def release_graphs():
+    """`GraphedStep.release()` on every live captured step of this process (call before `dist.destroy_process_group()`)."""
+    for g in list(_live_graphs):
+        g.release()
 
 
 # ---------------------------------------------------------------------------------------------------- input side

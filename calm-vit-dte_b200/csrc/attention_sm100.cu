@@ -770,11 +770,11 @@ int calm_attention_fwd_tc(const void* q, const void* k, const void* v, const voi
   if ((rc = tc::make_map_2d(&mK, k, cols, rows, ld_k, S))) return rc;
   if ((rc = tc::make_map_2d(&mV, v, cols, rows, ld_v, S))) return rc;
   if ((rc = tc::make_map_2d(&mB, bias, (uint64_t)S, rows, S, 128))) return rc;   // bias viewed as (B*S rows, S columns)
-  static bool configured = false;
-  if (!configured) {
+  static CalmDeviceOnce configured;
+  if (configured.pending()) {
     cudaError_t e = cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FWD_SMEM);
     if (e != cudaSuccess) { calm_set_error("calm_attention_fwd(tcgen05): smem: %s", cudaGetErrorString(e)); return CALM_ERR_CUDA; }
-    configured = true;
+    configured.done();
   }
   const int items = B * heads;
   const int grid = items < calm_num_sms() ? items : calm_num_sms();
@@ -810,11 +810,11 @@ int calm_attention_bwd_tc(const void* q, const void* k, const void* v, const voi
   if ((rc = tc::make_map_2d(&mV, v, cols, rows, ld_v, S))) return rc;
   if ((rc = tc::make_map_2d(&mDO, d_o, cols, rows, ld_do, 128))) return rc;
   if ((rc = make_map_ds(&mDS, ds_scratch, (uint64_t)S, (uint64_t)B * heads))) return rc;
-  static bool configured = false;
-  if (!configured) {
+  static CalmDeviceOnce configured;
+  if (configured.pending()) {
     cudaError_t e = cudaFuncSetAttribute(attn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BWD_SMEM);
     if (e != cudaSuccess) { calm_set_error("calm_attention_bwd(tcgen05): smem: %s", cudaGetErrorString(e)); return CALM_ERR_CUDA; }
-    configured = true;
+    configured.done();
   }
   const int bwd_items = B * heads;
   const int grid = bwd_items < calm_num_sms() ? bwd_items : calm_num_sms();

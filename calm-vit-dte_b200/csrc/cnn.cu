@@ -486,11 +486,11 @@ extern "C" int32_t calm_cnn_fwd(const float* x, float* y, const float* w1, const
   const long long cap = 3LL * calm_num_sms();
   const unsigned grid = (unsigned)(total < cap ? total : cap);
   const size_t smem = (size_t)FWD_SMEM_FLOATS * sizeof(float);
-  static bool configured = false;
-  if (!configured) {
+  static CalmDeviceOnce configured;
+  if (configured.pending()) {
     cudaError_t e = cudaFuncSetAttribute(cnn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { calm_set_error("calm_cnn_fwd: smem %zu: %s", smem, cudaGetErrorString(e)); return CALM_ERR_CUDA; }
-    configured = true;
+    configured.done();
   }
   CnnW W{w1, b1, w2, b2, w3, b3};
   cnn_fwd_kernel<<<grid, NT, smem, stream>>>(x, y, W, B, S, tiles_side);
@@ -521,12 +521,12 @@ extern "C" int32_t calm_cnn_bwd(const float* x, const float* dy, float* dx, void
   const int th = bwd_tile_height(S);
   const int tiles_x = (S + BT - 1) / BT, tiles_y = (S + th - 1) / th;
   const size_t smem = (size_t)BWD_SMEM_FLOATS * sizeof(float);
-  static bool configured = false;
-  if (!configured) {
+  static CalmDeviceOnce configured;
+  if (configured.pending()) {
     cudaError_t e = cudaFuncSetAttribute(cnn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(cnn_bwd_kernel_occ2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { calm_set_error("calm_cnn_bwd: smem %zu: %s", smem, cudaGetErrorString(e)); return CALM_ERR_CUDA; }
-    configured = true;
+    configured.done();
   }
   CnnW W{w1, b1, w2, b2, w3, b3};
   bf16* dx16 = reinterpret_cast<bf16*>(dx_bf16);

@@ -4,6 +4,7 @@
 #include <cuda_bf16.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <atomic>
 
 #define CALM_OK 0
 #define CALM_ERR_ARG (-1)
@@ -30,15 +31,31 @@ extern int* g_calm_err_flag;
     }                                                                         \
   } while (0)
 
-static inline int calm_num_sms() {
-  static int sms = 0;
-  if (sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
-  }
-  return sms;
+static inline int calm_current_device() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return dev;
 }
+
+// SM count of the CURRENT device (cached per device ordinal: one process may drive several GPUs)
+static inline int calm_num_sms() {
+  static std::atomic<int> sms[64];
+  const int dev = calm_current_device() & 63;
+  int v = sms[dev].load(std::memory_order_relaxed);
+  if (v == 0) {
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+    sms[dev].store(v, std::memory_order_relaxed);
+  }
+  return v;
+}
+
+// cudaFuncSetAttribute is a per-device setting: a call site keeps one "configured" bit per device ordinal.
+//   static CalmDeviceOnce once;  if (once.pending()) { cudaFuncSetAttribute(...); once.done(); }
+struct CalmDeviceOnce {
+  std::atomic<unsigned long long> mask{0};
+  bool pending() const { return !((mask.load(std::memory_order_acquire) >> (calm_current_device() & 63)) & 1ull); }
+  void done() { mask.fetch_or(1ull << (calm_current_device() & 63), std::memory_order_release); }
+};
 
 typedef __nv_bfloat16 bf16;
 typedef __nv_bfloat162 bf162;

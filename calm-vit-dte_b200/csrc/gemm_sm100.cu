@@ -902,13 +902,13 @@ struct EpiMaps { CUtensorMap c, add, aux; };
 
 template <int A_MN, int B_MN>
 int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mbh, const EpiMaps& em, const GemmParams& p, int pair, cudaStream_t stream) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  static CalmDeviceOnce attr_set;
+  if (attr_set.pending()) {
     cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel<A_MN, B_MN, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tcgen05_kernel<A_MN, B_MN, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tcgen05_kernel<A_MN, B_MN, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     if (e != cudaSuccess) { calm_set_error("gemm: cannot raise dynamic smem: %s", cudaGetErrorString(e)); return CALM_ERR_CUDA; }
-    attr_set = true;
+    attr_set.done();
   }
   if (pair) {
     const int max_clusters = calm_num_sms() / 2;

@@ -477,8 +477,8 @@ extern "C" int32_t calm_rope_fwd(const void* content, int64_t ld_content, const 
       const bool pair = (dr / 2) % 2 == 0 && dc % 2 == 0;
 #define CALM_ROPE_ROWS_FWD(DC0, PAIR)                                                                                            \
   do {                                                                                                                           \
-    static bool carve = false;                                                                                                   \
-    if (!carve) { cudaFuncSetAttribute(rope_rows_fwd_kernel<DC0, PAIR>, cudaFuncAttributePreferredSharedMemoryCarveout, 100); carve = true; } \
+    static CalmDeviceOnce carve;                                                                                                   \
+    if (carve.pending()) { cudaFuncSetAttribute(rope_rows_fwd_kernel<DC0, PAIR>, cudaFuncAttributePreferredSharedMemoryCarveout, 100); carve.done(); } \
     rope_rows_fwd_kernel<DC0, PAIR><<<grid, nthreads, smem, stream>>>(reinterpret_cast<const bf16*>(content), ld_content,        \
         reinterpret_cast<const bf16*>(ropein), ld_rope, reinterpret_cast<bf16*>(out), ld_out, cos_sin, B, S, heads, dc, dr, R, chunks); \
   } while (0)
@@ -520,8 +520,8 @@ extern "C" int32_t calm_rope_bwd(const void* dout, int64_t ld_dout, const void* 
       const bool pair = half % 2 == 0 && dc % 2 == 0;
 #define CALM_ROPE_ROWS_BWD(DC0, PAIR)                                                                                            \
   do {                                                                                                                           \
-    static bool carve = false;                                                                                                   \
-    if (!carve) { cudaFuncSetAttribute(rope_rows_bwd_kernel<DC0, PAIR>, cudaFuncAttributePreferredSharedMemoryCarveout, 100); carve = true; } \
+    static CalmDeviceOnce carve;                                                                                                   \
+    if (carve.pending()) { cudaFuncSetAttribute(rope_rows_bwd_kernel<DC0, PAIR>, cudaFuncAttributePreferredSharedMemoryCarveout, 100); carve.done(); } \
     rope_rows_bwd_kernel<DC0, PAIR><<<grid, nthreads, rs_smem, stream>>>(                                                        \
         reinterpret_cast<const bf16*>(dout), ld_dout, reinterpret_cast<const bf16*>(out), ld_out, reinterpret_cast<bf16*>(dcontent), \
         ld_dcontent, reinterpret_cast<bf16*>(dropein), ld_drope, cos_sin, dtheta_part, B, S, heads, dc, dr, R, chunks);          \

