@@ -108,8 +108,8 @@ class VMLA_Block(torch.nn.Module):
             raise NotImplementedError("the B200 path implements the trainers' dropout=0.0 configuration")
         hc, hr, M = heads * self.head_dim_content, heads * self.head_dim_rope, mean_var_hidden
         # --- registration order below mirrors the reference so that state_dict() enumerates identically ---
-        self.ln_q = norm_layer(dim1, bias=False)
-        self.ln_kv = norm_layer(dim1, bias=False) if is_cross else None
+        self.ln_q = ops.check_norm(norm_layer(dim1, bias=False))
+        self.ln_kv = ops.check_norm(norm_layer(dim1, bias=False)) if is_cross else None
         self.t_encoder_q = self.t_encoder_kv = None
         if self.t_reduce:
             self.t_encoder_q = _sn_linear(seq_length, seq_len_reduce)
@@ -146,7 +146,7 @@ class VMLA_Block(torch.nn.Module):
         )
         self.out_proj = _sn_linear(dim2, dim2)
         self.dropout = torch.nn.Dropout(dropout)
-        self.ln_2 = norm_layer(dim2, bias=False)
+        self.ln_2 = ops.check_norm(norm_layer(dim2, bias=False))
         self.mlp = None
         if use_mlp:
             self.mlp = torch.nn.Sequential(
@@ -196,8 +196,8 @@ class VMLA_Block(torch.nn.Module):
         lin = lambda x, m, addend=None, out_f32=False: ops.LinearFn.apply(x, tok, addend, bank, gid(m), out_f32)
         seq = lambda x, *ms: ops.SeqLinearFn.apply(x, tok, bank, *[gid(m) for m in ms])
         input_q = input_q.float()
-        xq, res = ops.LayerNormFn.apply(input_q, self.ln_q.weight, False)
-        xkv = xq if input_kv is None else ops.LayerNormFn.apply(input_kv.float(), self.ln_kv.weight, False)[0]
+        xq, res = ops.LayerNormFn.apply(input_q, self.ln_q.weight, False, False, self.ln_q.eps)
+        xkv = xq if input_kv is None else ops.LayerNormFn.apply(input_kv.float(), self.ln_kv.weight, False, False, self.ln_kv.eps)[0]
         if self.reduce:
             kr_t = xkv
             tq, tkv = xq, xkv
@@ -248,8 +248,8 @@ class VMLA_Block(torch.nn.Module):
             res = r
         x = lin(att, self.out_proj, addend=res, out_f32=True)                    # (attn Wo^T) * ls_att + residual, fp32
         if self.mlp is None:
-            return ops.LayerNormFn.apply(x, self.ln_2.weight, True)[0]
-        y, res2 = ops.LayerNormFn.apply(x, self.ln_2.weight, False, True)   # d x feeds out_proj's backward GEMMs
+            return ops.LayerNormFn.apply(x, self.ln_2.weight, True, False, self.ln_2.eps)[0]
+        y, res2 = ops.LayerNormFn.apply(x, self.ln_2.weight, False, True, self.ln_2.eps)   # d x feeds out_proj's backward GEMMs
         return ops.MlpFn.apply(y, tok, res2, bank, gid(self.mlp[0]), gid(self.mlp[3]), True)   # x + mlp(y) * ls_mlp
 
 
@@ -336,7 +336,7 @@ class EncoderDecoder_8(torch.nn.Module):
         self.block_bottle_neck_2 = mk(0, 0)(1, dim1, seq_length)
         self.decoder_blocks, dim1, seq_length = _stage_blocks(3, mk(dim_step, seq_len_step, last=True, ofo=out_features_override),
                                                               dim1, seq_length, dim_step, seq_len_step)
-        self.ln_final = norm_layer(dim1, bias=False)
+        self.ln_final = ops.check_norm(norm_layer(dim1, bias=False))
 
     def forward(self, x):
         csm = ResidualStateManager(mode="sum")
@@ -350,7 +350,7 @@ class EncoderDecoder_8(torch.nn.Module):
         x = add(run(self.decoder_blocks[0], x), skip_2, None)
         x = add(run(self.decoder_blocks[1], x), skip_1, None)
         x = run(self.decoder_blocks[2], x)
-        x = ops.LayerNormFn.apply(x, self.ln_final.weight, True)[0]
+        x = ops.LayerNormFn.apply(x, self.ln_final.weight, True, False, self.ln_final.eps)[0]
         kl = csm.get_kl_loss()
         return x, (kl.reshape(()) if torch.is_tensor(kl) else kl)
 
@@ -373,7 +373,7 @@ class CALMLatentDiffusion(torch.nn.Module):
                                                               -dim_step, -seq_len_step)
         self.decoder_blocks, dim1, seq_length = _stage_blocks(3, mk(dim_step, seq_len_step, last=True), dim1, seq_length,
                                                               dim_step, seq_len_step)
-        self.ln_final = norm_layer(dim1, bias=False)
+        self.ln_final = ops.check_norm(norm_layer(dim1, bias=False))
 
 
 class Encoder_8(torch.nn.Module):
@@ -396,7 +396,7 @@ class Encoder_8(torch.nn.Module):
             if step:
                 dim1 -= dim_step * 3
                 seq_length -= seq_len_step * 3
-        self.ln_final = norm_layer(dim1, bias=False)
+        self.ln_final = ops.check_norm(norm_layer(dim1, bias=False))
 
     def forward(self, x):
         skip = None
@@ -405,4 +405,4 @@ class Encoder_8(torch.nn.Module):
             if skip is not None and x.shape == skip.shape:
                 x = ops.Add3Fn.apply(x, skip, None)
             skip = x
-        return ops.LayerNormFn.apply(x, self.ln_final.weight, True)[0]
+        return ops.LayerNormFn.apply(x, self.ln_final.weight, True, False, self.ln_final.eps)[0]

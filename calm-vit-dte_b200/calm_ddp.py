@@ -95,7 +95,9 @@ class DataParallel(torch.nn.Module):
 
     def _finalize(self):
         """End of backward: wait for the buckets, then let every .grad alias its (averaged) bucket slice."""
-        if any(n not in (0, len(b)) for n, b in zip(self.pending, self.buckets)):
+        # once any hook has fired, EVERY bucket must be complete: a bucket without gradients would otherwise hand last step's
+        # averaged gradient back through the aliased .grad
+        if any(n != len(b) for n, b in zip(self.pending, self.buckets)):
             raise RuntimeError("a parameter produced no gradient this step; data-parallel buckets cannot be completed "
                                "(the reference runs DDP without find_unused_parameters as well)")
         if self.on_cuda:

@@ -27,7 +27,7 @@ def _dt(t):
 
 def gemm(a, b, c, M, N, K, *, lda, ldb, ldc, batch=1, stride_a=0, stride_b=0, stride_c=0, a_major=MAJOR_K,
          b_major=MAJOR_K, alpha=1.0, bias=None, addend=None, ld_addend=0, stride_addend=0, epilogue=EPI_NONE, aux=None,
-         ld_aux=0, stride_aux=0, reduce_batch=False, splits=1, stride_split=0):
+         ld_aux=0, stride_aux=0, reduce_batch=False, splits=1, stride_split=0, flags=0, bn=0):
     """C[b](M,N) = epi(alpha * A[b](M,K) . B[b](N,K)^T + bias + addend) — see calm_gemm in include/calm_b200.h."""
     assert a.dtype == bf16 and b.dtype == bf16
     g = L.GemmArgs()
@@ -43,11 +43,19 @@ def gemm(a, b, c, M, N, K, *, lda, ldb, ldc, batch=1, stride_a=0, stride_b=0, st
     g.aux, g.ld_aux, g.stride_aux = ptr(aux), ld_aux, stride_aux
     g.reduce_batch, g.splits, g.stride_split = int(reduce_batch), splits, stride_split
     g.alpha = alpha
+    g.flags, g.bn_override = flags, bn          # per-call schedule selectors (tests / tuning); 0 = the heuristics
     tag = None
     if L.profile is not None:
-        tag = "M%d N%d K%d b%d %s%s%s%s%s" % (M, N, K, batch, "AK" if a_major == MAJOR_K else "AM", "BK" if b_major == MAJOR_K else "BM",
+        # algorithmic bytes of this launch: every operand read once, the result (and the side outputs) written once
+        nbytes = 2 * M * K * (batch if stride_a else 1) + 2 * N * K * (batch if stride_b else 1)
+        nbytes += M * N * c.element_size() * (1 if reduce_batch else batch) * max(splits, 1)
+        if addend is not None:
+            nbytes += M * N * addend.element_size() * batch
+        if aux is not None:
+            nbytes += M * N * 2 * batch
+        tag = "M%d N%d K%d b%d %s%s%s%s%s bytes=%d" % (M, N, K, batch, "AK" if a_major == MAJOR_K else "AM", "BK" if b_major == MAJOR_K else "BM",
                                                " f32" if c.dtype == f32 else "", " add" if addend is not None else "",
-                                               (" epi%d" % epilogue if epilogue else "") + (" red" if reduce_batch else "") + (" s%d" % splits if splits > 1 else ""))
+                                               (" epi%d" % epilogue if epilogue else "") + (" red" if reduce_batch else "") + (" s%d" % splits if splits > 1 else ""), nbytes)
     L.call("calm_gemm", C.byref(g), work=2.0 * M * N * K * batch, tag=tag)
     return c
 
@@ -79,26 +87,20 @@ def layernorm_bwd(dy, x, w, mean, rstd, dres=None, want_bf16=False):
     dw = torch.empty(D, dtype=f32, device=x.device)
     dx16 = torch.empty(x.shape, dtype=bf16, device=x.device) if want_bf16 else None
     L.call("calm_layernorm_bwd", ptr(dy), _dt(dy), ptr(x), ptr(w), ptr(mean), ptr(rstd), ptr(dres), ptr(dx), ptr(dx16), ptr(part),
-           nparts, ptr(dw), rows, D)
+           nparts, ptr(dw), rows, D, work=float(rows) * D * (dy.element_size() + 4 + (4 if dres is not None else 0) + 4 + (2 if want_bf16 else 0)))
     return (dx, dw, dx16) if want_bf16 else (dx, dw)
 
 
 # ------------------------------------------------------------------------------------------------ RoPE
-def rope_table(inv_freq, S):
-    half = inv_freq.numel()
-    cs = torch.empty(S * half * 2, dtype=f32, device=inv_freq.device)
-    L.call("calm_rope_table", ptr(inv_freq), ptr(cs), S, half)
-    return cs
-
-
-def rope_fwd(content, ld_content, ropein, ld_rope, cos_sin, tokens, S, heads, dc, dr):
+def rope_fwd(content, ld_content, ropein, ld_rope, inv_freq, tokens, S, heads, dc, dr):
+    """inv_freq f32 (dr/2): the learned frequencies; the kernels form cos / sin of position * inv_freq themselves."""
     out = torch.empty(tokens, heads * (dc + dr), dtype=bf16, device=ropein.device)
-    L.call("calm_rope_fwd", ptr(content), ld_content, ptr(ropein), ld_rope, ptr(out), out.stride(0), ptr(cos_sin), tokens, S,
-           heads, dc, dr)
+    L.call("calm_rope_fwd", ptr(content), ld_content, ptr(ropein), ld_rope, ptr(out), out.stride(0), ptr(inv_freq), tokens, S,
+           heads, dc, dr, work=4.0 * tokens * heads * (dc + dr))
     return out
 
 
-def rope_bwd(dout, ld_dout, out, cos_sin, tokens, S, heads, dc, dr, dcontent=None, ld_dcontent=0, dropein=None, ld_drope=0):
+def rope_bwd(dout, ld_dout, out, inv_freq, tokens, S, heads, dc, dr, dcontent=None, ld_dcontent=0, dropein=None, ld_drope=0):
     """Returns (dcontent, dropein, dinv_freq); dcontent/dropein may be pre-allocated views (e.g. slices of one buffer)."""
     dev = dout.device
     if dc > 0 and dcontent is None:
@@ -110,7 +112,7 @@ def rope_bwd(dout, ld_dout, out, cos_sin, tokens, S, heads, dc, dr, dcontent=Non
     scratch = torch.empty(L.load().calm_rope_bwd_scratch_floats(S, dr), dtype=f32, device=dev)
     dinv = torch.empty(dr // 2, dtype=f32, device=dev)
     L.call("calm_rope_bwd", ptr(dout), ld_dout, ptr(out), out.stride(0), ptr(dcontent), ld_dcontent, ptr(dropein), ld_drope,
-           ptr(cos_sin), ptr(scratch), ptr(dinv), tokens, S, heads, dc, dr)
+           ptr(inv_freq), ptr(scratch), ptr(dinv), tokens, S, heads, dc, dr, work=6.0 * tokens * heads * (dc + dr))
     return dcontent, dropein, dinv
 
 
@@ -177,7 +179,7 @@ def latent_bwd(mv, eps, dz, kl_scale, dkl, dz_bf16=None, want_total=False):
 # ------------------------------------------------------------------------------------------------ CNN residual
 def cnn_fwd(x, w1, b1, w2, b2, w3, b3, B, S):
     y = torch.empty_like(x)
-    L.call("calm_cnn_fwd", ptr(x), ptr(y), ptr(w1), ptr(b1), ptr(w2), ptr(b2), ptr(w3), ptr(b3), B, S)
+    L.call("calm_cnn_fwd", ptr(x), ptr(y), ptr(w1), ptr(b1), ptr(w2), ptr(b2), ptr(w3), ptr(b3), B, S, work=24.0 * B * S * S)
     return y
 
 
@@ -190,7 +192,7 @@ def cnn_bwd(x, dy, w1, b1, w2, b2, w3, b3, B, S, gp=None, want_bf16=False):
         gp = torch.empty(L.CNN_NPARAM, dtype=f32, device=x.device)
     dx16 = torch.empty(x.shape, dtype=bf16, device=x.device) if want_bf16 else None
     L.call("calm_cnn_bwd", ptr(x), ptr(dy), ptr(dx), ptr(dx16), ptr(w1), ptr(b1), ptr(w2), ptr(b2), ptr(w3), ptr(b3), ptr(part), nblocks,
-           ptr(gp), B, S)
+           ptr(gp), B, S, work=(36.0 + (6.0 if want_bf16 else 0.0)) * B * S * S)
     return (dx, gp, dx16) if want_bf16 else (dx, gp)
 
 
@@ -198,7 +200,8 @@ def cnn_bwd(x, dy, w1, b1, w2, b2, w3, b3, B, S, gp=None, want_bf16=False):
 def token_transpose(x, B, S, addend=None, want_bf16=False):
     out = torch.empty_like(x)
     out16 = torch.empty(x.shape, dtype=bf16, device=x.device) if want_bf16 else None
-    L.call("calm_token_transpose", ptr(x), ptr(addend), ptr(out), ptr(out16), B, S)
+    L.call("calm_token_transpose", ptr(x), ptr(addend), ptr(out), ptr(out16), B, S,
+           work=3.0 * B * S * S * (8 + (4 if addend is not None else 0) + (2 if want_bf16 else 0)))
     return (out, out16) if want_bf16 else out
 
 
@@ -213,7 +216,7 @@ def colsum(x, rows, N, ld):
     nparts = L.load().calm_colsum_parts(rows, N)
     part = torch.empty(nparts * N, dtype=f32, device=x.device)
     out = torch.empty(N, dtype=f32, device=x.device)
-    L.call("calm_colsum", ptr(x), ld, ptr(part), nparts, ptr(out), rows, N)
+    L.call("calm_colsum", ptr(x), ld, ptr(part), nparts, ptr(out), rows, N, work=2.0 * rows * N)
     return out
 
 

@@ -16,6 +16,7 @@ LIB_PATH = os.path.join(HERE, "libcalm_b200.so")
 BF16, F32 = 0, 1
 MAJOR_K, MAJOR_MN = 0, 1
 EPI_NONE, EPI_GELU, EPI_DGELU = 0, 1, 2
+GEMM_SIMT, GEMM_NO_CLUSTER, GEMM_FORCE_CLUSTER, GEMM_PAIR_MULTICAST, GEMM_DIRECT_EPILOGUE = 1, 4, 8, 16, 32   # calm_gemm_args.flags (per call)
 CNN_NPARAM = 547
 OPT_CHUNK = 8192
 OPT_SCALE, OPT_GROWTH_TRACKER, OPT_STEP, OPT_LR, OPT_GRAD_NORM, OPT_FOUND_INF, OPT_MULT, OPT_BIAS1, OPT_BIAS2_SQRT = range(9)
@@ -33,10 +34,10 @@ class GemmArgs(C.Structure):
         ("stride_a", i64), ("stride_b", i64), ("stride_c", i64),
         ("a_major", i32), ("b_major", i32), ("c_dtype", i32), ("epilogue", i32),
         ("bias", vp),
-        ("addend", vp), ("addend_dtype", i32), ("_pad0", i32), ("ld_addend", i64), ("stride_addend", i64),
+        ("addend", vp), ("addend_dtype", i32), ("bn_override", i32), ("ld_addend", i64), ("stride_addend", i64),
         ("aux", vp), ("ld_aux", i64), ("stride_aux", i64),
         ("reduce_batch", i32), ("splits", i32), ("stride_split", i64),
-        ("alpha", f32), ("_pad1", i32),
+        ("alpha", f32), ("flags", i32),
     ]
 
 
@@ -71,11 +72,6 @@ class SnItem(C.Structure):
 PROTOTYPES = {
     "calm_abi_version": (i32, []),
     "calm_last_error": (C.c_char_p, []),
-    "calm_set_debug_flags": (None, [i32]),
-    "calm_get_debug_flags": (i32, []),
-    "calm_debug_set_gemm_bn": (None, [i32]),
-    "calm_debug_set_trace_buffer": (None, [vp, i32]),
-    "calm_set_error_flag_buffer": (i32, [vp]),
     "calm_gemm": (i32, [C.POINTER(GemmArgs), vp]),
     "calm_gemm_default_splits": (i32, [i32, i32, i32, i32, i32]),
     "calm_sn_forward": (i32, [vp, i32, vp, i32, i32, f32, vp]),
@@ -83,7 +79,6 @@ PROTOTYPES = {
     "calm_layernorm_fwd": (i32, [vp, vp, vp, i32, vp, vp, i64, i32, f32, vp]),
     "calm_layernorm_bwd": (i32, [vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp, i64, i32, vp]),
     "calm_layernorm_bwd_parts": (i32, [i64, i32]),
-    "calm_rope_table": (i32, [vp, vp, i32, i32, vp]),
     "calm_rope_fwd": (i32, [vp, i64, vp, i64, vp, i64, vp, i64, i32, i32, i32, i32, vp]),
     "calm_rope_bwd_scratch_floats": (i32, [i32, i32]),
     "calm_rope_bwd": (i32, [vp, i64, vp, i64, vp, i64, vp, i64, vp, vp, vp, i64, i32, i32, i32, i32, vp]),
@@ -147,8 +142,6 @@ def load(build_if_missing=True):
             fn.argtypes = args
         if lib.calm_abi_version() != 1:
             raise CalmError("libcalm_b200.so ABI version %d, expected 1" % lib.calm_abi_version())
-        if os.environ.get("CALM_DEBUG_FLAGS"):      # A/B switches of include/calm_b200.h (CALM_DEBUG_*), e.g. 64 = legacy RoPE kernels
-            lib.calm_set_debug_flags(int(os.environ["CALM_DEBUG_FLAGS"], 0))
         _lib = lib
     return _lib
 

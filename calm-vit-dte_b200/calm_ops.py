@@ -70,6 +70,17 @@ class SNBank:
         dev = self.specs[0].modules[0].weight_orig.device
         _require_cuda(dev)
         self.device = dev
+        if dev.type == "cuda":
+            # the tcgen05 GEMM moves 16-byte rows with TMA: every Linear's fan-in and fan-out must be a multiple of 8 (bf16).
+            # Said here, with the layer's shape, instead of as a failed launch in the middle of the first forward.
+            for sp in self.specs:
+                if sp.conv:
+                    continue
+                for m in sp.modules:
+                    o, i = m.weight_orig.shape[0], m.weight_orig[0].numel()
+                    if o % 8 or i % 8:
+                        raise L.CalmError("calm_b200: sn(Linear(%d -> %d)) is not supported: in/out features must be multiples of 8 (e.g. "
+                                          "ViT(out_features=...) and every stage width dim +- k*3*dim_step, seq +- k*3*seq_len_step)" % (i, o))
         self.groups, self.gid_of, self.layers = [], {}, []
         off = 0
         for gid, sp in enumerate(self.specs):
@@ -100,8 +111,16 @@ class SNBank:
         self.fingerprint = self._fingerprint()
 
     def _fingerprint(self):
-        a, b = self.layers[0]["module"], self.layers[-1]["module"]
-        return (a.weight_orig.data_ptr(), a.weight_u.data_ptr(), b.weight_orig.data_ptr(), b.weight_v.data_ptr())
+        """Addresses of EVERY tensor whose pointer is baked into the device table (weight_orig / u / v of each layer, the
+        LayerScale vectors): `.to()`, `p.data = ...`, `load_state_dict(assign=True)` or `remove_spectral_norm` on any single layer
+        changes it, and the bank is rebuilt before the kernels could touch freed memory."""
+        fp = []
+        for l in self.layers:
+            m = l["module"]
+            fp += [m.weight_orig.data_ptr(), m.weight_u.data_ptr(), m.weight_v.data_ptr()]
+            if l["rowscale"] is not None:
+                fp.append(l["rowscale"].data_ptr())
+        return tuple(fp)
 
     def _upload(self):
         ents = []
@@ -279,15 +298,24 @@ def _bf16_grad(g):
 # =====================================================================================================================
 # Functions
 # =====================================================================================================================
+def check_norm(m):
+    """The path implements the trainers' norm_layer: weight-only torch.nn.LayerNorm (`partial(LayerNorm, eps=1e-6)` with
+    bias=False, Vi_Tools_CNN_less_V2.py:115,131). Anything else is refused at construction instead of being silently ignored."""
+    if not isinstance(m, torch.nn.LayerNorm) or m.bias is not None or m.weight is None or len(m.normalized_shape) != 1:
+        raise NotImplementedError("calm_b200 implements weight-only torch.nn.LayerNorm over the feature axis (norm_layer(dim, bias=False)); "
+                                  "got %r" % (m,))
+    return m
+
+
 class LayerNormFn(Function):
     """y = LN(x)*w in bf16 (or fp32), plus an alias of x so that the residual consumer's gradient is fused into dx."""
 
     @staticmethod
-    def forward(ctx, x, w, out_f32, grad_feeds_gemm=False):
+    def forward(ctx, x, w, out_f32, grad_feeds_gemm=False, eps=1e-6):
         """grad_feeds_gemm: the gradient of x goes straight into a Linear's backward (ln_2 -> out_proj): LayerNorm backward then
         also writes it as bf16, the form that GEMM reads."""
         x = x.contiguous()
-        y, mean, rstd = K.layernorm_fwd(x, w, 1e-6, f32 if out_f32 else bf16)
+        y, mean, rstd = K.layernorm_fwd(x, w, float(eps), f32 if out_f32 else bf16)
         ctx.save_for_backward(x, w, mean, rstd)
         ctx.set_materialize_grads(False)
         ctx.side = bool(grad_feeds_gemm) and _SIDE_ON
@@ -297,14 +325,14 @@ class LayerNormFn(Function):
     def backward(ctx, dy, dres):
         x, w, mean, rstd = ctx.saved_tensors
         if dy is None:
-            return dres, None, None, None
+            return dres, None, None, None, None
         dres = dres.contiguous() if dres is not None else None
         if not ctx.side:
             dx, dw = K.layernorm_bwd(dy.contiguous(), x, w, mean, rstd, dres)
-            return dx, dw, None, None
+            return dx, dw, None, None, None
         dx, dw, dx16 = K.layernorm_bwd(dy.contiguous(), x, w, mean, rstd, dres, want_bf16=True)
         _offer_bf16(dx, dx16)       # the producing Linear's backward takes this gradient as a bf16 GEMM operand
-        return dx, dw, None, None
+        return dx, dw, None, None, None
 
 
 class LinearFn(Function):
@@ -476,19 +504,18 @@ class AttnCoreFn(Function):
             t2, _, ld = src2[i]
             return t2[:, off:], ld
 
-        cs_q, cs_k = K.rope_table(inv_q, S), K.rope_table(inv_k, S)
         qc, ld_qc = role("qc"); qr, ld_qr = role("qr")
         kc, ld_kc = role("kc"); kr, ld_kr = role("kr")
         v, ld_v = role("v")
-        q = K.rope_fwd(qc, ld_qc, qr, ld_qr, cs_q, T, S, heads, dc, dr)
-        k = K.rope_fwd(kc, ld_kc, kr, ld_kr, cs_k, T, S, heads, dc, dr)
+        q = K.rope_fwd(qc, ld_qc, qr, ld_qr, inv_q, T, S, heads, dc, dr)
+        k = K.rope_fwd(kc, ld_kc, kr, ld_kr, inv_k, T, S, heads, dc, dr)
         logits = torch.empty(B, S, S, dtype=bf16, device=q.device)
         K.gemm(q, k, logits, S, S, D, batch=B, lda=D, ldb=D, ldc=S, stride_a=S * D, stride_b=S * D, stride_c=S * S)
         bias = torch.empty(B, S, S, dtype=bf16, device=q.device)
         pre, hid = _mlp_forward(bank, g1, g2, logits.view(T, S), T, S, b1, b2, None, 0, bias)
         o, lse = K.attention_fwd(q, k, v, bias, B, S, heads, hd, D, D, ld_v)
         ctx.save_for_backward(inv_q, inv_k, *srcs)
-        ctx.saved = (q, k, logits, pre, hid, bias, o, lse, cs_q, cs_k)
+        ctx.saved = (q, k, logits, pre, hid, bias, o, lse)
         ctx.bank, ctx.g1, ctx.g2, ctx.version = bank, g1, g2, bank.version
         ctx.roles, ctx.dims = roles, dims
         return o.view(B, S, D)
@@ -496,7 +523,7 @@ class AttnCoreFn(Function):
     @staticmethod
     def backward(ctx, d_o):
         inv_q, inv_k, *srcs = ctx.saved_tensors
-        q, k, logits, pre, hid, bias, o, lse, cs_q, cs_k = ctx.saved
+        q, k, logits, pre, hid, bias, o, lse = ctx.saved
         bank = ctx.bank
         _check_version(bank, ctx.version)
         B, S, heads, dc, dr = ctx.dims
@@ -531,8 +558,8 @@ class AttnCoreFn(Function):
                a_major=MAJOR_MN, b_major=MAJOR_MN, addend=dk, ld_addend=D, stride_addend=S * D)
         dqc, ld_dqc = role("qc", dsrc2); dqr, ld_dqr = role("qr", dsrc2)
         dkc, ld_dkc = role("kc", dsrc2); dkr, ld_dkr = role("kr", dsrc2)
-        _, _, dinv_q = K.rope_bwd(dq, D, q, cs_q, T, S, heads, dc, dr, dcontent=dqc, ld_dcontent=ld_dqc, dropein=dqr, ld_drope=ld_dqr)
-        _, _, dinv_k = K.rope_bwd(dk, D, k, cs_k, T, S, heads, dc, dr, dcontent=dkc, ld_dcontent=ld_dkc, dropein=dkr, ld_drope=ld_dkr)
+        _, _, dinv_q = K.rope_bwd(dq, D, q, inv_q, T, S, heads, dc, dr, dcontent=dqc, ld_dcontent=ld_dqc, dropein=dqr, ld_drope=ld_dqr)
+        _, _, dinv_k = K.rope_bwd(dk, D, k, inv_k, T, S, heads, dc, dr, dcontent=dkc, ld_dcontent=ld_dkc, dropein=dkr, ld_drope=ld_dkr)
         ctx.saved = None
         return (None, dinv_q, dinv_k, db1, db2, None, None, None, None, None, *dsrc)
 

@@ -293,7 +293,8 @@ class TrainerStep:
         self.elem_off = torch.tensor(off, dtype=i64, device=dev)
         self.chunk_tensor = torch.tensor(chunk_tensor, dtype=i32, device=dev)
         self.chunk_start = torch.tensor(chunk_start, dtype=i32, device=dev)
-        self.param_ptrs = torch.tensor([p.data_ptr() for p in self.params], dtype=i64, device=dev)
+        self._param_ptr_list = [p.data_ptr() for p in self.params]
+        self.param_ptrs = torch.tensor(self._param_ptr_list, dtype=i64, device=dev)
         self.grad_ptrs = torch.zeros(self.n_tensors, dtype=i64, device=dev)
         self._grad_ptr_list = None
         # pinned staging for the gradient pointer table: two alternate in eager mode (each guarded by an event), a third is
@@ -360,8 +361,9 @@ class TrainerStep:
     # -- the step --------------------------------------------------------------------------------------------------------
     def _stage_grad_ptrs(self):
         """Returns the pinned host table to upload (or None when no .grad moved since the last upload)."""
-        ptrs = []
+        ptrs, pptrs = [], []
         for p in self.params:
+            pptrs.append(p.data_ptr())
             g = p.grad
             if g is None:
                 raise L.CalmError("TrainerStep.step: a parameter has no gradient (the reference runs DDP without "
@@ -369,6 +371,15 @@ class TrainerStep:
             if g.dtype != f32 or not g.is_contiguous() or g.device != self.device:
                 raise L.CalmError("TrainerStep.step: gradients must be contiguous fp32 tensors on the parameters' device")
             ptrs.append(g.data_ptr())
+        if pptrs != self._param_ptr_list:
+            # a parameter's storage was replaced after construction (model.to(), p.data = ..., load_state_dict(assign=True)):
+            # re-upload the table — the AdamW kernel would otherwise update freed memory
+            if torch.cuda.is_current_stream_capturing():
+                raise L.CalmError("TrainerStep: a parameter was re-allocated since the last step; run one eager step before capturing")
+            if any(p.dtype != f32 or not p.is_contiguous() or p.device != self.device for p in self.params):
+                raise L.CalmError("TrainerStep: parameters must stay contiguous fp32 tensors on %s" % self.device)
+            self.param_ptrs.copy_(torch.tensor(pptrs, dtype=torch.int64))
+            self._param_ptr_list = pptrs
         if ptrs == self._grad_ptr_list:
             return None, None
         if torch.cuda.is_current_stream_capturing():

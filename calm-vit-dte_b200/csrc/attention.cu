@@ -517,7 +517,7 @@ extern "C" int32_t calm_attention_fwd(const void* q, const void* k, const void* 
   {
     const int64_t lds[3] = {ld_q, ld_k, ld_v};
     const void* ptrs[4] = {q, k, v, bias};
-    if (!(calm_get_debug_flags() & CALM_DEBUG_LEGACY_ATTENTION) && calm_attention_tc_eligible(B, S, heads, hd, lds, 3, ptrs, 4))
+    if (calm_attention_tc_eligible(B, S, heads, hd, lds, 3, ptrs, 4))
       return calm_attention_fwd_tc(q, k, v, bias, o, lse, ld_q, ld_k, ld_v, ld_o, B, S, heads, hd, stream);
   }
   DISPATCH_HDP(hd, return launch_fwd<HDP>(q, k, v, bias, o, lse, ld_q, ld_k, ld_v, ld_o, B, S, heads, hd, stream));
@@ -547,7 +547,7 @@ extern "C" int32_t calm_attention_bwd(const void* q, const void* k, const void* 
   {
     const int64_t lds[4] = {ld_q, ld_k, ld_v, ld_do};
     const void* ptrs[6] = {q, k, v, d_o, bias, dbias};
-    if (ds_scratch && !(calm_get_debug_flags() & CALM_DEBUG_LEGACY_ATTENTION) && calm_attention_tc_eligible(B, S, heads, hd, lds, 4, ptrs, 6))
+    if (ds_scratch && calm_attention_tc_eligible(B, S, heads, hd, lds, 4, ptrs, 6))
       return calm_attention_bwd_tc(q, k, v, bias, d_o, lse, delta, dq, dk, dv, dbias, ds_scratch, ld_q, ld_k, ld_v, ld_do, ld_dq, ld_dk,
                                    ld_dv, B, S, heads, hd, stream);
   }

@@ -783,12 +783,15 @@ int calm_attention_fwd_tc(const void* q, const void* k, const void* v, const voi
   return CALM_OK;
 }
 
+// bring-up only (-DCALM_BRINGUP): CTA 0 of the backward kernel writes [count, (event id, globaltimer ns)...] into this buffer
 static unsigned long long* g_trace_buf = nullptr;
 static int g_trace_cap = 0;
+#ifdef CALM_BRINGUP
 extern "C" void calm_debug_set_trace_buffer(void* device_u64, int32_t capacity_events) {
   g_trace_buf = reinterpret_cast<unsigned long long*>(device_u64);
   g_trace_cap = capacity_events;
 }
+#endif
 
 size_t calm_attention_bwd_tc_scratch_bytes(int B, int S, int heads) { return (size_t)2 * B * heads * S * S; }
 

@@ -5,454 +5,528 @@
 // four (B,32,S,S) tensors per call; here the 32-channel intermediates only ever live in shared memory, so HBM traffic is
 // the 3-channel read + 3-channel write (forward) — the backward recomputes them from x with a 2-pixel halo.
 //
-// Mapping (v2): the depthwise structure makes channels independent, so the CHANNEL loop is the outer loop and a thread owns
-// PIXELS: per chunk of channels one shared-memory plane per channel holds the hidden map of the tile (+halo); a thread
-// then produces 4 horizontally adjacent pixels from 3 x (LDS.128 + LDS.64) per channel and accumulates the 32->3
-// projection in registers — no cross-lane reductions in the data path, weights are warp-uniform shared-memory loads.
-// The kernel is bound by the 2 GELU evaluations per pixel-channel (FP32 + MUFU pipes), not by HBM: GELU(erf) uses the
-// Abramowitz-Stegun 7.1.26 erfc form (|abs err| < 1.5e-7; one MUFU.RCP + one MUFU.EX2), and its derivative reuses the
-// exponential. Parameter gradients: per-warp shuffle reductions per channel into per-warp shared accumulators (no atomics,
-// deterministic), one partial row per CTA, then a second-stage reduce.
+// v3 (round 2). Round 1's kernels issued ~110 (forward) / ~240 (backward) instructions per pixel-channel for ~45 / ~90 of fp32
+// arithmetic (ncu: issue-bound, 2 % of the HBM roofline). This version changes the arithmetic, not just the schedule:
+//   * CHANNEL PAIRS IN fp16x2. The hidden activations (pre1, h1 = gelu(pre1), pre2, h2 = gelu(pre2) and the two GELU
+//     derivatives) are O(1) quantities that the reference's autocast path stores in bf16 (8-bit mantissa); here they are
+//     computed and held as packed half2 (11-bit mantissa) with one channel pair per register: one HFMA2 does the work of two
+//     FFMAs and one MUFU op serves two channels. GELU(erf) in half2: Phi(x) = 0.5 + 0.5 tanh(x (a + b x^2)), a = 0.79880144,
+//     b = 0.03528205 (minimax fit of atanh(erf(x/sqrt2)), |error| < 2.9e-4 — below the fp16 resolution of Phi; both
+//     coefficients positive, so the polynomial saturates monotonically and needs no clamp), gelu' = Phi + x exp(-x^2/2)/sqrt(2 pi):
+//     5 HFMA2-class + 1 MUFU (value) or 8 + 2 MUFU (value and derivative) per channel PAIR.
+//     Everything on the gradient side (dy, dp2, dp1, all parameter-gradient sums, dx) stays fp32 / bf16-with-fp32-accumulate:
+//     the GradScaler-scaled gradients do not fit fp16's range.
+//   * A WARP OWNS ONE CHANNEL PAIR for the life of the CTA (16 warps = 32 channels). Its planes (h1, g1/dp1, dp2 of the tile)
+//     are private, so the three phases of a tile only need __syncwarp between them; its weights live in registers; its 34
+//     parameter-gradient sums are per-lane register accumulators across ALL tiles of the persistent CTA (no per-tile / per-channel
+//     shuffle reductions: one butterfly per kernel). A lane owns one pixel column of the 32-wide tile and walks down the rows
+//     with a rotating 3-row register window (3 new taps per pixel instead of 9).
+//   * THE TWO CONTRACTIONS OVER CHANNELS RUN ON TENSOR CORES. y = W3 h2 (forward) and dx = W1^T dp1 (backward) contract over
+//     the 32 channels that live in 16 different warps: the per-warp planes [channel pair][pixel] ARE the A-fragment layout of
+//     mma.sync.m16n8k16 (row = pixel, k = channel; one LDS.32 per fragment register, conflict-free because the warp stride is
+//     8 mod 32 words), so after a block barrier each warp finishes 16-pixel segments with 2 MMAs (fp16 x fp16 forward,
+//     bf16 x bf16 backward, fp32 accumulate), adds the fp32 residual / dy in shared memory and writes 192-byte coalesced rows.
+//   * Tiles are prefetched with cp.async (zero-fill outside the image) one tile ahead, so the global latency of the next
+//     tile's x / dy is hidden behind the current tile's arithmetic.
 #include "common.cuh"
-#include <stdlib.h>
 #include "../../include/calm_b200.h"
 
 namespace {
 
-constexpr int CH = 32;
-constexpr int NT = 256;
-constexpr int NW = NT / 32;
-constexpr int WSM = 644;  // w1b[32][4] | w2p[32][12] | w3t[32][4] | b3[4]
+constexpr int NWARP = 16;
+constexpr int NT = NWARP * 32;
+constexpr int TW = 32;            // tile width = one lane per pixel column
+constexpr int RAW_COLS = 36;      // raw tile rows hold image columns tx0-2 .. tx0+33 (even start: 8-byte cp.async chunks)
+constexpr int RAW_ROW = RAW_COLS * 3;
+constexpr int NPARAM = CALM_CNN_NPARAM;   // w1[96] b1[32] w2[288] b2[32] w3[96] b3[3]
+constexpr int P_W1 = 0, P_B1 = 96, P_W2 = 128, P_B2 = 416, P_W3 = 448, P_B3 = 544;
+constexpr int WSM_FLOATS = 552;
 
 struct CnnW { const float *w1, *b1, *w2, *b2, *w3, *b3; };
 
-__device__ __forceinline__ float gelu_fast(float x) { return gelu_erf(x); }
-
-
-// Sum N register values over the 32 lanes with N - 1 + log2(32/N)... shuffles instead of 5 N: at every butterfly step a lane
-// keeps one half of its values and ships the other half to its partner. On return v[0] of lane L holds the all-lane sum of
-// value (L >> (5 - log2 N)): the lanes of a group all hold the same total, in the same (fixed) summation order.
-__device__ __forceinline__ void warp_sum16(float (&v)[16], int lane) {
-#pragma unroll
-  for (int step = 0; step < 4; ++step) {
-    const int off = 16 >> step, half = 8 >> step;
-    const bool hi = (lane & off) != 0;
-#pragma unroll
-    for (int i = 0; i < half; ++i) {
-      const float send = hi ? v[i] : v[i + half];
-      const float keep = hi ? v[i + half] : v[i];
-      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-    }
-  }
-  v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
+__device__ __forceinline__ void mma_bf16(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
-__device__ __forceinline__ void warp_sum8(float (&v)[8], int lane) {
-#pragma unroll
-  for (int step = 0; step < 3; ++step) {
-    const int off = 16 >> step, half = 4 >> step;
-    const bool hi = (lane & off) != 0;
-#pragma unroll
-    for (int i = 0; i < half; ++i) {
-      const float send = hi ? v[i] : v[i + half];
-      const float keep = hi ? v[i + half] : v[i];
-      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+__device__ __forceinline__ void mma_f16(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+__device__ __forceinline__ void cp_async8(void* dst_smem, const void* src, int src_bytes) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst_smem);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(d), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* dst_smem, const void* src, int src_bytes) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst_smem);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// Asynchronous copy of image rows [gy0, gy0 + nrows) x columns [gx0, gx0 + 36) (3 floats per pixel) into dst[nrows][108];
+// everything outside the S x S image is zero-filled. gx0 is even; with S even a 2-float chunk never straddles the image border.
+__device__ __forceinline__ void prefetch_rows(float* dst, const float* __restrict__ img, int S, int gy0, int gx0, int nrows) {
+  const int lim = S * 3, f0 = gx0 * 3;
+  if (!(S & 1)) {
+    for (int i = threadIdx.x; i < nrows * (RAW_ROW / 2); i += NT) {
+      const int row = i / (RAW_ROW / 2), ch = i - row * (RAW_ROW / 2);
+      const int gy = gy0 + row, f = f0 + 2 * ch;
+      const bool ok = gy >= 0 && gy < S && f >= 0 && f < lim;
+      cp_async8(dst + row * RAW_ROW + 2 * ch, ok ? img + (long long)gy * lim + f : img, ok ? 8 : 0);
+    }
+  } else {
+    for (int i = threadIdx.x; i < nrows * RAW_ROW; i += NT) {
+      const int row = i / RAW_ROW, e = i - row * RAW_ROW;
+      const int gy = gy0 + row, f = f0 + e;
+      const bool ok = gy >= 0 && gy < S && f >= 0 && f < lim;
+      cp_async4(dst + row * RAW_ROW + e, ok ? img + (long long)gy * lim + f : img, ok ? 4 : 0);
     }
   }
-  v[0] += __shfl_xor_sync(0xffffffffu, v[0], 2);
-  v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
 }
 
 __device__ __forceinline__ void load_weights(float* wsm, const CnnW& W) {
-  for (int i = threadIdx.x; i < CH; i += NT) {
-    wsm[i * 4 + 0] = W.w1[i * 3 + 0]; wsm[i * 4 + 1] = W.w1[i * 3 + 1]; wsm[i * 4 + 2] = W.w1[i * 3 + 2]; wsm[i * 4 + 3] = W.b1[i];
-    float* w2p = wsm + 128 + i * 12;
-#pragma unroll
-    for (int k = 0; k < 9; ++k) w2p[k] = W.w2[i * 9 + k];
-    w2p[9] = W.b2[i]; w2p[10] = 0.f; w2p[11] = 0.f;
-    float* w3t = wsm + 512 + i * 4;
-    w3t[0] = W.w3[i]; w3t[1] = W.w3[CH + i]; w3t[2] = W.w3[2 * CH + i]; w3t[3] = 0.f;
+  for (int i = threadIdx.x; i < NPARAM; i += NT) {
+    float v;
+    if (i < P_B1) v = W.w1[i];
+    else if (i < P_W2) v = W.b1[i - P_B1];
+    else if (i < P_B2) v = W.w2[i - P_W2];
+    else if (i < P_W3) v = W.b2[i - P_B2];
+    else if (i < P_B3) v = W.w3[i - P_W3];
+    else v = W.b3[i - P_B3];
+    wsm[i] = v;
   }
-  if (threadIdx.x < 3) wsm[640 + threadIdx.x] = W.b3[threadIdx.x];
 }
 
-// ------------------------------------------------------------------------------------------------------------------
-// forward: 32 x 32 pixel tiles, 4 channels per chunk, double-buffered planes (one __syncthreads per chunk)
-// ------------------------------------------------------------------------------------------------------------------
-constexpr int FT = 32;                      // tile side
-constexpr int FCC = 4;                      // channels per chunk
-constexpr int FPW = 36;                     // plane pitch (34 columns used)
-constexpr int FPLANE = (FT + 2) * FPW;      // 1224
-constexpr int FXS = (FT + 2) * (FT + 2) * 3;  // 3468
-constexpr int FWD_SMEM_FLOATS = FXS + WSM + 2 * FCC * FPLANE;
-
-__global__ void __launch_bounds__(NT, 3)
-cnn_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, CnnW W, int B, int S, int tiles_side) {
-  extern __shared__ __align__(16) float sm[];
-  float* xs = sm;
-  float* wsm = xs + FXS;
-  float* planes = wsm + WSM;
-  load_weights(wsm, W);
-  const int tid = threadIdx.x;
-  const int tx = tid & 7, ty = tid >> 3;
-  const int tiles_per_img = tiles_side * tiles_side;
-  const long long total_tiles = (long long)B * tiles_per_img;
-
-  for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-    const int b = (int)(tile / tiles_per_img);
-    const int tr = (int)(tile - (long long)b * tiles_per_img);
-    const int ty0 = (tr / tiles_side) * FT, tx0 = (tr % tiles_side) * FT;
-    const float* xb = x + (long long)b * S * S * 3;
-    __syncthreads();
-    for (int i = tid; i < FXS; i += NT) {
-      const int row = i / ((FT + 2) * 3), rem = i - row * ((FT + 2) * 3);
-      const int gy = ty0 + row - 1, gx3 = (tx0 - 1) * 3 + rem;
-      xs[i] = (gy >= 0 && gy < S && gx3 >= 0 && gx3 < S * 3) ? xb[(long long)gy * S * 3 + gx3] : 0.f;
-    }
-    __syncthreads();
-    float out[4][3];
+// One 16-pixel row segment leaves shared memory (48 floats at seg, 8-byte aligned) for global memory: 24 lanes x float2 when the
+// segment lies inside the image and rows are 8-byte aligned (S even), element-wise guarded otherwise.
+__device__ __forceinline__ void store_segment(const float* seg, float* __restrict__ out, bf16* __restrict__ out16, long long row_base /* pixel index of column 0 of this image row */,
+                                              int gx0, int S, int lane) {
+  if (lane >= 24) return;
+  const long long o = (row_base + gx0) * 3 + 2 * lane;
+  if (!(S & 1) && gx0 + 16 <= S) {
+    const float2 v = *reinterpret_cast<const float2*>(seg + 2 * lane);
+    *reinterpret_cast<float2*>(out + o) = v;
+    if (out16) *reinterpret_cast<bf162*>(out16 + o) = __floats2bfloat162_rn(v.x, v.y);
+  } else {
 #pragma unroll
-    for (int j = 0; j < 4; ++j) out[j][0] = out[j][1] = out[j][2] = 0.f;
-
-    for (int chunk = 0; chunk < CH / FCC; ++chunk) {
-      float* buf = planes + (chunk & 1) * FCC * FPLANE;
-      // phase B: hidden map h1 = gelu(conv1x1(x)) on the 34 x 34 halo region (zero outside the image: conv zero padding)
-      for (int idx = tid; idx < (FT + 2) * (FT + 2); idx += NT) {
-        const int py = idx / (FT + 2), px = idx - py * (FT + 2);
-        const int gy = ty0 + py - 1, gx = tx0 + px - 1;
-        const bool inside = gy >= 0 && gy < S && gx >= 0 && gx < S;
-        const float x0 = xs[idx * 3], x1 = xs[idx * 3 + 1], x2 = xs[idx * 3 + 2];
-#pragma unroll
-        for (int k = 0; k < FCC; ++k) {
-          const float4 w = *reinterpret_cast<const float4*>(wsm + (chunk * FCC + k) * 4);
-          const float pre = fmaf(w.x, x0, fmaf(w.y, x1, fmaf(w.z, x2, w.w)));
-          buf[k * FPLANE + py * FPW + px] = inside ? gelu_fast(pre) : 0.f;
-        }
-      }
-      __syncthreads();
-      // phase C: depthwise 3x3 + GELU + 32->3 projection for this thread's 4 pixels
-#pragma unroll
-      for (int k = 0; k < FCC; ++k) {
-        const int c = chunk * FCC + k;
-        const float* pl = buf + k * FPLANE + ty * FPW + 4 * tx;
-        float r[3][6];
-#pragma unroll
-        for (int q = 0; q < 3; ++q) {
-          const float4 a = *reinterpret_cast<const float4*>(pl + q * FPW);
-          const float2 bb = *reinterpret_cast<const float2*>(pl + q * FPW + 4);
-          r[q][0] = a.x; r[q][1] = a.y; r[q][2] = a.z; r[q][3] = a.w; r[q][4] = bb.x; r[q][5] = bb.y;
-        }
-        const float4 wa = *reinterpret_cast<const float4*>(wsm + 128 + c * 12);
-        const float4 wb = *reinterpret_cast<const float4*>(wsm + 128 + c * 12 + 4);
-        const float4 wc = *reinterpret_cast<const float4*>(wsm + 128 + c * 12 + 8);
-        const float4 w3 = *reinterpret_cast<const float4*>(wsm + 512 + c * 4);
-        const float w2[9] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w, wc.x};
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          float pre = wc.y;  // b2
-#pragma unroll
-          for (int ky = 0; ky < 3; ++ky)
-#pragma unroll
-            for (int kx = 0; kx < 3; ++kx) pre = fmaf(w2[ky * 3 + kx], r[ky][j + kx], pre);
-          const float h2 = gelu_fast(pre);
-          out[j][0] = fmaf(w3.x, h2, out[j][0]);
-          out[j][1] = fmaf(w3.y, h2, out[j][1]);
-          out[j][2] = fmaf(w3.z, h2, out[j][2]);
-        }
-      }
-    }
-    // y = x + cnn(x) + b3
-    const int gy = ty0 + ty;
-    if (gy < S) {
-      const float b30 = wsm[640], b31 = wsm[641], b32 = wsm[642];
-      float* yrow = y + ((long long)b * S * S + (long long)gy * S) * 3;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int gx = tx0 + 4 * tx + j;
-        if (gx < S) {
-          const float* xc = xs + ((ty + 1) * (FT + 2) + (4 * tx + j + 1)) * 3;
-          yrow[gx * 3 + 0] = xc[0] + out[j][0] + b30;
-          yrow[gx * 3 + 1] = xc[1] + out[j][1] + b31;
-          yrow[gx * 3 + 2] = xc[2] + out[j][2] + b32;
-        }
+    for (int e = 0; e < 2; ++e) {
+      const int f = 2 * lane + e;
+      if (gx0 + f / 3 < S) {
+        out[o + e] = seg[f];
+        if (out16) out16[o + e] = __float2bfloat16(seg[f]);
       }
     }
   }
 }
 
-// ------------------------------------------------------------------------------------------------------------------
-// backward: 32 x th pixel tiles (th <= 24), 2 channels per chunk.
-//   phase B: h1 = gelu(pre1), g1 = gelu'(pre1) on the 2-pixel halo        (recomputed from x)
-//   phase C: pre2 -> h2, dp2 = (W3^T dy) * gelu'(pre2) on the 1-pixel halo; dW3, db2, dW2 from the owned pixels
-//   phase D: dh1 = dwconv^T(dp2), dp1 = dh1 * g1 ; dx += W1^T dp1 ; dW1, db1
-// parameter-gradient layout (CALM_CNN_NPARAM = 547): w1[96] b1[32] w2[288] b2[32] w3[96] b3[3]
-// ------------------------------------------------------------------------------------------------------------------
-constexpr int BT = 32;          // tile width
-constexpr int BTH = 24;         // max tile height
-constexpr int BCC = 2;
-constexpr int H1P = 40, DPP = 36, G1P = 32;
-constexpr int B_XS = (BTH + 4) * (BT + 4) * 3;     // 3024
-constexpr int B_DYS = (BTH + 2) * (BT + 2) * 3;    // 2652
-constexpr int B_H1 = BCC * (BTH + 4) * H1P;        // 2240
-constexpr int B_G1 = 2 * BCC * BTH * G1P;          // 3072 (double-buffered)
-constexpr int B_DP2 = BCC * (BTH + 2) * DPP;       // 1872
-constexpr int WACC = 548;                          // per-warp accumulators: 32 x 17 + 3 (+1 pad)
-constexpr int BWD_SMEM_FLOATS = B_XS + B_DYS + B_H1 + B_G1 + B_DP2 + WSM + NW * WACC;
+// ======================================================================================================================
+// forward: 32 x th tiles (th <= 16), 2 CTAs / SM
+// ======================================================================================================================
+constexpr int THF = 16;
+constexpr int F_XIN_COLS = 34;                                 // image columns tx0-1 .. tx0+32
+constexpr int F_XIN_BYTES = (THF + 2) * F_XIN_COLS * 16;       // {x0,x0 | x1,x1 | x2,x2 | mask} as half2 per pixel
+constexpr int F_RAW_BYTES = (THF + 2) * RAW_ROW * 4;           // fp32 x rows ty0-1 .. ty0+th, double-buffered
+constexpr int F_H1 = 0, F_H2 = (THF + 2) * F_XIN_COLS;         // per-warp plane offsets (words)
+constexpr int F_WARP_WORDS = 1128;                             // 612 + 512 = 1124, padded to 8 mod 32
+constexpr int FWD_SMEM = F_XIN_BYTES + 2 * F_RAW_BYTES + NWARP * F_WARP_WORDS * 4 + WSM_FLOATS * 4;
+static_assert(F_WARP_WORDS % 32 == 8 && F_WARP_WORDS >= F_H2 + THF * TW, "forward plane stride");
 
-__device__ __forceinline__ void
-cnn_bwd_body(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dx, bf16* __restrict__ dx16, const CnnW& W,
-             float* __restrict__ gpartial, int B, int S, int tiles_x, int tiles_y, int th) {
-  extern __shared__ __align__(16) float sm[];
-  float* xs = sm;
-  float* dys = xs + B_XS;
-  float* h1s = dys + B_DYS;
-  float* g1s = h1s + B_H1;
-  float* dp2s = g1s + B_G1;
-  float* wsm = dp2s + B_DP2;
-  float* wacc = wsm + WSM;
-  load_weights(wsm, W);
+__global__ void __launch_bounds__(NT, 2)
+cnn_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, CnnW W, int B, int S, int tiles_x, int tiles_y, int th) {
+  extern __shared__ __align__(16) unsigned char smraw[];
+  uint4* xin = reinterpret_cast<uint4*>(smraw);
+  float* raw0 = reinterpret_cast<float*>(smraw + F_XIN_BYTES);
+  uint32_t* planes = reinterpret_cast<uint32_t*>(smraw + F_XIN_BYTES + 2 * F_RAW_BYTES);
+  float* wsm = reinterpret_cast<float*>(planes + NWARP * F_WARP_WORDS);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  for (int i = tid; i < NW * WACC; i += NT) wacc[i] = 0.f;
-  float* myacc = wacc + warp * WACC;
+  const int g = lane >> 2, t = lane & 3;
+  load_weights(wsm, W);
+  uint32_t* h1 = planes + warp * F_WARP_WORDS + F_H1;
+  uint32_t* h2p = planes + warp * F_WARP_WORDS + F_H2;
   const int tiles_per_img = tiles_x * tiles_y;
-  const long long total_tiles = (long long)B * tiles_per_img;
-  const int h1_plane = (BTH + 4) * H1P, g1_plane = BTH * G1P, dp_plane = (BTH + 2) * DPP;
-  // phase C task: row rr (0..th+1) of the 1-halo region, 4-pixel group gc (0..8)
-  const bool c_active = tid < 9 * (th + 2);
-  // row and 4-pixel group packed into one opaque register: ptxas otherwise re-derives tid / 9 inside the channel loop
-  unsigned c_pack = (unsigned)(tid / 9) | (unsigned)(tid % 9) << 8;
-  asm volatile("" : "+r"(c_pack));
-#define c_rr ((int)(c_pack & 255u))
-#define c_g ((int)(c_pack >> 8))
-  // phase D task: row dr (0..th-1), group dg (0..7)
-  const bool d_active = tid < 8 * th;
-  const int d_r = tid >> 3, d_g = tid & 7;
-
-  for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-    const int b = (int)(tile / tiles_per_img);
-    const int tr = (int)(tile - (long long)b * tiles_per_img);
-    const int ty0 = (tr / tiles_x) * th, tx0 = (tr % tiles_x) * BT;
-    const float* xb = x + (long long)b * S * S * 3;
-    const float* dyb = dy + (long long)b * S * S * 3;
-    __syncthreads();
-    for (int i = tid; i < (th + 4) * (BT + 4) * 3; i += NT) {
-      const int row = i / ((BT + 4) * 3), rem = i - row * ((BT + 4) * 3);
-      const int gy = ty0 + row - 2, gx3 = (tx0 - 2) * 3 + rem;
-      xs[i] = (gy >= 0 && gy < S && gx3 >= 0 && gx3 < S * 3) ? xb[(long long)gy * S * 3 + gx3] : 0.f;
-    }
-    for (int i = tid; i < (th + 2) * (BT + 2) * 3; i += NT) {
-      const int row = i / ((BT + 2) * 3), rem = i - row * ((BT + 2) * 3);
-      const int gy = ty0 + row - 1, gx3 = (tx0 - 1) * 3 + rem;
-      dys[i] = (gy >= 0 && gy < S && gx3 >= 0 && gx3 < S * 3) ? dyb[(long long)gy * S * 3 + gx3] : 0.f;
-    }
-    __syncthreads();
-    float dxa[4][3];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) dxa[j][0] = dxa[j][1] = dxa[j][2] = 0.f;
-    // phase C pixel classes of this thread are the same for all 32 channels: bit j = inside the image (and the 1-pixel halo
-    // columns of the tile), bit 4 + j = owned by this tile
-    unsigned cmask = 0;
-    {
-      const int rloc = c_rr - 1, gy = ty0 + rloc;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int cloc = 4 * c_g + j - 1, gx = tx0 + cloc;
-        const bool valid = cloc <= BT && gy >= 0 && gy < S && gx >= 0 && gx < S;
-        const bool owned = valid && rloc >= 0 && rloc < th && cloc >= 0 && cloc < BT;
-        cmask |= (valid ? 1u : 0u) << j | (owned ? 16u : 0u) << j;
-      }
-    }
-    asm volatile("" : "+r"(cmask));   // opaque from here on: ptxas otherwise re-derives the eight comparisons inside the channel loop
-
-    for (int chunk = 0; chunk < CH / BCC; ++chunk) {
-      float* g1b = g1s + (chunk & 1) * BCC * g1_plane;
-      // ---------------- phase B
-      for (int idx = tid; idx < (th + 4) * (BT + 4); idx += NT) {
-        const int rr = idx / (BT + 4), cc = idx - rr * (BT + 4);
-        const int r = rr - 2, c = cc - 2;
-        const int gy = ty0 + r, gx = tx0 + c;
-        const bool inside = gy >= 0 && gy < S && gx >= 0 && gx < S;
-        const bool interior = r >= 0 && r < th && c >= 0 && c < BT;
-        const float x0 = xs[idx * 3], x1 = xs[idx * 3 + 1], x2 = xs[idx * 3 + 2];
-#pragma unroll
-        for (int k = 0; k < BCC; ++k) {
-          const float4 w = *reinterpret_cast<const float4*>(wsm + (chunk * BCC + k) * 4);
-          const float pre = fmaf(w.x, x0, fmaf(w.y, x1, fmaf(w.z, x2, w.w)));
-          float h, g;
-          gelu_pair(pre, h, g);
-          h1s[k * h1_plane + rr * H1P + cc] = inside ? h : 0.f;
-          if (interior) g1b[k * g1_plane + r * G1P + c] = inside ? g : 0.f;
-        }
-      }
-      __syncthreads();
-      // ---------------- phase C
-#pragma unroll
-      for (int k = 0; k < BCC; ++k) {
-        const int ch = chunk * BCC + k;
-        float gw3[3] = {0.f, 0.f, 0.f}, gb2 = 0.f, gw2[9];
-#pragma unroll
-        for (int q = 0; q < 9; ++q) gw2[q] = 0.f;
-        if (c_active) {
-          const float* pl = h1s + k * h1_plane + c_rr * H1P + 4 * c_g;
-          float r[3][6];
-#pragma unroll
-          for (int q = 0; q < 3; ++q) {
-            const float4 a = *reinterpret_cast<const float4*>(pl + q * H1P);
-            const float2 bb = *reinterpret_cast<const float2*>(pl + q * H1P + 4);
-            r[q][0] = a.x; r[q][1] = a.y; r[q][2] = a.z; r[q][3] = a.w; r[q][4] = bb.x; r[q][5] = bb.y;
-          }
-          const float4 wa = *reinterpret_cast<const float4*>(wsm + 128 + ch * 12);
-          const float4 wb = *reinterpret_cast<const float4*>(wsm + 128 + ch * 12 + 4);
-          const float4 wc = *reinterpret_cast<const float4*>(wsm + 128 + ch * 12 + 8);
-          const float4 w3 = *reinterpret_cast<const float4*>(wsm + 512 + ch * 4);
-          const float w2[9] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w, wc.x};
-          float dpv[4];
-          const float* dyp = dys + (c_rr * (BT + 2) + 4 * c_g) * 3;   // pixel cloc = 4 c_g + j - 1 sits at column cloc + 1
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const bool valid = (cmask >> j) & 1u;
-            float pre = wc.y;
-#pragma unroll
-            for (int ky = 0; ky < 3; ++ky)
-#pragma unroll
-              for (int kx = 0; kx < 3; ++kx) pre = fmaf(w2[ky * 3 + kx], r[ky][j + kx], pre);
-            float h2, d2;
-            gelu_pair(pre, h2, d2);
-            // dy is zero outside the image; the two right-most pixels of the last group lie past the halo and read whatever
-            // follows in shared memory (planes, other rows): their product is discarded, never a NaN in dp2
-            const float d0 = dyp[3 * j], d1 = dyp[3 * j + 1], d2y = dyp[3 * j + 2];
-            const float dpre = valid ? (w3.x * d0 + w3.y * d1 + w3.z * d2y) * d2 : 0.f;
-            dpv[j] = dpre;
-            if ((cmask >> (4 + j)) & 1u) {
-              gw3[0] = fmaf(d0, h2, gw3[0]); gw3[1] = fmaf(d1, h2, gw3[1]); gw3[2] = fmaf(d2y, h2, gw3[2]);
-              gb2 += dpre;
-#pragma unroll
-              for (int ky = 0; ky < 3; ++ky)
-#pragma unroll
-                for (int kx = 0; kx < 3; ++kx) gw2[ky * 3 + kx] = fmaf(dpre, r[ky][j + kx], gw2[ky * 3 + kx]);
-            }
-          }
-          *reinterpret_cast<float4*>(dp2s + k * dp_plane + c_rr * DPP + 4 * c_g) = make_float4(dpv[0], dpv[1], dpv[2], dpv[3]);
-        }
-        // per-warp reduction of the 13 per-channel sums (all lanes take part; inactive lanes hold zeros): lane L ends up
-        // with the total of value L >> 1, the even lanes of the first 13 pairs add it to the warp's accumulator row
-        float v[16] = {gw2[0], gw2[1], gw2[2], gw2[3], gw2[4], gw2[5], gw2[6], gw2[7], gw2[8], gb2, gw3[0], gw3[1], gw3[2], 0.f, 0.f, 0.f};
-        warp_sum16(v, lane);
-        if (!(lane & 1) && lane < 26) myacc[ch * 17 + 4 + (lane >> 1)] += v[0];
-      }
-      __syncthreads();
-      // ---------------- phase D
-      float dsum[4 * BCC];
-#pragma unroll
-      for (int k = 0; k < BCC; ++k) {
-        const int ch = chunk * BCC + k;
-        float gw1[3] = {0.f, 0.f, 0.f}, gb1 = 0.f;
-        if (d_active) {
-          const float* pl = dp2s + k * dp_plane + d_r * DPP + 4 * d_g;
-          float r[3][6];
-#pragma unroll
-          for (int q = 0; q < 3; ++q) {
-            const float4 a = *reinterpret_cast<const float4*>(pl + q * DPP);
-            const float2 bb = *reinterpret_cast<const float2*>(pl + q * DPP + 4);
-            r[q][0] = a.x; r[q][1] = a.y; r[q][2] = a.z; r[q][3] = a.w; r[q][4] = bb.x; r[q][5] = bb.y;
-          }
-          const float4 wa = *reinterpret_cast<const float4*>(wsm + 128 + ch * 12);
-          const float4 wb = *reinterpret_cast<const float4*>(wsm + 128 + ch * 12 + 4);
-          const float4 wc = *reinterpret_cast<const float4*>(wsm + 128 + ch * 12 + 8);
-          const float4 w1 = *reinterpret_cast<const float4*>(wsm + ch * 4);
-          const float w2[9] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w, wc.x};
-          const float4 gv = *reinterpret_cast<const float4*>(g1b + k * g1_plane + d_r * G1P + 4 * d_g);
-          const float g1v[4] = {gv.x, gv.y, gv.z, gv.w};
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            float dh = 0.f;  // out(q) used h1(q + (ky-1,kx-1))  =>  h1(p) fed out(p - (ky-1,kx-1))
-#pragma unroll
-            for (int ky = 0; ky < 3; ++ky)
-#pragma unroll
-              for (int kx = 0; kx < 3; ++kx) dh = fmaf(w2[ky * 3 + kx], r[2 - ky][j + 2 - kx], dh);
-            const float dp1 = dh * g1v[j];  // g1 = 0 outside the image
-            const float* xc = xs + ((d_r + 2) * (BT + 4) + (4 * d_g + j + 2)) * 3;
-            dxa[j][0] = fmaf(w1.x, dp1, dxa[j][0]);
-            dxa[j][1] = fmaf(w1.y, dp1, dxa[j][1]);
-            dxa[j][2] = fmaf(w1.z, dp1, dxa[j][2]);
-            gw1[0] = fmaf(dp1, xc[0], gw1[0]); gw1[1] = fmaf(dp1, xc[1], gw1[1]); gw1[2] = fmaf(dp1, xc[2], gw1[2]);
-            gb1 += dp1;
-          }
-        }
-        dsum[4 * k] = gw1[0]; dsum[4 * k + 1] = gw1[1]; dsum[4 * k + 2] = gw1[2]; dsum[4 * k + 3] = gb1;
-      }
-      static_assert(BCC == 2, "phase D reduces the 2 x 4 sums of a chunk in one 8-value butterfly");
-      warp_sum8(dsum, lane);   // lane L: total of value L >> 2 = (channel (L >> 4), slot (L >> 2) & 3)
-      if (!(lane & 3)) myacc[(chunk * BCC + (lane >> 4)) * 17 + ((lane >> 2) & 3)] += dsum[0];
-      // no barrier here: the next phase B writes h1 (last read before the barrier above) and the OTHER g1 buffer;
-      // dp2 is rewritten only after the next barrier
-    }
-    // dx = dy + W1^T dp1 ; db3 += dy over the owned pixels
-    float gb3[3] = {0.f, 0.f, 0.f};
-    if (d_active) {
-      const int gy = ty0 + d_r;
-      if (gy < S) {
-        float* dxrow = dx + ((long long)b * S * S + (long long)gy * S) * 3;
-        bf16* dxrow16 = dx16 ? dx16 + ((long long)b * S * S + (long long)gy * S) * 3 : nullptr;   // optional bf16 copy of dx
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int gx = tx0 + 4 * d_g + j;
-          if (gx < S) {
-            const float* dc = dys + ((d_r + 1) * (BT + 2) + (4 * d_g + j + 1)) * 3;
-            dxrow[gx * 3 + 0] = dxa[j][0] + dc[0];
-            dxrow[gx * 3 + 1] = dxa[j][1] + dc[1];
-            dxrow[gx * 3 + 2] = dxa[j][2] + dc[2];
-            if (dxrow16) {
-              dxrow16[gx * 3 + 0] = __float2bfloat16(dxa[j][0] + dc[0]);
-              dxrow16[gx * 3 + 1] = __float2bfloat16(dxa[j][1] + dc[1]);
-              dxrow16[gx * 3 + 2] = __float2bfloat16(dxa[j][2] + dc[2]);
-            }
-            gb3[0] += dc[0]; gb3[1] += dc[1]; gb3[2] += dc[2];
-          }
-        }
-      }
-    }
-#pragma unroll
-    for (int q = 0; q < 3; ++q) gb3[q] = warp_sum(gb3[q]);
-    if (lane == 0) { myacc[544] += gb3[0]; myacc[545] += gb3[1]; myacc[546] += gb3[2]; }
-  }
-  // one partial row per CTA, in the public parameter order
+  const long long total = (long long)B * tiles_per_img;
+  long long tile = blockIdx.x;
+  auto issue = [&](long long tl, int buf) {
+    const int b = (int)(tl / tiles_per_img), tr = (int)(tl - (long long)b * tiles_per_img);
+    prefetch_rows(raw0 + buf * (F_RAW_BYTES / 4), x + (long long)b * S * S * 3, S, (tr / tiles_x) * th - 1, (tr % tiles_x) * TW - 2, th + 2);
+  };
+  if (tile < total) issue(tile, 0);
+  cp_async_commit();
   __syncthreads();
-  float* gp = gpartial + (size_t)blockIdx.x * CALM_CNN_NPARAM;
-  for (int i = tid; i < 547; i += NT) {
-    float s = 0.f;
+  const int ca = 2 * warp, cb = ca + 1;
+  // this warp's weights (registers for the life of the CTA)
+  uint32_t w1h[3], w2h[9];
 #pragma unroll
-    for (int w = 0; w < NW; ++w) s += wacc[w * WACC + i];
-    int dst;
-    if (i >= 544) dst = i;
-    else {
-      const int ch = i / 17, q = i - ch * 17;
-      if (q < 3) dst = ch * 3 + q;                    // w1[c][k]
-      else if (q == 3) dst = 96 + ch;                 // b1[c]
-      else if (q < 13) dst = 128 + ch * 9 + (q - 4);  // w2[c][tap]
-      else if (q == 13) dst = 416 + ch;               // b2[c]
-      else dst = 448 + (q - 14) * CH + ch;            // w3[o][c]
-    }
-    gp[dst] = s;
+  for (int k = 0; k < 3; ++k) w1h[k] = h2pack(wsm[P_W1 + ca * 3 + k], wsm[P_W1 + cb * 3 + k]);
+#pragma unroll
+  for (int q = 0; q < 9; ++q) w2h[q] = h2pack(wsm[P_W2 + ca * 9 + q], wsm[P_W2 + cb * 9 + q]);
+  const uint32_t b1h = h2pack(wsm[P_B1 + ca], wsm[P_B1 + cb]), b2h = h2pack(wsm[P_B2 + ca], wsm[P_B2 + cb]);
+  // B fragments of y = W3 h2: B[k = channel][n = output channel] = w3[n][channel], zero for n >= 3
+  uint32_t bw[2][2];
+#pragma unroll
+  for (int ks = 0; ks < 2; ++ks) {
+    bw[ks][0] = g < 3 ? h2pack(wsm[P_W3 + g * 32 + 16 * ks + 2 * t], wsm[P_W3 + g * 32 + 16 * ks + 2 * t + 1]) : 0u;
+    bw[ks][1] = g < 3 ? h2pack(wsm[P_W3 + g * 32 + 16 * ks + 2 * t + 8], wsm[P_W3 + g * 32 + 16 * ks + 2 * t + 9]) : 0u;
   }
+  const float b3a = wsm[P_B3 + 0], b3b = wsm[P_B3 + 1], b3c = wsm[P_B3 + 2];
+
+  for (int it = 0; tile < total; tile += gridDim.x, ++it) {
+    const int b = (int)(tile / tiles_per_img), tr = (int)(tile - (long long)b * tiles_per_img);
+    const int ty0 = (tr / tiles_x) * th, tx0 = (tr % tiles_x) * TW;
+    float* raw = raw0 + (it & 1) * (F_RAW_BYTES / 4);
+    cp_async_wait_all();
+    __syncthreads();                         // this tile's rows have landed; the previous tile is fully consumed
+    if (tile + gridDim.x < total) issue(tile + gridDim.x, (it + 1) & 1);
+    cp_async_commit();
+    for (int i = tid; i < (th + 2) * F_XIN_COLS; i += NT) {
+      const int row = i / F_XIN_COLS, col = i - row * F_XIN_COLS;
+      const int gy = ty0 - 1 + row, gx = tx0 - 1 + col;
+      const bool inside = gy >= 0 && gy < S && gx >= 0 && gx < S;
+      const float* p = raw + row * RAW_ROW + (col + 1) * 3;
+      uint4 e;
+      e.x = h2pack(p[0], p[0]); e.y = h2pack(p[1], p[1]); e.z = h2pack(p[2], p[2]); e.w = inside ? H2_ONE : 0u;
+      xin[i] = e;
+    }
+    __syncthreads();
+    // ---- phase B: h1 = gelu(conv1x1(x)) on the 1-pixel halo region, zero outside the image (the dwconv's zero padding)
+    for (int rr = 0; rr < th + 2; ++rr) {
+      const uint4 e = xin[rr * F_XIN_COLS + lane];
+      const uint32_t pre = h2fma(w1h[0], e.x, h2fma(w1h[1], e.y, h2fma(w1h[2], e.z, b1h)));
+      h1[rr * F_XIN_COLS + lane] = h2mul(gelu_h2(pre), e.w);
+    }
+    for (int rr = lane >> 1; rr < th + 2; rr += 16) {
+      const int cc = 32 + (lane & 1);
+      const uint4 e = xin[rr * F_XIN_COLS + cc];
+      const uint32_t pre = h2fma(w1h[0], e.x, h2fma(w1h[1], e.y, h2fma(w1h[2], e.z, b1h)));
+      h1[rr * F_XIN_COLS + cc] = h2mul(gelu_h2(pre), e.w);
+    }
+    __syncwarp();
+    // ---- phase C: h2 = gelu(dwconv3x3(h1)) for pixel column `lane`, rotating 3-row window
+    {
+      uint32_t r0[3], r1[3], r2[3];
+#pragma unroll
+      for (int j = 0; j < 3; ++j) { r0[j] = h1[lane + j]; r1[j] = h1[F_XIN_COLS + lane + j]; }
+      auto step = [&](const uint32_t (&a)[3], const uint32_t (&bq)[3], uint32_t (&c)[3], int r) {
+#pragma unroll
+        for (int j = 0; j < 3; ++j) c[j] = h1[(r + 2) * F_XIN_COLS + lane + j];
+        uint32_t s0 = h2fma(w2h[0], a[0], b2h), s1 = h2mul(w2h[3], bq[0]), s2 = h2mul(w2h[6], c[0]);
+        s0 = h2fma(w2h[1], a[1], s0); s1 = h2fma(w2h[4], bq[1], s1); s2 = h2fma(w2h[7], c[1], s2);
+        s0 = h2fma(w2h[2], a[2], s0); s1 = h2fma(w2h[5], bq[2], s1); s2 = h2fma(w2h[8], c[2], s2);
+        const uint32_t pre = h2fma(H2_ONE, s0, h2fma(H2_ONE, s1, s2));
+        h2p[r * TW + lane] = gelu_h2(pre);
+      };
+      for (int r = 0; r < th; r += 3) {
+        step(r0, r1, r2, r);
+        if (r + 1 < th) step(r1, r2, r0, r + 1);
+        if (r + 2 < th) step(r2, r0, r1, r + 2);
+      }
+    }
+    __syncthreads();
+    // ---- y = x + b3 + W3 h2 : 16-pixel segments on the tensor cores, finished in the raw x tile and stored coalesced
+    for (int mt = warp; mt < th * 2; mt += NWARP) {
+      const int r = mt >> 1, c0 = (mt & 1) * 16;
+      const int gy = ty0 + r;
+      if (gy >= S || tx0 + c0 >= S) continue;
+      const uint32_t* pb = planes + F_H2 + r * TW + c0 + g;
+      float d[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks) {
+        const uint32_t* q = pb + (8 * ks + t) * F_WARP_WORDS;
+        mma_f16(d, q[0], q[8], q[4 * F_WARP_WORDS], q[4 * F_WARP_WORDS + 8], bw[ks][0], bw[ks][1]);
+      }
+      float* seg = raw + (r + 1) * RAW_ROW + (c0 + 2) * 3;
+      if (t == 0) {
+        seg[g * 3 + 0] += d[0] + b3a; seg[g * 3 + 1] += d[1] + b3b;
+        seg[(g + 8) * 3 + 0] += d[2] + b3a; seg[(g + 8) * 3 + 1] += d[3] + b3b;
+      } else if (t == 1) {
+        seg[g * 3 + 2] += d[0] + b3c; seg[(g + 8) * 3 + 2] += d[2] + b3c;
+      }
+      __syncwarp();
+      store_segment(seg, y, nullptr, ((long long)b * S + gy) * S, tx0 + c0, S, lane);
+    }
+  }
+  cp_async_wait_all();
 }
 
-#undef c_rr
-#undef c_g
+// ======================================================================================================================
+// backward: 32 x th tiles (th <= 24), 1 CTA / SM
+//   phase B: h1 = gelu(pre1), g1 = gelu'(pre1) on the 2-pixel halo            (recomputed from x, fp16x2)
+//   phase C: pre2 -> h2, d2 ; dp2 = (W3^T dy) * d2 on the 1-pixel halo ; dW3, db2, dW2 from the owned pixels
+//   phase D: dh1 = dwconv^T(dp2), dp1 = dh1 * g1 ; dW1, db1 ; dp1 -> plane (bf16x2, over g1)
+//   final  : dx = dy + W1^T dp1 on the tensor cores ; db3
+// ======================================================================================================================
+constexpr int THB = 24;
+constexpr int B_XIN_COLS = 36;                                  // image columns tx0-2 .. tx0+33
+constexpr int B_XIN_BYTES = (THB + 4) * B_XIN_COLS * 16;
+constexpr int B_XRAW_BYTES = (THB + 4) * RAW_ROW * 4;           // staging of the next tile's x rows ty0-2 .. ty0+th+1
+constexpr int B_DY_BYTES = (THB + 2) * RAW_ROW * 4;             // dy rows ty0-1 .. ty0+th (36 columns), double-buffered
+constexpr int B_H1 = 0, B_G1 = (THB + 4) * B_XIN_COLS, B_DP2 = B_G1 + THB * TW;
+constexpr int DP2_COLS = 34;                                    // image columns tx0-1 .. tx0+32
+constexpr int B_WARP_WORDS = 2664;                              // 1008 + 768 + 884 = 2660, padded to 8 mod 32
+constexpr int BWD_SMEM = B_XIN_BYTES + B_XRAW_BYTES + 2 * B_DY_BYTES + NWARP * B_WARP_WORDS * 4 + WSM_FLOATS * 4 + NWARP * 4 * 4;
+static_assert(B_WARP_WORDS % 32 == 8 && B_WARP_WORDS >= B_DP2 + (THB + 2) * DP2_COLS, "backward plane stride");
+static_assert(BWD_SMEM <= 227 * 1024, "backward shared memory");
 
-// two register budgets of the same body: 3 CTAs/SM (80 registers, a few spills) or 2 CTAs/SM (no spills)
-__global__ void __launch_bounds__(NT, 3)
+struct RowC { uint32_t h[3]; float lo[3], hi[3]; };   // 3 taps of one h1 row: packed pair + unpacked channels a / b
+struct RowD { float lo[3], hi[3]; };                  // 3 taps of one dp2 row
+
+__global__ void __launch_bounds__(NT, 1)
 cnn_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dx, bf16* __restrict__ dx16, CnnW W,
                float* __restrict__ gpartial, int B, int S, int tiles_x, int tiles_y, int th) {
-  cnn_bwd_body(x, dy, dx, dx16, W, gpartial, B, S, tiles_x, tiles_y, th);
-}
-__global__ void __launch_bounds__(NT, 2)
-cnn_bwd_kernel_occ2(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dx, bf16* __restrict__ dx16, CnnW W,
-                    float* __restrict__ gpartial, int B, int S, int tiles_x, int tiles_y, int th) {
-  cnn_bwd_body(x, dy, dx, dx16, W, gpartial, B, S, tiles_x, tiles_y, th);
+  extern __shared__ __align__(16) unsigned char smraw[];
+  uint4* xin = reinterpret_cast<uint4*>(smraw);
+  float* xraw = reinterpret_cast<float*>(smraw + B_XIN_BYTES);
+  float* dy0 = reinterpret_cast<float*>(smraw + B_XIN_BYTES + B_XRAW_BYTES);
+  uint32_t* planes = reinterpret_cast<uint32_t*>(smraw + B_XIN_BYTES + B_XRAW_BYTES + 2 * B_DY_BYTES);
+  float* wsm = reinterpret_cast<float*>(planes + NWARP * B_WARP_WORDS);
+  float* wred = wsm + WSM_FLOATS;   // [NWARP][4]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  load_weights(wsm, W);
+  uint32_t* h1 = planes + warp * B_WARP_WORDS + B_H1;
+  uint32_t* g1 = planes + warp * B_WARP_WORDS + B_G1;
+  uint32_t* dp2 = planes + warp * B_WARP_WORDS + B_DP2;
+  const int tiles_per_img = tiles_x * tiles_y;
+  const long long total = (long long)B * tiles_per_img;
+  long long tile = blockIdx.x;
+  auto issue = [&](long long tl, int buf) {
+    const int b = (int)(tl / tiles_per_img), tr = (int)(tl - (long long)b * tiles_per_img);
+    const int ty0 = (tr / tiles_x) * th, tx0 = (tr % tiles_x) * TW;
+    const long long img = (long long)b * S * S * 3;
+    prefetch_rows(xraw, x + img, S, ty0 - 2, tx0 - 2, th + 4);
+    prefetch_rows(dy0 + buf * (B_DY_BYTES / 4), dy + img, S, ty0 - 1, tx0 - 2, th + 2);
+  };
+  if (tile < total) issue(tile, 0);
+  cp_async_commit();
+  __syncthreads();
+  const int ca = 2 * warp, cb = ca + 1;
+  // per-lane parameter-gradient sums of this warp's two channels, accumulated over every tile of this CTA
+  float gw1a[3] = {0.f, 0.f, 0.f}, gw1b[3] = {0.f, 0.f, 0.f}, gb1a = 0.f, gb1b = 0.f;
+  float gw2a[9], gw2b[9], gb2a = 0.f, gb2b = 0.f;
+  float gw3a[3] = {0.f, 0.f, 0.f}, gw3b[3] = {0.f, 0.f, 0.f};
+  float gb3x = 0.f, gb3y = 0.f;     // t == 0 lanes: output channels 0 / 1 ; t == 1 lanes: gb3x = output channel 2
+#pragma unroll
+  for (int q = 0; q < 9; ++q) gw2a[q] = gw2b[q] = 0.f;
+  // B fragments of dx = W1^T dp1: B[k = channel][n = input channel] = w1[channel][n], zero for n >= 3
+  uint32_t bw[2][2];
+#pragma unroll
+  for (int ks = 0; ks < 2; ++ks) {
+    bw[ks][0] = g < 3 ? bf2pack(wsm[P_W1 + (16 * ks + 2 * t) * 3 + g], wsm[P_W1 + (16 * ks + 2 * t + 1) * 3 + g]) : 0u;
+    bw[ks][1] = g < 3 ? bf2pack(wsm[P_W1 + (16 * ks + 2 * t + 8) * 3 + g], wsm[P_W1 + (16 * ks + 2 * t + 9) * 3 + g]) : 0u;
+  }
+
+  for (int it = 0; tile < total; tile += gridDim.x, ++it) {
+    const int b = (int)(tile / tiles_per_img), tr = (int)(tile - (long long)b * tiles_per_img);
+    const int ty0 = (tr / tiles_x) * th, tx0 = (tr % tiles_x) * TW;
+    float* dys = dy0 + (it & 1) * (B_DY_BYTES / 4);
+    cp_async_wait_all();
+    __syncthreads();                         // x / dy of this tile have landed; the previous tile is fully consumed
+    for (int i = tid; i < (th + 4) * B_XIN_COLS; i += NT) {
+      const int row = i / B_XIN_COLS, col = i - row * B_XIN_COLS;
+      const int gy = ty0 - 2 + row, gx = tx0 - 2 + col;
+      const bool inside = gy >= 0 && gy < S && gx >= 0 && gx < S;
+      const float* p = xraw + row * RAW_ROW + col * 3;
+      uint4 e;
+      e.x = h2pack(p[0], p[0]); e.y = h2pack(p[1], p[1]); e.z = h2pack(p[2], p[2]); e.w = inside ? H2_ONE : 0u;
+      xin[i] = e;
+    }
+    __syncthreads();                         // xin complete, the x staging buffer is free again
+    if (tile + gridDim.x < total) issue(tile + gridDim.x, (it + 1) & 1);
+    cp_async_commit();
+
+    // ---------------- phase B
+    {
+      uint32_t w1h[3];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) w1h[k] = h2pack(wsm[P_W1 + ca * 3 + k], wsm[P_W1 + cb * 3 + k]);
+      const uint32_t b1h = h2pack(wsm[P_B1 + ca], wsm[P_B1 + cb]);
+      for (int rr = 0; rr < th + 4; ++rr) {
+        const uint4 e = xin[rr * B_XIN_COLS + lane];
+        const uint32_t pre = h2fma(w1h[0], e.x, h2fma(w1h[1], e.y, h2fma(w1h[2], e.z, b1h)));
+        uint32_t hv, gv;
+        gelu_pair_h2(pre, hv, gv);
+        h1[rr * B_XIN_COLS + lane] = h2mul(hv, e.w);
+        if (rr >= 2 && rr < th + 2 && lane >= 2) g1[(rr - 2) * TW + lane - 2] = h2mul(gv, e.w);
+      }
+      for (int rr = lane >> 2; rr < th + 4; rr += 8) {
+        const int cc = 32 + (lane & 3);
+        const uint4 e = xin[rr * B_XIN_COLS + cc];
+        const uint32_t pre = h2fma(w1h[0], e.x, h2fma(w1h[1], e.y, h2fma(w1h[2], e.z, b1h)));
+        uint32_t hv, gv;
+        gelu_pair_h2(pre, hv, gv);
+        h1[rr * B_XIN_COLS + cc] = h2mul(hv, e.w);
+        if (rr >= 2 && rr < th + 2 && cc < 34) g1[(rr - 2) * TW + cc - 2] = h2mul(gv, e.w);
+      }
+    }
+    __syncwarp();
+    // ---------------- phase C : tile rows rloc = -1 .. th, pixel column `lane`
+    {
+      uint32_t w2h[9];
+#pragma unroll
+      for (int q = 0; q < 9; ++q) w2h[q] = h2pack(wsm[P_W2 + ca * 9 + q], wsm[P_W2 + cb * 9 + q]);
+      const uint32_t b2h = h2pack(wsm[P_B2 + ca], wsm[P_B2 + cb]);
+      float w3a[3], w3b[3];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) { w3a[k] = wsm[P_W3 + k * 32 + ca]; w3b[k] = wsm[P_W3 + k * 32 + cb]; }
+      auto pre2 = [&](const uint32_t (&a)[3], const uint32_t (&bq)[3], const uint32_t (&c)[3]) {
+        uint32_t s0 = h2fma(w2h[0], a[0], b2h), s1 = h2mul(w2h[3], bq[0]), s2 = h2mul(w2h[6], c[0]);
+        s0 = h2fma(w2h[1], a[1], s0); s1 = h2fma(w2h[4], bq[1], s1); s2 = h2fma(w2h[7], c[1], s2);
+        s0 = h2fma(w2h[2], a[2], s0); s1 = h2fma(w2h[5], bq[2], s1); s2 = h2fma(w2h[8], c[2], s2);
+        return h2fma(H2_ONE, s0, h2fma(H2_ONE, s1, s2));
+      };
+      auto load_row = [&](RowC& R, int prow) {     // h1 plane row prow, image columns lane-1 .. lane+1
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          R.h[j] = h1[prow * B_XIN_COLS + lane + 1 + j];
+          const float2 f = h2unpack(R.h[j]);
+          R.lo[j] = f.x; R.hi[j] = f.y;
+        }
+      };
+      RowC ra, rb, rc;
+      load_row(ra, 0);
+      load_row(rb, 1);
+      auto step = [&](const RowC& A, const RowC& Bq, RowC& C, int rloc) {
+        load_row(C, rloc + 3);
+        uint32_t h2v, d2v;
+        gelu_pair_h2(pre2(A.h, Bq.h, C.h), h2v, d2v);
+        const float* dp = dys + ((rloc + 1) * RAW_COLS + lane + 2) * 3;
+        const float d0 = dp[0], d1 = dp[1], d2y = dp[2];
+        const float2 d2f = h2unpack(d2v);
+        const float pa = (w3a[0] * d0 + w3a[1] * d1 + w3a[2] * d2y) * d2f.x;
+        const float pb = (w3b[0] * d0 + w3b[1] * d1 + w3b[2] * d2y) * d2f.y;
+        dp2[(rloc + 1) * DP2_COLS + lane + 1] = bf2pack(pa, pb);
+        if (rloc >= 0 && rloc < th) {          // owned rows (warp-uniform); pixels outside the image have dy = 0
+          const float2 hf = h2unpack(h2v);
+          gb2a += pa; gb2b += pb;
+          gw3a[0] = fmaf(d0, hf.x, gw3a[0]); gw3a[1] = fmaf(d1, hf.x, gw3a[1]); gw3a[2] = fmaf(d2y, hf.x, gw3a[2]);
+          gw3b[0] = fmaf(d0, hf.y, gw3b[0]); gw3b[1] = fmaf(d1, hf.y, gw3b[1]); gw3b[2] = fmaf(d2y, hf.y, gw3b[2]);
+#pragma unroll
+          for (int j = 0; j < 3; ++j) {
+            gw2a[j] = fmaf(pa, A.lo[j], gw2a[j]); gw2a[3 + j] = fmaf(pa, Bq.lo[j], gw2a[3 + j]); gw2a[6 + j] = fmaf(pa, C.lo[j], gw2a[6 + j]);
+            gw2b[j] = fmaf(pb, A.hi[j], gw2b[j]); gw2b[3 + j] = fmaf(pb, Bq.hi[j], gw2b[3 + j]); gw2b[6 + j] = fmaf(pb, C.hi[j], gw2b[6 + j]);
+          }
+        }
+      };
+      for (int rloc = -1; rloc <= th; rloc += 3) {
+        step(ra, rb, rc, rloc);
+        if (rloc + 1 <= th) step(rb, rc, ra, rloc + 1);
+        if (rloc + 2 <= th) step(rc, ra, rb, rloc + 2);
+      }
+      // the two halo columns (image columns tx0-1 and tx0+32), one row per lane: only dp2 is needed there
+      if (lane < th + 2) {
+#pragma unroll
+        for (int side = 0; side < 2; ++side) {
+          const int pc = side ? 33 : 0;          // h1 plane columns pc .. pc+2 ; dp2 column side ? 33 : 0 ; dy column index pc+1
+          uint32_t a[3], bq[3], c[3];
+#pragma unroll
+          for (int j = 0; j < 3; ++j) {
+            a[j] = h1[lane * B_XIN_COLS + pc + j]; bq[j] = h1[(lane + 1) * B_XIN_COLS + pc + j]; c[j] = h1[(lane + 2) * B_XIN_COLS + pc + j];
+          }
+          uint32_t h2v, d2v;
+          gelu_pair_h2(pre2(a, bq, c), h2v, d2v);
+          const float* dp = dys + (lane * RAW_COLS + pc + 1) * 3;
+          const float d0 = dp[0], d1 = dp[1], d2y = dp[2];
+          const float2 d2f = h2unpack(d2v);
+          dp2[lane * DP2_COLS + pc] = bf2pack((w3a[0] * d0 + w3a[1] * d1 + w3a[2] * d2y) * d2f.x, (w3b[0] * d0 + w3b[1] * d1 + w3b[2] * d2y) * d2f.y);
+        }
+      }
+    }
+    __syncwarp();
+    // ---------------- phase D : tile rows 0 .. th-1, pixel column `lane`
+    {
+      float w2a[9], w2b[9];
+#pragma unroll
+      for (int q = 0; q < 9; ++q) { w2a[q] = wsm[P_W2 + ca * 9 + q]; w2b[q] = wsm[P_W2 + cb * 9 + q]; }
+      auto load_row = [&](RowD& R, int prow) {     // dp2 plane row prow (image row ty0 + prow - 1), image columns lane-1 .. lane+1
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          const uint32_t v = dp2[prow * DP2_COLS + lane + j];
+          R.lo[j] = __uint_as_float(v << 16); R.hi[j] = __uint_as_float(v & 0xffff0000u);
+        }
+      };
+      RowD ra, rb, rc;
+      load_row(ra, 0);
+      load_row(rb, 1);
+      auto step = [&](const RowD& A, const RowD& Bq, RowD& C, int r) {   // A = row r-1, Bq = row r, C = row r+1
+        load_row(C, r + 2);
+        // h1(p) fed out(p - (ky-1, kx-1)) with weight w2[ky][kx]: row r+1-ky, column tap 2-kx
+        float da = 0.f, db = 0.f;
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          da = fmaf(w2a[kx], C.lo[2 - kx], da); da = fmaf(w2a[3 + kx], Bq.lo[2 - kx], da); da = fmaf(w2a[6 + kx], A.lo[2 - kx], da);
+          db = fmaf(w2b[kx], C.hi[2 - kx], db); db = fmaf(w2b[3 + kx], Bq.hi[2 - kx], db); db = fmaf(w2b[6 + kx], A.hi[2 - kx], db);
+        }
+        const float2 gf = h2unpack(g1[r * TW + lane]);       // gelu'(pre1), zero outside the image
+        const float pa = da * gf.x, pb = db * gf.y;
+        const uint4 e = xin[(r + 2) * B_XIN_COLS + lane + 2];
+        const float x0 = h2low(e.x), x1 = h2low(e.y), x2 = h2low(e.z);
+        gw1a[0] = fmaf(pa, x0, gw1a[0]); gw1a[1] = fmaf(pa, x1, gw1a[1]); gw1a[2] = fmaf(pa, x2, gw1a[2]);
+        gw1b[0] = fmaf(pb, x0, gw1b[0]); gw1b[1] = fmaf(pb, x1, gw1b[1]); gw1b[2] = fmaf(pb, x2, gw1b[2]);
+        gb1a += pa; gb1b += pb;
+        g1[r * TW + lane] = bf2pack(pa, pb);                 // dp1 replaces g1 (same lane, same word): the MMA operand
+      };
+      for (int r = 0; r < th; r += 3) {
+        step(ra, rb, rc, r);
+        if (r + 1 < th) step(rb, rc, ra, r + 1);
+        if (r + 2 < th) step(rc, ra, rb, r + 2);
+      }
+    }
+    __syncthreads();
+    // ---------------- dx = dy + W1^T dp1 (tensor cores), db3 = sum dy
+    for (int mt = warp; mt < th * 2; mt += NWARP) {
+      const int r = mt >> 1, c0 = (mt & 1) * 16;
+      const int gy = ty0 + r;
+      if (gy >= S || tx0 + c0 >= S) continue;
+      const uint32_t* pbase = planes + B_G1 + r * TW + c0 + g;
+      float d[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks) {
+        const uint32_t* q = pbase + (8 * ks + t) * B_WARP_WORDS;
+        mma_bf16(d, q[0], q[8], q[4 * B_WARP_WORDS], q[4 * B_WARP_WORDS + 8], bw[ks][0], bw[ks][1]);
+      }
+      float* seg = dys + ((r + 1) * RAW_COLS + c0 + 2) * 3;
+      if (t == 0) {
+        const float v0 = seg[g * 3], v1 = seg[g * 3 + 1], v2 = seg[(g + 8) * 3], v3 = seg[(g + 8) * 3 + 1];
+        gb3x += v0 + v2; gb3y += v1 + v3;
+        seg[g * 3] = v0 + d[0]; seg[g * 3 + 1] = v1 + d[1]; seg[(g + 8) * 3] = v2 + d[2]; seg[(g + 8) * 3 + 1] = v3 + d[3];
+      } else if (t == 1) {
+        const float v0 = seg[g * 3 + 2], v2 = seg[(g + 8) * 3 + 2];
+        gb3x += v0 + v2;
+        seg[g * 3 + 2] = v0 + d[0]; seg[(g + 8) * 3 + 2] = v2 + d[2];
+      }
+      __syncwarp();
+      store_segment(seg, dx, dx16, ((long long)b * S + gy) * S, tx0 + c0, S, lane);
+    }
+  }
+  cp_async_wait_all();
+  // ---------------- one partial row per CTA, in the public parameter order
+  float* gp = gpartial + (size_t)blockIdx.x * NPARAM;
+  auto put = [&](float v, int dst) {
+    v = warp_sum(v);
+    if (lane == 0) gp[dst] = v;
+  };
+#pragma unroll
+  for (int k = 0; k < 3; ++k) { put(gw1a[k], P_W1 + ca * 3 + k); put(gw1b[k], P_W1 + cb * 3 + k); }
+  put(gb1a, P_B1 + ca); put(gb1b, P_B1 + cb);
+#pragma unroll
+  for (int q = 0; q < 9; ++q) { put(gw2a[q], P_W2 + ca * 9 + q); put(gw2b[q], P_W2 + cb * 9 + q); }
+  put(gb2a, P_B2 + ca); put(gb2b, P_B2 + cb);
+#pragma unroll
+  for (int k = 0; k < 3; ++k) { put(gw3a[k], P_W3 + k * 32 + ca); put(gw3b[k], P_W3 + k * 32 + cb); }
+  // db3: lanes with t == 0 hold output channels 0 / 1, lanes with t == 1 hold channel 2 (other lanes hold zeros)
+  const float s0 = warp_sum(t == 0 ? gb3x : 0.f), s1 = warp_sum(t == 0 ? gb3y : 0.f), s2 = warp_sum(t == 1 ? gb3x : 0.f);
+  if (lane == 0) { wred[warp * 4 + 0] = s0; wred[warp * 4 + 1] = s1; wred[warp * 4 + 2] = s2; }
+  __syncthreads();
+  if (tid < 3) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < NWARP; ++w) s += wred[w * 4 + tid];
+    gp[P_B3 + tid] = s;
+  }
 }
 
-// out[c] = sum_p partial[p][c]: 32 parameters per CTA, 8 groups of partial rows combined through shared memory in a fixed
-// order (one thread walking all ~444 rows of a column took 30 us of pure latency per call)
+// out[c] = sum_p partial[p][c]: 32 parameters per CTA, 8 groups of partial rows combined through shared memory in a fixed order
 __global__ void __launch_bounds__(256)
 cnn_reduce_kernel(const float* __restrict__ partial, float* __restrict__ out, int nparts, int n) {
   __shared__ float red[8][33];
@@ -464,15 +538,15 @@ cnn_reduce_kernel(const float* __restrict__ partial, float* __restrict__ out, in
   red[ry][cx] = s;
   __syncthreads();
   if (ry == 0 && c < n) {
-    float t = 0.f;
+    float tsum = 0.f;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) t += red[k][cx];
-    out[c] = t;
+    for (int k = 0; k < 8; ++k) tsum += red[k][cx];
+    out[c] = tsum;
   }
 }
 
-int bwd_tile_height(int S) {
-  const int ny = (S + BTH - 1) / BTH;
+int tile_height(int S, int cap) {
+  const int ny = (S + cap - 1) / cap;
   return (S + ny - 1) / ny;
 }
 
@@ -481,35 +555,28 @@ int bwd_tile_height(int S) {
 extern "C" int32_t calm_cnn_fwd(const float* x, float* y, const float* w1, const float* b1, const float* w2, const float* b2,
                                 const float* w3, const float* b3, int32_t B, int32_t S, cudaStream_t stream) {
   CALM_CHECK_ARG(B > 0 && S > 0, "calm_cnn_fwd: B=%d S=%d", B, S);
-  const int tiles_side = (S + FT - 1) / FT;
-  const long long total = (long long)B * tiles_side * tiles_side;
-  const long long cap = 3LL * calm_num_sms();
+  CALM_CHECK_ARG(((uintptr_t)x | (uintptr_t)y) % 16 == 0, "calm_cnn_fwd: x / y must be 16-byte aligned");
+  const int th = tile_height(S, THF);
+  const int tiles_x = (S + TW - 1) / TW, tiles_y = (S + th - 1) / th;
+  const long long total = (long long)B * tiles_x * tiles_y;
+  const long long cap = 2LL * calm_num_sms();
   const unsigned grid = (unsigned)(total < cap ? total : cap);
-  const size_t smem = (size_t)FWD_SMEM_FLOATS * sizeof(float);
   static CalmDeviceOnce configured;
   if (configured.pending()) {
-    cudaError_t e = cudaFuncSetAttribute(cnn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) { calm_set_error("calm_cnn_fwd: smem %zu: %s", smem, cudaGetErrorString(e)); return CALM_ERR_CUDA; }
+    cudaError_t e = cudaFuncSetAttribute(cnn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FWD_SMEM);
+    if (e != cudaSuccess) { calm_set_error("calm_cnn_fwd: smem %d: %s", (int)FWD_SMEM, cudaGetErrorString(e)); return CALM_ERR_CUDA; }
     configured.done();
   }
   CnnW W{w1, b1, w2, b2, w3, b3};
-  cnn_fwd_kernel<<<grid, NT, smem, stream>>>(x, y, W, B, S, tiles_side);
+  cnn_fwd_kernel<<<grid, NT, FWD_SMEM, stream>>>(x, y, W, B, S, tiles_x, tiles_y, th);
   CALM_CHECK_LAUNCH("calm_cnn_fwd");
   return CALM_OK;
 }
 
-namespace {
-int bwd_ctas_per_sm() {
-  static int v = 0;
-  if (!v) { const char* e = getenv("CALM_CNN_BWD_OCC"); v = (e && e[0] == '2') ? 2 : 3; }
-  return v;
-}
-}  // namespace
-
 extern "C" int32_t calm_cnn_bwd_blocks(int32_t B, int32_t S) {
-  const int th = bwd_tile_height(S);
-  const long long total = (long long)B * ((S + BT - 1) / BT) * ((S + th - 1) / th);
-  const long long cap = (long long)bwd_ctas_per_sm() * calm_num_sms();
+  const int th = tile_height(S, THB);
+  const long long total = (long long)B * ((S + TW - 1) / TW) * ((S + th - 1) / th);
+  const long long cap = calm_num_sms();
   return (int32_t)(total < cap ? total : cap);
 }
 
@@ -518,22 +585,19 @@ extern "C" int32_t calm_cnn_bwd(const float* x, const float* dy, float* dx, void
                                 int32_t B, int32_t S, cudaStream_t stream) {
   CALM_CHECK_ARG(B > 0 && S > 0, "calm_cnn_bwd: B=%d S=%d", B, S);
   CALM_CHECK_ARG(nblocks == calm_cnn_bwd_blocks(B, S), "calm_cnn_bwd: nblocks=%d expected %d", nblocks, calm_cnn_bwd_blocks(B, S));
-  const int th = bwd_tile_height(S);
-  const int tiles_x = (S + BT - 1) / BT, tiles_y = (S + th - 1) / th;
-  const size_t smem = (size_t)BWD_SMEM_FLOATS * sizeof(float);
+  CALM_CHECK_ARG(((uintptr_t)x | (uintptr_t)dy | (uintptr_t)dx | (uintptr_t)dx_bf16) % 16 == 0, "calm_cnn_bwd: x / dy / dx must be 16-byte aligned");
+  const int th = tile_height(S, THB);
+  const int tiles_x = (S + TW - 1) / TW, tiles_y = (S + th - 1) / th;
   static CalmDeviceOnce configured;
   if (configured.pending()) {
-    cudaError_t e = cudaFuncSetAttribute(cnn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(cnn_bwd_kernel_occ2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) { calm_set_error("calm_cnn_bwd: smem %zu: %s", smem, cudaGetErrorString(e)); return CALM_ERR_CUDA; }
+    cudaError_t e = cudaFuncSetAttribute(cnn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BWD_SMEM);
+    if (e != cudaSuccess) { calm_set_error("calm_cnn_bwd: smem %d: %s", (int)BWD_SMEM, cudaGetErrorString(e)); return CALM_ERR_CUDA; }
     configured.done();
   }
   CnnW W{w1, b1, w2, b2, w3, b3};
-  bf16* dx16 = reinterpret_cast<bf16*>(dx_bf16);
-  if (bwd_ctas_per_sm() == 2) cnn_bwd_kernel_occ2<<<nblocks, NT, smem, stream>>>(x, dy, dx, dx16, W, gpartial, B, S, tiles_x, tiles_y, th);
-  else cnn_bwd_kernel<<<nblocks, NT, smem, stream>>>(x, dy, dx, dx16, W, gpartial, B, S, tiles_x, tiles_y, th);
+  cnn_bwd_kernel<<<nblocks, NT, BWD_SMEM, stream>>>(x, dy, dx, reinterpret_cast<bf16*>(dx_bf16), W, gpartial, B, S, tiles_x, tiles_y, th);
   CALM_CHECK_LAUNCH("calm_cnn_bwd");
-  cnn_reduce_kernel<<<(CALM_CNN_NPARAM + 31) / 32, 256, 0, stream>>>(gpartial, gparams, nblocks, CALM_CNN_NPARAM);
+  cnn_reduce_kernel<<<(NPARAM + 31) / 32, 256, 0, stream>>>(gpartial, gparams, nblocks, NPARAM);
   CALM_CHECK_LAUNCH("calm_cnn_bwd(reduce)");
   return CALM_OK;
 }

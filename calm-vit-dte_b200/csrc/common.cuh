@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <atomic>
@@ -10,6 +11,13 @@
 #define CALM_ERR_ARG (-1)
 #define CALM_ERR_CUDA (-2)
 #define CALM_ERR_UNSUPPORTED (-3)
+
+// Bound of the mbarrier waits of the tcgen05 kernels: a protocol bug becomes a trap (a sticky CUDA error with the barrier id in
+// the error-flag buffer) instead of a hung GPU. The default (2^37 cycles, about 70 s) is far above anything a legitimate wait
+// can take, also under compute-sanitizer, cuda-gdb or a time-sliced GPU; -DCALM_MBAR_TIMEOUT_CYCLES=... tightens it for bring-up.
+#ifndef CALM_MBAR_TIMEOUT_CYCLES
+#define CALM_MBAR_TIMEOUT_CYCLES (1LL << 37)
+#endif
 
 void calm_set_error(const char* fmt, ...);
 extern int* g_calm_err_flag;
@@ -122,3 +130,40 @@ __device__ __forceinline__ float2 unpack_bf16x2(uint32_t v) {
   bf162 h = *reinterpret_cast<bf162*>(&v);
   return __bfloat1622float2(h);
 }
+
+// ---- packed fp16 arithmetic (explicit PTX: the half2 intrinsics of cuda_fp16.h have no tanh / ex2 forms) ----------------
+// GELU(erf) on channel / column PAIRS: Phi(x) = 0.5 + 0.5 tanh(x (a + b x^2)), a = 0.79880144, b = 0.03528205 (minimax fit of
+// atanh(erf(x / sqrt2)) on [0, 4], |error| < 2.9e-4 = below the fp16 resolution of Phi; both coefficients positive, so the
+// polynomial saturates monotonically and needs no clamp), gelu'(x) = Phi + x exp(-x^2/2) / sqrt(2 pi). Simulated in fp16
+// arithmetic the value is 3.9e-4 rms from the exact function for x ~ N(0, 1.5): 6x finer than the bf16 rounding the
+// reference's autocast path applies to the same activations (2.4e-3 rms).
+__device__ __forceinline__ uint32_t h2fma(uint32_t a, uint32_t b, uint32_t c) { uint32_t d; asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); return d; }
+__device__ __forceinline__ uint32_t h2mul(uint32_t a, uint32_t b) { uint32_t d; asm("mul.rn.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b)); return d; }
+__device__ __forceinline__ uint32_t h2tanh(uint32_t a) { uint32_t d; asm("tanh.approx.f16x2 %0, %1;" : "=r"(d) : "r"(a)); return d; }
+__device__ __forceinline__ uint32_t h2ex2(uint32_t a) { uint32_t d; asm("ex2.approx.f16x2 %0, %1;" : "=r"(d) : "r"(a)); return d; }
+__device__ __forceinline__ uint32_t h2pack(float lo, float hi) { __half2 h = __floats2half2_rn(lo, hi); return *reinterpret_cast<uint32_t*>(&h); }
+__device__ __forceinline__ float2 h2unpack(uint32_t v) { return __half22float2(*reinterpret_cast<__half2*>(&v)); }
+__device__ __forceinline__ float h2low(uint32_t v) { return __low2float(*reinterpret_cast<__half2*>(&v)); }
+__device__ __forceinline__ uint32_t bf2pack(float lo, float hi) { __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi); return *reinterpret_cast<uint32_t*>(&h); }
+
+constexpr uint32_t H2_HALF = 0x38003800u, H2_ONE = 0x3c003c00u;
+constexpr uint32_t H2_GA = 0x3a643a64u;   // 0.79880144
+constexpr uint32_t H2_GB = 0x28842884u;   // 0.03528205
+constexpr uint32_t H2_GK = 0xb9c5b9c5u;   // -0.5 log2(e)
+constexpr uint32_t H2_GC = 0x36623662u;   // 1/sqrt(2 pi)
+
+__device__ __forceinline__ uint32_t gelu_h2(uint32_t x) {
+  const uint32_t x2 = h2mul(x, x);
+  const uint32_t u = h2mul(h2fma(x2, H2_GB, H2_GA), x);
+  const uint32_t phi = h2fma(h2tanh(u), H2_HALF, H2_HALF);
+  return h2mul(x, phi);
+}
+__device__ __forceinline__ void gelu_pair_h2(uint32_t x, uint32_t& g, uint32_t& dg) {
+  const uint32_t x2 = h2mul(x, x);
+  const uint32_t u = h2mul(h2fma(x2, H2_GB, H2_GA), x);
+  const uint32_t phi = h2fma(h2tanh(u), H2_HALF, H2_HALF);
+  g = h2mul(x, phi);
+  const uint32_t e = h2ex2(h2mul(x2, H2_GK));        // exp(-x^2/2)
+  dg = h2fma(h2mul(x, H2_GC), e, phi);
+}
+

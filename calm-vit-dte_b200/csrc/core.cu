@@ -12,8 +12,10 @@ void calm_set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
-int* g_calm_err_flag = nullptr;  // optional int the kernels write a barrier id into before trapping on a protocol time-out
+int* g_calm_err_flag = nullptr;  // bring-up only: int the kernels write a barrier id into before trapping on a protocol time-out
+#ifdef CALM_BRINGUP
 extern "C" int32_t calm_set_error_flag_buffer(int32_t* device_int) { g_calm_err_flag = device_int; return CALM_OK; }
+#endif
 
 extern "C" int32_t calm_abi_version(void) { return CALM_ABI_VERSION; }
 extern "C" const char* calm_last_error(void) { return g_err; }

@@ -93,7 +93,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* er
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > (1LL << 32)) {  // ~2 s at 2 GHz
+    if (clock64() - t0 > CALM_MBAR_TIMEOUT_CYCLES) {
       if (err_flag) atomicExch(err_flag, code);
       __threadfence_system();
       __trap();
@@ -256,6 +256,24 @@ __device__ __forceinline__ uint4 pack8(const float* f) {
   u.x = pack_bf16x2(f[0], f[1]); u.y = pack_bf16x2(f[2], f[3]); u.z = pack_bf16x2(f[4], f[5]); u.w = pack_bf16x2(f[6], f[7]);
   return u;
 }
+// GELU(erf) value and derivative of 8 accumulator columns, as bf16: the pre-activation is rounded to bf16 first (the reference's
+// autocast Linear output is bf16, and backward needs the derivative at the very point the value was taken), the function itself
+// runs on fp16 PAIRS (common.cuh: 8 HFMA2-class + 2 MUFU per pair instead of 2 x (15 FP32 + 2 MUFU)): with 36 instructions per
+// element the eight epilogue warps, not the tensor core, set the pace of every GELU GEMM (276-760 TFLOP/s against 900-1200 plain).
+__device__ __forceinline__ void gelu8_h2(const float* v, uint4& g, uint4& dg) {
+  uint32_t go[4], dgo[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float2 u = unpack_bf16x2(pack_bf16x2(v[2 * k], v[2 * k + 1]));
+    uint32_t gh, dh;
+    gelu_pair_h2(h2pack(u.x, u.y), gh, dh);
+    const float2 gf = h2unpack(gh), df = h2unpack(dh);
+    go[k] = pack_bf16x2(gf.x, gf.y);
+    dgo[k] = pack_bf16x2(df.x, df.y);
+  }
+  g = make_uint4(go[0], go[1], go[2], go[3]);
+  dg = make_uint4(dgo[0], dgo[1], dgo[2], dgo[3]);
+}
 
 __device__ __forceinline__ void epi_finish(const GemmParams& p, const EpiPre& e, float* v, long long row, int col0, int b, int split,
                                            int nvalid) {
@@ -294,11 +312,10 @@ __device__ __forceinline__ void epi_finish(const GemmParams& p, const EpiPre& e,
       // GELU acts on the bf16-rounded pre-activation (the reference's autocast Linear output); what backward needs is the
       // derivative at that point: it is evaluated here, next to the value (shared rcp / ex2), and saved instead of the
       // pre-activation, so the dgrad epilogue is a plain multiply
-      float f[8], dg[8];
-      unpack8(pack8(v + 8 * j), f);
-#pragma unroll
-      for (int k = 0; k < 8; ++k) gelu_pair(f[k], v[8 * j + k], dg[k]);
-      if (8 * j < nvalid && !(p.dbg & 1)) up[j] = pack8(dg);
+      uint4 gq, dq;
+      gelu8_h2(v + 8 * j, gq, dq);
+      unpack8(gq, v + 8 * j);          // bf16-rounded activation, stored by the common tail below
+      if (8 * j < nvalid && !(p.dbg & 1)) up[j] = dq;
     }
   } else if (p.epi == CALM_EPI_DGELU) {
 #pragma unroll
@@ -489,12 +506,10 @@ __device__ __forceinline__ void epilogue_tma(const GemmParams& p, const CUtensor
               }
               *gp = pack8(vj);
             } else if (gelu) {
-              float f[8], dg[8];
-              unpack8(pack8(vj), f);         // GELU acts on the bf16-rounded pre-activation (the reference's bf16 Linear output)
-#pragma unroll
-              for (int k = 0; k < 8; ++k) gelu_pair(f[k], f[k], dg[k]);
-              *gp = pack8(dg);               // aux <- gelu'(pre): the dgrad epilogue multiplies by it
-              *reinterpret_cast<uint4*>(slot + EPI_SLOT_BYTES + ((j ^ sw) << 4)) = pack8(f);
+              uint4 gq, dq;
+              gelu8_h2(vj, gq, dq);
+              *gp = dq;                      // aux <- gelu'(pre): the dgrad epilogue multiplies by it
+              *reinterpret_cast<uint4*>(slot + EPI_SLOT_BYTES + ((j ^ sw) << 4)) = gq;
             } else {
               *gp = pack8(vj);
             }
@@ -780,7 +795,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
 // ---------------------------------------------------------------------------------------------------------
 // Bring-up / debug path: plain CUDA-core tiled GEMM with the same argument semantics. Never used unless
-// calm_set_debug_flags(CALM_DEBUG_SIMT_GEMM) was called (kernel bring-up on a new driver / bisecting a fault).
+// calm_gemm_args.flags has CALM_GEMM_SIMT (kernel bring-up on a new driver / bisecting a fault).
 // ---------------------------------------------------------------------------------------------------------
 __global__ void gemm_simt_debug_kernel(const bf16* A, const bf16* B, GemmParams p, long long lda, long long ldb,
                                        long long stride_a, long long stride_b, int a_mn, int b_mn) {
@@ -870,8 +885,6 @@ int make_map(CUtensorMap* map, const void* base, uint64_t inner, uint64_t outer,
   return CALM_OK;
 }
 
-int g_debug_flags = 0;
-int g_bn_override = 0;  // tuning hook (calm_debug_set_gemm_bn): force the N tile width
 
 
 // 4-D map {cols, rows, batch, split} over an epilogue operand with a {64 B, 32 rows, 1, 1} box and 64B swizzle.
@@ -936,9 +949,6 @@ int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& m
 
 }  // namespace
 
-extern "C" void calm_set_debug_flags(int32_t flags) { g_debug_flags = flags; }
-extern "C" void calm_debug_set_gemm_bn(int32_t bn) { g_bn_override = bn; }
-extern "C" int32_t calm_get_debug_flags(void) { return g_debug_flags; }
 
 extern "C" int32_t calm_gemm_default_splits(int32_t M, int32_t N, int32_t K, int32_t batch, int32_t reduce_batch) {
   // Split the contraction so that a small-output GEMM (wgrad) still fills the 148 SMs.
@@ -973,6 +983,7 @@ extern "C" int32_t calm_gemm(const calm_gemm_args* a, cudaStream_t stream) {
   if (a->aux) CALM_CHECK_ARG(a->ld_aux % 8 == 0 && (reinterpret_cast<uintptr_t>(a->aux) & 15) == 0, "calm_gemm: aux alignment");
   if (a->bias) CALM_CHECK_ARG((reinterpret_cast<uintptr_t>(a->bias) & 15) == 0, "calm_gemm: bias alignment");
 
+  const int g_debug_flags = a->flags, g_bn_override = a->bn_override;   // per call: no global switches
   GemmParams p;
   memset(&p, 0, sizeof(p));
   p.M = a->M; p.N = a->N; p.K = a->K; p.batch = a->batch;
@@ -997,9 +1008,9 @@ extern "C" int32_t calm_gemm(const calm_gemm_args* a, cudaStream_t stream) {
   // Odd tile counts and short contractions measured 10-40 % slower in pair mode and stay single-CTA.
   const bool many_wave = p.total_pairs >= 2 * calm_num_sms() && (p.tiles_m % 2 == 0 || p.tiles_m >= 32);
   const bool long_k_even = p.tiles_m % 2 == 0 && p.kb_per_split >= 128;
-  const bool want_pair = !(g_debug_flags & CALM_DEBUG_NO_CLUSTER) && (g_debug_flags & CALM_DEBUG_FORCE_CLUSTER || many_wave || long_k_even) && p.tiles_m >= 2;
+  const bool want_pair = !(g_debug_flags & CALM_GEMM_NO_CLUSTER) && (g_debug_flags & CALM_GEMM_FORCE_CLUSTER || many_wave || long_k_even) && p.tiles_m >= 2;
   // mode 2 = tcgen05.mma.cta_group::2 (each CTA of the pair holds half of B), mode 1 = cta_group::1 + multicast B
-  const int pair = !want_pair ? 0 : (g_debug_flags & CALM_DEBUG_PAIR_MULTICAST) ? 1 : 2;
+  const int pair = !want_pair ? 0 : (g_debug_flags & CALM_GEMM_PAIR_MULTICAST) ? 1 : 2;
   // TMA-staged epilogue unless the operand mix has no in-place form (addend of another dtype than C, GELU into fp32, ...)
   const bool add_ok = !a->addend || (a->epilogue == CALM_EPI_NONE && (a->addend_dtype == CALM_F32) == (a->c_dtype == CALM_F32) &&
                                       a->stride_addend % 8 == 0);
@@ -1008,7 +1019,7 @@ extern "C" int32_t calm_gemm(const calm_gemm_args* a, cudaStream_t stream) {
   // or a saved pre-activation is read back (-20..-40 %), on bf16 outputs of many-wave problems (-20 %), and by 0-15 % on the
   // small / split-K shapes; the only losses are +2..4 % on the three largest split-K weight gradients. It is the default
   // wherever the operand mix has an in-place form.
-  p.epi_tma = !(g_debug_flags & CALM_DEBUG_DIRECT_EPILOGUE) && add_ok && act_ok && a->stride_split % 4 == 0;
+  p.epi_tma = !(g_debug_flags & CALM_GEMM_DIRECT_EPILOGUE) && add_ok && act_ok && a->stride_split % 4 == 0;
   // slots per epilogue warp: 3 in-flight stores; GELU stores two slots per unit; units with an input keep 3 loads in flight
   p.epi_slots = !p.epi_tma ? 0 : (a->addend || a->epilogue == CALM_EPI_DGELU) ? 5 : a->epilogue == CALM_EPI_GELU ? 4 : 3;
   {
@@ -1030,7 +1041,7 @@ extern "C" int32_t calm_gemm(const calm_gemm_args* a, cudaStream_t stream) {
   p.err_flag = g_calm_err_flag;
   p.dbg = (g_debug_flags >> 8) & 3;
 
-  if (g_debug_flags & CALM_DEBUG_SIMT_GEMM) {
+  if (g_debug_flags & CALM_GEMM_SIMT) {
     dim3 block(16, 16), grid((a->N + 15) / 16, (a->M + 15) / 16, p.splits * (p.reduce_batch ? 1 : a->batch));
     gemm_simt_debug_kernel<<<grid, block, 0, stream>>>(reinterpret_cast<const bf16*>(a->a), reinterpret_cast<const bf16*>(a->b), p,
                                                         a->lda, a->ldb, a->stride_a, a->stride_b, a->a_major, a->b_major);

@@ -171,6 +171,17 @@ ln_bwd_reg_kernel(const void* __restrict__ dy, const float* __restrict__ x, cons
   for (long long row = (long long)blockIdx.x * LN_WARPS + warp; row < rows; row += (long long)gridDim.x * LN_WARPS) {
     const float mu = mean[row], rs = rstd[row];
     float4 hv[VPL], dv[VPL];
+    // the residual-stream gradient is requested together with x and dy (VPL <= 6: it fits the register budget of 2 CTAs / SM):
+    // loaded after the row reduction it put one full HBM latency per row on the critical path of a warp (0.45 of the copy rate)
+    constexpr bool EARLY = VPL <= 6;
+    float4 rv[EARLY ? VPL : 1];
+    if (EARLY && dres) {
+#pragma unroll
+      for (int i = 0; i < VPL; ++i) {
+        const int idx = lane + 32 * i;
+        rv[EARLY ? i : 0] = idx < nv ? __ldcs(reinterpret_cast<const float4*>(dres + row * D) + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int i = 0; i < VPL; ++i) {
@@ -202,7 +213,7 @@ ln_bwd_reg_kernel(const void* __restrict__ dy, const float* __restrict__ x, cons
         o.z = rs * (dv[i].z * wq.z - c2 - hv[i].z * c1);
         o.w = rs * (dv[i].w * wq.w - c2 - hv[i].w * c1);
         if (dres) {
-          const float4 r = reinterpret_cast<const float4*>(dres + row * D)[idx];
+          const float4 r = EARLY ? rv[EARLY ? i : 0] : reinterpret_cast<const float4*>(dres + row * D)[idx];
           o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
         }
         reinterpret_cast<float4*>(dx + row * D)[idx] = o;

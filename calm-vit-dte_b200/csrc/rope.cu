@@ -1,6 +1,6 @@
 // RoPE with learned inverse frequencies (Vi_Tools_CNN_less_V2.py:55-95, NeoX rotate-half) fused with the per-head
 // [content | rope] concat of the decoupled-RoPE latent blocks (:278-281). Non-reduce blocks use dc = 0 (:283-285).
-// cos/sin are rebuilt from inv_freq every call (the parameter is learned, :70-72,86-91); backward returns d inv_freq.
+// cos/sin are rebuilt from inv_freq inside every kernel (the parameter is learned, :70-72,86-91); backward returns d inv_freq.
 // All math fp32, storage bf16 — the reference promotes to fp32 against the fp32 cos table and SDPA/bmm re-round to bf16.
 #include "common.cuh"
 #include <initializer_list>
@@ -10,15 +10,19 @@ namespace {
 
 constexpr int ROPE_BCH = 8;  // batch chunks for the d-theta partial sums
 
-__global__ void rope_table_kernel(const float* __restrict__ inv_freq, float* __restrict__ cs, int S, int half) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= S * half) return;
-  const int s = i / half, j = i % half;
-  const float ang = (float)s * inv_freq[j];
-  float sn, cn;
-  sincosf(ang, &sn, &cn);
-  cs[2 * i] = cn;
-  cs[2 * i + 1] = sn;
+// cos / sin of this CTA's sequence position for every frequency, computed from the learned inv_freq at the top of each
+// kernel (<= 64 sincosf per CTA) — the stand-alone table kernel this replaces was 48 extra launches per training step.
+// Same arithmetic as the reference: angle = fp32(pos) * inv_freq[j] (torch.outer), full-precision cos / sin (Vi_Tools...:86-91).
+constexpr int ROPE_MAX_HALF = 64;
+__device__ __forceinline__ const float2* rope_cos_sin(const float* __restrict__ inv_freq, int pos, int half) {
+  __shared__ float2 cs_sm[ROPE_MAX_HALF];
+  for (int j = threadIdx.x; j < half; j += blockDim.x) {
+    float sn, cn;
+    sincosf((float)pos * inv_freq[j], &sn, &cn);
+    cs_sm[j] = make_float2(cn, sn);
+  }
+  __syncthreads();
+  return cs_sm;
 }
 
 // V consecutive bf16 values moved as one 2V-byte access
@@ -56,7 +60,7 @@ rope_fwd_kernel(const bf16* __restrict__ content, long long ld_content, const bf
   const int pos = blockIdx.x;
   const int bpc = (B + (int)gridDim.y - 1) / (int)gridDim.y;
   const int b0 = blockIdx.y * bpc, b1 = min(B, b0 + bpc);
-  const float2* cs2 = reinterpret_cast<const float2*>(cs) + (long long)pos * half;
+  const float2* cs2 = rope_cos_sin(cs, pos, half);
   for (int w = threadIdx.x; w < heads * per_head; w += blockDim.x) {
     const int h = w / per_head, i = (w - h * per_head) * V;
     if (i < dc) {
@@ -114,7 +118,7 @@ rope_bwd_kernel(const bf16* __restrict__ dout, long long ld_dout, const bf16* __
   const int pos = blockIdx.x, chunk = blockIdx.y;
   const int bpc = (B + ROPE_BCH - 1) / ROPE_BCH;
   const int b0 = chunk * bpc, b1 = min(B, b0 + bpc);
-  const float2* cs2 = reinterpret_cast<const float2*>(cs) + (long long)pos * half;
+  const float2* cs2 = rope_cos_sin(cs, pos, half);
   for (int w = threadIdx.x; w < heads * per_head; w += blockDim.x) {
     const int h = w / per_head, i = (w - h * per_head) * V;
     if (i < dc) {
@@ -253,7 +257,7 @@ rope_rows_fwd_kernel(const bf16* __restrict__ content, long long ld_content, con
   const int b0 = blockIdx.y * bpc, b1 = min(B, b0 + bpc);
   float c[8], sn[8];
   unsigned short self[8], partner[8];
-  rope_row_map<false>(active ? k : 0, heads, dc, dr, reinterpret_cast<const float2*>(cs) + (long long)pos * half, c, sn, self, partner);
+  rope_row_map<false>(active ? k : 0, heads, dc, dr, rope_cos_sin(cs, pos, half), c, sn, self, partner);
   const bool from_content = 8 * k < HC;
   const bf16* src = from_content ? content + 8 * k : ropein + (8 * k - HC);
   const long long src_ld = from_content ? ld_content : ld_rope;
@@ -323,7 +327,7 @@ rope_rows_bwd_kernel(const bf16* __restrict__ dout, long long ld_dout, const bf1
   const int b0 = chunk * bpc, b1 = min(B, b0 + bpc);
   float c[8], sn[8], acc[8];
   unsigned short dest[8], partner[8];
-  rope_row_map<true>(active ? k : 0, heads, dc, dr, reinterpret_cast<const float2*>(cs) + (long long)pos * half, c, sn, dest, partner);
+  rope_row_map<true>(active ? k : 0, heads, dc, dr, rope_cos_sin(cs, pos, half), c, sn, dest, partner);
 #pragma unroll
   for (int e = 0; e < 8; ++e) acc[e] = 0.f;
   const bool to_content = 8 * k < HC;
@@ -453,27 +457,20 @@ __global__ void rope_dfreq_kernel(const float* __restrict__ dtheta_part, float* 
 
 }  // namespace
 
-extern "C" int32_t calm_rope_table(const float* inv_freq, float* cos_sin, int32_t S, int32_t half, cudaStream_t stream) {
-  CALM_CHECK_ARG(S > 0 && half > 0, "calm_rope_table: S=%d half=%d", S, half);
-  const int n = S * half;
-  rope_table_kernel<<<(n + 255) / 256, 256, 0, stream>>>(inv_freq, cos_sin, S, half);
-  CALM_CHECK_LAUNCH("calm_rope_table");
-  return CALM_OK;
-}
-
 extern "C" int32_t calm_rope_fwd(const void* content, int64_t ld_content, const void* ropein, int64_t ld_rope, void* out,
                                  int64_t ld_out, const float* cos_sin, int64_t tokens, int32_t S, int32_t heads, int32_t dc,
                                  int32_t dr, cudaStream_t stream) {
   CALM_CHECK_ARG(tokens > 0 && S > 0 && heads > 0 && dr > 0 && dr % 2 == 0 && dc >= 0, "calm_rope_fwd: bad dims");
+  CALM_CHECK_ARG(dr / 2 <= ROPE_MAX_HALF, "calm_rope_fwd: rope width %d > %d", dr, 2 * ROPE_MAX_HALF);
   CALM_CHECK_ARG(dc == 0 || content != nullptr, "calm_rope_fwd: content missing");
   CALM_CHECK_ARG(tokens % S == 0, "calm_rope_fwd: tokens=%lld is not a multiple of S=%d", (long long)tokens, S);
   const int B = (int)(tokens / S);
   dim3 grid(S, B < ROPE_BCH ? B : ROPE_BCH);
-  if (!(calm_get_debug_flags() & CALM_DEBUG_LEGACY_ROPE) && rope_rows_ok(heads, dc, dr, {(long long)(dc ? ld_content : 8), (long long)ld_rope, (long long)ld_out}, {content, ropein, out})) {
+  if (rope_rows_ok(heads, dc, dr, {(long long)(dc ? ld_content : 8), (long long)ld_rope, (long long)ld_out}, {content, ropein, out})) {
     const int rowlen = heads * (dc + dr), chunks = rowlen / 8, R = RS_NT / chunks;
     const int nthreads = ((R * chunks + 31) / 32) * 32;
     const size_t smem = (size_t)2 * RS_UF * R * rope_pitch(rowlen) * sizeof(bf16);
-    if (smem <= 48 * 1024) {
+    if (smem + sizeof(float2) * ROPE_MAX_HALF <= 48 * 1024) {
       const bool pair = (dr / 2) % 2 == 0 && dc % 2 == 0;
 #define CALM_ROPE_ROWS_FWD(DC0, PAIR)                                                                                            \
   do {                                                                                                                           \
@@ -508,15 +505,16 @@ extern "C" int32_t calm_rope_bwd(const void* dout, int64_t ld_dout, const void* 
                                  float* dinv_freq, int64_t tokens, int32_t S, int32_t heads, int32_t dc, int32_t dr,
                                  cudaStream_t stream) {
   CALM_CHECK_ARG(tokens > 0 && S > 0 && tokens % S == 0 && heads > 0 && dr > 0 && dr % 2 == 0 && dc >= 0, "calm_rope_bwd: bad dims");
+  CALM_CHECK_ARG(dr / 2 <= ROPE_MAX_HALF, "calm_rope_bwd: rope width %d > %d", dr, 2 * ROPE_MAX_HALF);
   CALM_CHECK_ARG(dc == 0 || dcontent != nullptr, "calm_rope_bwd: dcontent missing");
   const int B = (int)(tokens / S), half = dr / 2;
   dim3 grid(S, ROPE_BCH);
-  if (!(calm_get_debug_flags() & CALM_DEBUG_LEGACY_ROPE) && rope_rows_ok(heads, dc, dr, {(long long)ld_dout, (long long)ld_out, (long long)(dc ? ld_dcontent : 8), (long long)ld_drope},
+  if (rope_rows_ok(heads, dc, dr, {(long long)ld_dout, (long long)ld_out, (long long)(dc ? ld_dcontent : 8), (long long)ld_drope},
                    {dout, out, dcontent, dropein})) {
     const int rowlen = heads * (dc + dr), chunks = rowlen / 8, R = RS_NT / chunks;
     const int nthreads = ((R * chunks + 31) / 32) * 32;
     const size_t rs_smem = (size_t)(dc ? 3 : 2) * RS_UB * R * rope_pitch(rowlen) * sizeof(bf16) + (size_t)R * rowlen * sizeof(float);
-    if (rs_smem <= 48 * 1024) {
+    if (rs_smem + sizeof(float2) * ROPE_MAX_HALF <= 48 * 1024) {
       const bool pair = half % 2 == 0 && dc % 2 == 0;
 #define CALM_ROPE_ROWS_BWD(DC0, PAIR)                                                                                            \
   do {                                                                                                                           \

@@ -34,7 +34,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* er
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > (1LL << 32)) {  // ~2 s
+    if (clock64() - t0 > CALM_MBAR_TIMEOUT_CYCLES) {
       if (err_flag) atomicExch(err_flag, code);
       __threadfence_system();
       __trap();

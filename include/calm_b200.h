@@ -28,19 +28,14 @@ typedef struct CUstream_st* cudaStream_t;
 enum { CALM_BF16 = 0, CALM_F32 = 1 };
 enum { CALM_MAJOR_K = 0, CALM_MAJOR_MN = 1 };
 enum { CALM_EPI_NONE = 0, CALM_EPI_GELU = 1, CALM_EPI_DGELU = 2 };
-enum { CALM_DEBUG_SIMT_GEMM = 1, CALM_DEBUG_LEGACY_ATTENTION = 2, CALM_DEBUG_NO_CLUSTER = 4, CALM_DEBUG_FORCE_CLUSTER = 8,
-       CALM_DEBUG_PAIR_MULTICAST = 16 /* clusters use cta_group::1 + multicast B instead of cta_group::2 */,
-       CALM_DEBUG_DIRECT_EPILOGUE = 32 /* GEMM epilogue: per-thread global loads/stores instead of TMA-staged */,
-       CALM_DEBUG_LEGACY_ROPE = 64 /* RoPE: per-head vector kernels instead of the row-staged 128-bit kernels */ };
+/* calm_gemm_args.flags — PER-CALL schedule selectors for tests and tuning (0 = the heuristics). The library keeps no global
+ * mutable state: there is no process-wide switch that selects kernels. */
+enum { CALM_GEMM_SIMT = 1 /* reference SIMT kernel (bring-up / bisecting) */, CALM_GEMM_NO_CLUSTER = 4, CALM_GEMM_FORCE_CLUSTER = 8,
+       CALM_GEMM_PAIR_MULTICAST = 16 /* clusters use cta_group::1 + multicast B instead of cta_group::2 */,
+       CALM_GEMM_DIRECT_EPILOGUE = 32 /* per-thread global loads/stores instead of the TMA-staged epilogue */ };
 
 int32_t calm_abi_version(void);
 const char* calm_last_error(void); /* thread-local, valid until the next failing call on this thread */
-void calm_set_debug_flags(int32_t flags);
-int32_t calm_get_debug_flags(void);
-void calm_debug_set_trace_buffer(void* device_u64, int32_t capacity_events); /* bring-up: attention-backward CTA 0 writes
-   [count, (event id, globaltimer ns)...] into this zero-initialised device buffer of 1 + 2 * capacity u64; NULL disables */
-void calm_debug_set_gemm_bn(int32_t bn); /* tuning hook: force the GEMM N-tile width (0 = automatic) */
-int32_t calm_set_error_flag_buffer(int32_t* device_int); /* optional: receives the id of a timed-out barrier */
 
 /* ------------------------------------------------------------------------------------------------------------------
  * GEMM  C[b](M,N) = epi(alpha * A[b](M,K) . B[b](N,K)^T + bias[n] + addend[b](m,n))        tcgen05 + TMA + TMEM
@@ -60,10 +55,10 @@ typedef struct {
   int64_t stride_a, stride_b, stride_c;
   int32_t a_major, b_major, c_dtype, epilogue;
   const float* bias;
-  const void* addend; int32_t addend_dtype; int32_t _pad0; int64_t ld_addend, stride_addend;
+  const void* addend; int32_t addend_dtype; int32_t bn_override /* tuning: force the N-tile width, 0 = automatic */; int64_t ld_addend, stride_addend;
   void* aux; int64_t ld_aux, stride_aux;
   int32_t reduce_batch, splits; int64_t stride_split;
-  float alpha; int32_t _pad1;
+  float alpha; int32_t flags /* CALM_GEMM_*, 0 = default */;
 } calm_gemm_args;
 int32_t calm_gemm(const calm_gemm_args* args, cudaStream_t stream);
 int32_t calm_gemm_default_splits(int32_t M, int32_t N, int32_t K, int32_t batch, int32_t reduce_batch);
@@ -118,12 +113,12 @@ int32_t calm_layernorm_bwd_parts(int64_t rows, int32_t D);
  *   out[t, h, dc:dc+dr] = rope(ropein[t, h, 0:dr]) at position s = t % S
  * bwd also returns d inv_freq partials.
  * ------------------------------------------------------------------------------------------------------------------ */
-int32_t calm_rope_table(const float* inv_freq, float* cos_sin /* (S, dr/2, 2) */, int32_t S, int32_t half, cudaStream_t stream);
 int32_t calm_rope_fwd(const void* content, int64_t ld_content, const void* ropein, int64_t ld_rope, void* out, int64_t ld_out,
-                      const float* cos_sin, int64_t tokens, int32_t S, int32_t heads, int32_t dc, int32_t dr, cudaStream_t stream);
+                      const float* inv_freq /* (dr/2) learned frequencies: cos / sin of position * inv_freq are formed in the kernel */,
+                      int64_t tokens, int32_t S, int32_t heads, int32_t dc, int32_t dr, cudaStream_t stream);
 int32_t calm_rope_bwd_scratch_floats(int32_t S, int32_t dr);
 int32_t calm_rope_bwd(const void* dout, int64_t ld_dout, const void* out, int64_t ld_out, void* dcontent, int64_t ld_dcontent,
-                      void* dropein, int64_t ld_drope, const float* cos_sin, float* dtheta_scratch /* calm_rope_bwd_scratch_floats */,
+                      void* dropein, int64_t ld_drope, const float* inv_freq, float* dtheta_scratch /* calm_rope_bwd_scratch_floats */,
                       float* dinv_freq /* (dr/2) */, int64_t tokens, int32_t S, int32_t heads, int32_t dc, int32_t dr,
                       cudaStream_t stream);
 
@@ -134,9 +129,9 @@ int32_t calm_rope_bwd(const void* dout, int64_t ld_dout, const void* out, int64_
  * bwd: dq/dk/dv bf16 (same layout), dbias bf16 (B,S,S) = sum_h dS_h, delta f32 (B, heads, S) scratch,
  *      ds_scratch: calm_attention_bwd_scratch_bytes(...) bytes, 16-byte aligned: the tcgen05 path stores every head's dS there
  *      (bf16, (B, heads, S, S)) and sums the heads with a second kernel (NULL forces the legacy kernels).
- * Two implementations behind these entry points: tcgen05/TMEM/TMA kernels (attention_sm100.cu) when S <= 256, S % 16 == 0,
- * head_dim <= 64, 16-byte aligned operands; warp-level mma.sync kernels (attention.cu) otherwise (384^2 / 512^2 configs) or
- * when calm_set_debug_flags(CALM_DEBUG_LEGACY_ATTENTION) is set.
+ * Two implementations behind these entry points, selected by the problem shape only: tcgen05/TMEM/TMA kernels
+ * (attention_sm100.cu) when S <= 256, S % 16 == 0, head_dim <= 64, 16-byte aligned operands; warp-level mma.sync kernels
+ * (attention.cu) otherwise (384^2 / 512^2 configs).
  * ------------------------------------------------------------------------------------------------------------------ */
 int32_t calm_attention_fwd(const void* q, const void* k, const void* v, const void* bias, void* o, float* lse,
                            int64_t ld_q, int64_t ld_k, int64_t ld_v, int64_t ld_o, int32_t B, int32_t S, int32_t heads,

@@ -78,18 +78,18 @@ def layernorm_bwd(dy, x, w, mean, rstd, dres=None, want_bf16=False):
     return (dx, dw, dx.to(torch.bfloat16)) if want_bf16 else (dx, dw)
 
 
-def rope_table(inv_freq, S):
+def _rope_table(inv_freq, S):
     ang = torch.outer(torch.arange(S, dtype=f32), inv_freq.detach())
-    return torch.stack((ang.cos(), ang.sin()), -1).reshape(-1)
+    return torch.stack((ang.cos(), ang.sin()), -1)
 
 
 def _rows(t, T, width, ld):
     return _view(t, (T, width), (ld, 1))
 
 
-def rope_fwd(content, ld_content, ropein, ld_rope, cos_sin, tokens, S, heads, dc, dr):
+def rope_fwd(content, ld_content, ropein, ld_rope, inv_freq, tokens, S, heads, dc, dr):
     half = dr // 2
-    cs = cos_sin.view(S, half, 2)
+    cs = _rope_table(inv_freq, S)
     pos = torch.arange(tokens) % S
     c, s = cs[pos, :, 0][:, None, :], cs[pos, :, 1][:, None, :]
     r = _rows(ropein, tokens, heads * dr, ld_rope).float().view(tokens, heads, dr)
@@ -101,9 +101,9 @@ def rope_fwd(content, ld_content, ropein, ld_rope, cos_sin, tokens, S, heads, dc
     return torch.cat(parts, -1).reshape(tokens, heads * (dc + dr)).to(bf16)
 
 
-def rope_bwd(dout, ld_dout, out, cos_sin, tokens, S, heads, dc, dr, dcontent=None, ld_dcontent=0, dropein=None, ld_drope=0):
+def rope_bwd(dout, ld_dout, out, inv_freq, tokens, S, heads, dc, dr, dcontent=None, ld_dcontent=0, dropein=None, ld_drope=0):
     half = dr // 2
-    cs = cos_sin.view(S, half, 2)
+    cs = _rope_table(inv_freq, S)
     pos = torch.arange(tokens) % S
     c, s = cs[pos, :, 0][:, None, :], cs[pos, :, 1][:, None, :]
     d = _rows(dout, tokens, heads * (dc + dr), ld_dout).float().view(tokens, heads, dc + dr)

@@ -169,16 +169,12 @@ def test_gemm_pair_mode(K, M, N, Kd, a_mn, b_mn):
     Bm = b.t().contiguous() if b_mn else b
     bias = rnd(N, dtype=f32, seed=53)
     outs = []
-    for flags in (8, 4, 8 | 16):                     # FORCE_CLUSTER, NO_CLUSTER, FORCE_CLUSTER | PAIR_MULTICAST
-        calm_lib.load().calm_set_debug_flags(flags)
-        try:
-            c = torch.full((M, N), float("nan"), dtype=bf16, device=dev())
-            aux = torch.empty(M, N, dtype=bf16, device=dev())
-            K.gemm(A, Bm, c, M, N, Kd, lda=M if a_mn else Kd, ldb=N if b_mn else Kd, ldc=N, a_major=a_mn, b_major=b_mn, bias=bias,
-                   epilogue=K.EPI_GELU, aux=aux, ld_aux=N)
-            outs.append((c, aux))
-        finally:
-            calm_lib.load().calm_set_debug_flags(0)
+    for flags in (8, 4, 8 | 16):                     # per-call calm_gemm_args.flags: FORCE_CLUSTER, NO_CLUSTER, FORCE_CLUSTER | PAIR_MULTICAST
+        c = torch.full((M, N), float("nan"), dtype=bf16, device=dev())
+        aux = torch.empty(M, N, dtype=bf16, device=dev())
+        K.gemm(A, Bm, c, M, N, Kd, lda=M if a_mn else Kd, ldb=N if b_mn else Kd, ldc=N, a_major=a_mn, b_major=b_mn, bias=bias,
+               epilogue=K.EPI_GELU, aux=aux, ld_aux=N, flags=flags)
+        outs.append((c, aux))
     u = (a.float() @ b.float().t() + bias).to(bf16).float().requires_grad_(True)
     act = torch.nn.functional.gelu(u)
     act.sum().backward()
@@ -198,8 +194,7 @@ def test_gemm_epilogue_forms(K, M, N, Kd, nb, form):
     bias = rnd(N, dtype=f32, seed=63)
     outs = []
     for flags in (0, 32):                           # default (TMA-staged), DIRECT_EPILOGUE
-        calm_lib.load().calm_set_debug_flags(flags)
-        try:
+        if True:
             cdt = f32 if form in ("f32", "f32+add") else bf16
             c = torch.full((nb * M, N), float("nan"), dtype=cdt, device=dev())
             kw = dict(lda=Kd, ldb=Kd, ldc=N, batch=nb, stride_a=M * Kd, stride_b=N * Kd, stride_c=M * N, bias=bias, alpha=0.75)
@@ -217,10 +212,8 @@ def test_gemm_epilogue_forms(K, M, N, Kd, nb, form):
             elif form == "dgelu":
                 extra = rnd(nb * M, N, seed=66)
                 kw.update(epilogue=K.EPI_DGELU, aux=extra, ld_aux=N, stride_aux=M * N)
-            K.gemm(a, b, c, M, N, Kd, **kw)
+            K.gemm(a, b, c, M, N, Kd, flags=flags, **kw)
             outs.append((c, extra))
-        finally:
-            calm_lib.load().calm_set_debug_flags(0)
     assert not torch.isnan(outs[0][0].float()).any()
     assert torch.equal(outs[0][0], outs[1][0])
     if form == "gelu":
@@ -279,8 +272,7 @@ def test_rope(K, B, S, h, dc, dr):
     inv = (1.0 / (10000.0 ** (torch.arange(0, dr, 2).float() / dr))).to(dev())
     ropein = rnd(tokens, h * dr, seed=25)
     content = rnd(tokens, h * dc, seed=26) if dc else None
-    cs = K.rope_table(inv, S)
-    out = K.rope_fwd(content, h * dc, ropein, h * dr, cs, tokens, S, h, dc, dr)
+    out = K.rope_fwd(content, h * dc, ropein, h * dr, inv, tokens, S, h, dc, dr)
     xr = ropein.float().view(B, S, h, dr).transpose(1, 2).requires_grad_(True)
     invr = inv.clone().requires_grad_(True)
     r = _rope_ref(xr, invr)
@@ -288,7 +280,7 @@ def test_rope(K, B, S, h, dc, dr):
     ref = torch.cat(parts, -1).transpose(1, 2).reshape(tokens, h * (dc + dr))
     assert rel(out, ref) < 4e-3
     dout = rnd(tokens, h * (dc + dr), seed=27)
-    dcontent, dropein, dinv = K.rope_bwd(dout, h * (dc + dr), out, cs, tokens, S, h, dc, dr)
+    dcontent, dropein, dinv = K.rope_bwd(dout, h * (dc + dr), out, inv, tokens, S, h, dc, dr)
     ref.backward(dout.float())
     assert rel(dropein, xr.grad.transpose(1, 2).reshape(tokens, h * dr)) < 4e-3
     # d inv_freq is computed from the bf16-rounded forward output: 2e-2 (the bf16 activation tolerance)
@@ -298,18 +290,14 @@ def test_rope(K, B, S, h, dc, dr):
 
 
 # ------------------------------------------------------------------------------------------------------ attention
-@pytest.mark.parametrize("legacy", [False, True])
 @pytest.mark.parametrize("B,S,h,hd", [(2, 224, 12, 56), (2, 176, 12, 44), (3, 128, 12, 32), (2, 80, 12, 20), (2, 16, 12, 4),
-                                       (1, 384, 12, 96), (5, 160, 12, 40), (3, 256, 4, 64)])
-def test_attention(K, B, S, h, hd, legacy):
-    """legacy=False: tcgen05/TMEM/TMA kernels where eligible (S <= 256, hd <= 64); legacy=True: the mma.sync kernels
-    (also what the 384^2 / 512^2 shapes use)."""
-    import calm_lib
-    calm_lib.load().calm_set_debug_flags(2 if legacy else 0)
-    try:
-        _attention_case(K, B, S, h, hd)
-    finally:
-        calm_lib.load().calm_set_debug_flags(0)
+                                       (5, 160, 12, 40), (3, 256, 4, 64),                 # tcgen05 / TMEM / TMA kernels (S <= 256, hd <= 64)
+                                       (1, 384, 12, 96), (2, 512, 12, 128), (1, 288, 12, 72), (2, 72, 12, 20), (2, 136, 4, 96)])   # mma.sync kernels
+def test_attention(K, B, S, h, hd):
+    """The implementation is selected by the shape alone (no process-wide switch): tcgen05 kernels where eligible (S <= 256,
+    S % 16 == 0, hd <= 64), the mma.sync kernels otherwise (what the 384^2 / 512^2 configs use; S = 72 / 136 exercise their
+    ragged-tile paths)."""
+    _attention_case(K, B, S, h, hd)
 
 
 def _attention_case(K, B, S, h, hd):
@@ -367,30 +355,58 @@ def test_latent(K, rows, Mh):
 
 
 # ------------------------------------------------------------------------------------------------------ CNN residual
-@pytest.mark.parametrize("B,S", [(2, 80), (1, 224), (3, 37)])
+@pytest.mark.parametrize("B,S", [(2, 80), (1, 224), (3, 37), (2, 176), (5, 16), (1, 36)])
 def test_cnn(K, B, S):
+    """Fused CNN residual against fp32 conv2d. The kernels hold the hidden activations in fp16x2 (11-bit mantissa) and the
+    hidden gradients in bf16 with fp32 accumulation; the reference's autocast path stores both in bf16 (8-bit mantissa). The
+    bar is therefore stated against that policy, measured in the same test: the kernel's distance to the fp32 result must be
+    below HALF of the distance torch's own autocast(bfloat16) conv path shows (and below 4e-3 absolute for the branch)."""
     torch.backends.cudnn.allow_tf32 = False  # the fp32 conv reference must not run on TF32 tensor cores
     x = rnd(B, S, S, 3, dtype=f32, seed=35)
     w1, b1 = rnd(32, 3, dtype=f32, seed=36), rnd(32, dtype=f32, seed=37)
     w2, b2 = rnd(32, 9, dtype=f32, scale=0.3, seed=38), rnd(32, dtype=f32, seed=39)
     w3, b3 = rnd(3, 32, dtype=f32, scale=0.3, seed=40), rnd(3, dtype=f32, seed=41)
-    y = K.cnn_fwd(x, w1, b1, w2, b2, w3, b3, B, S)
-    ps = [t.clone().requires_grad_(True) for t in (x, w1, b1, w2, b2, w3, b3)]
-    xr, w1r, b1r, w2r, b2r, w3r, b3r = ps
     F = torch.nn.functional
-    img = xr.permute(0, 3, 1, 2)
-    hmid = F.gelu(F.conv2d(img, w1r.view(32, 3, 1, 1), b1r))
-    hmid = F.gelu(F.conv2d(hmid, w2r.view(32, 1, 3, 3), b2r, padding=1, groups=32))
-    ref = xr + F.conv2d(hmid, w3r.view(3, 32, 1, 1), b3r).permute(0, 2, 3, 1)
-    assert rel(y, ref) < 1e-5
-    dy = rnd(B, S, S, 3, dtype=f32, seed=42)
+
+    def torch_path(autocast):
+        ps = [t.clone().requires_grad_(True) for t in (x, w1, b1, w2, b2, w3, b3)]
+        xr, w1r, b1r, w2r, b2r, w3r, b3r = ps
+        with torch.autocast("cuda", dtype=bf16, enabled=autocast):
+            img = xr.permute(0, 3, 1, 2)
+            hmid = F.gelu(F.conv2d(img, w1r.view(32, 3, 1, 1), b1r))
+            hmid = F.gelu(F.conv2d(hmid, w2r.view(32, 1, 3, 3), b2r, padding=1, groups=32))
+            branch = F.conv2d(hmid, w3r.view(3, 32, 1, 1), b3r).permute(0, 2, 3, 1)
+            out = xr + branch
+        return ps, branch.float(), out
+
+    y = K.cnn_fwd(x, w1, b1, w2, b2, w3, b3, B, S)
+    ps, branch, ref = torch_path(False)
+    _, branch_bf, _ = torch_path(True)
+    e_fwd, e_pol = rel(y - x, branch), rel(branch_bf, branch)
+    print("\n[cnn B=%d S=%d] forward branch: ours %.2e, torch autocast(bf16) %.2e" % (B, S, e_fwd, e_pol))
+    assert e_fwd < 4e-3 and e_fwd < 0.5 * e_pol
+    assert rel(y, ref) < 2e-3
+    dy = rnd(B, S, S, 3, dtype=f32, seed=42) * 300.0      # GradScaler-scaled gradients are large: nothing on that side may be fp16
     dx, gp = K.cnn_bwd(x, dy, w1, b1, w2, b2, w3, b3, B, S)
     dx_b, gp_b, dx16 = K.cnn_bwd(x, dy, w1, b1, w2, b2, w3, b3, B, S, want_bf16=True)
-    assert torch.equal(dx_b, dx) and torch.equal(gp_b, gp) and torch.equal(dx16, dx.to(bf16))
+    assert torch.equal(dx_b, dx) and torch.equal(gp_b, gp) and torch.equal(dx16, dx.to(bf16))     # deterministic, bf16 copy exact
     ref.backward(dy)
-    assert rel(dx, xr.grad) < 1e-4
-    refg = torch.cat([w1r.grad.flatten(), b1r.grad, w2r.grad.flatten(), b2r.grad, w3r.grad.flatten(), b3r.grad])
-    assert rel(gp, refg) < 1e-4
+    grads = lambda ps: torch.cat([ps[1].grad.flatten(), ps[2].grad, ps[3].grad.flatten(), ps[4].grad, ps[5].grad.flatten(), ps[6].grad])
+    refg, refdx = grads(ps), ps[0].grad
+    ps_bf, _, out_bf = torch_path(True)
+    out_bf.backward(dy)
+    e_dx, e_dx_pol = rel(dx - dy, refdx - dy), rel(ps_bf[0].grad - dy, refdx - dy)
+    names = ["w1", "b1", "w2", "b2", "w3", "b3"]
+    offs = [0, 96, 128, 416, 448, 544, 547]
+    print("[cnn B=%d S=%d] dx branch: ours %.2e, torch autocast(bf16) %.2e" % (B, S, e_dx, e_dx_pol))
+    assert e_dx < 6e-3 and e_dx < 0.75 * e_dx_pol + 1e-3
+    assert rel(dx, refdx) < 3e-3
+    gbf = grads(ps_bf)
+    for n, lo, hi in zip(names, offs[:-1], offs[1:]):
+        eo, ep = rel(gp[lo:hi], refg[lo:hi]), rel(gbf[lo:hi], refg[lo:hi])
+        print("[cnn B=%d S=%d] d%s: ours %.2e, torch autocast(bf16) %.2e" % (B, S, n, eo, ep))
+        assert eo < 5e-3, (n, eo)
+    assert rel(gp, refg) < 3e-3
 
 
 # ------------------------------------------------------------------------------------------------------ helpers

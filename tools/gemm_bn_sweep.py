@@ -20,9 +20,7 @@ for M, N, Kd in shapes:
     res = []
     for bn in (0, 256, 240, 224, 192, 176, 160, 144, 128, 112, 96, 80, 64, 48):
         if bn and bn > (N + 15) // 16 * 16: continue
-        lib.calm_debug_set_gemm_bn(bn)
-        us = timeit(lambda: K.gemm(x, w, y, M, N, Kd, lda=Kd, ldb=Kd, ldc=N))
+        us = timeit(lambda: K.gemm(x, w, y, M, N, Kd, lda=Kd, ldb=Kd, ldc=N, bn=bn))
         res.append((bn, us))
-    lib.calm_debug_set_gemm_bn(0)
     best = min(res, key=lambda t: t[1])
     print("M%d N%d K%d  auto %.1fus  best bn=%d %.1fus  | %s" % (M, N, Kd, res[0][1], best[0], best[1], " ".join("%d:%.0f" % r for r in res[1:])), flush=True)

@@ -18,6 +18,8 @@ bf16, f32 = torch.bfloat16, torch.float32
 dev = torch.device("cuda:0")
 B = int(os.environ.get("KB_BATCH", 256))
 STAGES = [(224, 672, 56), (176, 528, 44), (128, 384, 32), (80, 240, 20)]
+if os.environ.get("KB_STAGES"):     # e.g. KB_STAGES=224 for an ncu capture of one shape
+    STAGES = [s for s in STAGES if str(s[0]) in os.environ["KB_STAGES"].split(",")]
 PEAK_TF = 1358.9
 PEAK_GB = 6549.4
 try:
@@ -28,24 +30,19 @@ except Exception:
 results = []
 
 
-AB = [int(x, 0) for x in os.environ["KB_AB"].split(",")] if os.environ.get("KB_AB") else None   # interleaved A/B of debug flags
+AB = None
 last_ab = {}
 
 
 def timeit(fn, nsets=3, iters=12):
-    import calm_lib
-    flags = AB or [None]
+    flags = [None]
     for i in range(3):
         for f in flags:
-            if f is not None:
-                calm_lib.load().calm_set_debug_flags(f)
             fn(i % nsets)
     torch.cuda.synchronize()
     ts = {f: [] for f in flags}
     for i in range(iters):
         for f in flags:
-            if f is not None:
-                calm_lib.load().calm_set_debug_flags(f)
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
             fn(i % nsets)
@@ -153,7 +150,7 @@ def bench_attn():
 
 
 def bench_cnn():
-    for S in (224, 176, 128, 80):
+    for S, _D, _hd in STAGES:
         x = rnd(B, S, S * 3, dtype=f32)
         ws = [rnd(32, 3, dtype=f32), rnd(32, dtype=f32), rnd(32, 9, dtype=f32, scale=0.3), rnd(32, dtype=f32),
               rnd(3, 32, dtype=f32, scale=0.3), rnd(3, dtype=f32)]
@@ -182,7 +179,7 @@ def bench_misc():
         report("misc", "token_transpose S%d" % S, timeit(lambda i: K.token_transpose(x, B, S)), bytes_=8.0 * x.numel())
         report("misc", "cast_bf16 S%d" % S, timeit(lambda i: K.cast_bf16(x)), bytes_=6.0 * x.numel())
         inv = (1.0 / (10000.0 ** (torch.arange(0, hd, 2).float() / hd))).to(dev)
-        cs = K.rope_table(inv, S)
+        cs = inv
         qk = rnd(B * S, 3 * D)
         out = K.rope_fwd(None, 0, qk, 3 * D, cs, B * S, S, 12, 0, hd)
         report("misc", "rope_fwd S%d hd%d" % (S, hd), timeit(lambda i: K.rope_fwd(None, 0, qk, 3 * D, cs, B * S, S, 12, 0, hd)),
@@ -196,9 +193,6 @@ def bench_misc():
 
 if __name__ == "__main__":
     which = sys.argv[1:] or ["gemm", "attn", "cnn", "ln", "misc"]
-    if os.environ.get("KB_FLAGS"):   # library debug flags (include/calm_b200.h) for A/B experiments
-        import calm_lib
-        calm_lib.load().calm_set_debug_flags(int(os.environ["KB_FLAGS"], 0))
     for w in which:
         globals()["bench_" + w]()
         torch.cuda.empty_cache()
