@@ -510,6 +510,8 @@ def main():
     # ---- one extra eager step with CUDA events around every C-ABI launch: per-kernel-family time and work -----------
     roof, breakdown, kernels, launches_per_step = None, None, None, None
     if not args.no_profile:
+        import calm_ops
+        calm_ops.PARALLEL = False            # kernels are timed one at a time (the captured step overlaps independent ones)
         calm_lib.profile = []
         n1 = calm_lib.launch_count
         # The eager launch path (Python + ctypes) is slower than the small kernels: without a head start every interval between
@@ -520,6 +522,7 @@ def main():
         torch.cuda.synchronize()
         launches_per_step = calm_lib.launch_count - n1
         prof, calm_lib.profile = calm_lib.profile, None
+        calm_ops.PARALLEL = True
         fam, shapes, gemm_bytes = {}, {}, 0
         for name, work, a, b, *tag in prof:
             dt = a.elapsed_time(b)

@@ -195,8 +195,11 @@ class VMLA_Block(torch.nn.Module):
         h, S2, D2 = self.heads, self.seq_len_new, self.dim2
         lin = lambda x, m, addend=None, out_f32=False: ops.LinearFn.apply(x, tok, addend, bank, gid(m), out_f32)
         seq = lambda x, *ms: ops.SeqLinearFn.apply(x, tok, bank, *[gid(m) for m in ms])
-        input_q = input_q.float()
-        xq, res = ops.LayerNormFn.apply(input_q, self.ln_q.weight, False, False, self.ln_q.eps)
+        if input_q.dim() == 4:      # the first Block hands the NCHW image over: tokenisation is fused into this LayerNorm (:389-391)
+            xq, res = ops.ImageLayerNormFn.apply(input_q, self.ln_q.weight, self.ln_q.eps)
+        else:
+            input_q = input_q.float()
+            xq, res = ops.LayerNormFn.apply(input_q, self.ln_q.weight, False, False, self.ln_q.eps)
         xkv = xq if input_kv is None else ops.LayerNormFn.apply(input_kv.float(), self.ln_kv.weight, False, False, self.ln_kv.eps)[0]
         if self.reduce:
             kr_t = xkv
@@ -297,8 +300,8 @@ class Block(torch.nn.Module):
 
     def forward(self, x, esm=None, dsm=None, csm=None, mask=True):
         with ops.Scope(self, self._sn_groups, self.training) as sc:
-            xq = ops.ImageToTokensFn.apply(x) if self.is_first_block else x
-            xq = self.encoder(xq, state_manager=esm, mask=mask)
+            # first block: the (B,3,S,S) image goes straight into the encoder, whose first LayerNorm also tokenises it
+            xq = self.encoder(x, state_manager=esm, mask=mask)
             xkv, xq = ops.TokenSwapFn.apply(xq)                       # columns as tokens (+ alias of the row tokens)
             xkv = self.decoder(xkv, state_manager=dsm, mask=mask)
             xkv = ops.TokenSwapFn.apply(xkv)[0]                       # back to row tokens

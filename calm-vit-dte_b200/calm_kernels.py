@@ -77,6 +77,17 @@ def layernorm_fwd(x, w, eps=1e-6, out_dtype=bf16):
     return y, mean, rstd
 
 
+def layernorm_fwd_image(img, w, eps=1e-6):
+    """img f32 (B,3,S,S) -> tokens f32 (B,S,3S) [= permute(0,2,3,1).reshape], y bf16 = LN(tokens) * w, mean, rstd: one pass."""
+    B, _, S, _ = img.shape
+    tokens = torch.empty(B, S, 3 * S, dtype=f32, device=img.device)
+    y = torch.empty(B, S, 3 * S, dtype=bf16, device=img.device)
+    mean = torch.empty(B * S, dtype=f32, device=img.device)
+    rstd = torch.empty(B * S, dtype=f32, device=img.device)
+    L.call("calm_layernorm_fwd_image", ptr(img), ptr(w), ptr(y), ptr(tokens), ptr(mean), ptr(rstd), B, S, eps, work=float(B) * 3 * S * S * 10)
+    return y, tokens, mean, rstd
+
+
 def layernorm_bwd(dy, x, w, mean, rstd, dres=None, want_bf16=False):
     """dx f32 = LN'(dy) (+ dres), dw f32 (D); with want_bf16 also the bf16 copy of dx (third result)."""
     D = x.shape[-1]

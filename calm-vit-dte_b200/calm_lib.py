@@ -77,6 +77,7 @@ PROTOTYPES = {
     "calm_sn_forward": (i32, [vp, i32, vp, i32, i32, f32, vp]),
     "calm_sn_backward": (i32, [vp, i32, vp, i32, vp]),
     "calm_layernorm_fwd": (i32, [vp, vp, vp, i32, vp, vp, i64, i32, f32, vp]),
+    "calm_layernorm_fwd_image": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, f32, vp]),
     "calm_layernorm_bwd": (i32, [vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp, i64, i32, vp]),
     "calm_layernorm_bwd_parts": (i32, [i64, i32]),
     "calm_rope_fwd": (i32, [vp, i64, vp, i64, vp, i64, vp, i64, i32, i32, i32, i32, vp]),

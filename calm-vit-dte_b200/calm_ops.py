@@ -53,16 +53,102 @@ class GroupSpec:
         assert rowscale is None or len(self.modules) == 1
 
 
+class WeightSet:
+    """Everything one FORWARD of a bank produces and its backward consumes: the bf16 effective weights W/sigma of every group,
+    sigma, the split-K partials of dL/dW_eff, the flat dL/dW_orig buffer and the device table that points at all of them.
+    A bank normally owns one set and reuses it every step. When a new forward starts while the previous forward's autograd graph
+    is still alive (gradient accumulation with a deferred backward, an evaluation pass between forward and backward) that set is
+    FROZEN — its table is repointed to a snapshot of u / v, which the new forward is about to advance — and the new forward gets
+    another set, so both backward passes see the weights, sigma and u / v of their own forward, as in the reference where every
+    forward's `weight` tensor lives in its own graph (torch/nn/utils/spectral_norm.py:92-114)."""
+
+    def __init__(self, bank):
+        self.bank = bank
+        dev = bank.device
+        self.w_eff = [torch.empty(g["rows"], g["cols"], dtype=f32 if g["conv"] else bf16, device=dev) for g in bank.groups]
+        self.g_eff = [None] * len(bank.groups)
+        self.splits = [1] * len(bank.groups)
+        self.sigma = torch.empty(len(bank.layers), dtype=f32, device=dev)
+        self.flat_grad = torch.zeros(bank.flat_numel, dtype=f32, device=dev)
+        self.cnn_gp = {}
+        self.table = None
+        self.dirty = True
+        self.uv_snap = None        # [(u copy, v copy)] per layer once frozen
+        self.lease = None          # weak reference to the autograd node of the forward that owns this set
+        self.busy = False          # True from that forward until its bank node has run backward
+        self.version = 0
+
+    groups = property(lambda self: self.bank.groups)
+
+    def in_use(self):
+        return self.busy and self.lease is not None and self.lease() is not None
+
+    def weight(self, gid):
+        return self.w_eff[gid]
+
+    def wgrad_buffer(self, gid, splits):
+        if self.g_eff[gid] is None or self.splits[gid] != splits:
+            g = self.bank.groups[gid]
+            self.g_eff[gid] = torch.empty(splits, g["rows"], g["cols"], dtype=f32, device=self.bank.device)
+            self.splits[gid] = splits
+            self.dirty = True
+        return self.g_eff[gid]
+
+    def cnn_grad_buffer(self, g1, g2, g3):
+        """Persistent 547-float parameter-gradient block of one fused CNN; the conv layers' dW_eff are slices of it."""
+        buf = self.cnn_gp.get(g1)
+        if buf is None:
+            buf = self.cnn_gp[g1] = torch.empty(L.CNN_NPARAM, dtype=f32, device=self.bank.device)
+            for gid, lo in ((g1, 0), (g2, 128), (g3, 448)):
+                g = self.bank.groups[gid]
+                self.g_eff[gid] = buf[lo: lo + g["rows"] * g["cols"]].view(1, g["rows"], g["cols"])
+                self.splits[gid] = 1
+            self.dirty = True
+        return buf
+
+    def freeze(self):
+        """Called when another forward of the bank is about to advance u / v while this set's backward is still pending."""
+        if self.uv_snap is None:
+            mods = [l["module"] for l in self.bank.layers]
+            self.uv_snap = [(m.weight_u.detach().clone(), m.weight_v.detach().clone()) for m in mods]
+            self.dirty = True
+
+    def thaw(self):
+        if self.uv_snap is not None:
+            self.uv_snap = None
+            self.dirty = True
+
+    def upload(self):
+        bank = self.bank
+        ents = []
+        for i, l in enumerate(bank.layers):
+            g = bank.groups[l["gid"]]
+            m = l["module"]
+            lo = l["row_off"] * l["cols"]
+            u, v = (m.weight_u, m.weight_v) if self.uv_snap is None else self.uv_snap[i]
+            e = dict(w=m.weight_orig, u=u, v=v, rows=l["rows"], cols=l["cols"], eff_f32=g["conv"],
+                     w_eff=self.w_eff[l["gid"]].view(-1)[lo:], grad_w=self.flat_grad[l["grad_off"]:], sigma=self.sigma[i:],
+                     g_splits=self.splits[l["gid"]], g_split_stride=g["rows"] * g["cols"])
+            if self.g_eff[l["gid"]] is not None:
+                e["g_eff"] = self.g_eff[l["gid"]].view(-1)[lo:]
+            if l["rowscale"] is not None:
+                e["rowscale"] = l["rowscale"]
+                e["grad_rowscale"] = self.flat_grad[l["rs_off"]:]
+            ents.append(e)
+        self.table = K.sn_table(ents, bank.device)
+        self.dirty = False
+
+
 class SNBank:
     def __init__(self, specs):
         assert specs
         self.specs = specs
-        self.version = 0
-        self.table = None
-        self.dirty = True
+        self.counter = 0
         self.fingerprint = None
         self.groups = []
         self.gid_of = {}
+        self.sets = []
+        self.active = None
         self._build()
 
     # ---- construction -------------------------------------------------------------------------------------------
@@ -87,8 +173,7 @@ class SNBank:
             rows = [m.weight_orig.shape[0] for m in sp.modules]
             cols = sp.modules[0].weight_orig[0].numel()
             assert all(m.weight_orig[0].numel() == cols for m in sp.modules), "fused layers need equal fan-in"
-            g = dict(gid=gid, rows=sum(rows), cols=cols, conv=sp.conv, splits=1, g_eff=None, layer_ids=[],
-                     w_eff=torch.empty(sum(rows), cols, dtype=f32 if sp.conv else bf16, device=dev))
+            g = dict(gid=gid, rows=sum(rows), cols=cols, conv=sp.conv, layer_ids=[])
             r0 = 0
             for m, r in zip(sp.modules, rows):
                 g["layer_ids"].append(len(self.layers))
@@ -101,13 +186,11 @@ class SNBank:
         for l in self.rs_layers:
             l["rs_off"] = off
             off += (l["rows"] + 3) & ~3
-        self.flat_grad = torch.zeros(off, dtype=f32, device=dev)
-        n = len(self.layers)
-        self.sigma = torch.empty(n, dtype=f32, device=dev)
+        self.flat_numel = off
         self.max_rows = max(l["rows"] for l in self.layers)
         self.max_cols = max(l["cols"] for l in self.layers)
         self.params = [l["module"].weight_orig for l in self.layers] + [l["rowscale"] for l in self.rs_layers]
-        self.dirty = True
+        self.sets, self.active = [], None
         self.fingerprint = self._fingerprint()
 
     def _fingerprint(self):
@@ -122,93 +205,70 @@ class SNBank:
                 fp.append(l["rowscale"].data_ptr())
         return tuple(fp)
 
-    def _upload(self):
-        ents = []
-        for i, l in enumerate(self.layers):
-            g = self.groups[l["gid"]]
-            m = l["module"]
-            lo = l["row_off"] * l["cols"]
-            e = dict(w=m.weight_orig, u=m.weight_u, v=m.weight_v, rows=l["rows"], cols=l["cols"], eff_f32=g["conv"],
-                     w_eff=g["w_eff"].view(-1)[lo:], grad_w=self.flat_grad[l["grad_off"]:], sigma=self.sigma[i:], g_splits=g["splits"], g_split_stride=g["rows"] * g["cols"])
-            if g["g_eff"] is not None:
-                e["g_eff"] = g["g_eff"].view(-1)[lo:]
-            if l["rowscale"] is not None:
-                e["rowscale"] = l["rowscale"]
-                e["grad_rowscale"] = self.flat_grad[l["rs_off"]:]
-            ents.append(e)
-        self.table = K.sn_table(ents, self.device)
-        self.dirty = False
-
     # ---- per-step API -------------------------------------------------------------------------------------------
     def gid(self, module):
         return self.gid_of[id(module)]
 
-    def weight(self, gid):
-        return self.groups[gid]["w_eff"]
-
-    def cnn_grad_buffer(self, g1, g2, g3):
-        """Persistent 547-float parameter-gradient block of one fused CNN; the conv layers' dW_eff are slices of it."""
-        key = ("cnn", g1)
-        buf = self.__dict__.setdefault("_cnn_gp", {}).get(key)
-        if buf is None:
-            buf = torch.empty(L.CNN_NPARAM, dtype=f32, device=self.device)
-            self._cnn_gp[key] = buf
-            for gid, lo in ((g1, 0), (g2, 128), (g3, 448)):
-                g = self.groups[gid]
-                g["g_eff"] = buf[lo: lo + g["rows"] * g["cols"]].view(1, g["rows"], g["cols"])
-                g["splits"] = 1
-            self.dirty = True
-        return buf
-
-    def wgrad_buffer(self, gid, splits):
-        g = self.groups[gid]
-        if g["g_eff"] is None or g["splits"] != splits:
-            g["g_eff"] = torch.empty(splits, g["rows"], g["cols"], dtype=f32, device=self.device)
-            g["splits"] = splits
-            self.dirty = True
-        return g["g_eff"]
+    def _acquire(self):
+        cur = self.active
+        if cur is not None and not cur.in_use():
+            ws = cur
+        else:
+            if cur is not None:
+                cur.freeze()                     # its backward is still to come: keep the u / v it was computed from
+            ws = next((w for w in self.sets if not w.in_use()), None)
+            if ws is None:
+                ws = WeightSet(self)
+                self.sets.append(ws)
+        ws.thaw()
+        self.active = ws
+        return ws
 
     def begin(self, training):
-        """Runs the batched power iteration; returns the autograd token (None when no parameter needs a gradient)."""
+        """Runs the batched power iteration into a free weight set; returns (set, autograd token or None)."""
         if self._fingerprint() != self.fingerprint:
             self._build()                      # parameters were moved (.to()) or replaced
-        if self.dirty:
-            self._upload()
-        self.version += 1
+        ws = self._acquire()
+        if ws.dirty:
+            ws.upload()
+        self.counter += 1
+        ws.version = self.counter
         if torch.is_grad_enabled() and any(p.requires_grad for p in self.params):
-            return _SNBankFn.apply(self, bool(training), *self.params)
-        K.sn_forward(self.table, len(self.layers), self.max_rows, self.max_cols, training)
-        return None
+            return ws, _SNBankFn.apply(self, ws, bool(training), *self.params)
+        ws.busy = False
+        K.sn_forward(ws.table, len(self.layers), self.max_rows, self.max_cols, training)
+        return ws, None
 
 
 class _SNBankFn(Function):
     @staticmethod
-    def forward(ctx, bank, training, *params):
-        K.sn_forward(bank.table, len(bank.layers), bank.max_rows, bank.max_cols, training)
-        ctx.bank = bank
-        ctx.version = bank.version
+    def forward(ctx, bank, ws, training, *params):
+        K.sn_forward(ws.table, len(bank.layers), bank.max_rows, bank.max_cols, training)
+        ctx.bank, ctx.ws, ctx.version = bank, ws, ws.version
+        ws.lease, ws.busy = weakref.ref(ctx), True
         return torch.zeros(1, dtype=f32, device=bank.device)
 
     @staticmethod
     def backward(ctx, _g):
-        bank = ctx.bank
-        _check_version(bank, ctx.version)
-        for g in bank.groups:
-            if g["g_eff"] is None:
+        bank, ws = ctx.bank, ctx.ws
+        _check_version(ws, ctx.version)
+        for g_eff in ws.g_eff:
+            if g_eff is None:
                 raise L.CalmError("an sn(...) layer of this scope received no weight gradient (unused in forward?)")
-        if bank.dirty:
-            bank._upload()
-        K.sn_backward(bank.table, len(bank.layers), bank.max_rows, bank.max_cols)
-        flat = bank.flat_grad.clone()          # persistent scratch -> tensors autograd may keep as .grad
+        if ws.dirty:
+            ws.upload()
+        K.sn_backward(ws.table, len(bank.layers), bank.max_rows, bank.max_cols)
+        flat = ws.flat_grad.clone()            # persistent scratch -> tensors autograd may keep as .grad
+        ws.busy = False                        # every consumer of this forward has run its backward: the set may be reused
         grads = [flat[l["grad_off"]: l["grad_off"] + l["rows"] * l["cols"]].view_as(l["module"].weight_orig) for l in bank.layers]
         grads += [flat[l["rs_off"]: l["rs_off"] + l["rows"]] for l in bank.rs_layers]
-        return (None, None, *grads)
+        return (None, None, None, *grads)
 
 
-def _check_version(bank, version):
-    if bank.version != version:
-        raise L.CalmError("a new forward of this module ran before the backward of the previous one; the spectral-norm "
-                          "bank keeps one set of effective weights (run forward -> backward in order)")
+def _check_version(ws, version):
+    if ws.version != version:
+        raise L.CalmError("this forward's effective weights have been released (its backward already ran once — retain_graph is not "
+                          "supported — or the spectral-norm bank was rebuilt after the parameters moved)")
 
 
 _banks = weakref.WeakKeyDictionary()   # owner module -> SNBank (kept out of module __dict__: pickle/deepcopy/state_dict safe)
@@ -228,7 +288,7 @@ class Scope:
             bank = SNBank(self.spec_fn())
             _banks[self.owner] = bank
         self.bank = bank
-        self.token = bank.begin(self.training)
+        self.ws, self.token = bank.begin(self.training)
         _tls.scope = self
         return self
 
@@ -254,24 +314,66 @@ def _as2d(x):
     return x2, x2.shape[0], x2.stride(0)
 
 
-def _lin_fwd(bank, gid, x2, M, lda, out, ldc, **kw):
-    g = bank.groups[gid]
-    K.gemm(x2, g["w_eff"], out, M, g["rows"], g["cols"], lda=lda, ldb=g["cols"], ldc=ldc, **kw)
+def _lin_fwd(ws, gid, x2, M, lda, out, ldc, **kw):
+    g = ws.groups[gid]
+    K.gemm(x2, ws.w_eff[gid], out, M, g["rows"], g["cols"], lda=lda, ldb=g["cols"], ldc=ldc, **kw)
 
 
-def _lin_dgrad(bank, gid, dy2, M, ld_dy, out, ld_out, **kw):
+def _lin_dgrad(ws, gid, dy2, M, ld_dy, out, ld_out, **kw):
     """dX(M, cols) = dY(M, rows) . W(rows, cols) — W read MN-major, no transposed copy."""
-    g = bank.groups[gid]
-    K.gemm(dy2, g["w_eff"], out, M, g["cols"], g["rows"], lda=ld_dy, ldb=g["cols"], ldc=ld_out, b_major=MAJOR_MN, **kw)
+    g = ws.groups[gid]
+    K.gemm(dy2, ws.w_eff[gid], out, M, g["cols"], g["rows"], lda=ld_dy, ldb=g["cols"], ldc=ld_out, b_major=MAJOR_MN, **kw)
 
 
-def _lin_wgrad(bank, gid, dy2, ld_dy, x2, ld_x, M):
-    """dW_eff(rows, cols) = dY^T X — contraction over the M tokens, split-K fp32 partials into the bank."""
-    g = bank.groups[gid]
+def _lin_wgrad(ws, gid, dy2, ld_dy, x2, ld_x, M):
+    """dW_eff(rows, cols) = dY^T X — contraction over the M tokens, split-K fp32 partials into the forward's weight set."""
+    g = ws.groups[gid]
     s = _splits(g["rows"], g["cols"], M)
-    buf = bank.wgrad_buffer(gid, s)
+    buf = ws.wgrad_buffer(gid, s)
     K.gemm(dy2, x2, buf, g["rows"], g["cols"], M, lda=ld_dy, ldb=ld_x, ldc=g["cols"], a_major=MAJOR_MN, b_major=MAJOR_MN,
            splits=s, stride_split=g["rows"] * g["cols"])
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# fork / join of independent launches
+# ---------------------------------------------------------------------------------------------------------------------
+# Many kernels of a step are small next to the GPU (a GEMM of 160 tiles on 148 SMs leaves the second wave 8 % full) and
+# independent of each other (dgrad / wgrad of one Linear, the three GEMMs that follow dpre in an MLP backward, the dq / dk mask
+# GEMMs): issued on forked streams they share the SMs — the CTAs of the second kernel start on the SMs the first one's last
+# wave leaves idle. Inside the captured training step the fork / join events become parallel branches of the CUDA graph.
+# Rules that keep it safe with the caching allocator: branches only LAUNCH (every output is allocated before the fork, on the
+# forking stream) and the join happens before the autograd Function returns.
+PARALLEL = os.environ.get("CALM_FORK", "1") != "0"      # bench.py's per-kernel timing pass switches it off (kernels timed alone)
+_side_streams = {}
+
+
+def _side(dev, i):
+    key = (dev.index, i)
+    st = _side_streams.get(key)
+    if st is None:
+        st = _side_streams[key] = torch.cuda.Stream(device=dev)
+    return st
+
+
+def fork_join(dev, *branches):
+    """Runs the callables concurrently: branches[0] on the current stream, the others on side streams forked from / joined to it."""
+    branches = [b for b in branches if b is not None]
+    if not PARALLEL or len(branches) < 2 or dev.type != "cuda":
+        for b in branches:
+            b()
+        return
+    cur = torch.cuda.current_stream(dev)
+    start = cur.record_event()
+    done = []
+    for i, b in enumerate(branches[1:]):
+        st = _side(dev, i)
+        st.wait_event(start)
+        with torch.cuda.stream(st):
+            b()
+            done.append(st.record_event())
+    branches[0]()
+    for e in done:
+        cur.wait_event(e)
 
 
 # bf16 copies of fp32 gradients that their producer (LayerNorm backward) already wrote: id(tensor) -> (weakref, bf16 tensor).
@@ -335,11 +437,38 @@ class LayerNormFn(Function):
         return dx, dw, None, None, None
 
 
+class ImageLayerNormFn(Function):
+    """First block: (B,3,S,S) image -> (LN(tokens) * w in bf16, the fp32 row tokens) in one kernel (Vi_Tools…:389-391 + :211)."""
+
+    @staticmethod
+    def forward(ctx, img, w, eps):
+        if img.dim() != 4 or img.shape[1] != 3 or img.shape[2] != img.shape[3]:
+            raise L.CalmError("expected a (B, 3, S, S) image, got %s" % (tuple(img.shape),))
+        y, tokens, mean, rstd = K.layernorm_fwd_image(img.contiguous().float(), w, float(eps))
+        ctx.save_for_backward(tokens, w, mean, rstd)
+        ctx.set_materialize_grads(False)
+        return y, tokens
+
+    @staticmethod
+    def backward(ctx, dy, dres):
+        tokens, w, mean, rstd = ctx.saved_tensors
+        if dy is None:
+            dx, dw = dres, None
+        else:
+            dx, dw = K.layernorm_bwd(dy.contiguous(), tokens, w, mean, rstd, dres.contiguous() if dres is not None else None)
+        dimg = None
+        if ctx.needs_input_grad[0] and dx is not None:      # cold path: only if the input image needs a gradient
+            B, S, _ = tokens.shape
+            dimg = dx.view(B, S, S, 3).permute(0, 3, 1, 2).contiguous()
+        return dimg, dw, None
+
+
 class LinearFn(Function):
     """y = x W_eff^T (+ addend) for one bank group; x bf16 (…, K); out bf16 or fp32."""
 
     @staticmethod
     def forward(ctx, x, token, addend, bank, gid, out_f32):
+        bank = bank.active          # the weight set of THIS forward (effective weights, sigma, wgrad partials)
         g = bank.groups[gid]
         x2, M, lda = _as2d(x)
         out = torch.empty(*x.shape[:-1], g["rows"], dtype=f32 if out_f32 else bf16, device=x.device)
@@ -362,12 +491,10 @@ class LinearFn(Function):
         dyb = _bf16_grad(dy)
         dy2, M, ld_dy = _as2d(dyb)
         x2, _, ld_x = _as2d(x)
-        dx = None
-        if ctx.needs_input_grad[0]:
-            dx = torch.empty(x.shape, dtype=bf16, device=x.device)
-            _lin_dgrad(bank, gid, dy2, M, ld_dy, dx, g["cols"])
-        if ctx.needs_input_grad[1]:
-            _lin_wgrad(bank, gid, dy2, ld_dy, x2, ld_x, M)
+        dx = torch.empty(x.shape, dtype=bf16, device=x.device) if ctx.needs_input_grad[0] else None
+        fork_join(x.device,
+                  (lambda: _lin_dgrad(bank, gid, dy2, M, ld_dy, dx, g["cols"])) if dx is not None else None,
+                  (lambda: _lin_wgrad(bank, gid, dy2, ld_dy, x2, ld_x, M)) if ctx.needs_input_grad[1] else None)
         dadd = None
         if ctx.needs_input_grad[2]:
             dadd = dy if ctx.addend_dtype == dy.dtype else (dyb if ctx.addend_dtype == bf16 else K.cast_f32(dy))
@@ -390,18 +517,22 @@ def _mlp_backward(bank, g1, g2, dy2, M, ld_dy, x2, ld_x, pre, hid, need_dx, need
     """Returns (dx bf16 | None, db1, db2)."""
     H, N2, K1 = bank.groups[g1]["rows"], bank.groups[g2]["rows"], bank.groups[g1]["cols"]
     dpre = torch.empty(M, H, dtype=bf16, device=dy2.device)
-    _lin_dgrad(bank, g2, dy2, M, ld_dy, dpre, H, epilogue=EPI_DGELU, aux=pre, ld_aux=H)
+    dx = torch.empty(M, K1, dtype=bf16, device=dy2.device) if need_dx else None
+    # the weight gradient of the second layer needs dy and the hidden activation only: it runs beside the dgrad that produces dpre
+    fork_join(dy2.device,
+              lambda: _lin_dgrad(bank, g2, dy2, M, ld_dy, dpre, H, epilogue=EPI_DGELU, aux=pre, ld_aux=H),
+              (lambda: _lin_wgrad(bank, g2, dy2, ld_dy, hid, H, M)) if need_w else None)
     db1 = db2 = None
-    if need_w:
-        _lin_wgrad(bank, g2, dy2, ld_dy, hid, H, M)
-        _lin_wgrad(bank, g1, dpre, H, x2, ld_x, M)
-    if need_bias:
+
+    def _bias():
+        nonlocal db1, db2
         db2 = K.colsum(dy2, M, N2, ld_dy)
         db1 = K.colsum(dpre, M, H, H)
-    dx = None
-    if need_dx:
-        dx = torch.empty(M, K1, dtype=bf16, device=dy2.device)
-        _lin_dgrad(bank, g1, dpre, M, H, dx, K1)
+    # first branch = forking stream: the only one that allocates (colsum partials)
+    fork_join(dy2.device,
+              _bias if need_bias else None,
+              (lambda: _lin_dgrad(bank, g1, dpre, M, H, dx, K1)) if need_dx else None,
+              (lambda: _lin_wgrad(bank, g1, dpre, H, x2, ld_x, M)) if need_w else None)
     return dx, db1, db2
 
 
@@ -410,6 +541,7 @@ class MlpFn(Function):
 
     @staticmethod
     def forward(ctx, x, token, addend, bank, g1, g2, out_f32):
+        bank = bank.active          # the weight set of THIS forward (effective weights, sigma, wgrad partials)
         x2, M, lda = _as2d(x)
         N2 = bank.groups[g2]["rows"]
         out = torch.empty(*x.shape[:-1], N2, dtype=f32 if out_f32 else bf16, device=x.device)
@@ -442,16 +574,20 @@ class SeqLinearFn(Function):
 
     @staticmethod
     def forward(ctx, x, token, bank, *gids):
+        bank = bank.active          # the weight set of THIS forward (effective weights, sigma, wgrad partials)
         x = x.contiguous()
         B, S1, D = x.shape
         outs = []
         for gid in gids:
             g = bank.groups[gid]
             assert g["cols"] == S1
-            y = torch.empty(B, g["rows"], D, dtype=bf16, device=x.device)
-            K.gemm(g["w_eff"], x, y, g["rows"], D, S1, batch=B, lda=S1, ldb=D, ldc=D, stride_a=0, stride_b=S1 * D,
-                   stride_c=g["rows"] * D, b_major=MAJOR_MN)
-            outs.append(y)
+            outs.append(torch.empty(B, g["rows"], D, dtype=bf16, device=x.device))
+
+        def _one(gid, y):
+            g = bank.groups[gid]
+            return lambda: K.gemm(bank.w_eff[gid], x, y, g["rows"], D, S1, batch=B, lda=S1, ldb=D, ldc=D, stride_a=0, stride_b=S1 * D,
+                                  stride_c=g["rows"] * D, b_major=MAJOR_MN)
+        fork_join(x.device, *[_one(gid, y) for gid, y in zip(gids, outs)])
         ctx.save_for_backward(x)
         ctx.bank, ctx.gids, ctx.version = bank, gids, bank.version
         ctx.set_materialize_grads(False)
@@ -463,25 +599,29 @@ class SeqLinearFn(Function):
         bank = ctx.bank
         _check_version(bank, ctx.version)
         B, S1, D = x.shape
-        dx = None
-        for gid, dy in zip(ctx.gids, dys):
-            g = bank.groups[gid]
-            S2 = g["rows"]
-            if dy is None:
-                dy = torch.zeros(B, S2, D, dtype=bf16, device=x.device)
-            dy = _bf16_grad(dy).contiguous()
-            if ctx.needs_input_grad[0]:
-                nx = torch.empty(B, S1, D, dtype=bf16, device=x.device)
-                kw = dict(addend=dx, ld_addend=D, stride_addend=S1 * D) if dx is not None else {}
-                K.gemm(g["w_eff"], dy, nx, S1, D, S2, batch=B, lda=S1, ldb=D, ldc=D, stride_a=0, stride_b=S2 * D,
+        dys = [_bf16_grad(dy).contiguous() if dy is not None else torch.zeros(B, bank.groups[gid]["rows"], D, dtype=bf16, device=x.device)
+               for gid, dy in zip(ctx.gids, dys)]
+        dxs = [torch.empty(B, S1, D, dtype=bf16, device=x.device) for _ in ctx.gids] if ctx.needs_input_grad[0] else []
+
+        def _dgrad_chain():                      # dX = sum_i W_i^T dY_i, accumulated through the epilogue addend
+            prev = None
+            for gid, dy, nx in zip(ctx.gids, dys, dxs):
+                g = bank.groups[gid]
+                S2 = g["rows"]
+                kw = dict(addend=prev, ld_addend=D, stride_addend=S1 * D) if prev is not None else {}
+                K.gemm(bank.w_eff[gid], dy, nx, S1, D, S2, batch=B, lda=S1, ldb=D, ldc=D, stride_a=0, stride_b=S2 * D,
                        stride_c=S1 * D, a_major=MAJOR_MN, b_major=MAJOR_MN, **kw)
-                dx = nx
-            if ctx.needs_input_grad[1]:
-                s = _splits(S2, S1, D, B, True)
-                buf = bank.wgrad_buffer(gid, s)
-                K.gemm(dy, x, buf, S2, S1, D, batch=B, lda=D, ldb=D, ldc=S1, stride_a=S2 * D, stride_b=S1 * D,
-                       reduce_batch=True, splits=s, stride_split=S2 * S1)
-        return (dx, None, None) + (None,) * len(ctx.gids)
+                prev = nx
+
+        def _wgrad(gid, dy):
+            S2 = bank.groups[gid]["rows"]
+            s = _splits(S2, S1, D, B, True)
+            buf = bank.wgrad_buffer(gid, s)
+            return lambda: K.gemm(dy, x, buf, S2, S1, D, batch=B, lda=D, ldb=D, ldc=S1, stride_a=S2 * D, stride_b=S1 * D,
+                                  reduce_batch=True, splits=s, stride_split=S2 * S1)
+        fork_join(x.device, _dgrad_chain if dxs else None,
+                  *([_wgrad(gid, dy) for gid, dy in zip(ctx.gids, dys)] if ctx.needs_input_grad[1] else []))
+        return ((dxs[-1] if dxs else None), None, None) + (None,) * len(ctx.gids)
 
 
 class AttnCoreFn(Function):
@@ -491,6 +631,7 @@ class AttnCoreFn(Function):
 
     @staticmethod
     def forward(ctx, token, inv_q, inv_k, b1, b2, bank, g1, g2, roles, dims, *srcs):
+        bank = bank.active          # the weight set of THIS forward (effective weights, sigma, wgrad partials)
         B, S, heads, dc, dr = dims
         hd = dc + dr
         D = heads * hd
@@ -552,10 +693,11 @@ class AttnCoreFn(Function):
         need_w = ctx.needs_input_grad[0]
         dlog, db1, db2 = _mlp_backward(bank, ctx.g1, ctx.g2, dbias.view(T, S), T, S, logits.view(T, S), S, pre, hid, True, need_w, True)
         # logits = q k^T (all heads, unscaled): dq += dL k ; dk += dL^T q   (accumulated in place through the addend)
-        K.gemm(dlog, k, dq, S, D, S, batch=B, lda=S, ldb=D, ldc=D, stride_a=S * S, stride_b=S * D, stride_c=S * D,
-               b_major=MAJOR_MN, addend=dq, ld_addend=D, stride_addend=S * D)
-        K.gemm(dlog, q, dk, S, D, S, batch=B, lda=S, ldb=D, ldc=D, stride_a=S * S, stride_b=S * D, stride_c=S * D,
-               a_major=MAJOR_MN, b_major=MAJOR_MN, addend=dk, ld_addend=D, stride_addend=S * D)
+        fork_join(q.device,
+                  lambda: K.gemm(dlog, k, dq, S, D, S, batch=B, lda=S, ldb=D, ldc=D, stride_a=S * S, stride_b=S * D, stride_c=S * D,
+                                 b_major=MAJOR_MN, addend=dq, ld_addend=D, stride_addend=S * D),
+                  lambda: K.gemm(dlog, q, dk, S, D, S, batch=B, lda=S, ldb=D, ldc=D, stride_a=S * S, stride_b=S * D, stride_c=S * D,
+                                 a_major=MAJOR_MN, b_major=MAJOR_MN, addend=dk, ld_addend=D, stride_addend=S * D))
         dqc, ld_dqc = role("qc", dsrc2); dqr, ld_dqr = role("qr", dsrc2)
         dkc, ld_dkc = role("kc", dsrc2); dkr, ld_dkr = role("kr", dsrc2)
         _, _, dinv_q = K.rope_bwd(dq, D, q, inv_q, T, S, heads, dc, dr, dcontent=dqc, ld_dcontent=ld_dqc, dropein=dqr, ld_drope=ld_dqr)
@@ -602,6 +744,7 @@ class CnnFn(Function):
 
     @staticmethod
     def forward(ctx, x, token, b1, b2, b3, bank, g1, g2, g3):
+        bank = bank.active          # the weight set of THIS forward (effective weights, sigma, wgrad partials)
         x = x.contiguous()
         B, S = x.shape[0], x.shape[1]
         w1, w2, w3 = bank.weight(g1), bank.weight(g2), bank.weight(g3)

@@ -244,6 +244,7 @@ template <int HDP>
 __global__ void __launch_bounds__(ATT_THREADS, 3)
 attn_bwd_dq_kernel(const bf16* __restrict__ q, const bf16* __restrict__ k, const bf16* __restrict__ v, const bf16* __restrict__ bias,
                    const bf16* __restrict__ d_o, const float* __restrict__ lse, const float* __restrict__ delta, bf16* __restrict__ dq,
+                   bf16* __restrict__ ds_out /* optional (B, heads, S, S) bf16: this head's dS, summed over heads by dbias_reduce */,
                    long long ld_q, long long ld_k, long long ld_v, long long ld_do, long long ld_dq, int S, int heads, int hd,
                    float scale, float scale_log2) {
   constexpr int P = HDP + 8, NT = HDP / 8;
@@ -304,6 +305,24 @@ attn_bwd_dq_kernel(const bf16* __restrict__ q, const bf16* __restrict__ k, const
         s[nt][2 * hh + 1] = p1 * (dp[nt][2 * hh + 1] - dlt[hh]);
       }
     }
+    if (ds_out) {
+      // this warp's 16 x 64 dS block goes through its own rows of the (consumed) bias tile and leaves as 16-byte row pieces
+      __syncwarp();
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh)
+          *reinterpret_cast<uint32_t*>(Bs + (warp * 16 + (lane >> 2) + hh * 8) * BP + nt * 8 + (lane & 3) * 2) = pack_bf16x2(s[nt][2 * hh], s[nt][2 * hh + 1]);
+      __syncwarp();
+      bf16* dsb = ds_out + ((long long)b * heads + h) * S * S;
+#pragma unroll
+      for (int i = lane; i < 128; i += 32) {
+        const int rr = i >> 3, cc = i & 7;
+        const int row = q0 + warp * 16 + rr, key = kb0 + 8 * cc;
+        if (row < S && key < S)
+          *reinterpret_cast<uint4*>(dsb + (long long)row * S + key) = *reinterpret_cast<const uint4*>(Bs + (warp * 16 + rr) * BP + 8 * cc);
+      }
+    }
     mma_p_t<HDP>(dqacc, s, Ks, lane);
   }
 #pragma unroll
@@ -324,7 +343,10 @@ attn_bwd_dq_kernel(const bf16* __restrict__ q, const bf16* __restrict__ k, const
 // backward, key-major: dK, dV and dbias = sum over heads of dS.  grid (ceil(S/64), B); loops heads x query tiles.
 // Works on transposed tiles (keys x queries) so that P^T / dS^T feed the next MMA straight from registers.
 // ---------------------------------------------------------------------------------------------------------------
-template <int HDP>
+// PER_HEAD: grid (key tiles, heads, B), no dbias (the dq kernel wrote every head's dS to the scratch, dbias_reduce sums them) —
+// 12x the parallelism of the all-heads-in-one-CTA form, whose S x 65 fp32 dbias tile also held it to one 4-warp CTA per SM
+// (measured at 384^2 / 512^2: 69 / 117 ms per step in this kernel, 1.4 % of the tensor peak).
+template <int HDP, bool PER_HEAD>
 __global__ void __launch_bounds__(ATT_THREADS, 2)
 attn_bwd_dkv_kernel(const bf16* __restrict__ q, const bf16* __restrict__ k, const bf16* __restrict__ v, const bf16* __restrict__ bias,
                     const bf16* __restrict__ d_o, const float* __restrict__ lse, const float* __restrict__ delta, bf16* __restrict__ dk,
@@ -342,13 +364,15 @@ attn_bwd_dkv_kernel(const bf16* __restrict__ q, const bf16* __restrict__ k, cons
   float* dlt_s = lse_s + TILE;                               // TILE
   float* db_s = dlt_s + TILE;                                // s_pad x DBP   [query][key]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int k0 = blockIdx.x * TILE, b = blockIdx.y;
+  const int k0 = blockIdx.x * TILE, b = PER_HEAD ? blockIdx.z : blockIdx.y;
   const long long tok0 = (long long)b * S;
   const bf16* bias_b = bias + (long long)b * S * S;
-  for (int i = threadIdx.x; i < s_pad * DBP; i += ATT_THREADS) db_s[i] = 0.f;
+  if (!PER_HEAD)
+    for (int i = threadIdx.x; i < s_pad * DBP; i += ATT_THREADS) db_s[i] = 0.f;
   const int key_lo = k0 + warp * 16 + (lane >> 2);  // this thread's keys: key_lo, key_lo + 8
+  const int h_begin = PER_HEAD ? blockIdx.y : 0, h_end = PER_HEAD ? blockIdx.y + 1 : heads;
 
-  for (int h = 0; h < heads; ++h) {
+  for (int h = h_begin; h < h_end; ++h) {
     __syncthreads();
     load_tile<HDP>(Ks, k + (tok0 + k0) * ld_k + (long long)h * hd, ld_k, S - k0, hd);
     load_tile<HDP>(Vs, v + (tok0 + k0) * ld_v + (long long)h * hd, ld_v, S - k0, hd);
@@ -394,7 +418,7 @@ attn_bwd_dkv_kernel(const bf16* __restrict__ q, const bf16* __restrict__ k, cons
           st[nt][e] = p;                                   // P^T
           const float ds = p * (dpt[nt][e] - dlt_s[ql]);
           dpt[nt][e] = ds;                                 // dS^T
-          if (key < S && qrow < S) db_s[qrow * DBP + (key - k0)] += ds;  // each (q,key) owned by exactly one thread
+          if (!PER_HEAD && key < S && qrow < S) db_s[qrow * DBP + (key - k0)] += ds;  // each (q,key) owned by exactly one thread
         }
       }
       mma_p_t<HDP>(dvacc, st, dOs, lane);  // dV += P^T dO
@@ -417,6 +441,7 @@ attn_bwd_dkv_kernel(const bf16* __restrict__ q, const bf16* __restrict__ k, cons
       }
     }
   }
+  if (PER_HEAD) return;
   __syncthreads();
   bf16* db_b = dbias + (long long)b * S * S;
   const int nk = min(TILE, S - k0);
@@ -457,9 +482,11 @@ int launch_fwd(const void* q, const void* k, const void* v, const void* bias, vo
 
 template <int HDP>
 int launch_bwd(const void* q, const void* k, const void* v, const void* bias, const void* d_o, const float* lse, const float* delta,
-               void* dq, void* dk, void* dv, void* dbias, int64_t ld_q, int64_t ld_k, int64_t ld_v, int64_t ld_do, int64_t ld_dq,
-               int64_t ld_dk, int64_t ld_dv, int B, int S, int heads, int hd, cudaStream_t stream) {
+               void* dq, void* dk, void* dv, void* dbias, void* ds_scratch, int64_t ld_q, int64_t ld_k, int64_t ld_v, int64_t ld_do,
+               int64_t ld_dq, int64_t ld_dk, int64_t ld_dv, int B, int S, int heads, int hd, cudaStream_t stream) {
   const float scale = 1.0f / sqrtf((float)hd);
+  // with a scratch (and 16-byte rows: S % 8 == 0) every head writes its dS once and dK / dV run one CTA per (key tile, head, image)
+  const bool per_head = ds_scratch != nullptr && S % 8 == 0;
   {
     const size_t smem = dq_smem<HDP>();
     int rc = ensure_smem(attn_bwd_dq_kernel<HDP>, smem, "calm_attention_bwd(dq)");
@@ -467,18 +494,30 @@ int launch_bwd(const void* q, const void* k, const void* v, const void* bias, co
     dim3 grid((S + TILE - 1) / TILE, heads, B);
     attn_bwd_dq_kernel<HDP><<<grid, ATT_THREADS, smem, stream>>>(
         reinterpret_cast<const bf16*>(q), reinterpret_cast<const bf16*>(k), reinterpret_cast<const bf16*>(v),
-        reinterpret_cast<const bf16*>(bias), reinterpret_cast<const bf16*>(d_o), lse, delta, reinterpret_cast<bf16*>(dq), ld_q, ld_k,
-        ld_v, ld_do, ld_dq, S, heads, hd, scale, scale * LOG2E);
+        reinterpret_cast<const bf16*>(bias), reinterpret_cast<const bf16*>(d_o), lse, delta, reinterpret_cast<bf16*>(dq),
+        per_head ? reinterpret_cast<bf16*>(ds_scratch) : nullptr, ld_q, ld_k, ld_v, ld_do, ld_dq, S, heads, hd, scale, scale * LOG2E);
     CALM_CHECK_LAUNCH("calm_attention_bwd(dq)");
+  }
+  if (per_head) {
+    const size_t smem = dkv_smem<HDP>(0);
+    int rc = ensure_smem(attn_bwd_dkv_kernel<HDP, true>, smem, "calm_attention_bwd(dkv)");
+    if (rc) return rc;
+    dim3 grid((S + TILE - 1) / TILE, heads, B);
+    attn_bwd_dkv_kernel<HDP, true><<<grid, ATT_THREADS, smem, stream>>>(
+        reinterpret_cast<const bf16*>(q), reinterpret_cast<const bf16*>(k), reinterpret_cast<const bf16*>(v),
+        reinterpret_cast<const bf16*>(bias), reinterpret_cast<const bf16*>(d_o), lse, delta, reinterpret_cast<bf16*>(dk),
+        reinterpret_cast<bf16*>(dv), nullptr, ld_q, ld_k, ld_v, ld_do, ld_dk, ld_dv, S, heads, hd, scale, scale * LOG2E, 0);
+    CALM_CHECK_LAUNCH("calm_attention_bwd(dkv)");
+    return calm_attention_dbias_reduce(ds_scratch, dbias, B, S, heads, stream);
   }
   {
     const int s_pad = ((S + TILE - 1) / TILE) * TILE;
     const size_t smem = dkv_smem<HDP>(s_pad);
     if (smem > 227 * 1024) { calm_set_error("calm_attention_bwd: S=%d hd=%d needs %zu B smem", S, hd, smem); return CALM_ERR_UNSUPPORTED; }
-    int rc = ensure_smem(attn_bwd_dkv_kernel<HDP>, smem, "calm_attention_bwd(dkv)");
+    int rc = ensure_smem(attn_bwd_dkv_kernel<HDP, false>, smem, "calm_attention_bwd(dkv)");
     if (rc) return rc;
     dim3 grid((S + TILE - 1) / TILE, B);
-    attn_bwd_dkv_kernel<HDP><<<grid, ATT_THREADS, smem, stream>>>(
+    attn_bwd_dkv_kernel<HDP, false><<<grid, ATT_THREADS, smem, stream>>>(
         reinterpret_cast<const bf16*>(q), reinterpret_cast<const bf16*>(k), reinterpret_cast<const bf16*>(v),
         reinterpret_cast<const bf16*>(bias), reinterpret_cast<const bf16*>(d_o), lse, delta, reinterpret_cast<bf16*>(dk),
         reinterpret_cast<bf16*>(dv), reinterpret_cast<bf16*>(dbias), ld_q, ld_k, ld_v, ld_do, ld_dk, ld_dv, S, heads, hd, scale,
@@ -551,7 +590,7 @@ extern "C" int32_t calm_attention_bwd(const void* q, const void* k, const void* 
       return calm_attention_bwd_tc(q, k, v, bias, d_o, lse, delta, dq, dk, dv, dbias, ds_scratch, ld_q, ld_k, ld_v, ld_do, ld_dq, ld_dk,
                                    ld_dv, B, S, heads, hd, stream);
   }
-  DISPATCH_HDP(hd, return launch_bwd<HDP>(q, k, v, bias, d_o, lse, delta, dq, dk, dv, dbias, ld_q, ld_k, ld_v, ld_do, ld_dq, ld_dk,
+  DISPATCH_HDP(hd, return launch_bwd<HDP>(q, k, v, bias, d_o, lse, delta, dq, dk, dv, dbias, ds_scratch, ld_q, ld_k, ld_v, ld_do, ld_dq, ld_dk,
                                           ld_dv, B, S, heads, hd, stream));
   return CALM_OK;
 }

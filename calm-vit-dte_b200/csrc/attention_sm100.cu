@@ -823,6 +823,10 @@ int calm_attention_bwd_tc(const void* q, const void* k, const void* v, const voi
   const int grid = bwd_items < calm_num_sms() ? bwd_items : calm_num_sms();
   attn_bwd_tc_kernel<<<grid, NTHREADS, BWD_SMEM, stream>>>(mQ, mK, mV, mDO, mDS, p);
   CALM_CHECK_LAUNCH("calm_attention_bwd(tcgen05)");
+  return calm_attention_dbias_reduce(ds_scratch, dbias, B, S, heads, stream);
+}
+
+int calm_attention_dbias_reduce(const void* ds_scratch, void* dbias, int B, int S, int heads, cudaStream_t stream) {
   const long long ss8 = (long long)S * S / 8, total8 = ss8 * B;
   dbias_reduce_kernel<<<(unsigned)((total8 + 255) / 256), 256, 0, stream>>>(reinterpret_cast<const bf16*>(ds_scratch),
                                                                             reinterpret_cast<bf16*>(dbias), heads, ss8, total8);

@@ -12,3 +12,5 @@ int calm_attention_bwd_tc(const void* q, const void* k, const void* v, const voi
                           int64_t ld_v, int64_t ld_do, int64_t ld_dq, int64_t ld_dk, int64_t ld_dv, int B, int S, int heads, int hd,
                           cudaStream_t stream);
 size_t calm_attention_bwd_tc_scratch_bytes(int B, int S, int heads);
+// dbias[b] = sum over heads of the per-head dS scratch (B, heads, S, S) bf16 -> (B, S, S) bf16 (fp32 sum in head order); S * S % 8 == 0
+int calm_attention_dbias_reduce(const void* ds_scratch, void* dbias, int B, int S, int heads, cudaStream_t stream);

@@ -66,16 +66,35 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 
 // Asynchronous copy of image rows [gy0, gy0 + nrows) x columns [gx0, gx0 + 36) (3 floats per pixel) into dst[nrows][108];
 // everything outside the S x S image is zero-filled. gx0 is even; with S even a 2-float chunk never straddles the image border.
-__device__ __forceinline__ void prefetch_rows(float* dst, const float* __restrict__ img, int S, int gy0, int gx0, int nrows) {
+// The (row, chunk) pairs a thread copies do not depend on the tile: they are decoded once per kernel into `slots` (row << 8 | chunk),
+// so a tile's prefetch costs ~10 instructions per 8-byte chunk instead of ~40 (the tile-top bookkeeping was 10-25 % of all
+// instructions of the first version of these kernels).
+constexpr int PF_SLOTS = 3;
+struct Prefetch { int slot[PF_SLOTS]; };
+__device__ __forceinline__ Prefetch make_prefetch(int nrows, bool even) {
+  Prefetch pf;
+  const int per_row = even ? RAW_ROW / 2 : RAW_ROW;
+#pragma unroll
+  for (int k = 0; k < PF_SLOTS; ++k) {
+    const int i = threadIdx.x + k * NT;
+    const int row = i / per_row;
+    pf.slot[k] = row < nrows ? (row << 8 | (i - row * per_row)) : -1;
+  }
+  return pf;
+}
+__device__ __forceinline__ void prefetch_rows(const Prefetch& pf, float* dst, const float* __restrict__ img, int S, int gy0, int gx0, int nrows) {
   const int lim = S * 3, f0 = gx0 * 3;
   if (!(S & 1)) {
-    for (int i = threadIdx.x; i < nrows * (RAW_ROW / 2); i += NT) {
-      const int row = i / (RAW_ROW / 2), ch = i - row * (RAW_ROW / 2);
-      const int gy = gy0 + row, f = f0 + 2 * ch;
-      const bool ok = gy >= 0 && gy < S && f >= 0 && f < lim;
-      cp_async8(dst + row * RAW_ROW + 2 * ch, ok ? img + (long long)gy * lim + f : img, ok ? 8 : 0);
+#pragma unroll
+    for (int k = 0; k < PF_SLOTS; ++k) {
+      if (pf.slot[k] >= 0) {
+        const int row = pf.slot[k] >> 8, ch = pf.slot[k] & 255;
+        const int gy = gy0 + row, f = f0 + 2 * ch;
+        const bool ok = (unsigned)gy < (unsigned)S && (unsigned)f < (unsigned)lim;
+        cp_async8(dst + row * RAW_ROW + 2 * ch, ok ? img + (long long)gy * lim + f : img, ok ? 8 : 0);
+      }
     }
-  } else {
+  } else {   // odd S (not a trainer shape): 4-byte elements, plain loop
     for (int i = threadIdx.x; i < nrows * RAW_ROW; i += NT) {
       const int row = i / RAW_ROW, e = i - row * RAW_ROW;
       const int gy = gy0 + row, f = f0 + e;
@@ -145,11 +164,13 @@ cnn_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, CnnW W, int B
   uint32_t* h1 = planes + warp * F_WARP_WORDS + F_H1;
   uint32_t* h2p = planes + warp * F_WARP_WORDS + F_H2;
   const int tiles_per_img = tiles_x * tiles_y;
-  const long long total = (long long)B * tiles_per_img;
-  long long tile = blockIdx.x;
-  auto issue = [&](long long tl, int buf) {
-    const int b = (int)(tl / tiles_per_img), tr = (int)(tl - (long long)b * tiles_per_img);
-    prefetch_rows(raw0 + buf * (F_RAW_BYTES / 4), x + (long long)b * S * S * 3, S, (tr / tiles_x) * th - 1, (tr % tiles_x) * TW - 2, th + 2);
+  const int total = B * tiles_per_img;          // < 2^31 (checked by the host)
+  int tile = blockIdx.x;
+  const Prefetch pf = make_prefetch(th + 2, !(S & 1));
+  auto issue = [&](int tl, int buf) {
+    const int b = tl / tiles_per_img, tr = tl - b * tiles_per_img;
+    const int trow = tr / tiles_x;
+    prefetch_rows(pf, raw0 + buf * (F_RAW_BYTES / 4), x + (long long)b * S * S * 3, S, trow * th - 1, (tr - trow * tiles_x) * TW - 2, th + 2);
   };
   if (tile < total) issue(tile, 0);
   cp_async_commit();
@@ -172,8 +193,9 @@ cnn_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, CnnW W, int B
   const float b3a = wsm[P_B3 + 0], b3b = wsm[P_B3 + 1], b3c = wsm[P_B3 + 2];
 
   for (int it = 0; tile < total; tile += gridDim.x, ++it) {
-    const int b = (int)(tile / tiles_per_img), tr = (int)(tile - (long long)b * tiles_per_img);
-    const int ty0 = (tr / tiles_x) * th, tx0 = (tr % tiles_x) * TW;
+    const int b = tile / tiles_per_img, tr = tile - b * tiles_per_img;
+    const int trow = tr / tiles_x;
+    const int ty0 = trow * th, tx0 = (tr - trow * tiles_x) * TW;
     float* raw = raw0 + (it & 1) * (F_RAW_BYTES / 4);
     cp_async_wait_all();
     __syncthreads();                         // this tile's rows have landed; the previous tile is fully consumed
@@ -288,14 +310,16 @@ cnn_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, float*
   uint32_t* g1 = planes + warp * B_WARP_WORDS + B_G1;
   uint32_t* dp2 = planes + warp * B_WARP_WORDS + B_DP2;
   const int tiles_per_img = tiles_x * tiles_y;
-  const long long total = (long long)B * tiles_per_img;
-  long long tile = blockIdx.x;
-  auto issue = [&](long long tl, int buf) {
-    const int b = (int)(tl / tiles_per_img), tr = (int)(tl - (long long)b * tiles_per_img);
-    const int ty0 = (tr / tiles_x) * th, tx0 = (tr % tiles_x) * TW;
+  const int total = B * tiles_per_img;          // < 2^31 (checked by the host)
+  int tile = blockIdx.x;
+  const Prefetch pfx = make_prefetch(th + 4, !(S & 1)), pfd = make_prefetch(th + 2, !(S & 1));
+  auto issue = [&](int tl, int buf) {
+    const int b = tl / tiles_per_img, tr = tl - b * tiles_per_img;
+    const int trow = tr / tiles_x;
+    const int ty0 = trow * th, tx0 = (tr - trow * tiles_x) * TW;
     const long long img = (long long)b * S * S * 3;
-    prefetch_rows(xraw, x + img, S, ty0 - 2, tx0 - 2, th + 4);
-    prefetch_rows(dy0 + buf * (B_DY_BYTES / 4), dy + img, S, ty0 - 1, tx0 - 2, th + 2);
+    prefetch_rows(pfx, xraw, x + img, S, ty0 - 2, tx0 - 2, th + 4);
+    prefetch_rows(pfd, dy0 + buf * (B_DY_BYTES / 4), dy + img, S, ty0 - 1, tx0 - 2, th + 2);
   };
   if (tile < total) issue(tile, 0);
   cp_async_commit();
@@ -317,8 +341,9 @@ cnn_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, float*
   }
 
   for (int it = 0; tile < total; tile += gridDim.x, ++it) {
-    const int b = (int)(tile / tiles_per_img), tr = (int)(tile - (long long)b * tiles_per_img);
-    const int ty0 = (tr / tiles_x) * th, tx0 = (tr % tiles_x) * TW;
+    const int b = tile / tiles_per_img, tr = tile - b * tiles_per_img;
+    const int trow = tr / tiles_x;
+    const int ty0 = trow * th, tx0 = (tr - trow * tiles_x) * TW;
     float* dys = dy0 + (it & 1) * (B_DY_BYTES / 4);
     cp_async_wait_all();
     __syncthreads();                         // x / dy of this tile have landed; the previous tile is fully consumed
@@ -401,6 +426,9 @@ cnn_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, float*
           gb2a += pa; gb2b += pb;
           gw3a[0] = fmaf(d0, hf.x, gw3a[0]); gw3a[1] = fmaf(d1, hf.x, gw3a[1]); gw3a[2] = fmaf(d2y, hf.x, gw3a[2]);
           gw3b[0] = fmaf(d0, hf.y, gw3b[0]); gw3b[1] = fmaf(d1, hf.y, gw3b[1]); gw3b[2] = fmaf(d2y, hf.y, gw3b[2]);
+          // dW2 from the UNROUNDED fp32 dp2 of this pixel. (Accumulating it in phase D from the bf16 dp2 plane — the taps are
+          // unpacked there anyway — saved ~3 instructions per pixel-channel, but the rounding noise of dp2 survives in this
+          // cancellation-dominated sum: the model-level distance of these 288-element gradients to the fp32 truth doubled.)
 #pragma unroll
           for (int j = 0; j < 3; ++j) {
             gw2a[j] = fmaf(pa, A.lo[j], gw2a[j]); gw2a[3 + j] = fmaf(pa, Bq.lo[j], gw2a[3 + j]); gw2a[6 + j] = fmaf(pa, C.lo[j], gw2a[6 + j]);
@@ -559,6 +587,7 @@ extern "C" int32_t calm_cnn_fwd(const float* x, float* y, const float* w1, const
   const int th = tile_height(S, THF);
   const int tiles_x = (S + TW - 1) / TW, tiles_y = (S + th - 1) / th;
   const long long total = (long long)B * tiles_x * tiles_y;
+  CALM_CHECK_ARG(total < (1LL << 31) - 4096, "calm_cnn_fwd: too many tiles");
   const long long cap = 2LL * calm_num_sms();
   const unsigned grid = (unsigned)(total < cap ? total : cap);
   static CalmDeviceOnce configured;
@@ -588,6 +617,7 @@ extern "C" int32_t calm_cnn_bwd(const float* x, const float* dy, float* dx, void
   CALM_CHECK_ARG(((uintptr_t)x | (uintptr_t)dy | (uintptr_t)dx | (uintptr_t)dx_bf16) % 16 == 0, "calm_cnn_bwd: x / dy / dx must be 16-byte aligned");
   const int th = tile_height(S, THB);
   const int tiles_x = (S + TW - 1) / TW, tiles_y = (S + th - 1) / th;
+  CALM_CHECK_ARG((long long)B * tiles_x * tiles_y < (1LL << 31) - 4096, "calm_cnn_bwd: too many tiles");
   static CalmDeviceOnce configured;
   if (configured.pending()) {
     cudaError_t e = cudaFuncSetAttribute(cnn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BWD_SMEM);

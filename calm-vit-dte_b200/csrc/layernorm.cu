@@ -85,6 +85,58 @@ ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, void* __
   }
 }
 
+// First block only: the row tokenisation of the NCHW image (Vi_Tools_CNN_less_V2.py:389-391: permute(0,2,3,1) +
+// reshape) fused into the block's first LayerNorm. One warp per token (b, image row): lane owns pixels lane, lane + 32, ...; the
+// three channel planes are read coalesced, the fp32 token row (the residual stream's first tensor) and the bf16 LayerNorm output
+// are written in the same pass — the stand-alone tokenise kernel's extra read of the batch is gone.
+constexpr int LN_IMG_PPL = 16;     // pixels per lane: S <= 512
+__global__ void __launch_bounds__(LN_THREADS)
+ln_fwd_image_kernel(const float* __restrict__ img, const float* __restrict__ w, bf16* __restrict__ y, float* __restrict__ tokens,
+                    float* __restrict__ mean, float* __restrict__ rstd, int B, int S, float eps) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long row = (long long)blockIdx.x * LN_WARPS + warp;      // token index b * S + image row
+  if (row >= (long long)B * S) return;
+  const int b = (int)(row / S), yr = (int)(row - (long long)b * S);
+  const int D = 3 * S;
+  const float* p0 = img + ((long long)b * 3 * S + yr) * S;              // channel c at p0 + c * S * S
+  const long long plane = (long long)S * S;
+  float v[LN_IMG_PPL][3];
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < LN_IMG_PPL; ++k) {
+    const int xc = lane + 32 * k;
+    if (xc < S) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) { v[k][c] = __ldcs(p0 + c * plane + xc); s += v[k][c]; }
+    } else {
+      v[k][0] = v[k][1] = v[k][2] = 0.f;
+    }
+  }
+  const float mu = warp_sum(s) / D;
+  float q = 0.f;
+#pragma unroll
+  for (int k = 0; k < LN_IMG_PPL; ++k)
+    if (lane + 32 * k < S) {
+      const float a = v[k][0] - mu, bb = v[k][1] - mu, c = v[k][2] - mu;
+      q += a * a + bb * bb + c * c;
+    }
+  const float rs = rsqrtf(warp_sum(q) / D + eps);
+  if (lane == 0) { mean[row] = mu; rstd[row] = rs; }
+  float* trow = tokens + row * D;
+  bf16* yrow = y + row * D;
+#pragma unroll
+  for (int k = 0; k < LN_IMG_PPL; ++k) {
+    const int xc = lane + 32 * k;
+    if (xc < S) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        trow[xc * 3 + c] = v[k][c];
+        yrow[xc * 3 + c] = __float2bfloat16((v[k][c] - mu) * rs * w[xc * 3 + c]);
+      }
+    }
+  }
+}
+
 template <bool DY_F32>
 __device__ __forceinline__ float4 load_dy4(const void* dy, long long row, int D, int i) {
   if (DY_F32) return reinterpret_cast<const float4*>(reinterpret_cast<const float*>(dy) + row * D)[i];
@@ -273,6 +325,16 @@ extern "C" int32_t calm_layernorm_fwd(const float* x, const float* w, void* y, i
   }
 #undef LN_FWD_LAUNCH
   CALM_CHECK_LAUNCH("calm_layernorm_fwd");
+  return CALM_OK;
+}
+
+extern "C" int32_t calm_layernorm_fwd_image(const float* img, const float* w, void* y_bf16, float* tokens, float* mean, float* rstd,
+                                            int32_t B, int32_t S, float eps, cudaStream_t stream) {
+  CALM_CHECK_ARG(B > 0 && S > 0 && S <= 32 * LN_IMG_PPL, "calm_layernorm_fwd_image: B=%d S=%d (S <= %d)", B, S, 32 * LN_IMG_PPL);
+  const long long rows = (long long)B * S;
+  ln_fwd_image_kernel<<<(unsigned)((rows + LN_WARPS - 1) / LN_WARPS), LN_THREADS, 0, stream>>>(img, w, reinterpret_cast<bf16*>(y_bf16), tokens, mean,
+                                                                                              rstd, B, S, eps);
+  CALM_CHECK_LAUNCH("calm_layernorm_fwd_image");
   return CALM_OK;
 }
 

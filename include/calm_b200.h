@@ -102,6 +102,10 @@ int32_t calm_sn_backward(const calm_sn_layer* table_dev, int32_t n_layers, const
  * ------------------------------------------------------------------------------------------------------------------ */
 int32_t calm_layernorm_fwd(const float* x, const float* w, void* y, int32_t y_dtype, float* mean, float* rstd,
                            int64_t rows, int32_t D, float eps, cudaStream_t stream);
+/* first block: row tokenisation of the (B,3,S,S) image (Vi_Tools_CNN_less_V2.py:389-391) fused into its first LayerNorm:
+ * tokens f32 (B, S, 3S) = img.permute(0,2,3,1).reshape(B, S, 3S) and y bf16 = LN(tokens) * w in one pass */
+int32_t calm_layernorm_fwd_image(const float* img, const float* w, void* y_bf16, float* tokens, float* mean, float* rstd,
+                                 int32_t B, int32_t S, float eps, cudaStream_t stream);
 int32_t calm_layernorm_bwd(const void* dy, int32_t dy_dtype, const float* x, const float* w, const float* mean,
                            const float* rstd, const float* dres, float* dx, void* dx_bf16, float* dw_partial, int32_t nparts,
                            float* dw, int64_t rows, int32_t D, cudaStream_t stream);

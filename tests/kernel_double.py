@@ -67,6 +67,13 @@ def layernorm_fwd(x, w, eps=1e-6, out_dtype=bf16):
     return y, mean.reshape(-1), rstd.reshape(-1)
 
 
+def layernorm_fwd_image(img, w, eps=1e-6):
+    B, _, S, _ = img.shape
+    tokens = img.permute(0, 2, 3, 1).reshape(B, S, 3 * S).contiguous()
+    y, mean, rstd = layernorm_fwd(tokens, w, eps, bf16)     # `bf16` looked up at call time: the fp32-double test rebinds it
+    return y, tokens, mean, rstd
+
+
 def layernorm_bwd(dy, x, w, mean, rstd, dres=None, want_bf16=False):
     D = x.shape[-1]
     xh = (x - mean.view(*x.shape[:-1], 1)) * rstd.view(*x.shape[:-1], 1)

@@ -137,6 +137,57 @@ def test_bf16_rounding_points_stay_in_band(product, monkeypatch, name):
     assert len(off) <= len(big) // 20, off[:10]
 
 
+def test_second_forward_before_backward(product, monkeypatch):
+    """Gradient accumulation with a deferred backward, and an evaluation pass between a forward and its backward (both legal in
+    the reference): out1 = model(x1); model.eval(); model(x1); model.train(); out2 = model(x2); backward of both. Every forward
+    must be differentiated with ITS OWN effective weights, sigma and u / v: the accumulated gradients equal the sum of the
+    gradients of the same two steps run one after the other from the same start state."""
+    _, meta = load_fixture("small_cls")
+    cfg = meta["config"]
+    state = synth.synth_state(meta["shapes"])
+    x1, _ = synth.synth_input(cfg)
+    x2, _ = synth.synth_input(cfg, seed=3)
+
+    def fresh():
+        model, _ = build(product, meta)
+        model.load_state_dict(state)
+        model.train()
+        return model
+
+    def fwd(model, x, seed):
+        noise = synth.NoiseStream(cfg, seed=seed)
+        with monkeypatch.context() as mp:
+            mp.setattr(torch, "randn", lambda *a, **k: next(noise))
+            out, kl = model(x)
+        return out.float().pow(2).mean() + 0.1 * kl
+    # sequential: forward 1, backward 1, forward 2, backward 2 (gradients accumulate in .grad)
+    seq = fresh()
+    fwd(seq, x1, 0).backward()
+    fwd(seq, x2, 1).backward()
+    want = {k: p.grad.clone() for k, p in seq.named_parameters()}
+    # deferred: both forwards (and an eval pass in between) before any backward
+    model = fresh()
+    l1 = fwd(model, x1, 0)
+    model.eval()
+    with torch.no_grad():
+        model(x1)
+    model.train()
+    l2 = fwd(model, x2, 1)
+    l1.backward()
+    l2.backward()
+    for k, p in model.named_parameters():
+        assert relerr(p.grad, want[k]) < 1e-5, k
+    for (k, a), b in zip(model.state_dict().items(), seq.state_dict().values()):
+        assert torch.equal(a, b), k                   # u / v advanced exactly twice in both runs
+    # a second backward through a released forward is refused (retain_graph is not supported), not silently wrong
+    import calm_lib
+    l3 = fwd(model, x1, 2)
+    l3.backward(retain_graph=True)
+    fwd(model, x2, 3).backward()
+    with pytest.raises(calm_lib.CalmError):
+        l3.backward()
+
+
 def test_product_requires_cuda():
     """Without the test double the modules refuse CPU tensors loudly — there is no CPU fallback in the product."""
     import CALM_ViT_V2 as rvh

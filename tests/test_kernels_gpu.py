@@ -255,6 +255,19 @@ def test_layernorm(K, rows, D):
     assert rel(dw, wr.grad) < 1e-4
 
 
+@pytest.mark.parametrize("B,S", [(3, 224), (2, 80), (1, 512), (2, 48)])
+def test_layernorm_image(K, B, S):
+    """First-block tokenisation fused into the LayerNorm: tokens bit-exact (a pure permutation), LN as the plain kernel."""
+    img = rnd(B, 3, S, S, dtype=f32, seed=71) * 2 + 0.3
+    w = rnd(3 * S, dtype=f32, seed=72) + 1
+    y, tokens, mean, rstd = K.layernorm_fwd_image(img, w)
+    ref_tok = img.permute(0, 2, 3, 1).reshape(B, S, 3 * S)
+    assert torch.equal(tokens, ref_tok)
+    y2, mean2, rstd2 = K.layernorm_fwd(ref_tok.contiguous(), w)
+    assert rel(y, torch.nn.functional.layer_norm(ref_tok, (3 * S,), w, None, 1e-6)) < 4e-3
+    assert rel(y, y2) < 1e-3 and rel(mean, mean2) < 1e-5 and rel(rstd, rstd2) < 1e-5
+
+
 # ------------------------------------------------------------------------------------------------------ RoPE
 def _rope_ref(x, inv_freq):
     # x (B, h, S, d) fp32; NeoX rotate-half with learned inv_freq
@@ -292,7 +305,7 @@ def test_rope(K, B, S, h, dc, dr):
 # ------------------------------------------------------------------------------------------------------ attention
 @pytest.mark.parametrize("B,S,h,hd", [(2, 224, 12, 56), (2, 176, 12, 44), (3, 128, 12, 32), (2, 80, 12, 20), (2, 16, 12, 4),
                                        (5, 160, 12, 40), (3, 256, 4, 64),                 # tcgen05 / TMEM / TMA kernels (S <= 256, hd <= 64)
-                                       (1, 384, 12, 96), (2, 512, 12, 128), (1, 288, 12, 72), (2, 72, 12, 20), (2, 136, 4, 96)])   # mma.sync kernels
+                                       (1, 384, 12, 96), (2, 512, 12, 128), (1, 288, 12, 72), (2, 72, 12, 20), (2, 136, 4, 96), (1, 76, 3, 20)])   # mma.sync kernels
 def test_attention(K, B, S, h, hd):
     """The implementation is selected by the shape alone (no process-wide switch): tcgen05 kernels where eligible (S <= 256,
     S % 16 == 0, hd <= 64), the mma.sync kernels otherwise (what the 384^2 / 512^2 configs use; S = 72 / 136 exercise their
@@ -355,7 +368,7 @@ def test_latent(K, rows, Mh):
 
 
 # ------------------------------------------------------------------------------------------------------ CNN residual
-@pytest.mark.parametrize("B,S", [(2, 80), (1, 224), (3, 37), (2, 176), (5, 16), (1, 36)])
+@pytest.mark.parametrize("B,S", [(2, 80), (1, 224), (3, 37), (2, 176), (5, 16), (1, 36), (3, 128), (1, 384), (2, 112)])
 def test_cnn(K, B, S):
     """Fused CNN residual against fp32 conv2d. The kernels hold the hidden activations in fp16x2 (11-bit mantissa) and the
     hidden gradients in bf16 with fp32 accumulation; the reference's autocast path stores both in bf16 (8-bit mantissa). The

@@ -208,21 +208,48 @@ def test_seeded_noise_matches_oracle_rng_order(monkeypatch):
     assert rel(out2, out) > 1e-4                       # different seed -> different latent noise
 
 
-def test_interleaved_forward_is_refused():
+def test_second_forward_before_backward():
+    """Two training forwards (and an eval pass in between) before any backward — gradient accumulation with a deferred backward,
+    legal in the reference: the accumulated gradients equal those of the same two steps run one after the other."""
     import CALM_ViT_V2 as rvh
-    import calm_lib
     dev = torch.device("cuda:0")
     _, meta = load_fixture("small_cls")
     cfg = meta["config"]
     kw = {k: v for k, v in cfg.items() if k != "batch"}
-    model = rvh.ViT(dev, type=8, force_reduce=False, **kw).to(dev)
-    model.load_state_dict(synth.synth_state(meta["shapes"]))
-    x, _ = synth.synth_input(cfg)
-    x = x.to(dev)
-    out1, _ = model(x)
-    model(x)                                           # second forward before the first backward
-    with pytest.raises(calm_lib.CalmError):
-        out1.sum().backward()
+    state = synth.synth_state(meta["shapes"])
+    x1, _ = synth.synth_input(cfg)
+    x2, _ = synth.synth_input(cfg, seed=3)
+    x1, x2 = x1.to(dev), x2.to(dev)
+
+    def fresh():
+        m = rvh.ViT(dev, type=8, force_reduce=False, **kw).to(dev)
+        m.load_state_dict(state)
+        m.train()
+        return m
+
+    def fwd(m, x, seed):
+        torch.manual_seed(seed)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            out, kl = m(x)
+        return out.float().pow(2).mean() + 0.1 * kl
+    seq = fresh()
+    fwd(seq, x1, 0).backward()
+    fwd(seq, x2, 1).backward()
+    want = {k: p.grad.clone() for k, p in seq.named_parameters()}
+    model = fresh()
+    l1 = fwd(model, x1, 0)
+    model.eval()
+    with torch.no_grad():
+        model(x1)
+    model.train()
+    l2 = fwd(model, x2, 1)
+    l1.backward()
+    l2.backward()
+    torch.cuda.synchronize()
+    for k, p in model.named_parameters():
+        assert rel(p.grad, want[k]) < 1e-5, k
+    for (k, a), b in zip(model.state_dict().items(), seq.state_dict().values()):
+        assert torch.equal(a, b), k
 
 
 @pytest.mark.parametrize("B", [1, 3])
