@@ -556,8 +556,14 @@ extern "C" int32_t calm_attention_fwd(const void* q, const void* k, const void* 
   {
     const int64_t lds[3] = {ld_q, ld_k, ld_v};
     const void* ptrs[4] = {q, k, v, bias};
+#ifndef CALM_FORCE_LONG_ATTENTION     // tuning builds only: route every eligible shape through the chunked kernels
     if (calm_attention_tc_eligible(B, S, heads, hd, lds, 3, ptrs, 4))
+#else
+    if (false)
+#endif
       return calm_attention_fwd_tc(q, k, v, bias, o, lse, ld_q, ld_k, ld_v, ld_o, B, S, heads, hd, stream);
+    if (ld_o % 4 == 0 && calm_attention_long_eligible(B, S, heads, hd, lds, 3, ptrs, 4))
+      return calm_attention_fwd_long(q, k, v, bias, o, lse, ld_q, ld_k, ld_v, ld_o, B, S, heads, hd, stream);
   }
   DISPATCH_HDP(hd, return launch_fwd<HDP>(q, k, v, bias, o, lse, ld_q, ld_k, ld_v, ld_o, B, S, heads, hd, stream));
   return CALM_OK;
@@ -586,9 +592,17 @@ extern "C" int32_t calm_attention_bwd(const void* q, const void* k, const void* 
   {
     const int64_t lds[4] = {ld_q, ld_k, ld_v, ld_do};
     const void* ptrs[6] = {q, k, v, d_o, bias, dbias};
+#ifndef CALM_FORCE_LONG_ATTENTION
     if (ds_scratch && calm_attention_tc_eligible(B, S, heads, hd, lds, 4, ptrs, 6))
+#else
+    if (false)
+#endif
       return calm_attention_bwd_tc(q, k, v, bias, d_o, lse, delta, dq, dk, dv, dbias, ds_scratch, ld_q, ld_k, ld_v, ld_do, ld_dq, ld_dk,
                                    ld_dv, B, S, heads, hd, stream);
+    if (ds_scratch && ld_dq % 4 == 0 && ld_dk % 4 == 0 && ld_dv % 4 == 0 && (reinterpret_cast<uintptr_t>(ds_scratch) & 15) == 0 &&
+        calm_attention_long_eligible(B, S, heads, hd, lds, 4, ptrs, 6))
+      return calm_attention_bwd_long(q, k, v, bias, d_o, lse, delta, dq, dk, dv, dbias, ds_scratch, ld_q, ld_k, ld_v, ld_do, ld_dq, ld_dk,
+                                     ld_dv, B, S, heads, hd, stream);
   }
   DISPATCH_HDP(hd, return launch_bwd<HDP>(q, k, v, bias, d_o, lse, delta, dq, dk, dv, dbias, ds_scratch, ld_q, ld_k, ld_v, ld_do, ld_dq, ld_dk,
                                           ld_dv, B, S, heads, hd, stream));

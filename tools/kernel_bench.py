@@ -18,6 +18,10 @@ bf16, f32 = torch.bfloat16, torch.float32
 dev = torch.device("cuda:0")
 B = int(os.environ.get("KB_BATCH", 256))
 STAGES = [(224, 672, 56), (176, 528, 44), (128, 384, 32), (80, 240, 20)]
+if os.environ.get("KB_RES") == "384":    # BASELINE configs[3] stage shapes (per-GPU batch 64 / 32)
+    STAGES, B = [(384, 1152, 96), (336, 1008, 84), (288, 864, 72), (240, 720, 60)], int(os.environ.get("KB_BATCH", 64))
+elif os.environ.get("KB_RES") == "512":
+    STAGES, B = [(512, 1536, 128), (464, 1392, 116), (416, 1248, 104), (368, 1104, 92)], int(os.environ.get("KB_BATCH", 32))
 if os.environ.get("KB_STAGES"):     # e.g. KB_STAGES=224 for an ncu capture of one shape
     STAGES = [s for s in STAGES if str(s[0]) in os.environ["KB_STAGES"].split(",")]
 PEAK_TF = 1358.9
