@@ -14,7 +14,7 @@ from calm_lib import BF16, F32, MAJOR_K, MAJOR_MN, EPI_NONE, EPI_GELU, EPI_DGELU
 
 bf16 = torch.bfloat16
 f32 = torch.float32
-SN_ITEM_WEIGHTS = int(os.environ.get("CALM_SN_ITEM_WEIGHTS", "4096"))   # tuning hook: work-item size of the spectral-norm kernels
+SN_ITEM_WEIGHTS = int(os.environ.get("CALM_SN_ITEM_WEIGHTS", "0"))   # tuning hook: work-item size of the spectral-norm kernels (0 = by table size)
 
 
 def _dt(t):
@@ -271,10 +271,15 @@ class SnTable:
         n = len(entries)
         arr = (L.SnLayer * n)()
         items = []
+        # ~4 K weights per item at the 224^2 scopes (5 M weights: ~1.2 k CTAs; same-box sweep 16 K 59.3, 8 K 59.1, 4 K 58.9 ms/step); the
+        # 384^2 / 512^2 scopes (20 - 45 M weights) take proportionally larger items: the per-layer reduction of the partials
+        # (one CTA per layer) grows with the item count, not with the weights
+        total = sum(e["rows"] * e["cols"] for e in entries)
+        item_weights = SN_ITEM_WEIGHTS or max(4096, min(65536, total // 1184))
         self.keep = [entries]
         for i, e in enumerate(entries):
             rows, cols = e["rows"], e["cols"]
-            chunk = max(4, min(rows, -(-SN_ITEM_WEIGHTS // cols)))  # ~4 K weights per item: ~3 k CTAs per scope (same-box sweep: 16 K 59.3, 8 K 59.1, 4 K 58.9 ms/step)
+            chunk = max(4, min(rows, -(-item_weights // cols)))
             nit = -(-rows // chunk)
             for j in range(nit):
                 items.append((i, j * chunk, min(rows, (j + 1) * chunk), j))

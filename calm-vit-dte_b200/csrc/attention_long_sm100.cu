@@ -211,27 +211,32 @@ attn_fwd_long_kernel(const __grid_constant__ CUtensorMap mQ, const __grid_consta
         mbar_wait(BAR(2 + s), ph_full[s], p.err_flag, 72); ph_full[s] ^= 1;      // the bias chunk landed (with K / V)
         mbar_wait(BAR(4 + s), ph_sready[s], p.err_flag, 73); ph_sready[s] ^= 1;
         fence_after();
+        // both 16-key pieces of this thread are requested from TMEM before the first wait (one exposed TMEM latency per step, not two)
+        uint32_t sr[2][16];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const int kl = (LGROUPS * j + grp) * 16;
+          if (kl < nk) tmem_ld16(trow + 128u * s + kl, sr[j]);
+        }
+        tmem_ld_wait();
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
           const int kl = (LGROUPS * j + grp) * 16;
           if (kl < nk) {
-            uint32_t sr[16];
-            tmem_ld16(trow + 128u * s + kl, sr);
             uint8_t* ba = st + ST_B + (kl >> 6) * ATOM;
             const int g8 = (kl & 63) >> 3;
             uint4* p0 = reinterpret_cast<uint4*>(ba + swz128(r, g8));
             uint4* p1 = reinterpret_cast<uint4*>(ba + swz128(r, g8 + 1));
             float bf[16];
             unpack16(*p0, *p1, bf);
-            tmem_ld_wait();
             if (!pass_b) {
 #pragma unroll
-              for (int e = 0; e < 16; ++e) m = fmaxf(m, fmaf(__uint_as_float(sr[e]), p.scale_log2, bf[e] * LOG2E));
+              for (int e = 0; e < 16; ++e) m = fmaxf(m, fmaf(__uint_as_float(sr[j][e]), p.scale_log2, bf[e] * LOG2E));
             } else {
               float pv[16];
 #pragma unroll
               for (int e = 0; e < 16; ++e) {
-                pv[e] = ex2_approx(fmaf(__uint_as_float(sr[e]), p.scale_log2, fmaf(bf[e], LOG2E, -m)));
+                pv[e] = ex2_approx(fmaf(__uint_as_float(sr[j][e]), p.scale_log2, fmaf(bf[e], LOG2E, -m)));
                 l += pv[e];
               }
               *p0 = pack8f(pv);                                   // P overwrites the bias it was computed from

@@ -199,29 +199,40 @@ ln_bwd_kernel(const void* __restrict__ dy, const float* __restrict__ x, const fl
   }
 }
 
-// Register-resident variant for D <= 128*VPL: each row is read ONCE (x, dy stay in registers between the statistics and
+// Register-resident variant for D <= 128 * VPL * WPR: each row is read ONCE (x, dy stay in registers between the statistics and
 // the output pass), a lane owns fixed columns so the dw accumulators live in registers too (no shared-memory
-// read-modify-write per element); shared memory is only used to combine the 8 warps of a CTA at the very end.
-template <int VPL, bool DY_F32>
+// read-modify-write per element); shared memory is only used to combine the warps of a CTA at the very end.
+// WPR = warps per row: 1 for D <= 768; 2 for the wide rows of the 384^2 / 512^2 configs (D up to 1536), where one warp per row
+// needed VPL = 12 (245 registers, one 8-warp CTA per SM, the residual-gradient load after the row reduction): 0.24 of the HBM rate.
+template <int VPL, bool DY_F32, int WPR>
 __global__ void __launch_bounds__(LN_THREADS, VPL <= 3 ? 3 : VPL <= 6 ? 2 : 1)
 ln_bwd_reg_kernel(const void* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ w,
                   const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ dres,
                   float* __restrict__ dx, bf16* __restrict__ dx16, float* __restrict__ dw_partial, long long rows, int D) {
-  extern __shared__ float acc_s[];  // LN_WARPS * D, then D floats of w
+  extern __shared__ float acc_s[];  // (LN_WARPS / WPR) * D, then D floats of w
+  __shared__ float pair_red[2][LN_WARPS];
+  constexpr int RPC = LN_WARPS / WPR;      // rows per CTA iteration
+  constexpr int LANES = 32 * WPR;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int sub = warp % WPR, slot = warp / WPR;
+  const int l = sub * 32 + lane;           // lane index within the row
   const int nv = D >> 2;
   // w is read from shared memory at every use: keeping it in registers next to x-hat, dy and the dw accumulators costs
   // 128-138 registers per thread = one 8-warp CTA per SM, too few loads in flight for the HBM (44 % of peak at D = 672)
-  float* w_s = acc_s + (size_t)LN_WARPS * D;
+  float* w_s = acc_s + (size_t)RPC * D;
   for (int i = threadIdx.x; i < D; i += LN_THREADS) w_s[i] = w[i];
   __syncthreads();
-  const float4* wv = reinterpret_cast<const float4*>(w_s) + lane;
+  const float4* wv = reinterpret_cast<const float4*>(w_s) + l;
   float4 dwa[VPL];
 #pragma unroll
   for (int i = 0; i < VPL; ++i) dwa[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   const float invD = 1.0f / D;
-  for (long long row = (long long)blockIdx.x * LN_WARPS + warp; row < rows; row += (long long)gridDim.x * LN_WARPS) {
-    const float mu = mean[row], rs = rstd[row];
+  // WPR > 1: the CTA walks the rows in lock step (the two warps of a row meet on __syncthreads), so the trip count is uniform
+  for (long long base = (long long)blockIdx.x * RPC; base < rows; base += (long long)gridDim.x * RPC) {
+    const long long row = base + slot;
+    const bool active = row < rows;
+    if (WPR == 1 && !active) break;
+    const float mu = active ? mean[row] : 0.f, rs = active ? rstd[row] : 0.f;
     float4 hv[VPL], dv[VPL];
     // the residual-stream gradient is requested together with x and dy (VPL <= 6: it fits the register budget of 2 CTAs / SM):
     // loaded after the row reduction it put one full HBM latency per row on the critical path of a warp (0.45 of the copy rate)
@@ -230,15 +241,15 @@ ln_bwd_reg_kernel(const void* __restrict__ dy, const float* __restrict__ x, cons
     if (EARLY && dres) {
 #pragma unroll
       for (int i = 0; i < VPL; ++i) {
-        const int idx = lane + 32 * i;
-        rv[EARLY ? i : 0] = idx < nv ? __ldcs(reinterpret_cast<const float4*>(dres + row * D) + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const int idx = l + LANES * i;
+        rv[EARLY ? i : 0] = (active && idx < nv) ? __ldcs(reinterpret_cast<const float4*>(dres + row * D) + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
     }
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int i = 0; i < VPL; ++i) {
-      const int idx = lane + 32 * i;
-      if (idx < nv) {
+      const int idx = l + LANES * i;
+      if (active && idx < nv) {
         const float4 xv = reinterpret_cast<const float4*>(x + row * D)[idx];
         dv[i] = load_dy4<DY_F32>(dy, row, D, idx);
         hv[i] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
@@ -246,19 +257,28 @@ ln_bwd_reg_kernel(const void* __restrict__ dy, const float* __restrict__ x, cons
         dv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         hv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
       }
-      const float4 wq = idx < nv ? wv[32 * i] : make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4 wq = idx < nv ? wv[LANES * i] : make_float4(0.f, 0.f, 0.f, 0.f);
       const float g0 = dv[i].x * wq.x, g1 = dv[i].y * wq.y, g2 = dv[i].z * wq.z, g3 = dv[i].w * wq.w;
       s1 += g0 + g1 + g2 + g3;
       s2 += g0 * hv[i].x + g1 * hv[i].y + g2 * hv[i].z + g3 * hv[i].w;
       dwa[i].x = fmaf(dv[i].x, hv[i].x, dwa[i].x); dwa[i].y = fmaf(dv[i].y, hv[i].y, dwa[i].y);
       dwa[i].z = fmaf(dv[i].z, hv[i].z, dwa[i].z); dwa[i].w = fmaf(dv[i].w, hv[i].w, dwa[i].w);
     }
-    const float c2 = warp_sum(s1) * invD, c1 = warp_sum(s2) * invD;
+    s1 = warp_sum(s1); s2 = warp_sum(s2);
+    if (WPR > 1) {                                   // combine the warps of the row (fixed order: deterministic)
+      if (lane == 0) { pair_red[0][warp] = s1; pair_red[1][warp] = s2; }
+      __syncthreads();
+      s1 = 0.f; s2 = 0.f;
+#pragma unroll
+      for (int k = 0; k < WPR; ++k) { s1 += pair_red[0][slot * WPR + k]; s2 += pair_red[1][slot * WPR + k]; }
+      __syncthreads();                               // the slots are rewritten in the next iteration
+    }
+    const float c2 = s1 * invD, c1 = s2 * invD;
 #pragma unroll
     for (int i = 0; i < VPL; ++i) {
-      const int idx = lane + 32 * i;
-      if (idx < nv) {
-        const float4 wq = wv[32 * i];
+      const int idx = l + LANES * i;
+      if (active && idx < nv) {
+        const float4 wq = wv[LANES * i];
         float4 o;
         o.x = rs * (dv[i].x * wq.x - c2 - hv[i].x * c1);
         o.y = rs * (dv[i].y * wq.y - c2 - hv[i].y * c1);
@@ -277,14 +297,14 @@ ln_bwd_reg_kernel(const void* __restrict__ dy, const float* __restrict__ x, cons
   }
 #pragma unroll
   for (int i = 0; i < VPL; ++i) {
-    const int idx = lane + 32 * i;
-    if (idx < nv) reinterpret_cast<float4*>(acc_s + (size_t)warp * D)[idx] = dwa[i];
+    const int idx = l + LANES * i;
+    if (idx < nv) reinterpret_cast<float4*>(acc_s + (size_t)slot * D)[idx] = dwa[i];
   }
   __syncthreads();
   for (int c = threadIdx.x; c < D; c += LN_THREADS) {
     float s = 0.f;
 #pragma unroll
-    for (int wv2 = 0; wv2 < LN_WARPS; ++wv2) s += acc_s[(size_t)wv2 * D + c];
+    for (int wv2 = 0; wv2 < RPC; ++wv2) s += acc_s[(size_t)wv2 * D + c];
     dw_partial[(size_t)blockIdx.x * D + c] = s;
   }
 }
@@ -361,9 +381,9 @@ extern "C" int32_t calm_layernorm_bwd(const void* dy, int32_t dy_dtype, const fl
     }                                                                                                                 \
     KERNEL<<<nparts, LN_THREADS, smem, stream>>>(dy, x, w, mean, rstd, dres, dx, reinterpret_cast<bf16*>(dx_bf16), dw_partial, rows, D);                  \
   } while (0)
-  if (vpl <= 3) { if (f32) LN_BWD_LAUNCH((ln_bwd_reg_kernel<3, true>)); else LN_BWD_LAUNCH((ln_bwd_reg_kernel<3, false>)); }
-  else if (vpl <= 6) { if (f32) LN_BWD_LAUNCH((ln_bwd_reg_kernel<6, true>)); else LN_BWD_LAUNCH((ln_bwd_reg_kernel<6, false>)); }
-  else if (vpl <= 12) { if (f32) LN_BWD_LAUNCH((ln_bwd_reg_kernel<12, true>)); else LN_BWD_LAUNCH((ln_bwd_reg_kernel<12, false>)); }
+  if (vpl <= 3) { if (f32) LN_BWD_LAUNCH((ln_bwd_reg_kernel<3, true, 1>)); else LN_BWD_LAUNCH((ln_bwd_reg_kernel<3, false, 1>)); }
+  else if (vpl <= 6) { if (f32) LN_BWD_LAUNCH((ln_bwd_reg_kernel<6, true, 1>)); else LN_BWD_LAUNCH((ln_bwd_reg_kernel<6, false, 1>)); }
+  else if (vpl <= 12) { if (f32) LN_BWD_LAUNCH((ln_bwd_reg_kernel<6, true, 2>)); else LN_BWD_LAUNCH((ln_bwd_reg_kernel<6, false, 2>)); }
   else { if (f32) LN_BWD_LAUNCH((ln_bwd_kernel<true>)); else LN_BWD_LAUNCH((ln_bwd_kernel<false>)); }
 #undef LN_BWD_LAUNCH
   CALM_CHECK_LAUNCH("calm_layernorm_bwd");

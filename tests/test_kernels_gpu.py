@@ -234,7 +234,7 @@ def test_gemm_rejects_bad_args(K):
 
 
 # ------------------------------------------------------------------------------------------------------ LayerNorm
-@pytest.mark.parametrize("rows,D", [(1000, 672), (333, 240), (4096, 528), (7, 48)])
+@pytest.mark.parametrize("rows,D", [(1000, 672), (333, 240), (4096, 528), (7, 48), (777, 1152), (1030, 1536), (64, 1008), (515, 864)])
 def test_layernorm(K, rows, D):
     x = rnd(rows, D, dtype=f32, seed=21) * 3 + 0.5
     w = rnd(D, dtype=f32, seed=22) + 1
