@@ -391,6 +391,7 @@ def main():
     ap.add_argument("--no-profile", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-reference-gpu", action="store_true")
+    ap.add_argument("--no-comm-split", action="store_true", help="N > 1: skip the second capture that times the step without all-reduces")
     ap.add_argument("--torch-glue", action="store_true", help="A/B: torch GradScaler/clip/AdamW/loss instead of calm_trainer")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
@@ -604,13 +605,43 @@ def main():
     if world > 1:
         line["buffers_in_sync"] = wrapped.check_buffers()
     tr.release()                               # destroy the captured graph (it references the NCCL communicator)
+    if world > 1 and use_graph and not args.no_comm_split:
+        # What the gradient exchange costs per step at this N: the same step captured again WITHOUT the all-reduces (every rank
+        # trains on alone for these few steps), timed the same way; the difference is the exposed communication plus what the
+        # NCCL kernels take from the compute they overlap with.
+        wrapped.require_sync = False
+        tr2 = Trainer(wrapped, task, dev, B, S, True, torch_glue=args.torch_glue)
+        tr2.x.copy_(tr.x)
+        if tr.y is not None:
+            tr2.y.copy_(tr.y)
+        del tr
+        torch.cuda.empty_cache()
+        tr2.capture()
+        for _ in range(3):
+            tr2.step()
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        for _ in range(args.steps):
+            tr2.step()
+        g1.record()
+        barrier()
+        t2 = torch.tensor([g0.elapsed_time(g1)], device=dev, dtype=torch.float64)
+        dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+        ms_alone = t2.item() / args.steps
+        tr2.release()
+        grad_bytes = 4 * sum(p.numel() for p in model.parameters())
+        line["comm"] = {"ms_per_step_without_allreduce": ms_alone, "allreduce_cost_ms_per_step": ms_step - ms_alone,
+                        "gradient_bytes_per_step": grad_bytes, "buckets": len(wrapped.buckets), "nccl_max_ctas": wrapped.comm_ctas or None,
+                        "note": "same captured step with calm_ddp's all-reduces switched off, same process, same timing; the difference "
+                                "is exposed communication + SM / HBM interference of the NCCL kernels"}
     if rank == 0:
         if breakdown is not None:
             os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
             json.dump(breakdown, open(os.path.join(ROOT, "gpurun_out", "bench_kernel_breakdown.json"), "w"), indent=1)
             json.dump(breakdown_shapes, open(os.path.join(ROOT, "gpurun_out", "bench_gemm_shapes.json"), "w"), indent=1)
         if world == 1 and not args.no_reference_gpu:
-            del tr, wrapped, model
+            tr = wrapped = model = None
             torch.cuda.empty_cache()
             line["reference_gpu_eager"] = reference_gpu_eager(dev, S, task, B)
             if "value" in line["reference_gpu_eager"]:

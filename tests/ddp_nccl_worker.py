@@ -83,11 +83,19 @@ def main():
     torch.cuda.synchronize()
     w_eager = compare(model, "eager")
     assert dp.check_buffers()
-    # ---- the same step captured into a CUDA graph together with its all-reduces
+    # ---- the same step captured into a CUDA graph together with its all-reduces. The captured step drops the gradients first
+    # (optimizer.zero_grad() of the loop): backward then allocates them from the graph's pool and DataParallel leaves every
+    # .grad aliasing its bucket slice, which each replay refills — so .grad must not be touched between capture and replay.
+    def graph_step():
+        for p in model.parameters():
+            p.grad = None
+        fwd_bwd(dp)
+
     reset(model, state)
-    graphed = calm_trainer.GraphedStep(lambda: fwd_bwd(dp), warmup=2, capture=True)
+    graphed = calm_trainer.GraphedStep(graph_step, warmup=2, capture=True)
     assert graphed.graph is not None
-    reset(model, state)
+    model.load_state_dict(state)
+    torch.manual_seed(1234 + rank)
     graphed()
     torch.cuda.synchronize()
     w_graph = compare(model, "graph")

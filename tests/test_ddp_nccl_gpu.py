@@ -26,5 +26,9 @@ def test_nccl_gradients_equal_mean_of_single_gpu_gradients():
            "--master-port", str(_free_port()), os.path.join(HERE, "ddp_nccl_worker.py")]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
     print(r.stdout[-4000:], r.stderr[-4000:])
+    out_dir = os.path.join(os.path.dirname(HERE), "gpurun_out")
+    if os.path.isdir(out_dir):
+        with open(os.path.join(out_dir, "ddp_nccl_worker.log"), "w") as f:
+            f.write(r.stdout + "\n--- stderr ---\n" + r.stderr)
     assert r.returncode == 0, r.stderr[-2000:]
     assert "DDP_NCCL_OK" in r.stdout
