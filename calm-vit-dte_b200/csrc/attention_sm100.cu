@@ -36,8 +36,12 @@ using namespace tc;
 // exactly one lane and needs no ELECT / R2UR.BROADCAST loop to feed the uniform-register operands of tcgen05.mma / TMA.
 #define leader (elect_one() != 0u)
 
-constexpr int NWORKERS = 256;            // 8 worker warps: warps w and w+4 share TMEM lane quadrant w%4 and split the columns
-constexpr int NTHREADS = NWORKERS + 32;  // + controller warp (warp 8)
+// backward: 16 worker warps, 4 per TMEM lane quadrant (warps w, w+4, w+8, w+12 share quadrant w%4): each takes one 16-column chunk
+// of every 64-key part. With 8 warps (2 per scheduler) the per-part chain TMEM load -> exp2 -> pack -> st.shared -> fence ran with
+// no other warp to hide its latencies: 2.2 us per part for 0.8 us of arithmetic (globaltimer trace, tools/attn_trace.py).
+constexpr int NWORKERS = 512;
+constexpr int NGROUPS = NWORKERS / 128;
+constexpr int NTHREADS = NWORKERS + 32;  // + controller warp
 constexpr int CTRL_WARP = NWORKERS / 32;
 // forward: 16 worker warps (4 per TMEM lane quadrant, each takes every 4th 16-column chunk): the two softmax passes are a serial
 // chain per thread, twice as many threads halve it
@@ -354,12 +358,16 @@ struct BwdParams {
 
 // trace[0] = event count, then (event id, globaltimer ns) pairs; id = role * 1000 + point * 10 + part
 __device__ __forceinline__ void trace_evt(const BwdParams& p, int id) {
+#ifndef CALM_BRINGUP
+  (void)p; (void)id;              // production builds carry no time-stamp code
+#else
   if (p.trace != nullptr && blockIdx.x == 0) {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     const unsigned long long i = atomicAdd(p.trace, 1ULL);
     if ((int)i < p.trace_cap) { p.trace[1 + 2 * i] = (unsigned long long)id; p.trace[2 + 2 * i] = t; }
   }
+#endif
 }
 
 constexpr int KPART = 64;  // key columns per S / dP part; two parts in flight (TMEM: 2 x (64 + 64) | dK 2 x 64 | dV 2 x 64)
@@ -551,23 +559,20 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap mQ, const __grid_constant
       if (lane == 0) bulk_wait0();
     }
   } else {
-    const int grp = warp >> 2;                    // 0: even 16-column chunks, 1: odd chunks
+    const int grp = warp >> 2;                    // 16-column chunk of every 64-key part this warp works on
     const int r = (warp & 3) * 32 + lane;         // row within the tile == TMEM lane
     const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16);
     uint32_t ph_kv = 0, ph_fin = 0, ph_sd[2] = {0, 0};
-    // bias row segment of a part: this thread's chunks (2 j + grp) * 16, j = 0, 1, of key columns [part * 64, part * 64 + 64)
-    uint4 bcur[4], bnxt[4];
+    // bias row segment of a part: this thread's chunk [grp * 16, grp * 16 + 16) of key columns [part * 64, part * 64 + 64)
+    uint4 bcur[2], bnxt[2];
     auto load_bias = [&](uint4* dst, int bb, int ii, int part) {
       const int qq = ii * 128 + r;
       const bf16* brow = c.bias + ((long long)bb * S + (qq < S ? qq : 0)) * S + part * KPART;
       const int w = min(KPART, S - part * KPART);
-#pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        const int cc = (2 * j + grp) * 16;
-        if (cc < w) {
-          dst[2 * j] = *reinterpret_cast<const uint4*>(brow + cc);
-          dst[2 * j + 1] = *reinterpret_cast<const uint4*>(brow + cc + 8);
-        }
+      const int cc = grp * 16;
+      if (cc < w) {
+        dst[0] = *reinterpret_cast<const uint4*>(brow + cc);
+        dst[1] = *reinterpret_cast<const uint4*>(brow + cc + 8);
       }
     };
     const int items = c.B * heads;
@@ -585,8 +590,10 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap mQ, const __grid_constant
             // S = Q K^T and dP = dO V^T then ignore the tails of Q and dO, and the tails only reach dQ / dK / dV columns nobody stores.
             mbar_wait(bar_kv, ph_kv, c.err_flag, 41); ph_kv ^= 1;
             if (threadIdx.x == 0) trace_evt(p, 2000);
-            uint8_t* tile = grp == 0 ? sK : sV;
-            for (int row = r; row < S; row += 128) zero_outside(tile, row, hc, hd);
+            if (grp < 2) {
+              uint8_t* tile = grp == 0 ? sK : sV;
+              for (int row = r; row < S; row += 128) zero_outside(tile, row, hc, hd);
+            }
             fence_proxy_async();
             mbar_arrive(bar_tile);
             if (threadIdx.x == 0) trace_evt(p, 2010);
@@ -613,9 +620,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap mQ, const __grid_constant
             mbar_wait(bar_sd0 + 8 * buf, ph_sd[buf], c.err_flag, 43); ph_sd[buf] ^= 1;
             fence_after();
             if (threadIdx.x == 0) trace_evt(p, 2030 + part);
-#pragma unroll
-            for (int j = 0; j < 2; ++j) {
-              const int cc = (2 * j + grp) * 16;
+            {
+              const int cc = grp * 16;
               if (cc < w) {
                 const int kc = k0 + cc;
                 uint32_t sr[16], dr[16];
@@ -623,7 +629,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap mQ, const __grid_constant
                 tmem_ld16(trow + T_SD + 128u * buf + 64 + cc, dr);
                 tmem_ld_wait();
                 float bf[16], pv[16], ds[16];
-                unpack16(bcur[2 * j], bcur[2 * j + 1], bf);
+                unpack16(bcur[0], bcur[1], bf);
 #pragma unroll
                 for (int e = 0; e < 16; ++e) {
                   const float pj = valid ? ex2_approx(fmaf(__uint_as_float(sr[e]), c.scale_log2, fmaf(bf[e], LOG2E, -lse2))) : 0.f;
@@ -639,8 +645,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap mQ, const __grid_constant
             fence_before();
             mbar_arrive(bar_free0 + 8 * buf);
             if (threadIdx.x == 0) trace_evt(p, 2050 + part);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) bcur[e] = bnxt[e];
+            bcur[0] = bnxt[0]; bcur[1] = bnxt[1];
           }
           mbar_wait(bar_fin, ph_fin, c.err_flag, 44); ph_fin ^= 1;
           fence_after();
@@ -649,20 +654,20 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap mQ, const __grid_constant
           // dS store) -> coalesced rows. After the head's last tile the same for dK_t (atoms t) and dV_t (atoms 2 + t).
           {
             const int quad = warp & 3;
-            const int row_begin = quad * 32 + grp * 16;
+            const int row_begin = quad * 32 + grp * (32 / NGROUPS);    // each warp of the quadrant stores 32 / NGROUPS of its rows
             const long long g_end = (long long)b * S + S;
-            for (int c0 = grp * 16; c0 < hdp; c0 += 32) {
+            for (int c0 = grp * 16; c0 < hdp; c0 += 16 * NGROUPS) {
               uint32_t v[16];
               tmem_ld16(trow + T_DQ + c0, v);
               tmem_ld_wait();
               stage_cols16(sP, r, v, c0, c.scale);
             }
-            quad_sync(quad);
-            store_rows16(sP, p.dq + (long long)h * hd, p.ld_dq, row_begin, (long long)b * S + i * 128, g_end, hc, hd, lane);
+            quad_sync128(quad);
+            store_rows16<32 / NGROUPS>(sP, p.dq + (long long)h * hd, p.ld_dq, row_begin, (long long)b * S + i * 128, g_end, hc, hd, lane);
             if (i == ntiles - 1) {
-              quad_sync(quad);                                   // atom 0 is reused
+              quad_sync128(quad);                                // atom 0 is reused
               for (int t = 0; t < ntiles; ++t) {                 // TMEM lanes are key rows of M-tile t
-                for (int c0 = grp * 16; c0 < hdp; c0 += 32) {
+                for (int c0 = grp * 16; c0 < hdp; c0 += 16 * NGROUPS) {
                   uint32_t kk[16], vv[16];
                   tmem_ld16(trow + T_DK + 64 * t + c0, kk);
                   tmem_ld16(trow + T_DV + 64 * t + c0, vv);
@@ -671,13 +676,13 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap mQ, const __grid_constant
                   stage_cols16(sP + (2 + t) * 16384, r, vv, c0, 1.0f);
                 }
               }
-              quad_sync(quad);
+              quad_sync128(quad);
               for (int t = 0; t < ntiles; ++t) {
-                store_rows16(sP + t * 16384, p.dk + (long long)h * hd, p.ld_dk, row_begin, (long long)b * S + t * 128, g_end, hc, hd, lane);
-                store_rows16(sP + (2 + t) * 16384, p.dv + (long long)h * hd, p.ld_dv, row_begin, (long long)b * S + t * 128, g_end, hc, hd, lane);
+                store_rows16<32 / NGROUPS>(sP + t * 16384, p.dk + (long long)h * hd, p.ld_dk, row_begin, (long long)b * S + t * 128, g_end, hc, hd, lane);
+                store_rows16<32 / NGROUPS>(sP + (2 + t) * 16384, p.dv + (long long)h * hd, p.ld_dv, row_begin, (long long)b * S + t * 128, g_end, hc, hd, lane);
               }
             }
-            quad_sync(quad);   // the staging rows are rewritten (P of the next tile) by the partner warp
+            quad_sync128(quad);   // the staging rows are rewritten (P of the next tile) by the partner warps
           }
           fence_before();
           mbar_arrive(bar_tile);

@@ -5,6 +5,8 @@
 #include <cuda_fp16.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
 #include <atomic>
 
 #define CALM_OK 0
@@ -64,6 +66,39 @@ struct CalmDeviceOnce {
   bool pending() const { return !((mask.load(std::memory_order_acquire) >> (calm_current_device() & 63)) & 1ull); }
   void done() { mask.fetch_or(1ull << (calm_current_device() & 63), std::memory_order_release); }
 };
+
+// ---- programmatic dependent launch (PDL) ------------------------------------------------------------------------------------
+// A training step is ~1,200 short kernels in one stream; between two of them the GPU idles for the grid-completion -> next-launch
+// latency plus the next kernel's prologue (barrier init, TMEM allocation, descriptor prefetch). Kernels launched through
+// calm_launch_pdl carry cudaLaunchAttributeProgrammaticStreamSerialization: their CTAs may be scheduled while the predecessor
+// drains, run their prologue, and block in pdl_wait() until the predecessor has completed and its writes are visible.
+// RULE: a kernel launched this way executes pdl_wait() in every thread before its first global-memory access (read OR write).
+// Since every such kernel waits for its predecessor before finishing, completion stays transitive along the stream.
+// CALM_PDL=0 in the environment (read once at load) launches the same kernels without the attribute (A/B and fault isolation).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+inline bool calm_pdl_enabled() {
+  static const bool on = [] { const char* e = getenv("CALM_PDL"); return !(e && e[0] == '0'); }();
+  return on;
+}
+// extra = further launch attributes (e.g. the cluster dimension); n_extra <= 3
+template <typename... KArgs, typename... Args>
+inline cudaError_t calm_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                   const cudaLaunchAttribute* extra, int n_extra, Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute attr[4];
+  int n = 0;
+  for (int i = 0; i < n_extra && i < 3; ++i) attr[n++] = extra[i];
+  if (calm_pdl_enabled()) {
+    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  cfg.attrs = attr; cfg.numAttrs = (unsigned)n;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 
 typedef __nv_bfloat16 bf16;
 typedef __nv_bfloat162 bf162;

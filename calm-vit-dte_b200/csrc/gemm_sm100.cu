@@ -613,6 +613,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   __syncthreads();
   if (PAIR) cluster_sync_all();   // the peer's barriers exist before anything is multicast into this CTA
   tc_fence_after();
+  // everything above (barriers, TMEM, descriptor prefetch) overlapped the previous kernel's tail; its results are needed from here on
+  pdl_wait();
+  pdl_launch_dependents();
   const uint32_t tmem_base = *tmem_slot;
   const int crank = PAIR ? (int)(blockIdx.x & 1) : 0;
   const int w_first = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
@@ -926,24 +929,22 @@ int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& m
   if (pair) {
     const int max_clusters = calm_num_sms() / 2;
     const int clusters = p.total_pairs < max_clusters ? p.total_pairs : max_clusters;
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3(2 * clusters);
-    cfg.blockDim = dim3(NUM_THREADS);
-    cfg.dynamicSmemBytes = SMEM_BYTES;
-    cfg.stream = stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
-    cudaError_t e = pair == 2 ? cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<A_MN, B_MN, 2>, ma, mb, mbh, em.c, em.add, em.aux, p)
-                              : cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<A_MN, B_MN, 1>, ma, mb, mbh, em.c, em.add, em.aux, p);
+    cudaError_t e = pair == 2 ? calm_launch_pdl(gemm_tcgen05_kernel<A_MN, B_MN, 2>, dim3(2 * clusters), dim3(NUM_THREADS), SMEM_BYTES, stream, attr, 1,
+                                                ma, mb, mbh, em.c, em.add, em.aux, p)
+                              : calm_launch_pdl(gemm_tcgen05_kernel<A_MN, B_MN, 1>, dim3(2 * clusters), dim3(NUM_THREADS), SMEM_BYTES, stream, attr, 1,
+                                                ma, mb, mbh, em.c, em.add, em.aux, p);
     if (e != cudaSuccess) { calm_set_error("calm_gemm(tcgen05, cluster): launch failed: %s", cudaGetErrorString(e)); return CALM_ERR_CUDA; }
     return CALM_OK;
   }
   const int grid = p.total_tiles < calm_num_sms() ? p.total_tiles : calm_num_sms();
-  gemm_tcgen05_kernel<A_MN, B_MN, 0><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(ma, mb, mbh, em.c, em.add, em.aux, p);
-  CALM_CHECK_LAUNCH("calm_gemm(tcgen05)");
+  {
+    cudaError_t e = calm_launch_pdl(gemm_tcgen05_kernel<A_MN, B_MN, 0>, dim3(grid), dim3(NUM_THREADS), SMEM_BYTES, stream, nullptr, 0,
+                                    ma, mb, mbh, em.c, em.add, em.aux, p);
+    if (e != cudaSuccess) { calm_set_error("calm_gemm(tcgen05): launch failed: %s", cudaGetErrorString(e)); return CALM_ERR_CUDA; }
+  }
   return CALM_OK;
 }
 
