@@ -27,8 +27,10 @@ using namespace tc;
 
 constexpr int LW = 512;                  // worker threads: 4 column groups x 4 TMEM lane quadrants x 32 lanes
 constexpr int LGROUPS = 4;
-constexpr int LTHREADS = LW + 32;
+constexpr int LTHREADS = LW + 32;        // dQ / dK-dV kernels: workers + one controller warp
 constexpr int LCTRL = LW / 32;           // controller warp
+constexpr int LFWD_THREADS = LW + 96;    // forward: workers + loader, S-MMA and PV-MMA warps
+constexpr int LW_LOAD = LW / 32, LW_SMMA = LW_LOAD + 1, LW_PV = LW_LOAD + 2;
 constexpr int KC = 128;                  // keys per chunk
 constexpr int ATOM = 16384;              // [128 rows][64 bf16], 128-byte swizzle
 constexpr int ST_K = 0, ST_V = 2 * ATOM, ST_B = 4 * ATOM, STAGE_BYTES = 6 * ATOM;
@@ -45,6 +47,7 @@ struct LongParams {
   bf16* o; long long ld_o;
   float* lse;
   int* err_flag;
+  CalmTrace trace;
 };
 
 struct HeadCols { int col0, shift, hdp; };
@@ -69,7 +72,7 @@ __device__ __forceinline__ uint4 pack8f(const float* f) {
   return u;
 }
 
-__global__ void __launch_bounds__(LTHREADS, 1)
+__global__ void __launch_bounds__(LFWD_THREADS, 1)
 attn_fwd_long_kernel(const __grid_constant__ CUtensorMap mQ, const __grid_constant__ CUtensorMap mK, const __grid_constant__ CUtensorMap mV,
                      const __grid_constant__ CUtensorMap mB, const LongParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -78,7 +81,7 @@ attn_fwd_long_kernel(const __grid_constant__ CUtensorMap mQ, const __grid_consta
   uint8_t* sStage = sQ + Q_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sStage + 2 * STAGE_BYTES);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
-  // barriers: 0 q | 1 qz | 2,3 full | 4,5 sready | 6,7 sfree | 8,9 pready | 10,11 pvdone | 12 ofinal | 13 ofree
+  // barriers: 0 q | 1 qz | 2,3 full (V + bias) | 4,5 sready | 6,7 sfree | 8,9 pready | 10,11 pvdone | 12 ofinal | 13 ofree | 14,15 kfull (K)
   const uint32_t bar0 = smem_u32(&bars[0]);
   auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -90,10 +93,10 @@ attn_fwd_long_kernel(const __grid_constant__ CUtensorMap mQ, const __grid_consta
     for (int s = 0; s < 2; ++s) {
       mbar_init(BAR(2 + s), 1); mbar_init(BAR(4 + s), 1); mbar_init(BAR(6 + s), LW); mbar_init(BAR(8 + s), LW); mbar_init(BAR(10 + s), 1);
     }
-    mbar_init(BAR(12), 1); mbar_init(BAR(13), LW);
+    mbar_init(BAR(12), 1); mbar_init(BAR(13), LW); mbar_init(BAR(14), 1); mbar_init(BAR(15), 1);
     fence_barrier_init();
   }
-  if (warp == LCTRL) tmem_alloc(smem_u32(tmem_slot), L_TMEM_COLS);
+  if (warp == LW_LOAD) tmem_alloc(smem_u32(tmem_slot), L_TMEM_COLS);
   fence_before();
   __syncthreads();
   fence_after();
@@ -103,69 +106,78 @@ attn_fwd_long_kernel(const __grid_constant__ CUtensorMap mQ, const __grid_consta
   const int T = 2 * nch;                     // steps per item: pass A chunks, then pass B chunks
   const int items = p.B * heads * ntq;
 
-  if (warp == LCTRL) {
-    // ============================ controller: TMA + MMA issue (warp-uniform control flow, side effects under elect.sync) ============
-    uint32_t ph_q = 0, ph_qz = 0, ph_ofree = 0, ph_full[2] = {0, 0}, ph_sfree[2] = {0, 0}, ph_pready[2] = {0, 0}, ph_pvdone[2] = {0, 0};
-    int pend[2] = {0, 0};                    // stage's last user still to complete: 0 none, 1 pass-A step (pready), 2 pass-B step (pvdone)
-    int sused[2] = {0, 0};                   // TMEM S buffer has been used before (workers' sfree arrival to wait for)
+  // Three single-purpose control warps. One warp doing all of it made the CONTROL FLOW the critical path: its blocking waits
+  // (pready -> issue P V, pvdone -> issue loads, kfull / sfree -> issue S MMA) ran one after the other, so the next S MMA was
+  // only issued ~3.6 us after the previous one (globaltimer trace) while the tensor core needs 0.9 us per step.
+  //   loader : TMA loads. K of step t + 2 as soon as the S MMA of step t has retired (K is only read by the S MMA);
+  //            V + bias of step t + 2 when step t's stage is done (pass A: the workers read the bias; pass B: its P V retired)
+  //   S-MMA  : S_t = Q K_t^T into TMEM buffer t & 1 as soon as K_t landed and the workers drained the buffer (step t - 2)
+  //   PV-MMA : O += P_t V_t as soon as the workers wrote P_t
+  // A barrier used once per step on a stage completes its j-th phase in the stage's j-th use: parity j & 1.
+  if (warp == LW_LOAD) {
+    uint32_t nk[2] = {0, 0};                 // K loads issued per stage == uses of the stage started
+    uint32_t nvb[2] = {0, 0};                // V / bias loads issued per stage
+    uint32_t npv[2] = {0, 0};                // pass-B uses per stage (pvdone phases)
+    int pend[2] = {0, 0};                    // the stage's previous use: 0 none, 1 pass A (wait pready), 2 pass B (wait pvdone)
+    uint32_t ph_ofree = 0;
     bool first_item = true;
-    const uint64_t dQ = smem_desc(smem_u32(sQ), 16, 1024);
     for (int it = blockIdx.x; it < items; it += gridDim.x) {
       const int i = it % ntq, bh = it / ntq;
       const int h = bh % heads, b = bh / heads;
       const HeadCols hc = head_cols(h, hd);
       const int na = (hc.shift + hd + 63) >> 6;                  // 64-column atoms of the head
-      const int nks = hc.hdp >> 4;                               // MMA k-steps over the head dim
-      const uint32_t id_o = idesc_bf16(128, hc.hdp, 0, 1);       // O = P V : A K-major, B (V: keys x hd) MN-major
-      auto stage_free = [&](int s) {
-        if (pend[s] == 1) { mbar_wait(BAR(8 + s), ph_pready[s], p.err_flag, 61); ph_pready[s] ^= 1; }
-        else if (pend[s] == 2) { mbar_wait(BAR(10 + s), ph_pvdone[s], p.err_flag, 62); ph_pvdone[s] ^= 1; }
-        pend[s] = 0;
-      };
-      auto issue_loads = [&](int t) {
+      auto load_k = [&](int t) {
         const int s = t & 1, c = t % nch;
-        const bool pass_b = t >= nch;
+        if (nk[s]) mbar_wait(BAR(4 + s), (nk[s] - 1) & 1, p.err_flag, 60);          // the S MMA of the stage's previous use retired
         uint8_t* st = sStage + s * STAGE_BYTES;
         if (leader) {
-          mbar_expect_tx(BAR(2 + s), (uint32_t)((pass_b ? 2 : 1) * na + 2) * ATOM);
-          for (int a = 0; a < na; ++a) tma_load_2d(smem_u32(st + ST_K + a * ATOM), &mK, BAR(2 + s), hc.col0 + 64 * a, b * S + c * KC);
+          mbar_expect_tx(BAR(14 + s), (uint32_t)na * ATOM);
+          for (int a = 0; a < na; ++a) tma_load_2d(smem_u32(st + ST_K + a * ATOM), &mK, BAR(14 + s), hc.col0 + 64 * a, b * S + c * KC);
+        }
+        ++nk[s];
+      };
+      auto load_vb = [&](int t) {                                // V (pass B) and the bias chunk
+        const int s = t & 1, c = t % nch;
+        const bool pass_b = t >= nch;
+        if (pend[s] == 1) mbar_wait(BAR(8 + s), (nvb[s] - 1) & 1, p.err_flag, 61);  // workers done with the previous use's bias
+        else if (pend[s] == 2) mbar_wait(BAR(10 + s), (npv[s] - 1) & 1, p.err_flag, 62);   // its P V retired (P and V free)
+        uint8_t* st = sStage + s * STAGE_BYTES;
+        if (leader) {
+          mbar_expect_tx(BAR(2 + s), (uint32_t)((pass_b ? na : 0) + 2) * ATOM);
           if (pass_b)
             for (int a = 0; a < na; ++a) tma_load_2d(smem_u32(st + ST_V + a * ATOM), &mV, BAR(2 + s), hc.col0 + 64 * a, b * S + c * KC);
           for (int a = 0; a < 2; ++a) tma_load_2d(smem_u32(st + ST_B + a * ATOM), &mB, BAR(2 + s), c * KC + 64 * a, b * S + i * 128);
         }
+        ++nvb[s];
+        pend[s] = pass_b ? 2 : 1;
+        if (pass_b) ++npv[s];
       };
-      auto issue_pv = [&](int t) {                               // O (+)= P_c V_c over the valid keys of chunk c
-        const int s = t & 1, c = t % nch;
-        const int nk16 = min(KC, S - c * KC) >> 4;
-        mbar_wait(BAR(8 + s), ph_pready[s], p.err_flag, 63); ph_pready[s] ^= 1;
-        fence_after();
-        const uint64_t dP = smem_desc(smem_u32(sStage + s * STAGE_BYTES + ST_B), 16, 1024);
-        const uint64_t dVmn = smem_desc(smem_u32(sStage + s * STAGE_BYTES + ST_V), ATOM, 1024);
-        if (leader) {
-          for (int kk = 0; kk < nk16; ++kk)
-            mma_bf16(tmem + T_O, dP + (uint32_t)((kk >> 2) * (ATOM >> 4) + 2 * (kk & 3)), dVmn + (uint32_t)(kk * 128), id_o, (c | kk) != 0);
-          commit(BAR(10 + s));
-        }
-        pend[s] = 2;
-      };
-      // the stage loads of the first two steps do not depend on Q / O: they go out before the previous item's epilogue is awaited
-      stage_free(0); issue_loads(0);
-      stage_free(1); issue_loads(1);
+      // the loads of the first two steps do not depend on Q / O: they go out before the previous item's epilogue is awaited
+      load_k(0); load_k(1);
+      load_vb(0); load_vb(1);
       if (!first_item) { mbar_wait(BAR(13), ph_ofree, p.err_flag, 64); ph_ofree ^= 1; }   // O read out, Q (the epilogue's staging) free
       first_item = false;
       if (leader) {
         mbar_expect_tx(BAR(0), (uint32_t)na * ATOM);
         for (int a = 0; a < na; ++a) tma_load_2d(smem_u32(sQ + a * ATOM), &mQ, BAR(0), hc.col0 + 64 * a, b * S + i * 128);
       }
+      for (int t = 0; t + 2 < T; ++t) { load_vb(t + 2); load_k(t + 2); }
+    }
+  } else if (warp == LW_SMMA) {
+    uint32_t ph_q = 0, ph_qz = 0, nuse[2] = {0, 0};
+    const uint64_t dQ = smem_desc(smem_u32(sQ), 16, 1024);
+    for (int it = blockIdx.x; it < items; it += gridDim.x) {
+      const int h = (it / ntq) % heads;
+      const HeadCols hc = head_cols(h, hd);
+      const int nks = hc.hdp >> 4;                               // MMA k-steps over the head dim
       mbar_wait(BAR(0), ph_q, p.err_flag, 65); ph_q ^= 1;
       mbar_wait(BAR(1), ph_qz, p.err_flag, 66); ph_qz ^= 1;        // the workers zeroed the neighbouring heads' columns of Q
-      fence_after();
       for (int t = 0; t < T; ++t) {
         const int s = t & 1, c = t % nch;
         const int nk = min(KC, S - c * KC);
-        mbar_wait(BAR(2 + s), ph_full[s], p.err_flag, 67); ph_full[s] ^= 1;
-        if (sused[s]) { mbar_wait(BAR(6 + s), ph_sfree[s], p.err_flag, 68); ph_sfree[s] ^= 1; }
-        sused[s] = 1;
+        mbar_wait(BAR(14 + s), nuse[s] & 1, p.err_flag, 67);                         // K_t landed
+        if (nuse[s]) mbar_wait(BAR(6 + s), (nuse[s] - 1) & 1, p.err_flag, 68);       // the workers read S of the buffer's previous use
+        ++nuse[s];
         fence_after();
         const uint64_t dK = smem_desc(smem_u32(sStage + s * STAGE_BYTES + ST_K), 16, 1024);
         const uint32_t id_s = idesc_bf16(128, nk, 0, 0);
@@ -176,12 +188,35 @@ attn_fwd_long_kernel(const __grid_constant__ CUtensorMap mQ, const __grid_consta
           }
           commit(BAR(4 + s));
         }
-        if (t < nch) pend[s] = 1;
-        if (t >= 1 && t - 1 >= nch) issue_pv(t - 1);              // the previous step's P V runs after this step's S MMA was queued
-        if (t + 1 < T && t >= 1) { stage_free((t + 1) & 1); issue_loads(t + 1); }
+        if (leader) calm_trace(p.trace, 1200 + t);                 // S MMA queued
       }
-      issue_pv(T - 1);
-      if (leader) commit(BAR(12));                                // every MMA of the item has retired: O is final
+    }
+  } else if (warp == LW_PV) {
+    uint32_t nuse[2] = {0, 0};               // uses of the stage seen
+    for (int it = blockIdx.x; it < items; it += gridDim.x) {
+      const int h = (it / ntq) % heads;
+      const HeadCols hc = head_cols(h, hd);
+      const uint32_t id_o = idesc_bf16(128, hc.hdp, 0, 1);       // O = P V : A K-major, B (V: keys x hd) MN-major
+      for (int t = 0; t < T; ++t) {
+        const int s = t & 1, c = t % nch;
+        const uint32_t j = nuse[s]++;
+        // every phase is awaited in order, pass A included: a parity wait only tells the current phase from the one before it, a
+        // warp that skipped ahead by two phases would read "complete" from the wrong one
+        mbar_wait(BAR(8 + s), j & 1, p.err_flag, 63);                                // the workers finished step t (pass B: wrote P_t)
+        if (t < nch) continue;
+        const int nk16 = min(KC, S - c * KC) >> 4;
+        mbar_wait(BAR(2 + s), j & 1, p.err_flag, 69);                                // V_t landed (the workers waited for the same phase)
+        fence_after();
+        const uint64_t dP = smem_desc(smem_u32(sStage + s * STAGE_BYTES + ST_B), 16, 1024);
+        const uint64_t dVmn = smem_desc(smem_u32(sStage + s * STAGE_BYTES + ST_V), ATOM, 1024);
+        if (leader) {
+          for (int kk = 0; kk < nk16; ++kk)
+            mma_bf16(tmem + T_O, dP + (uint32_t)((kk >> 2) * (ATOM >> 4) + 2 * (kk & 3)), dVmn + (uint32_t)(kk * 128), id_o, (c | kk) != 0);
+          commit(BAR(10 + s));
+        }
+        if (leader) calm_trace(p.trace, 1300 + t);                 // P V queued
+      }
+      if (leader) commit(BAR(12));                                // every P V of the item has retired: O is final
     }
   } else {
     // ============================ workers ============================
@@ -208,9 +243,12 @@ attn_fwd_long_kernel(const __grid_constant__ CUtensorMap mQ, const __grid_consta
         const bool pass_b = t >= nch;
         const int nk = min(KC, S - c * KC);
         uint8_t* st = sStage + s * STAGE_BYTES;
-        mbar_wait(BAR(2 + s), ph_full[s], p.err_flag, 72); ph_full[s] ^= 1;      // the bias chunk landed (with K / V)
+        if (threadIdx.x == 0) calm_trace(p.trace, 2000 + t);
+        mbar_wait(BAR(2 + s), ph_full[s], p.err_flag, 72); ph_full[s] ^= 1;      // the bias chunk (and V) landed
+        if (threadIdx.x == 0) calm_trace(p.trace, 2100 + t);
         mbar_wait(BAR(4 + s), ph_sready[s], p.err_flag, 73); ph_sready[s] ^= 1;
         fence_after();
+        if (threadIdx.x == 0) calm_trace(p.trace, 2200 + t);
         // both 16-key pieces of this thread are requested from TMEM before the first wait (one exposed TMEM latency per step, not two)
         uint32_t sr[2][16];
 #pragma unroll
@@ -245,9 +283,11 @@ attn_fwd_long_kernel(const __grid_constant__ CUtensorMap mQ, const __grid_consta
           }
         }
         if (c == nch - 1) {
-          // the four column groups of a row combine their partial max (pass A) / sum (pass B) through the K region of this stage
-          // (consumed: the S MMA of this step has retired, the stage is not reloaded before the arrivals below)
-          float* xchg = reinterpret_cast<float*>(st + ST_K);
+          // the four column groups of a row combine their partial max (pass A) / sum (pass B) through shared memory.
+          // pass A: the V region of the stage (no V is loaded into it before the pready arrivals below); pass B (the item's last
+          // step): the Q tile — every S MMA of the item has retired (this step's sready) and the next Q is only loaded after the
+          // epilogue below. (Not the K region: the loader refills it as soon as the step's S MMA has retired.)
+          float* xchg = reinterpret_cast<float*>(pass_b ? sQ : st + ST_V);
           xchg[grp * 128 + r] = pass_b ? l : m;
           asm volatile("bar.sync 1, %0;" ::"n"(LW) : "memory");
           if (!pass_b) {
@@ -260,14 +300,17 @@ attn_fwd_long_kernel(const __grid_constant__ CUtensorMap mQ, const __grid_consta
           }
           asm volatile("bar.sync 1, %0;" ::"n"(LW) : "memory");               // nobody overwrites the slots before everyone has read
         }
+        if (threadIdx.x == 0) calm_trace(p.trace, 2300 + t);
         if (pass_b) fence_proxy_async();
         fence_before();
         mbar_arrive(BAR(6 + s));
         mbar_arrive(BAR(8 + s));
       }
       // ---- epilogue: O / l -> bf16 rows through the (consumed) Q atoms, lanes along the rows
+      if (threadIdx.x == 0) calm_trace(p.trace, 2500);
       mbar_wait(BAR(12), ph_ofinal, p.err_flag, 74); ph_ofinal ^= 1;
       fence_after();
+      if (threadIdx.x == 0) calm_trace(p.trace, 2600);
       const float inv = 1.0f / l;
       for (int c0 = grp * 16; c0 < hc.hdp; c0 += 16 * LGROUPS) {
         uint32_t orr[16];
@@ -303,7 +346,7 @@ attn_fwd_long_kernel(const __grid_constant__ CUtensorMap mQ, const __grid_consta
   }
   fence_before();
   __syncthreads();
-  if (warp == LCTRL) {
+  if (warp == LW_LOAD) {
     fence_after();
     tmem_dealloc(tmem, L_TMEM_COLS);
   }
@@ -328,6 +371,7 @@ int calm_attention_fwd_long(const void* q, const void* k, const void* v, const v
   p.scale_log2 = LOG2E / sqrtf((float)hd);
   p.o = reinterpret_cast<bf16*>(o); p.ld_o = ld_o; p.lse = lse;
   p.err_flag = g_calm_err_flag;
+  p.trace = calm_trace_target();
   CUtensorMap mQ, mK, mV, mB;
   int rc;
   const uint64_t rows = (uint64_t)B * S, cols = (uint64_t)heads * hd;
@@ -343,7 +387,7 @@ int calm_attention_fwd_long(const void* q, const void* k, const void* v, const v
   }
   const int items = B * heads * ((S + 127) / 128);
   const int grid = items < calm_num_sms() ? items : calm_num_sms();
-  attn_fwd_long_kernel<<<grid, LTHREADS, LONG_FWD_SMEM, stream>>>(mQ, mK, mV, mB, p);
+  attn_fwd_long_kernel<<<grid, LFWD_THREADS, LONG_FWD_SMEM, stream>>>(mQ, mK, mV, mB, p);
   CALM_CHECK_LAUNCH("calm_attention_fwd(long)");
   return CALM_OK;
 }
@@ -362,7 +406,9 @@ namespace {
 constexpr int KC2 = 64;                       // keys per step of the dQ kernel
 constexpr int ATOM_H = 8192;                  // [64 rows][64 bf16]
 constexpr int DQ_ST_K = 0, DQ_ST_V = 2 * ATOM_H, DQ_ST_B = 4 * ATOM_H, DQ_STAGE = 4 * ATOM_H + ATOM;   // K | V | bias -> dS
-constexpr size_t LONG_DQ_SMEM = 2 * Q_BYTES + 2 * DQ_STAGE + 256 + 1024;
+constexpr int DQ_NS = 3;                      // shared-memory stages of the dQ kernel (the S | dP buffers in TMEM stay two)
+constexpr int LDQ_THREADS = LW + 96;          // workers + loader, S / dP MMA and dQ MMA warps
+constexpr size_t LONG_DQ_SMEM = 2 * Q_BYTES + DQ_NS * DQ_STAGE + 256 + 1024;
 
 struct LongBwdParams {
   int B, S, heads, hd;
@@ -402,7 +448,7 @@ __device__ __forceinline__ void stage_tmem_rows(uint8_t* stg, uint32_t taddr, in
   }
 }
 
-__global__ void __launch_bounds__(LTHREADS, 1)
+__global__ void __launch_bounds__(LDQ_THREADS, 1)
 attn_bwd_long_dq_kernel(const __grid_constant__ CUtensorMap mQ, const __grid_constant__ CUtensorMap mK, const __grid_constant__ CUtensorMap mV,
                         const __grid_constant__ CUtensorMap mDO, const __grid_constant__ CUtensorMap mB, const LongBwdParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -410,23 +456,26 @@ attn_bwd_long_dq_kernel(const __grid_constant__ CUtensorMap mQ, const __grid_con
   uint8_t* sQ = smem;
   uint8_t* sDO = sQ + Q_BYTES;
   uint8_t* sStage = sDO + Q_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sStage + 2 * DQ_STAGE);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
-  // barriers: 0 q (Q + dO) | 1 qz | 2,3 full | 4,5 sready | 6,7 sfree | 8,9 dsready | 10,11 dqdone | 12 final | 13 ofree
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sStage + DQ_NS * DQ_STAGE);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
+  // Steps are numbered g = 0, 1, 2, ... over the whole life of the CTA (all its items): the shared-memory stage (K | V | bias -> dS)
+  // of a step is g % DQ_NS, its TMEM buffer (S | dP) is g & 1. A barrier completes one phase per use of its stage / buffer, so the
+  // phase of step g has parity (g / DQ_NS) & 1 resp. (g >> 1) & 1; every role awaits every phase of the barriers it uses, in order.
+  // barriers: 0 q (Q + dO) | 1 qz | 2.. full[NS] | 5,6 sready | 7,8 sfree | 9.. dsready[NS] | 12.. dqdone[NS] | 15 final | 16 ofree
   const uint32_t bar0 = smem_u32(&bars[0]);
   auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
+  constexpr int B_FULL = 2, B_SREADY = 5, B_SFREE = 7, B_DS = 9, B_DQ = 12, B_FINAL = 15, B_OFREE = 16;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int S = p.S, hd = p.hd, heads = p.heads;
   if (threadIdx.x == LW) {
     prefetch_tensormap(&mQ); prefetch_tensormap(&mK); prefetch_tensormap(&mV); prefetch_tensormap(&mDO); prefetch_tensormap(&mB);
     mbar_init(BAR(0), 1); mbar_init(BAR(1), LW);
-    for (int s = 0; s < 2; ++s) {
-      mbar_init(BAR(2 + s), 1); mbar_init(BAR(4 + s), 1); mbar_init(BAR(6 + s), LW); mbar_init(BAR(8 + s), LW); mbar_init(BAR(10 + s), 1);
-    }
-    mbar_init(BAR(12), 1); mbar_init(BAR(13), LW);
+    for (int s = 0; s < DQ_NS; ++s) { mbar_init(BAR(B_FULL + s), 1); mbar_init(BAR(B_DS + s), LW); mbar_init(BAR(B_DQ + s), 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(BAR(B_SREADY + s), 1); mbar_init(BAR(B_SFREE + s), LW); }
+    mbar_init(BAR(B_FINAL), 1); mbar_init(BAR(B_OFREE), LW);
     fence_barrier_init();
   }
-  if (warp == LCTRL) tmem_alloc(smem_u32(tmem_slot), L_TMEM_COLS);
+  if (warp == LW_LOAD) tmem_alloc(smem_u32(tmem_slot), L_TMEM_COLS);
   fence_before();
   __syncthreads();
   fence_after();
@@ -436,49 +485,32 @@ attn_bwd_long_dq_kernel(const __grid_constant__ CUtensorMap mQ, const __grid_con
   const int nch = (S + KC2 - 1) / KC2;
   const int items = p.B * heads * ntq;
 
-  if (warp == LCTRL) {
-    uint32_t ph_q = 0, ph_qz = 0, ph_ofree = 0, ph_full[2] = {0, 0}, ph_sfree[2] = {0, 0}, ph_ds[2] = {0, 0}, ph_dq[2] = {0, 0};
-    int pend[2] = {0, 0}, sused[2] = {0, 0};
+  // Three single-purpose control warps (see the forward kernel): the loader runs up to DQ_NS steps ahead of the S / dP MMA warp, the
+  // dQ MMA warp trails the workers.
+  if (warp == LW_LOAD) {
+    uint32_t g0 = 0, ph_ofree = 0;
     bool first_item = true;
-    const uint64_t dQd = smem_desc(smem_u32(sQ), 16, 1024), dDOd = smem_desc(smem_u32(sDO), 16, 1024);
-    for (int it = blockIdx.x; it < items; it += gridDim.x) {
+    for (int it = blockIdx.x; it < items; it += gridDim.x, g0 += (uint32_t)nch) {
       const int i = it % ntq, bh = it / ntq;
       const int h = bh % heads, b = bh / heads;
       const HeadCols hc = head_cols(h, hd);
       const int na = (hc.shift + hd + 63) >> 6;
-      const int nks = hc.hdp >> 4;
-      const uint32_t id_dq = idesc_bf16(128, hc.hdp, 0, 1);      // dQ = dS K : A K-major, B (K: keys x hd) MN-major
-      auto stage_free = [&](int s) {
-        if (pend[s]) { mbar_wait(BAR(10 + s), ph_dq[s], p.err_flag, 81); ph_dq[s] ^= 1; pend[s] = 0; }
-      };
-      auto issue_loads = [&](int c) {
-        const int s = c & 1;
-        uint8_t* st = sStage + s * DQ_STAGE;
+      auto load_step = [&](int c) {
+        const uint32_t g = g0 + (uint32_t)c, st_i = g % DQ_NS, u = g / DQ_NS;
+        if (u) mbar_wait(BAR(B_DQ + st_i), (u - 1) & 1, p.err_flag, 81);            // the dQ MMA of the stage's previous use retired
+        uint8_t* st = sStage + st_i * DQ_STAGE;
         if (leader) {
-          mbar_expect_tx(BAR(2 + s), (uint32_t)(2 * na) * ATOM_H + ATOM);
+          mbar_expect_tx(BAR(B_FULL + st_i), (uint32_t)(2 * na) * ATOM_H + ATOM);
           for (int a = 0; a < na; ++a) {
-            tma_load_2d(smem_u32(st + DQ_ST_K + a * ATOM_H), &mK, BAR(2 + s), hc.col0 + 64 * a, b * S + c * KC2);
-            tma_load_2d(smem_u32(st + DQ_ST_V + a * ATOM_H), &mV, BAR(2 + s), hc.col0 + 64 * a, b * S + c * KC2);
+            tma_load_2d(smem_u32(st + DQ_ST_K + a * ATOM_H), &mK, BAR(B_FULL + st_i), hc.col0 + 64 * a, b * S + c * KC2);
+            tma_load_2d(smem_u32(st + DQ_ST_V + a * ATOM_H), &mV, BAR(B_FULL + st_i), hc.col0 + 64 * a, b * S + c * KC2);
           }
-          tma_load_2d(smem_u32(st + DQ_ST_B), &mB, BAR(2 + s), c * KC2, b * S + i * 128);
+          tma_load_2d(smem_u32(st + DQ_ST_B), &mB, BAR(B_FULL + st_i), c * KC2, b * S + i * 128);
         }
       };
-      auto issue_dq = [&](int c) {                               // dQ (+)= dS_c K_c over the valid keys of chunk c
-        const int s = c & 1;
-        const int nk16 = min(KC2, S - c * KC2) >> 4;
-        mbar_wait(BAR(8 + s), ph_ds[s], p.err_flag, 82); ph_ds[s] ^= 1;
-        fence_after();
-        const uint64_t dDS = smem_desc(smem_u32(sStage + s * DQ_STAGE + DQ_ST_B), 16, 1024);
-        const uint64_t dKmn = smem_desc(smem_u32(sStage + s * DQ_STAGE + DQ_ST_K), ATOM_H, 1024);
-        if (leader) {
-          for (int kk = 0; kk < nk16; ++kk) mma_bf16(tmem + T_DQ, dDS + (uint32_t)(2 * kk), dKmn + (uint32_t)(kk * 128), id_dq, (c | kk) != 0);
-          commit(BAR(10 + s));
-        }
-        pend[s] = 1;
-      };
-      stage_free(0); issue_loads(0);
-      if (nch > 1) { stage_free(1); issue_loads(1); }
-      if (!first_item) { mbar_wait(BAR(13), ph_ofree, p.err_flag, 83); ph_ofree ^= 1; }
+      const int npre = nch < DQ_NS ? nch : DQ_NS;
+      for (int c = 0; c < npre; ++c) load_step(c);               // these do not depend on Q / dO: out before the previous epilogue is awaited
+      if (!first_item) { mbar_wait(BAR(B_OFREE), ph_ofree, p.err_flag, 83); ph_ofree ^= 1; }
       first_item = false;
       if (leader) {
         mbar_expect_tx(BAR(0), (uint32_t)(2 * na) * ATOM);
@@ -487,42 +519,67 @@ attn_bwd_long_dq_kernel(const __grid_constant__ CUtensorMap mQ, const __grid_con
           tma_load_2d(smem_u32(sDO + a * ATOM), &mDO, BAR(0), hc.col0 + 64 * a, b * S + i * 128);
         }
       }
+      for (int c = npre; c < nch; ++c) load_step(c);
+    }
+  } else if (warp == LW_SMMA) {
+    uint32_t g0 = 0, ph_q = 0, ph_qz = 0;
+    const uint64_t dQd = smem_desc(smem_u32(sQ), 16, 1024), dDOd = smem_desc(smem_u32(sDO), 16, 1024);
+    for (int it = blockIdx.x; it < items; it += gridDim.x, g0 += (uint32_t)nch) {
+      const int h = (it / ntq) % heads;
+      const HeadCols hc = head_cols(h, hd);
+      const int nks = hc.hdp >> 4;
       mbar_wait(BAR(0), ph_q, p.err_flag, 84); ph_q ^= 1;
       mbar_wait(BAR(1), ph_qz, p.err_flag, 87); ph_qz ^= 1;      // the workers zeroed the neighbouring heads' columns of Q and dO
-      fence_after();
       for (int c = 0; c < nch; ++c) {
-        const int s = c & 1;
+        const uint32_t g = g0 + (uint32_t)c, st_i = g % DQ_NS, u = g / DQ_NS, tb = g & 1, ub = g >> 1;
         const int nk = min(KC2, S - c * KC2);
-        mbar_wait(BAR(2 + s), ph_full[s], p.err_flag, 85); ph_full[s] ^= 1;
-        if (sused[s]) { mbar_wait(BAR(6 + s), ph_sfree[s], p.err_flag, 86); ph_sfree[s] ^= 1; }
-        sused[s] = 1;
+        mbar_wait(BAR(B_FULL + st_i), u & 1, p.err_flag, 85);
+        if (ub) mbar_wait(BAR(B_SFREE + tb), (ub - 1) & 1, p.err_flag, 86);          // the workers drained the buffer's previous use
         fence_after();
-        const uint64_t dK = smem_desc(smem_u32(sStage + s * DQ_STAGE + DQ_ST_K), 16, 1024);
-        const uint64_t dV = smem_desc(smem_u32(sStage + s * DQ_STAGE + DQ_ST_V), 16, 1024);
+        const uint64_t dK = smem_desc(smem_u32(sStage + st_i * DQ_STAGE + DQ_ST_K), 16, 1024);
+        const uint64_t dV = smem_desc(smem_u32(sStage + st_i * DQ_STAGE + DQ_ST_V), 16, 1024);
         const uint32_t id_s = idesc_bf16(128, nk, 0, 0);
         if (leader) {
           for (int ks = 0; ks < nks; ++ks) {
             const uint32_t oa = (uint32_t)((ks >> 2) * (ATOM >> 4) + 2 * (ks & 3)), ob = (uint32_t)((ks >> 2) * (ATOM_H >> 4) + 2 * (ks & 3));
-            mma_bf16(tmem + 128u * s, dQd + oa, dK + ob, id_s, ks > 0);
+            mma_bf16(tmem + 128u * tb, dQd + oa, dK + ob, id_s, ks > 0);
           }
           for (int ks = 0; ks < nks; ++ks) {
             const uint32_t oa = (uint32_t)((ks >> 2) * (ATOM >> 4) + 2 * (ks & 3)), ob = (uint32_t)((ks >> 2) * (ATOM_H >> 4) + 2 * (ks & 3));
-            mma_bf16(tmem + 128u * s + 64, dDOd + oa, dV + ob, id_s, ks > 0);
+            mma_bf16(tmem + 128u * tb + 64, dDOd + oa, dV + ob, id_s, ks > 0);
           }
-          commit(BAR(4 + s));
+          commit(BAR(B_SREADY + tb));
         }
-        if (c >= 1) issue_dq(c - 1);
-        if (c + 1 < nch && c >= 1) { stage_free((c + 1) & 1); issue_loads(c + 1); }
       }
-      issue_dq(nch - 1);
-      if (leader) commit(BAR(12));
+    }
+  } else if (warp == LW_PV) {
+    // dQ (+)= dS_c K_c over the valid keys of chunk c
+    uint32_t g0 = 0;
+    for (int it = blockIdx.x; it < items; it += gridDim.x, g0 += (uint32_t)nch) {
+      const int h = (it / ntq) % heads;
+      const HeadCols hc = head_cols(h, hd);
+      const uint32_t id_dq = idesc_bf16(128, hc.hdp, 0, 1);      // dQ = dS K : A K-major, B (K: keys x hd) MN-major
+      for (int c = 0; c < nch; ++c) {
+        const uint32_t g = g0 + (uint32_t)c, st_i = g % DQ_NS, u = g / DQ_NS;
+        const int nk16 = min(KC2, S - c * KC2) >> 4;
+        mbar_wait(BAR(B_DS + st_i), u & 1, p.err_flag, 82);                            // the workers wrote dS_c
+        mbar_wait(BAR(B_FULL + st_i), u & 1, p.err_flag, 88);                          // K_c landed (the workers waited for the same phase)
+        fence_after();
+        const uint64_t dDS = smem_desc(smem_u32(sStage + st_i * DQ_STAGE + DQ_ST_B), 16, 1024);
+        const uint64_t dKmn = smem_desc(smem_u32(sStage + st_i * DQ_STAGE + DQ_ST_K), ATOM_H, 1024);
+        if (leader) {
+          for (int kk = 0; kk < nk16; ++kk) mma_bf16(tmem + T_DQ, dDS + (uint32_t)(2 * kk), dKmn + (uint32_t)(kk * 128), id_dq, (c | kk) != 0);
+          commit(BAR(B_DQ + st_i));
+        }
+      }
+      if (leader) commit(BAR(B_FINAL));
     }
   } else {
     const int grp = warp >> 2, quad = warp & 3;
     const int r = quad * 32 + lane;
     const uint32_t trow = tmem + ((uint32_t)(quad * 32) << 16);
-    uint32_t ph_q = 0, ph_final = 0, ph_full[2] = {0, 0}, ph_sready[2] = {0, 0};
-    for (int it = blockIdx.x; it < items; it += gridDim.x) {
+    uint32_t g0 = 0, ph_q = 0, ph_final = 0;
+    for (int it = blockIdx.x; it < items; it += gridDim.x, g0 += (uint32_t)nch) {
       const int i = it % ntq, bh = it / ntq;
       const int h = bh % heads, b = bh / heads;
       const HeadCols hc = head_cols(h, hd);
@@ -542,17 +599,17 @@ attn_bwd_long_dq_kernel(const __grid_constant__ CUtensorMap mQ, const __grid_con
       fence_proxy_async();
       mbar_arrive(BAR(1));
       for (int c = 0; c < nch; ++c) {
-        const int s = c & 1;
+        const uint32_t g = g0 + (uint32_t)c, st_i = g % DQ_NS, u = g / DQ_NS, tb = g & 1, ub = g >> 1;
         const int nk = min(KC2, S - c * KC2);
-        uint8_t* st = sStage + s * DQ_STAGE;
-        mbar_wait(BAR(2 + s), ph_full[s], p.err_flag, 91); ph_full[s] ^= 1;
-        mbar_wait(BAR(4 + s), ph_sready[s], p.err_flag, 92); ph_sready[s] ^= 1;
+        uint8_t* st = sStage + st_i * DQ_STAGE;
+        mbar_wait(BAR(B_FULL + st_i), u & 1, p.err_flag, 91);
+        mbar_wait(BAR(B_SREADY + tb), ub & 1, p.err_flag, 92);
         fence_after();
         const int kl = grp * 16;
         if (kl < nk) {
           uint32_t sr[16], dr[16];
-          tmem_ld16(trow + 128u * s + kl, sr);
-          tmem_ld16(trow + 128u * s + 64 + kl, dr);
+          tmem_ld16(trow + 128u * tb + kl, sr);
+          tmem_ld16(trow + 128u * tb + 64 + kl, dr);
           uint4* p0 = reinterpret_cast<uint4*>(st + DQ_ST_B + swz128(r, kl >> 3));
           uint4* p1 = reinterpret_cast<uint4*>(st + DQ_ST_B + swz128(r, (kl >> 3) + 1));
           float bf[16], ds[16];
@@ -568,21 +625,21 @@ attn_bwd_long_dq_kernel(const __grid_constant__ CUtensorMap mQ, const __grid_con
         }
         fence_proxy_async();
         fence_before();
-        mbar_arrive(BAR(6 + s));
-        mbar_arrive(BAR(8 + s));
+        mbar_arrive(BAR(B_SFREE + tb));
+        mbar_arrive(BAR(B_DS + st_i));
       }
-      mbar_wait(BAR(12), ph_final, p.err_flag, 93); ph_final ^= 1;
+      mbar_wait(BAR(B_FINAL), ph_final, p.err_flag, 93); ph_final ^= 1;
       fence_after();
       stage_tmem_rows(sQ, trow + T_DQ, r, grp, hc.hdp, p.scale);
       asm volatile("bar.sync %0, 128;" ::"r"(2 + quad) : "memory");
       store_head_rows(sQ, p.dq + (long long)h * hd, p.ld_dq, (long long)b * S + i * 128, (long long)b * S + S, quad * 32 + grp * 8, hc, hd, lane);
       fence_before();
-      mbar_arrive(BAR(13));
+      mbar_arrive(BAR(B_OFREE));
     }
   }
   fence_before();
   __syncthreads();
-  if (warp == LCTRL) {
+  if (warp == LW_LOAD) {
     fence_after();
     tmem_dealloc(tmem, L_TMEM_COLS);
   }
@@ -830,7 +887,7 @@ int calm_attention_bwd_long(const void* q, const void* k, const void* v, const v
   }
   const int items = B * heads * ((S + 127) / 128);
   const int grid = items < calm_num_sms() ? items : calm_num_sms();
-  attn_bwd_long_dq_kernel<<<grid, LTHREADS, LONG_DQ_SMEM, stream>>>(mQ, mK64, mV64, mDO, mB, p);
+  attn_bwd_long_dq_kernel<<<grid, LDQ_THREADS, LONG_DQ_SMEM, stream>>>(mQ, mK64, mV64, mDO, mB, p);
   CALM_CHECK_LAUNCH("calm_attention_bwd(long dq)");
   attn_bwd_long_dkv_kernel<<<grid, LTHREADS, LONG_DKV_SMEM, stream>>>(mQ, mK, mV, mDO, mB, mDS, p);
   CALM_CHECK_LAUNCH("calm_attention_bwd(long dkv)");

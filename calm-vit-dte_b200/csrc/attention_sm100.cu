@@ -353,22 +353,11 @@ struct BwdParams {
   Common c;
   const float* lse; const float* delta;  // (B, heads, S)
   bf16* dq; bf16* dk; bf16* dv; long long ld_dq, ld_dk, ld_dv;
-  unsigned long long* trace; int trace_cap;   // bring-up: CTA 0 time stamps (calm_debug_set_trace_buffer), null in production
+  CalmTrace trace;                           // bring-up: CTA 0 time stamps (calm_debug_set_trace_buffer), null in production
 };
 
 // trace[0] = event count, then (event id, globaltimer ns) pairs; id = role * 1000 + point * 10 + part
-__device__ __forceinline__ void trace_evt(const BwdParams& p, int id) {
-#ifndef CALM_BRINGUP
-  (void)p; (void)id;              // production builds carry no time-stamp code
-#else
-  if (p.trace != nullptr && blockIdx.x == 0) {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    const unsigned long long i = atomicAdd(p.trace, 1ULL);
-    if ((int)i < p.trace_cap) { p.trace[1 + 2 * i] = (unsigned long long)id; p.trace[2 + 2 * i] = t; }
-  }
-#endif
-}
+__device__ __forceinline__ void trace_evt(const BwdParams& p, int id) { calm_trace(p.trace, id); }
 
 constexpr int KPART = 64;  // key columns per S / dP part; two parts in flight (TMEM: 2 x (64 + 64) | dK 2 x 64 | dV 2 x 64)
 
@@ -797,6 +786,7 @@ extern "C" void calm_debug_set_trace_buffer(void* device_u64, int32_t capacity_e
   g_trace_cap = capacity_events;
 }
 #endif
+CalmTrace calm_trace_target() { return CalmTrace{g_trace_buf, g_trace_cap}; }
 
 size_t calm_attention_bwd_tc_scratch_bytes(int B, int S, int heads) { return (size_t)2 * B * heads * S * S; }
 
@@ -809,7 +799,7 @@ int calm_attention_bwd_tc(const void* q, const void* k, const void* v, const voi
   p.lse = lse; p.delta = delta;
   p.dq = reinterpret_cast<bf16*>(dq); p.dk = reinterpret_cast<bf16*>(dk); p.dv = reinterpret_cast<bf16*>(dv);
   p.ld_dq = ld_dq; p.ld_dk = ld_dk; p.ld_dv = ld_dv;
-  p.trace = g_trace_buf; p.trace_cap = g_trace_cap;
+  p.trace = calm_trace_target();
   CUtensorMap mQ, mK, mV, mDO, mDS;
   int rc;
   const uint64_t rows = (uint64_t)B * S, cols = (uint64_t)heads * hd;

@@ -22,3 +22,22 @@ int calm_attention_bwd_long(const void* q, const void* k, const void* v, const v
                             const float* delta, void* dq, void* dk, void* dv, void* dbias, void* ds_scratch, int64_t ld_q, int64_t ld_k,
                             int64_t ld_v, int64_t ld_do, int64_t ld_dq, int64_t ld_dk, int64_t ld_dv, int B, int S, int heads, int hd,
                             cudaStream_t stream);
+
+// Bring-up time stamps (-DCALM_BRINGUP builds only): CTA 0 appends (event id, globaltimer ns) pairs to the device buffer handed to
+// calm_debug_set_trace_buffer (tools/attn_trace.py reads them back); production builds compile calm_trace() to nothing.
+struct CalmTrace { unsigned long long* buf; int cap; };
+CalmTrace calm_trace_target();
+#ifdef __CUDACC__
+__device__ __forceinline__ void calm_trace(const CalmTrace& t, int id) {
+#ifdef CALM_BRINGUP
+  if (t.buf != nullptr && blockIdx.x == 0) {
+    unsigned long long now;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+    const unsigned long long i = atomicAdd(t.buf, 1ULL);
+    if ((int)i < t.cap) { t.buf[1 + 2 * i] = (unsigned long long)id; t.buf[2 + 2 * i] = now; }
+  }
+#else
+  (void)t; (void)id;
+#endif
+}
+#endif

@@ -14,7 +14,9 @@ import calm_lib  # noqa: E402
 
 dev = torch.device("cuda:0")
 S, D, hd, B = int(sys.argv[1]) if len(sys.argv) > 1 else 224, None, None, 256
+WHAT = sys.argv[2] if len(sys.argv) > 2 else "bwd"      # bwd | fwd (the forward is only instrumented in attention_long_sm100.cu)
 D, hd = 3 * S, S // 4
+B = {384: 64, 512: 32}.get(S, 256)
 bf16 = torch.bfloat16
 qkv = (torch.randn(B * S, 3 * D, device=dev)).to(bf16)
 bias = (torch.randn(B, S, S, device=dev) * 0.5).to(bf16)
@@ -29,7 +31,10 @@ import ctypes  # noqa: E402
 set_trace = calm_lib.load().calm_debug_set_trace_buffer      # only exported by -DCALM_BRINGUP builds (CALM_NVCC_FLAGS=-DCALM_BRINGUP)
 set_trace.argtypes, set_trace.restype = [ctypes.c_void_p, ctypes.c_int32], None
 set_trace(buf.data_ptr(), cap)
-K.attention_bwd(q, k, v, bias, o, do, lse, B, S, 12, hd, 3 * D, 3 * D, 3 * D, D)
+if WHAT == "fwd":
+    K.attention_fwd(q, k, v, bias, B, S, 12, hd, 3 * D, 3 * D, 3 * D)
+else:
+    K.attention_bwd(q, k, v, bias, o, do, lse, B, S, 12, hd, 3 * D, 3 * D, 3 * D, D)
 torch.cuda.synchronize()
 set_trace(None, 0)
 t = buf.cpu().tolist()
@@ -44,10 +49,14 @@ for role in (1, 2):
     seq = [(ts, eid) for ts, eid in ev if eid // 1000 == role]
     gaps = {}
     for (t_a, a), (t_b, b_) in zip(seq, seq[1:]):
+        if WHAT == "fwd":       # long forward ids carry the step number in the last two digits: fold pass A / pass B steps together
+            nch = (S + 127) // 128
+            fa = lambda e: e - e % 100 + (0 if e % 100 < nch else 50) if e % 1000 < 500 else e
+            a, b_ = fa(a), fa(b_)
         g = gaps.setdefault((a, b_), [0, 0.0])
         g[0] += 1
         g[1] += (t_b - t_a) / 1000.0
     total = sum(g[1] for g in gaps.values())
     print("role %d: %.1f us traced" % (role, total))
-    for (a, b_), g in sorted(gaps.items(), key=lambda kv: -kv[1][1])[:14]:
+    for (a, b_), g in sorted(gaps.items(), key=lambda kv: -kv[1][1])[:18]:
         print("   %d -> %d   n %4d   avg %6.2f us   share %4.1f %%" % (a, b_, g[0], g[1] / g[0], 100 * g[1] / total))
