@@ -86,6 +86,8 @@ attn_fwd_long_kernel(const __grid_constant__ CUtensorMap mQ, const __grid_consta
   auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int S = p.S, hd = p.hd, heads = p.heads;
+  CalmTraceCursor tcur = calm_trace_begin(p.trace, warp == LW_SMMA ? 0 : warp == LW_PV ? 2 : warp == LW_LOAD ? 3 : 1);
+  (void)tcur;
 
   if (threadIdx.x == LW) {
     prefetch_tensormap(&mQ); prefetch_tensormap(&mK); prefetch_tensormap(&mV); prefetch_tensormap(&mB);
@@ -188,7 +190,7 @@ attn_fwd_long_kernel(const __grid_constant__ CUtensorMap mQ, const __grid_consta
           }
           commit(BAR(4 + s));
         }
-        if (leader) calm_trace(p.trace, 1200 + t);                 // S MMA queued
+        if (leader) calm_trace(tcur, 1200 + t);                 // S MMA queued
       }
     }
   } else if (warp == LW_PV) {
@@ -214,7 +216,7 @@ attn_fwd_long_kernel(const __grid_constant__ CUtensorMap mQ, const __grid_consta
             mma_bf16(tmem + T_O, dP + (uint32_t)((kk >> 2) * (ATOM >> 4) + 2 * (kk & 3)), dVmn + (uint32_t)(kk * 128), id_o, (c | kk) != 0);
           commit(BAR(10 + s));
         }
-        if (leader) calm_trace(p.trace, 1300 + t);                 // P V queued
+        if (leader) calm_trace(tcur, 1300 + t);                 // P V queued
       }
       if (leader) commit(BAR(12));                                // every P V of the item has retired: O is final
     }
@@ -243,12 +245,12 @@ attn_fwd_long_kernel(const __grid_constant__ CUtensorMap mQ, const __grid_consta
         const bool pass_b = t >= nch;
         const int nk = min(KC, S - c * KC);
         uint8_t* st = sStage + s * STAGE_BYTES;
-        if (threadIdx.x == 0) calm_trace(p.trace, 2000 + t);
+        if (threadIdx.x == 0) calm_trace(tcur, 2000 + t);
         mbar_wait(BAR(2 + s), ph_full[s], p.err_flag, 72); ph_full[s] ^= 1;      // the bias chunk (and V) landed
-        if (threadIdx.x == 0) calm_trace(p.trace, 2100 + t);
+        if (threadIdx.x == 0) calm_trace(tcur, 2100 + t);
         mbar_wait(BAR(4 + s), ph_sready[s], p.err_flag, 73); ph_sready[s] ^= 1;
         fence_after();
-        if (threadIdx.x == 0) calm_trace(p.trace, 2200 + t);
+        if (threadIdx.x == 0) calm_trace(tcur, 2200 + t);
         // both 16-key pieces of this thread are requested from TMEM before the first wait (one exposed TMEM latency per step, not two)
         uint32_t sr[2][16];
 #pragma unroll
@@ -300,17 +302,17 @@ attn_fwd_long_kernel(const __grid_constant__ CUtensorMap mQ, const __grid_consta
           }
           asm volatile("bar.sync 1, %0;" ::"n"(LW) : "memory");               // nobody overwrites the slots before everyone has read
         }
-        if (threadIdx.x == 0) calm_trace(p.trace, 2300 + t);
+        if (threadIdx.x == 0) calm_trace(tcur, 2300 + t);
         if (pass_b) fence_proxy_async();
         fence_before();
         mbar_arrive(BAR(6 + s));
         mbar_arrive(BAR(8 + s));
       }
       // ---- epilogue: O / l -> bf16 rows through the (consumed) Q atoms, lanes along the rows
-      if (threadIdx.x == 0) calm_trace(p.trace, 2500);
+      if (threadIdx.x == 0) calm_trace(tcur, 2500);
       mbar_wait(BAR(12), ph_ofinal, p.err_flag, 74); ph_ofinal ^= 1;
       fence_after();
-      if (threadIdx.x == 0) calm_trace(p.trace, 2600);
+      if (threadIdx.x == 0) calm_trace(tcur, 2600);
       const float inv = 1.0f / l;
       for (int c0 = grp * 16; c0 < hc.hdp; c0 += 16 * LGROUPS) {
         uint32_t orr[16];

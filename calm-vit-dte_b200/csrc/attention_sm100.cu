@@ -356,8 +356,8 @@ struct BwdParams {
   CalmTrace trace;                           // bring-up: CTA 0 time stamps (calm_debug_set_trace_buffer), null in production
 };
 
-// trace[0] = event count, then (event id, globaltimer ns) pairs; id = role * 1000 + point * 10 + part
-__device__ __forceinline__ void trace_evt(const BwdParams& p, int id) { calm_trace(p.trace, id); }
+// bring-up time stamps: id = role * 1000 + point * 10 + part (see attention_tc.h; `tcur` is the kernel's per-thread cursor)
+#define trace_evt(p, id) calm_trace(tcur, id)
 
 constexpr int KPART = 64;  // key columns per S / dP part; two parts in flight (TMEM: 2 x (64 + 64) | dK 2 x 64 | dV 2 x 64)
 
@@ -378,8 +378,8 @@ __device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int c0, 
 //               drained buffer p & 1 (bar_free) -> the tensor core and the mbarrier round trip run under the workers'
 //               exp2 / dS arithmetic of the other buffer instead of in series with it.
 //   workers   : per part wait bar_sd[buf] -> P, dS -> bf16 tiles in shared memory, dbias accumulation, arrive bar_free[buf].
-//   tile end  : dQ = dS K (into the drained buffer 0), dK += dS^T Q, dV += P^T dO; commit bar_fin -> workers store dQ
-//               (and dK / dV after the last query tile) -> bar_tile.
+//   tile end  : dQ = dS K (into the drained buffer 0), dK += dS^T Q, dV += P^T dO; commit bar_fin -> workers read dQ (and dK / dV
+//               after the last query tile) out of TMEM -> bar_acc (the next tile's MMAs may start) -> staged, coalesced global stores.
 // dbias = sum over heads of dS: the bf16 dS tile the MMAs consume is also TMA-stored, per head, into a (B, H, S, S) scratch;
 // dbias_reduce_kernel sums the heads afterwards. (Accumulating in the row-owner threads cost one 128-byte line per lane and
 // instruction: 8 warps x 8 scattered 16-byte RMWs per part kept the L1 busy for ~2 us of every part; the TMA store moves
@@ -397,16 +397,19 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap mQ, const __grid_constant
   uint8_t* sP = sDO + QT_BYTES;
   uint8_t* sDS = sP + P_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sDS + P_BYTES);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
   const uint32_t bar_kv = smem_u32(&bars[0]), bar_q = smem_u32(&bars[1]), bar_fin = smem_u32(&bars[2]), bar_tile = smem_u32(&bars[3]);
+  const uint32_t bar_acc = smem_u32(&bars[8]);   // the workers have read this tile's accumulators (dQ; dK / dV after the last tile) out of TMEM
   const uint32_t bar_sd0 = smem_u32(&bars[4]), bar_free0 = smem_u32(&bars[6]);   // [buf] at +8 bytes
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const Common& c = p.c;
   const int S = c.S, hd = c.hd, heads = c.heads;
+  CalmTraceCursor tcur = calm_trace_begin(p.trace, warp == CTRL_WARP ? 0 : 1);
+  (void)tcur;
 
   if (threadIdx.x == NWORKERS) {
     prefetch_tensormap(&mQ); prefetch_tensormap(&mK); prefetch_tensormap(&mV); prefetch_tensormap(&mDO); prefetch_tensormap(&mDS);
-    mbar_init(bar_kv, 1); mbar_init(bar_q, 1); mbar_init(bar_fin, 1); mbar_init(bar_tile, NWORKERS);
+    mbar_init(bar_kv, 1); mbar_init(bar_q, 1); mbar_init(bar_fin, 1); mbar_init(bar_tile, NWORKERS); mbar_init(bar_acc, NWORKERS);
     mbar_init(bar_sd0, 1); mbar_init(bar_sd0 + 8, 1); mbar_init(bar_free0, NWORKERS); mbar_init(bar_free0 + 8, NWORKERS);
     fence_barrier_init();
   }
@@ -424,7 +427,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap mQ, const __grid_constant
       // The whole warp walks the control flow (loop counters, descriptors and barrier addresses stay warp-uniform, so they live
       // in uniform registers); only the instructions with side effects are issued by lane 0. Under `if (lane == 0) { loops }`
       // ptxas moves every tcgen05.mma operand through an ELECT / R2UR.BROADCAST loop: ~20 instructions per MMA.
-      uint32_t ph_kv = 0, ph_q = 0, ph_tile = 0, ph_fin = 0, ph_free[2] = {0, 0};
+      uint32_t ph_kv = 0, ph_q = 0, ph_tile = 0, ph_fin = 0, ph_acc = 0, ph_free[2] = {0, 0};
       // The tiles never move: their UMMA descriptors are built once, an MMA's operand is base + (byte offset >> 4) in the
       // low word (the 14-bit address field cannot carry: every tile lies below 256 KB). One thread issues ~80 MMAs per
       // query tile; rebuilding two descriptors per MMA made that thread, not the tensor core, the critical path.
@@ -540,7 +543,9 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap mQ, const __grid_constant
               if (ni == ntiles) { ni = 0; nit = it + (int)gridDim.x; }
               if (nit < items) issue_loads(nit / heads, nit % heads, ni);
             }
-            mbar_wait(bar_tile, ph_tile, c.err_flag, 36); ph_tile ^= 1;         // epilogues done: P / dS tiles and TMEM free
+            // TMEM is free again once the workers have READ the accumulators: the next tile's S / dP MMAs run under their staging and
+            // global stores (the P / dS tiles are only rewritten by the workers themselves, after their own epilogue)
+            mbar_wait(bar_acc, ph_acc, c.err_flag, 36); ph_acc ^= 1;
             if (leader) trace_evt(p, 1050);
           }
         }
@@ -651,6 +656,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap mQ, const __grid_constant
               tmem_ld_wait();
               stage_cols16(sP, r, v, c0, c.scale);
             }
+            if (i != ntiles - 1) { fence_before(); mbar_arrive(bar_acc); }
             quad_sync128(quad);
             store_rows16<32 / NGROUPS>(sP, p.dq + (long long)h * hd, p.ld_dq, row_begin, (long long)b * S + i * 128, g_end, hc, hd, lane);
             if (i == ntiles - 1) {
@@ -665,6 +671,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap mQ, const __grid_constant
                   stage_cols16(sP + (2 + t) * 16384, r, vv, c0, 1.0f);
                 }
               }
+              fence_before();
+              mbar_arrive(bar_acc);
               quad_sync128(quad);
               for (int t = 0; t < ntiles; ++t) {
                 store_rows16<32 / NGROUPS>(sP + t * 16384, p.dk + (long long)h * hd, p.ld_dk, row_begin, (long long)b * S + t * 128, g_end, hc, hd, lane);
@@ -673,8 +681,6 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap mQ, const __grid_constant
             }
             quad_sync128(quad);   // the staging rows are rewritten (P of the next tile) by the partner warps
           }
-          fence_before();
-          mbar_arrive(bar_tile);
           if (threadIdx.x == 0) trace_evt(p, 2070);
         }
       }

@@ -23,21 +23,39 @@ int calm_attention_bwd_long(const void* q, const void* k, const void* v, const v
                             int64_t ld_v, int64_t ld_do, int64_t ld_dq, int64_t ld_dk, int64_t ld_dv, int B, int S, int heads, int hd,
                             cudaStream_t stream);
 
-// Bring-up time stamps (-DCALM_BRINGUP builds only): CTA 0 appends (event id, globaltimer ns) pairs to the device buffer handed to
-// calm_debug_set_trace_buffer (tools/attn_trace.py reads them back); production builds compile calm_trace() to nothing.
-struct CalmTrace { unsigned long long* buf; int cap; };
+// Bring-up time stamps (-DCALM_BRINGUP builds only). Up to four threads of CTA 0 (region 0: controller / S-MMA lane, 1: worker thread 0,
+// 2: PV-MMA lane, 3: loader lane) write (event id, globaltimer ns) pairs into their own region of `cap` pairs of the device buffer
+// handed to calm_debug_set_trace_buffer, with the write position in a register: no atomics, no loads, two fire-and-forget stores per event (an atomic
+// counter cost ~0.4 us per event, as much as the phases being measured). tools/attn_trace.py reads them back (a pair with id 0
+// ends a region). Production builds compile all of it to nothing.
+struct CalmTrace { unsigned long long* buf; int cap; };       // cap = pairs per region
 CalmTrace calm_trace_target();
 #ifdef __CUDACC__
-__device__ __forceinline__ void calm_trace(const CalmTrace& t, int id) {
+struct CalmTraceCursor {
 #ifdef CALM_BRINGUP
-  if (t.buf != nullptr && blockIdx.x == 0) {
+  unsigned long long* at; unsigned long long* end;
+#endif
+};
+__device__ __forceinline__ CalmTraceCursor calm_trace_begin(const CalmTrace& t, int half) {
+  CalmTraceCursor c;
+#ifdef CALM_BRINGUP
+  c.at = c.end = nullptr;
+  if (t.buf != nullptr && blockIdx.x == 0) { c.at = t.buf + 2 * (size_t)half * t.cap; c.end = c.at + 2 * (size_t)t.cap; }
+#else
+  (void)t; (void)half;
+#endif
+  return c;
+}
+__device__ __forceinline__ void calm_trace(CalmTraceCursor& c, int id) {
+#ifdef CALM_BRINGUP
+  if (c.at != c.end) {
     unsigned long long now;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
-    const unsigned long long i = atomicAdd(t.buf, 1ULL);
-    if ((int)i < t.cap) { t.buf[1 + 2 * i] = (unsigned long long)id; t.buf[2 + 2 * i] = now; }
+    c.at[0] = (unsigned long long)id; c.at[1] = now;
+    c.at += 2;
   }
 #else
-  (void)t; (void)id;
+  (void)c; (void)id;
 #endif
 }
 #endif

@@ -25,8 +25,8 @@ o, lse = K.attention_fwd(q, k, v, bias, B, S, 12, hd, 3 * D, 3 * D, 3 * D)
 do = torch.randn_like(o)
 for _ in range(2):
     K.attention_bwd(q, k, v, bias, o, do, lse, B, S, 12, hd, 3 * D, 3 * D, 3 * D, D)
-cap = 4000
-buf = torch.zeros(1 + 2 * cap, dtype=torch.int64, device=dev)
+cap = 4000                                  # pairs per region; 4 regions (controller / S-MMA lane, worker thread 0, PV-MMA lane, loader lane)
+buf = torch.zeros(4 * 2 * cap, dtype=torch.int64, device=dev)
 import ctypes  # noqa: E402
 set_trace = calm_lib.load().calm_debug_set_trace_buffer      # only exported by -DCALM_BRINGUP builds (CALM_NVCC_FLAGS=-DCALM_BRINGUP)
 set_trace.argtypes, set_trace.restype = [ctypes.c_void_p, ctypes.c_int32], None
@@ -38,10 +38,16 @@ else:
 torch.cuda.synchronize()
 set_trace(None, 0)
 t = buf.cpu().tolist()
-n = min(t[0], cap)
-ev = sorted(((t[2 + 2 * i], t[1 + 2 * i]) for i in range(n)))
+ev = []
+for region in range(4):
+    for i in range(cap):
+        eid, ts = t[2 * (region * cap + i)], t[2 * (region * cap + i) + 1]
+        if eid == 0:
+            break
+        ev.append((ts, eid))
+ev.sort()
 t0 = ev[0][0]
-print("events", t[0])
+print("events", len(ev))
 for ts, eid in ev[:int(os.environ.get("TRACE_PRINT", 120))]:
     print("%9.2f us  %d" % ((ts - t0) / 1000.0, eid))
 # where the time goes: per role (1xxx controller lane, 2xxx worker thread 0), the average gap before each event id
