@@ -143,21 +143,29 @@ colsum_vec_kernel(const bf16* __restrict__ x, long long ld, float* __restrict__ 
   }
 }
 
-// out[c] = sum_p partial[p][c]: 32 columns per CTA, 8 row-groups combined through shared memory (deterministic)
-__global__ void __launch_bounds__(256)
+// out[c] = sum_p partial[p][c]: 32 columns per CTA, 32 row-groups (one warp each, two loads in flight per thread) combined through
+// shared memory (deterministic)
+constexpr int RC_GROUPS = 32;
+__global__ void __launch_bounds__(32 * RC_GROUPS)
 reduce_cols_kernel(const float* __restrict__ partial, float* __restrict__ out, int nparts, int n) {
-  __shared__ float red[8][33];
+  __shared__ float red[RC_GROUPS][33];
   const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + cx;
-  float s = 0.f;
-  if (c < n)
-    for (int p = ry; p < nparts; p += 8) s += partial[(size_t)p * n + c];
-  red[ry][cx] = s;
+  float s0 = 0.f, s1 = 0.f;
+  if (c < n) {
+    int p = ry;
+    for (; p + RC_GROUPS < nparts; p += 2 * RC_GROUPS) {
+      s0 += partial[(size_t)p * n + c];
+      s1 += partial[(size_t)(p + RC_GROUPS) * n + c];
+    }
+    if (p < nparts) s0 += partial[(size_t)p * n + c];
+  }
+  red[ry][cx] = s0 + s1;
   __syncthreads();
   if (ry == 0 && c < n) {
     float t = 0.f;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) t += red[k][cx];
+    for (int k = 0; k < RC_GROUPS; ++k) t += red[k][cx];
     out[c] = t;
   }
 }
@@ -256,7 +264,7 @@ extern "C" int32_t calm_colsum(const void* x, int64_t ld, float* partial, int32_
   else
     colsum_kernel<<<nparts, 256, 0, stream>>>(reinterpret_cast<const bf16*>(x), ld, partial, rows, N);
   CALM_CHECK_LAUNCH("calm_colsum");
-  reduce_cols_kernel<<<(N + 31) / 32, 256, 0, stream>>>(partial, out, nparts, N);
+  reduce_cols_kernel<<<(N + 31) / 32, 32 * RC_GROUPS, 0, stream>>>(partial, out, nparts, N);
   CALM_CHECK_LAUNCH("calm_colsum(reduce)");
   return CALM_OK;
 }

@@ -14,8 +14,15 @@ Gradient bar (north_star: 2e-2 in bf16; VERDICT r1: per tensor, against the tens
     bar is therefore stated on pooled statistics plus a per-tensor cap:
       - per class (same kind of tensor), RMS over the class:  rms(rel(P,T)) <= 1.5 x rms(rel(R,T))  (1.25 x was exceeded by 0.3 % at 512^2, where both
         implementations sit 8-10e-2 from fp32 on these tensors);
-      - per tensor:  rel(P, T) <= max(2e-2, 2 x the LARGEST rel(R, T) the reference shows in that class) (the extreme of ~45 noisy
-        samples is itself noisy: 1.5 x was exceeded by 2 % on two 3- and 32-element CNN bias gradients at the small config).
+      - per class, MAGNITUDE-WEIGHTED:  sqrt(sum_k |P_k - T_k|^2) / sqrt(sum_k |T_k|^2) <= 1.25 x the same for R. This is the sharp one: it pools
+        hundreds of degrees of freedom (the ratio of two such sums concentrates within a few % of 1 for equal noise levels), tensors whose fp32
+        gradient happens to cancel to almost nothing do not dominate it, and an O(1) error in any tensor that carries weight fails it;
+      - per tensor:  rel(P, T) <= max(2e-2, 2 x the LARGEST rel(R, T) the reference shows in that class, 4 x the tensor's own rel(R, T)).
+        For an n-element sum-with-cancellation the per-tensor ratio rel(P,T)/rel(R,T) of two equally noisy implementations is a ratio of two
+        chi variables; for n = 2 (the bottleneck inv_freq vectors) that is a ratio of two Rayleigh variables, P(ratio > r) = 1 / (1 + r^2):
+        among ~48 such tensors a few exceed 3 in EVERY build (measured maxima 3.3 .. 9.6, different tensors each time a summation order
+        changes anywhere upstream). The cap is a net for gross errors only; 2 x the class maximum alone tripped on such a 2-element tensor
+        (1.74e-1 vs 1.60e-1 allowed, own reference distance 5.2e-2) after an unrelated reduction-order change.
 """
 import numpy as np
 
@@ -50,19 +57,26 @@ def gradient_report(truth, ref_bf16, product):
     class_stats = {}
     for c, rs in classes.items():
         o, f = np.array([r[2] for r in rs]), np.array([r[3] for r in rs])
+        num_p = sum(float((product[r[0]].double() - truth[r[0]].double()).pow(2).sum()) for r in rs)
+        num_r = sum(float((ref_bf16[r[0]].double() - truth[r[0]].double()).pow(2).sum()) for r in rs)
+        den = max(sum(float(truth[r[0]].double().pow(2).sum()) for r in rs), 1e-300)
         class_stats[c] = dict(n=len(rs), ours_rms=float(np.sqrt((o ** 2).mean())), ref_rms=float(np.sqrt((f ** 2).mean())),
+                              ours_weighted=float(np.sqrt(num_p / den)), ref_weighted=float(np.sqrt(num_r / den)),
                               ref_max=float(f.max()), ours_max=float(o.max()), ratio_median=float(np.median(o / np.maximum(f, 1e-30))),
                               ratio_max=float((o / np.maximum(f, 1e-30)).max()))
     for k, n, ours, ref, _ in rows:
         if n >= SMALL:
             bound = max(2e-2, 1.5 * ref)
         else:
-            bound = max(2e-2, 2.0 * class_stats[tensor_class(k)]["ref_max"])
+            bound = max(2e-2, 2.0 * class_stats[tensor_class(k)]["ref_max"], 4.0 * ref)
         if not ours <= bound:
             offenders.append(dict(key=k, numel=n, ours=ours, ref=ref, bound=bound))
     for c, s in class_stats.items():
         if not s["ours_rms"] <= 1.5 * s["ref_rms"]:
             offenders.append(dict(key="<class %s pooled rms>" % c, numel=s["n"], ours=s["ours_rms"], ref=s["ref_rms"], bound=1.5 * s["ref_rms"]))
+        if not s["ours_weighted"] <= max(2e-2, 1.25 * s["ref_weighted"]):
+            offenders.append(dict(key="<class %s magnitude-weighted>" % c, numel=s["n"], ours=s["ours_weighted"], ref=s["ref_weighted"],
+                                  bound=max(2e-2, 1.25 * s["ref_weighted"])))
     eo, er = np.array([r[2] for r in rows]), np.array([r[3] for r in rows])
     big = np.array([r[1] >= SMALL for r in rows])
     summary = {"n": len(rows), "n_big": int(big.sum()), "ours_median": float(np.median(eo)), "ours_p95": float(np.quantile(eo, 0.95)),
@@ -80,7 +94,8 @@ def print_report(tag, rows, offenders, s):
               tag, s["n"], s["ours_median"], s["ours_p95"], s["ours_max"], s["n_ours_below_2e-2"], s["ref_median"], s["ref_p95"], s["ref_max"],
               s["n_ref_below_2e-2"], s["n_big"], SMALL, s["ratio_median_big"] or 0.0, s["ratio_max_big"] or 0.0))
     for c, st in s["small_classes"].items():
-        print("[%s]   small tensors, class %-9s n=%3d  rms ours %.3e / reference %.3e   max ours %.3e / reference %.3e   per-tensor ratio median %.2f "
-              "max %.2f" % (tag, c, st["n"], st["ours_rms"], st["ref_rms"], st["ours_max"], st["ref_max"], st["ratio_median"], st["ratio_max"]))
+        print("[%s]   small tensors, class %-9s n=%3d  weighted ours %.3e / reference %.3e   rms ours %.3e / reference %.3e   max ours %.3e / reference %.3e   "
+              "per-tensor ratio median %.2f max %.2f" % (tag, c, st["n"], st["ours_weighted"], st["ref_weighted"], st["ours_rms"], st["ref_rms"], st["ours_max"],
+                                                         st["ref_max"], st["ratio_median"], st["ratio_max"]))
     for o in offenders:
         print("   OFFENDER %-70s numel %-8d ours %.3e  reference-bf16 %.3e  bound %.3e" % (o["key"], o["numel"], o["ours"], o["ref"], o["bound"]))
