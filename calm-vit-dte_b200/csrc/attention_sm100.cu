@@ -347,6 +347,264 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap mQ, const __grid_constant
 }
 
 // ====================================================================================================================
+// forward, pipelined variant (S <= 224: two S accumulators of S columns + O fit the 512 TMEM columns)
+// ====================================================================================================================
+// The kernel above runs the phases of a tile one after the other — Q / bias load -> S MMA -> softmax -> P.V MMA -> epilogue — and the next
+// tile starts when the last one ended (5.6 us per 128-query tile at S = 224, of which the workers compute ~3). Here S is
+// double-buffered in TMEM and the control flow is split over three single-purpose warps, so that the load of Q_{t+1}, the S MMA of
+// tile t+1 and the load of the next item's K run under the softmax of tile t:
+//   loader : per tile  sready_t -> Q_{t+1} (and the next item's K: zeroes its neighbouring-head columns itself -> k_ready),
+//                      wdone_t  -> bias_{t+1},   oready_t -> the next item's V
+//   S-MMA  : q_full_t, k_ready, sfree (the workers left S buffer t & 1, tile t-2) -> S_t = Q_t K^T -> sready_t
+//   PV-MMA : wdone_t (P_t written; it follows the workers' epilogue of tile t-1, so O is free), v_full -> O = P_t V -> oready_t
+//   workers: b_full_t, sready_t -> softmax (as above) -> wdone_t -> oready_t -> epilogue
+// Tiles are numbered t = 0, 1, ... over the life of the CTA; a barrier completes once per tile (or per item: k_*, v_full): the phase
+// of tile t has parity t & 1 (S buffers: (t >> 1) & 1). Every role awaits every phase of its barriers in order.
+constexpr int F2_THREADS = FWD_WORKERS + 96;
+constexpr int F2_LOAD = FWD_WORKERS / 32, F2_SMMA = F2_LOAD + 1, F2_PV = F2_LOAD + 2;
+constexpr uint32_t F2_SCOLS = 224, F2_TO = 448;     // S buffer b at TMEM column 224 b, O at 448
+
+__global__ void __launch_bounds__(F2_THREADS, 1)
+attn_fwd_pipe_kernel(const __grid_constant__ CUtensorMap mQ, const __grid_constant__ CUtensorMap mK, const __grid_constant__ CUtensorMap mV,
+                     const __grid_constant__ CUtensorMap mB, const FwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sK = smem;
+  uint8_t* sV = sK + KV_BYTES;
+  uint8_t* sQ = sV + KV_BYTES;
+  uint8_t* sP = sQ + QT_BYTES;
+  uint8_t* sB = sP + P_BYTES;
+  float* xchg = reinterpret_cast<float*>(sB + P_BYTES);          // [2][FWD_GROUPS][128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(xchg + 2 * FWD_GROUPS * 128);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+  // barriers: 0 k_full | 1 k_ready | 2 v_full | 3 q_full | 4 b_full | 5,6 sready | 7 wdone | 8 oready | 9,10 sfree
+  const uint32_t bar0 = smem_u32(&bars[0]);
+  auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
+  constexpr int B_KFULL = 0, B_KREADY = 1, B_VFULL = 2, B_QFULL = 3, B_BFULL = 4, B_SREADY = 5, B_WDONE = 7, B_OREADY = 8, B_SFREE = 9;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const Common& c = p.c;
+  const int S = c.S, hd = c.hd;
+
+  if (threadIdx.x == FWD_WORKERS) {
+    prefetch_tensormap(&mQ); prefetch_tensormap(&mK); prefetch_tensormap(&mV); prefetch_tensormap(&mB);
+    mbar_init(BAR(B_KFULL), 1); mbar_init(BAR(B_KREADY), 1); mbar_init(BAR(B_VFULL), 1); mbar_init(BAR(B_QFULL), 1); mbar_init(BAR(B_BFULL), 1);
+    mbar_init(BAR(B_SREADY), 1); mbar_init(BAR(B_SREADY + 1), 1); mbar_init(BAR(B_WDONE), FWD_WORKERS); mbar_init(BAR(B_OREADY), 1);
+    mbar_init(BAR(B_SFREE), FWD_WORKERS); mbar_init(BAR(B_SFREE + 1), FWD_WORKERS);
+    fence_barrier_init();
+  }
+  if (warp == F2_LOAD) tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
+  fence_before();
+  __syncthreads();
+  fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const int ntiles = (S + 127) >> 7;
+  const int natoms = (S + 63) >> 6;
+  const int items = c.B * c.heads;
+
+  if (warp == F2_LOAD) {
+    // ============================ loader ============================
+    auto load_q = [&](int it, int i) {
+      const int b = it / c.heads, h = it - b * c.heads;
+      const HeadCols lc = head_cols(h, hd);
+      if (leader) {
+        mbar_expect_tx(BAR(B_QFULL), QT_BYTES);
+        tma_load_2d(smem_u32(sQ), &mQ, BAR(B_QFULL), lc.col0, b * S + i * 128);
+      }
+    };
+    auto load_bias = [&](int it, int i) {
+      const int b = it / c.heads;
+      if (leader) {
+        mbar_expect_tx(BAR(B_BFULL), natoms * 16384u);
+        for (int a = 0; a < natoms; ++a) tma_load_2d(smem_u32(sB) + a * 16384, &mB, BAR(B_BFULL), a * 64, b * S + i * 128);
+      }
+    };
+    auto load_k = [&](int it) {
+      const int b = it / c.heads, h = it - b * c.heads;
+      const HeadCols lc = head_cols(h, hd);
+      if (leader) {
+        mbar_expect_tx(BAR(B_KFULL), (uint32_t)S * 128u);
+        tma_load_2d(smem_u32(sK), &mK, BAR(B_KFULL), lc.col0, b * S);
+      }
+    };
+    auto load_v = [&](int it) {
+      const int b = it / c.heads, h = it - b * c.heads;
+      const HeadCols lc = head_cols(h, hd);
+      if (leader) {
+        mbar_expect_tx(BAR(B_VFULL), (uint32_t)S * 128u);
+        tma_load_2d(smem_u32(sV), &mV, BAR(B_VFULL), lc.col0, b * S);
+      }
+    };
+    // the 64-column boxes also bring the neighbouring heads' columns: zeroing them in K (once per item) keeps them out of
+    // S = Q K^T; the tails of V only reach O columns nobody stores
+    auto finish_k = [&](int it, uint32_t n_item) {
+      const int h = it % c.heads;
+      const HeadCols hc = head_cols(h, hd);
+      mbar_wait(BAR(B_KFULL), n_item & 1, c.err_flag, 17);
+      for (int row = lane; row < S; row += 32) zero_outside(sK, row, hc, hd);
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(BAR(B_KREADY));
+      __syncwarp();
+    };
+    uint32_t t = 0, n_item = 0;
+    if ((int)blockIdx.x < items) {
+      load_k(blockIdx.x); load_v(blockIdx.x); load_q(blockIdx.x, 0); load_bias(blockIdx.x, 0);
+      finish_k(blockIdx.x, 0);
+    }
+    for (int it = blockIdx.x; it < items; it += gridDim.x, ++n_item) {
+      const int nit = it + (int)gridDim.x;
+      for (int i = 0; i < ntiles; ++i, ++t) {
+        const bool last = i == ntiles - 1;
+        mbar_wait(BAR(B_SREADY + (t & 1)), (t >> 1) & 1, c.err_flag, 11);           // S MMA of tile t retired: Q (and, after the item's last tile, K) free
+        if (!last) load_q(it, i + 1);
+        else if (nit < items) { load_k(nit); load_q(nit, 0); finish_k(nit, n_item + 1); }
+        mbar_wait(BAR(B_WDONE), t & 1, c.err_flag, 12);                             // the workers consumed the bias tile
+        if (!last) load_bias(it, i + 1);
+        else if (nit < items) load_bias(nit, 0);
+        mbar_wait(BAR(B_OREADY), t & 1, c.err_flag, 13);                            // P.V of tile t retired: after the item's last tile V is free
+        if (last && nit < items) load_v(nit);
+      }
+    }
+  } else if (warp == F2_SMMA) {
+    // ============================ S = Q K^T ============================
+    const uint32_t id_s = idesc_bf16(128, S, 0, 0);
+    const uint64_t dQk = smem_desc(smem_u32(sQ), 16, 1024), dKk = smem_desc(smem_u32(sK), 16, 1024);
+    uint32_t t = 0, n_item = 0;
+    for (int it = blockIdx.x; it < items; it += gridDim.x, ++n_item) {
+      const int h = it % c.heads;
+      const int hdp = head_cols(h, hd).hdp;
+      mbar_wait(BAR(B_KREADY), n_item & 1, c.err_flag, 14);
+      for (int i = 0; i < ntiles; ++i, ++t) {
+        mbar_wait(BAR(B_QFULL), t & 1, c.err_flag, 15);
+        // The workers left this S buffer (tile t - 2). A barrier of its own per buffer: a parity wait is only right while the waiter is
+        // in step with the barrier, and wdone may already be a phase further (tile t - 1 done) when this warp comes back from a K wait.
+        if (t >= 2) mbar_wait(BAR(B_SFREE + (t & 1)), ((t >> 1) - 1) & 1, c.err_flag, 16);
+        fence_after();
+        if (leader) {
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) if (ks < hdp / 16) mma_bf16(tmem + F2_SCOLS * (t & 1), dQk + 2 * ks, dKk + 2 * ks, id_s, ks > 0);
+          commit(BAR(B_SREADY + (t & 1)));
+        }
+      }
+    }
+  } else if (warp == F2_PV) {
+    // ============================ O = P V ============================
+    const uint64_t dPk = smem_desc(smem_u32(sP), 16, 1024), dVmn = smem_desc(smem_u32(sV), 8192, 1024);
+    uint32_t t = 0, n_item = 0;
+    for (int it = blockIdx.x; it < items; it += gridDim.x, ++n_item) {
+      const int h = it % c.heads;
+      const uint32_t id_o = idesc_bf16(128, head_cols(h, hd).hdp, 0, 1);   // A K-major, B (V: keys x hd) MN-major
+      mbar_wait(BAR(B_VFULL), n_item & 1, c.err_flag, 18);
+      for (int i = 0; i < ntiles; ++i, ++t) {
+        mbar_wait(BAR(B_WDONE), t & 1, c.err_flag, 19);                             // P_t written (and O of tile t - 1 read out before that)
+        fence_after();
+        if (leader) {
+          const int nk16 = S / 16;
+          for (int a = 0; 4 * a < nk16; ++a) {
+            const uint64_t da = dPk + (uint32_t)(a * 1024), db = dVmn + (uint32_t)(a * 512);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              if (4 * a + j < nk16) mma_bf16(tmem + F2_TO, da + 2 * j, db + 128 * j, id_o, (a | j) != 0);
+          }
+          commit(BAR(B_OREADY));
+        }
+      }
+    }
+  } else {
+    // ============================ workers (softmax as in attn_fwd_tc_kernel) ============================
+    const int grp = warp >> 2;
+    const int quad = warp & 3;
+    const int r = quad * 32 + lane;
+    const uint32_t trow = tmem + ((uint32_t)(quad * 32) << 16);
+    uint32_t t = 0;
+    for (int it = blockIdx.x; it < items; it += gridDim.x) {
+      const int b = it / c.heads, h = it - b * c.heads;
+      const HeadCols hc = head_cols(h, hd);
+      const int hdp = hc.hdp;
+      for (int i = 0; i < ntiles; ++i, ++t) {
+        const int q = i * 128 + r;
+        const bool valid = q < S;
+        const uint32_t ts = trow + F2_SCOLS * (t & 1);
+        mbar_wait(BAR(B_BFULL), t & 1, c.err_flag, 22);
+        mbar_wait(BAR(B_SREADY + (t & 1)), (t >> 1) & 1, c.err_flag, 23);
+        fence_after();
+        float mx = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int kc = (FWD_GROUPS * j + grp) * 16;
+          if (kc < S) {
+            uint32_t sr[16];
+            tmem_ld16(ts + kc, sr);
+            const uint8_t* ba = sB + (kc >> 6) * 16384;
+            const int g = (kc & 63) >> 3;
+            const uint4 b0 = *reinterpret_cast<const uint4*>(ba + swz128(r, g)), b1 = *reinterpret_cast<const uint4*>(ba + swz128(r, g + 1));
+            float bf[16];
+            unpack16(b0, b1, bf);
+            tmem_ld_wait();
+#pragma unroll
+            for (int jj = 0; jj < 16; ++jj) mx = fmaxf(mx, fmaf(__uint_as_float(sr[jj]), c.scale_log2, bf[jj] * LOG2E));
+          }
+        }
+        xchg[grp * 128 + r] = mx;
+        asm volatile("bar.sync 1, %0;" ::"n"(FWD_WORKERS) : "memory");
+#pragma unroll
+        for (int gq = 0; gq < FWD_GROUPS; ++gq) mx = fmaxf(mx, xchg[gq * 128 + r]);
+        float l = 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int kc = (FWD_GROUPS * j + grp) * 16;
+          if (kc < S) {
+            uint32_t sr[16];
+            tmem_ld16(ts + kc, sr);
+            const uint8_t* ba = sB + (kc >> 6) * 16384;
+            const int g = (kc & 63) >> 3;
+            const uint4 b0 = *reinterpret_cast<const uint4*>(ba + swz128(r, g)), b1 = *reinterpret_cast<const uint4*>(ba + swz128(r, g + 1));
+            float bf[16], pv[16];
+            unpack16(b0, b1, bf);
+            tmem_ld_wait();
+#pragma unroll
+            for (int jj = 0; jj < 16; ++jj) {
+              pv[jj] = ex2_approx(fmaf(__uint_as_float(sr[jj]), c.scale_log2, fmaf(bf[jj], LOG2E, -mx)));
+              l += pv[jj];
+            }
+            store_row16(sP, r, kc, pv);
+          }
+        }
+        xchg[(FWD_GROUPS + grp) * 128 + r] = l;
+        fence_proxy_async();
+        fence_before();
+        mbar_arrive(BAR(B_SFREE + (t & 1)));
+        mbar_arrive(BAR(B_WDONE));
+        mbar_wait(BAR(B_OREADY), t & 1, c.err_flag, 24);                // (every worker arrived at wdone before the MMA ran)
+        fence_after();
+        l = 0.f;
+#pragma unroll
+        for (int gq = 0; gq < FWD_GROUPS; ++gq) l += xchg[(FWD_GROUPS + gq) * 128 + r];   // same order in every thread of the row
+        const float inv = 1.0f / l;
+        for (int c0 = grp * 16; c0 < hdp; c0 += 16 * FWD_GROUPS) {
+          uint32_t orr[16];
+          tmem_ld16(trow + F2_TO + c0, orr);
+          tmem_ld_wait();
+          stage_cols16(sP, r, orr, c0, inv);
+        }
+        if (valid && grp == 0) p.lse[((long long)b * c.heads + h) * S + q] = (mx + log2f(l)) * LN2;
+        quad_sync128(quad);
+        store_rows16<8>(sP, p.o + (long long)h * hd, p.ld_o, quad * 32 + grp * 8, (long long)b * S + i * 128, (long long)b * S + S, hc, hd, lane);
+        quad_sync128(quad);   // the partner warps rewrite these staging rows with the next tile's P
+        // the next pass-1 exchange overwrites xchg[0..]: every thread has passed the bar.sync above AFTER reading the maxima, and the
+        // sums xchg[FWD_GROUPS..] were read after oready, i.e. before any thread of the next tile writes them (bar.sync 1 in between)
+      }
+    }
+  }
+  fence_before();
+  __syncthreads();
+  if (warp == F2_LOAD) {
+    fence_after();
+    tmem_dealloc(tmem, TMEM_COLS);
+  }
+}
+
+// ====================================================================================================================
 // backward
 // ====================================================================================================================
 struct BwdParams {
@@ -778,6 +1036,17 @@ int calm_attention_fwd_tc(const void* q, const void* k, const void* v, const voi
   }
   const int items = B * heads;
   const int grid = items < calm_num_sms() ? items : calm_num_sms();
+  if (S <= (int)F2_SCOLS) {      // two S accumulators + O fit TMEM: the pipelined kernel
+    static CalmDeviceOnce configured2;
+    if (configured2.pending()) {
+      cudaError_t e = cudaFuncSetAttribute(attn_fwd_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FWD_SMEM);
+      if (e != cudaSuccess) { calm_set_error("calm_attention_fwd(tcgen05, pipelined): smem: %s", cudaGetErrorString(e)); return CALM_ERR_CUDA; }
+      configured2.done();
+    }
+    attn_fwd_pipe_kernel<<<grid, F2_THREADS, FWD_SMEM, stream>>>(mQ, mK, mV, mB, p);
+    CALM_CHECK_LAUNCH("calm_attention_fwd(tcgen05, pipelined)");
+    return CALM_OK;
+  }
   attn_fwd_tc_kernel<<<grid, FWD_THREADS, FWD_SMEM, stream>>>(mQ, mK, mV, mB, p);
   CALM_CHECK_LAUNCH("calm_attention_fwd(tcgen05)");
   return CALM_OK;

@@ -306,7 +306,11 @@ def test_rope(K, B, S, h, dc, dr):
 @pytest.mark.parametrize("B,S,h,hd", [(2, 224, 12, 56), (2, 176, 12, 44), (3, 128, 12, 32), (2, 80, 12, 20), (2, 16, 12, 4),
                                        (5, 160, 12, 40), (3, 256, 4, 64),                 # tcgen05 / TMEM / TMA kernels (S <= 256, hd <= 64)
                                        (1, 384, 12, 96), (2, 512, 12, 128), (1, 288, 12, 72), (2, 336, 12, 84), (1, 464, 12, 116), (1, 128, 3, 72), (3, 320, 2, 64),   # long-row tcgen05 forward
-                                       (2, 72, 12, 20), (2, 136, 4, 96), (1, 76, 3, 20)])   # mma.sync kernels
+                                       (2, 72, 12, 20), (2, 136, 4, 96), (1, 76, 3, 20),   # mma.sync kernels
+                                       # more (image, head, tile) items than SMs: every persistent CTA walks several items (barrier phases,
+                                       # buffer hand-over between items) — whole-row kernels with 2 tiles and 1 tile per item, long-row kernels
+                                       (40, 224, 12, 56), (30, 176, 12, 44), (45, 128, 12, 32), (50, 80, 12, 20), (16, 240, 12, 60),
+                                       (8, 384, 12, 96), (5, 512, 12, 128), (9, 336, 12, 84)])
 def test_attention(K, B, S, h, hd):
     """The implementation is selected by the shape alone (no process-wide switch): tcgen05 kernels where eligible (S <= 256,
     S % 16 == 0, hd <= 64), the mma.sync kernels otherwise (what the 384^2 / 512^2 configs use; S = 72 / 136 exercise their
