@@ -15,7 +15,7 @@ CSRC = os.path.join(HERE, "csrc")
 ROOT = os.path.dirname(HERE)
 OUT = os.path.join(HERE, "libcalm_b200.so")
 OBJ = os.path.join(HERE, "build")
-SOURCES = ["core.cu", "gemm_sm100.cu", "attention.cu", "attention_sm100.cu", "attention_long_sm100.cu", "spectral.cu", "layernorm.cu", "rope.cu", "latent.cu", "cnn.cu", "misc.cu", "trainer.cu"]
+SOURCES = ["core.cu", "gemm_sm100.cu", "attention.cu", "attention_sm100.cu", "attention_long_sm100.cu", "attention_small.cu", "spectral.cu", "layernorm.cu", "rope.cu", "latent.cu", "cnn.cu", "misc.cu", "trainer.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC"]
 NVCC_FLAGS += os.environ.get("CALM_NVCC_FLAGS", "").split()   # bring-up builds, e.g. -DCALM_MBAR_TIMEOUT_CYCLES=2000000000 -DCALM_BRINGUP
 

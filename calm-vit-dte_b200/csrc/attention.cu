@@ -556,6 +556,11 @@ extern "C" int32_t calm_attention_fwd(const void* q, const void* k, const void* 
   {
     const int64_t lds[3] = {ld_q, ld_k, ld_v};
     const void* ptrs[4] = {q, k, v, bias};
+    {
+      const void* sp[5] = {q, k, v, bias, o};
+      if (calm_attention_small_eligible(B, S, heads, hd, lds, 3, sp, 5))     // short rows, narrow heads: a warp per item, scores in registers
+        return calm_attention_fwd_small(q, k, v, bias, o, lse, ld_q, ld_k, ld_v, ld_o, B, S, heads, hd, stream);
+    }
 #ifndef CALM_FORCE_LONG_ATTENTION     // tuning builds only: route every eligible shape through the chunked kernels
     if (calm_attention_tc_eligible(B, S, heads, hd, lds, 3, ptrs, 4))
 #else

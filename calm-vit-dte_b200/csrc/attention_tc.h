@@ -22,6 +22,10 @@ int calm_attention_bwd_long(const void* q, const void* k, const void* v, const v
                             const float* delta, void* dq, void* dk, void* dv, void* dbias, void* ds_scratch, int64_t ld_q, int64_t ld_k,
                             int64_t ld_v, int64_t ld_do, int64_t ld_dq, int64_t ld_dk, int64_t ld_dv, int B, int S, int heads, int hd,
                             cudaStream_t stream);
+// attention_small.cu: forward with one warp per (image, head) item, scores in registers (mma.sync) — S <= 96, S % 16 == 0, head_dim <= 32
+bool calm_attention_small_eligible(int B, int S, int heads, int hd, const int64_t* lds, int nlds, const void* const* ptrs, int nptrs);
+int calm_attention_fwd_small(const void* q, const void* k, const void* v, const void* bias, void* o, float* lse, int64_t ld_q, int64_t ld_k,
+                             int64_t ld_v, int64_t ld_o, int B, int S, int heads, int hd, cudaStream_t stream);
 
 // Bring-up time stamps (-DCALM_BRINGUP builds only). Up to four threads of CTA 0 (region 0: controller / S-MMA lane, 1: worker thread 0,
 // 2: PV-MMA lane, 3: loader lane) write (event id, globaltimer ns) pairs into their own region of `cap` pairs of the device buffer

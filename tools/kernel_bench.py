@@ -139,7 +139,10 @@ def bench_gemm():
 
 
 def bench_attn():
-    for S, D, hd in STAGES:
+    stages = STAGES
+    if os.environ.get("KB_ATTN"):       # e.g. KB_ATTN=72x20,80x20 : extra (S x head_dim) shapes at 12 heads
+        stages = [(int(a.split("x")[0]), 12 * int(a.split("x")[1]), int(a.split("x")[1])) for a in os.environ["KB_ATTN"].split(",")]
+    for S, D, hd in stages:
         h = 12
         qkv = rnd(B * S, 3 * D)
         q, k, v = qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:]
