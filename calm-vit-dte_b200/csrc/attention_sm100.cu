@@ -6,11 +6,12 @@
 // online rescaling, and P (bf16) goes back to shared memory as the A operand of the P.V MMA. One thread owns one query row
 // (= one TMEM lane), so row max / row sum are plain register reductions — no shuffles.
 //
-// Roles per CTA (288 threads, one CTA per SM, persistent): warps 0-7 = row workers (softmax, epilogues): warp w reads TMEM
-// lanes 32(w%4)..32(w%4)+31, the two warps of a lane quadrant take alternate 16-column chunks of every row (row max / row
-// sum of the forward are combined through two floats of shared memory per row); warp 8 lane 0 = controller (TMA loads +
-// MMA issue). Hand-offs are mbarriers:
-//   bar_kv / bar_q : TMA transaction barriers          bar_mma : tcgen05.commit -> workers      bar_work : 128 worker arrivals -> controller
+// Roles per CTA (one CTA per SM, persistent over (image, head) items): 16 row-worker warps (softmax, epilogues) — warp w reads TMEM
+// lanes 32 (w % 4) .. +31, the four warps of a lane quadrant take every 4th 16-column chunk of a row (row max / row sum of the forward
+// are combined through four floats of shared memory per row) — plus control warps whose elected lane issues the TMA loads and the MMAs:
+// one controller warp in the backward and in the serial forward, three single-purpose warps (loader, S-MMA, PV-MMA) in the pipelined
+// forward (attn_fwd_pipe_kernel, S <= 224). Hand-offs are mbarriers: TMA transaction barriers for loads, tcgen05.commit for finished
+// MMAs, worker-count arrivals for "P / dS written" and "accumulator read".
 //
 // Layouts: Q/K/V/dO tiles are TMA boxes {64 columns, rows} with the 128-byte swizzle, i.e. directly the K-major UMMA
 // operand layout (rows of 128 B). Head dims 56/44/20 are not multiples of the 16-wide MMA K step: the box still brings 64
@@ -23,8 +24,8 @@
 //   S = Q K^T and dP = dO V^T in key parts of <= 64 columns, two parts in flight  ->  P = exp2(S c + bias - lse), dS = P (dP - delta)
 //   dQ = dS K (complete per tile), dK += dS^T Q, dV += P^T dO (accumulated in TMEM over the query tiles)
 // TMEM budget (512 columns): 2 x (S part 64 | dP part 64), dQ reuses the first S part | dK 2 x 64 | dV 2 x 64.
-// dbias[b] = sum over heads of dS is accumulated by the row's owner thread in an fp32 scratch matrix (same thread, same
-// address for every head, updates issued in head order: deterministic) and written as bf16 by the last head.
+// dbias[b] = sum over heads of dS: the bf16 dS tile the MMAs consume is also TMA-stored, per head, into a (B, H, S, S) scratch and
+// dbias_reduce_kernel sums the heads afterwards in head order (deterministic; see the note above attn_bwd_tc_kernel).
 #include "tcgen05.cuh"
 #include "attention_tc.h"
 
@@ -113,7 +114,6 @@ __device__ __forceinline__ void stage_cols16(uint8_t* atom, int r, const uint32_
   *reinterpret_cast<uint4*>(atom + swz128(r, c0 >> 3)) = pack8f(f);
   *reinterpret_cast<uint4*>(atom + swz128(r, (c0 >> 3) + 1)) = pack8f(f + 8);
 }
-__device__ __forceinline__ void quad_sync(int quad) { asm volatile("bar.sync %0, 64;" ::"r"(2 + quad) : "memory"); }
 __device__ __forceinline__ void quad_sync128(int quad) { asm volatile("bar.sync %0, 128;" ::"r"(2 + quad) : "memory"); }
 // rows [row_begin, row_begin + 16) of the tile (tile-relative), global row g = g0 + row (valid while g < g_end)
 template <int NROWS = 16>
