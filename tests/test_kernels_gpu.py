@@ -312,7 +312,9 @@ def test_rope(K, B, S, h, dc, dr):
                                        (40, 224, 12, 56), (30, 176, 12, 44), (45, 128, 12, 32), (50, 80, 12, 20), (16, 240, 12, 60),
                                        (8, 384, 12, 96), (5, 512, 12, 128), (9, 336, 12, 84),
                                        # warp-per-item register kernels (S <= 128, hd <= 32): every S / 16, padded and unpadded head dims
-                                       (2, 96, 3, 24), (1, 48, 5, 12), (2, 112, 12, 28), (1, 64, 2, 32), (2, 32, 1, 8), (700, 16, 12, 16)])
+                                       (2, 96, 3, 24), (1, 48, 5, 12), (2, 112, 12, 28), (1, 64, 2, 32), (2, 32, 1, 8), (700, 16, 12, 16),
+                                       # pipelined whole-row forward at its corners: short rows with wide heads, one head, 64-wide heads at S = 224
+                                       (2, 64, 3, 48), (1, 96, 2, 64), (1, 224, 2, 64), (150, 48, 1, 36)])
 def test_attention(K, B, S, h, hd):
     """The implementation is selected by the shape alone (no process-wide switch): tcgen05 kernels where eligible (S <= 256,
     S % 16 == 0, hd <= 64), the mma.sync kernels otherwise (what the 384^2 / 512^2 configs use; S = 72 / 136 exercise their
