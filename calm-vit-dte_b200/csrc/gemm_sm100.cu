@@ -966,6 +966,26 @@ extern "C" int32_t calm_gemm_default_splits(int32_t M, int32_t N, int32_t K, int
   return (total_kb + per - 1) / per;
 }
 
+// Tile width. The widest tile that divides N evenly (<= 256 columns) is right when the launch has several waves of tiles; a launch with
+// FEWER tiles than SMs (split-K weight gradients, reduce-over-batch, M <= 256) leaves SMs idle unless the tiles get narrower. Candidates:
+// N cut into ntn0 .. 2 ntn0 + 2 column tiles; cost = waves x (BN + 112), the constant standing for the per-tile work that does not
+// shrink with BN (A operand, prologue / epilogue latency). Fitted on the schedule search over one training step (tools/gemm_tune.py,
+// profiles/r02d_gemm_schedule_search.txt: -0.23 ms of 19.8 ms over the 786 GEMMs, worst single regression 8 us); ties go to the wider tile.
+static int pick_bn(int M, int N, int splits, int batch_tiles) {
+  const int tm = (M + BM - 1) / BM, ntn0 = (N + BN_MAX - 1) / BN_MAX, sms = calm_num_sms();
+  const int cand[5] = {ntn0, ntn0 + 1, ntn0 + 2, 2 * ntn0, 2 * ntn0 + 2};
+  int best_bn = 0;
+  long long best_cost = 0;
+  for (int i = 0; i < 5; ++i) {
+    const int bn = ((N + cand[i] - 1) / cand[i] + 15) / 16 * 16;
+    if (bn < 16 || bn > BN_MAX) continue;
+    const long long tiles = (long long)tm * ((N + bn - 1) / bn) * splits * batch_tiles;
+    const long long cost = ((tiles + sms - 1) / sms) * (bn + 112);
+    if (best_bn == 0 || cost < best_cost || (cost == best_cost && bn > best_bn)) { best_bn = bn; best_cost = cost; }
+  }
+  return best_bn;
+}
+
 extern "C" int32_t calm_gemm(const calm_gemm_args* a, cudaStream_t stream) {
   CALM_CHECK_ARG(a != nullptr, "calm_gemm: null args");
   CALM_CHECK_ARG(a->M > 0 && a->N > 0 && a->K > 0 && a->batch > 0, "calm_gemm: empty problem M=%d N=%d K=%d batch=%d", a->M, a->N, a->K, a->batch);
@@ -988,8 +1008,7 @@ extern "C" int32_t calm_gemm(const calm_gemm_args* a, cudaStream_t stream) {
   GemmParams p;
   memset(&p, 0, sizeof(p));
   p.M = a->M; p.N = a->N; p.K = a->K; p.batch = a->batch;
-  const int ntn = (a->N + BN_MAX - 1) / BN_MAX;
-  p.BN = ((a->N + ntn - 1) / ntn + 15) / 16 * 16;
+  p.BN = pick_bn(a->M, a->N, splits, a->reduce_batch ? 1 : a->batch);
   if (g_bn_override >= 16 && g_bn_override <= BN_MAX && g_bn_override % 16 == 0) p.BN = g_bn_override < ((a->N + 15) / 16 * 16) ? g_bn_override : (a->N + 15) / 16 * 16;
   p.tiles_m = (a->M + BM - 1) / BM;
   p.tiles_n = (a->N + p.BN - 1) / p.BN;

@@ -80,7 +80,7 @@ def main():
                 bn = -(-(-(-N // ntn)) // 16) * 16
                 if 16 <= bn <= 256 and bn not in bns:
                     bns.append(bn)
-            variants = [(0, 0)] + [(0, bn) for bn in bns[1:]] + [(L.GEMM_NO_CLUSTER, 0), (L.GEMM_FORCE_CLUSTER, 0)]
+            variants = [(0, 0)] + [(0, bn) for bn in bns] + [(L.GEMM_NO_CLUSTER, 0), (L.GEMM_FORCE_CLUSTER, 0)]   # bns[0] = the widest even tile
             variants += [(L.GEMM_FORCE_CLUSTER, bn) for bn in bns[1:2]] + [(L.GEMM_NO_CLUSTER, bn) for bn in bns[1:2]]
             rec = results.setdefault(key, {"n": 0, "t": {}})
             rec["n"] += 1
@@ -106,7 +106,15 @@ def main():
         tot_def += d
         tot_best += rec["t"][best]
     rows.sort(key=lambda r: r["best_us"] - r["default_us"])
-    print("GEMM time per step (back-to-back, warm L2): default %.2f ms, best-of-variants %.2f ms" % (tot_def / 1e3, tot_best / 1e3))
+    tot_wide = 0.0
+    for r in rows:
+        m = __import__("re").match(r"M(\d+) N(\d+)", r["shape"])
+        N = int(m.group(2))
+        ntn0 = -(-N // 256)
+        bn0 = -(-(-(-N // ntn0)) // 16) * 16
+        tot_wide += r["all"].get("f0 bn%d" % bn0, r["default_us"])
+    print("GEMM time per step (back-to-back, warm L2): default (built-in heuristics) %.2f ms, widest-even-tile rule %.2f ms, "
+          "best-of-variants %.2f ms" % (tot_def / 1e3, tot_wide / 1e3, tot_best / 1e3))
     for r in rows[:60]:
         print("%-52s n %2d default %7.1f us  best %-12s %7.1f us  gain %6.1f us | %s" % (
             r["shape"], r["n"], r["default_us"], r["best"], r["best_us"], r["default_us"] - r["best_us"],
