@@ -1026,7 +1026,11 @@ extern "C" int32_t calm_gemm(const calm_gemm_args* a, cudaStream_t stream) {
   // ... and on one-wave problems with a long contraction and an even M-tile count (the big weight gradients: -24 % at
   // M = 2016 / 672, K = 57344 / 3-4 splits): the pair halves the B traffic per CTA and nothing is lost to a phantom tile.
   // Odd tile counts and short contractions measured 10-40 % slower in pair mode and stay single-CTA.
-  const bool many_wave = p.total_pairs >= 2 * calm_num_sms() && (p.tiles_m % 2 == 0 || p.tiles_m >= 32);
+  // Round 2 (schedule search at all four configs, tools/gemm_tune.py): with a K-major A (the activation-row GEMMs: forward and dgrad)
+  // one full wave of pairs is enough — 230..290-pair problems such as 11776 x 1104 x 2208 run 10-20 % faster paired (-0.4 ms of GEMM
+  // time per step at 384^2, -0.7 ms at 512^2, -0.1 ms at 224^2; worst single regression 10 us); MN-major A (weight gradients) keeps 2 waves.
+  const int pair_waves = a->a_major == CALM_MAJOR_K ? 1 : 2;
+  const bool many_wave = p.total_pairs >= pair_waves * calm_num_sms() && (p.tiles_m % 2 == 0 || p.tiles_m >= 32);
   const bool long_k_even = p.tiles_m % 2 == 0 && p.kb_per_split >= 128;
   const bool want_pair = !(g_debug_flags & CALM_GEMM_NO_CLUSTER) && (g_debug_flags & CALM_GEMM_FORCE_CLUSTER || many_wave || long_k_even) && p.tiles_m >= 2;
   // mode 2 = tcgen05.mma.cta_group::2 (each CTA of the pair holds half of B), mode 1 = cta_group::1 + multicast B
