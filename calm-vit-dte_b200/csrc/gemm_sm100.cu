@@ -971,7 +971,7 @@ extern "C" int32_t calm_gemm_default_splits(int32_t M, int32_t N, int32_t K, int
 // N cut into ntn0 .. 2 ntn0 + 2 column tiles; cost = waves x (BN + 112), the constant standing for the per-tile work that does not
 // shrink with BN (A operand, prologue / epilogue latency). Fitted on the schedule search over one training step (tools/gemm_tune.py,
 // profiles/r02d_gemm_schedule_search.txt: -0.23 ms of 19.8 ms over the 786 GEMMs, worst single regression 8 us); ties go to the wider tile.
-static int pick_bn(int M, int N, int splits, int batch_tiles) {
+static int pick_bn(int M, int N, int splits, int batch_tiles, bool b_mn_major) {
   const int tm = (M + BM - 1) / BM, ntn0 = (N + BN_MAX - 1) / BN_MAX, sms = calm_num_sms();
   const int cand[5] = {ntn0, ntn0 + 1, ntn0 + 2, 2 * ntn0, 2 * ntn0 + 2};
   int best_bn = 0;
@@ -980,7 +980,9 @@ static int pick_bn(int M, int N, int splits, int batch_tiles) {
     const int bn = ((N + cand[i] - 1) / cand[i] + 15) / 16 * 16;
     if (bn < 16 || bn > BN_MAX) continue;
     const long long tiles = (long long)tm * ((N + bn - 1) / bn) * splits * batch_tiles;
-    const long long cost = ((tiles + sms - 1) / sms) * (bn + 112);
+    // an MN-major B tile is loaded in boxes of 64 columns: a width that is no multiple of 64 pays for the full boxes
+    const int eff = b_mn_major ? (bn + 63) / 64 * 64 : bn;
+    const long long cost = ((tiles + sms - 1) / sms) * (eff + 112);
     if (best_bn == 0 || cost < best_cost || (cost == best_cost && bn > best_bn)) { best_bn = bn; best_cost = cost; }
   }
   return best_bn;
@@ -1008,7 +1010,7 @@ extern "C" int32_t calm_gemm(const calm_gemm_args* a, cudaStream_t stream) {
   GemmParams p;
   memset(&p, 0, sizeof(p));
   p.M = a->M; p.N = a->N; p.K = a->K; p.batch = a->batch;
-  p.BN = pick_bn(a->M, a->N, splits, a->reduce_batch ? 1 : a->batch);
+  p.BN = pick_bn(a->M, a->N, splits, a->reduce_batch ? 1 : a->batch, a->b_major == CALM_MAJOR_MN);
   if (g_bn_override >= 16 && g_bn_override <= BN_MAX && g_bn_override % 16 == 0) p.BN = g_bn_override < ((a->N + 15) / 16 * 16) ? g_bn_override : (a->N + 15) / 16 * 16;
   p.tiles_m = (a->M + BM - 1) / BM;
   p.tiles_n = (a->N + p.BN - 1) / p.BN;
