@@ -1034,7 +1034,15 @@ extern "C" int32_t calm_gemm(const calm_gemm_args* a, cudaStream_t stream) {
   const int pair_waves = a->a_major == CALM_MAJOR_K ? 1 : 2;
   const bool many_wave = p.total_pairs >= pair_waves * calm_num_sms() && (p.tiles_m % 2 == 0 || p.tiles_m >= 32);
   const bool long_k_even = p.tiles_m % 2 == 0 && p.kb_per_split >= 128;
-  const bool want_pair = !(g_debug_flags & CALM_GEMM_NO_CLUSTER) && (g_debug_flags & CALM_GEMM_FORCE_CLUSTER || many_wave || long_k_even) && p.tiles_m >= 2;
+  // Weight gradients (MN-major A) whose PAIRED launch still fits one wave — odd M-tile counts included, the phantom tile then costs no
+  // second wave — with >= 24 k-blocks per split and a half tile that fills its 64-column B boxes to >= 74 %: 0.74 - 0.9x the single-CTA
+  // time on 8 - 22 shapes per config (-0.16 / -0.39 / -0.52 ms of GEMM time per step at 224^2 / 384^2 / 512^2). The same shapes with a
+  // paired launch of 150+ CTAs (tm = 5, 7, 9 with the split count chosen for single tiles) are 1.2 - 1.9x SLOWER paired.
+  const int half_bn = p.BN / 2;
+  const bool one_wave_pairs = a->a_major == CALM_MAJOR_MN && 2 * p.total_pairs <= calm_num_sms() && p.kb_per_split >= 24 &&
+                              (a->b_major != CALM_MAJOR_MN || (half_bn + 63) / 64 * 64 * 100 <= 135 * half_bn);
+  const bool want_pair = !(g_debug_flags & CALM_GEMM_NO_CLUSTER) &&
+                         (g_debug_flags & CALM_GEMM_FORCE_CLUSTER || many_wave || long_k_even || one_wave_pairs) && p.tiles_m >= 2;
   // mode 2 = tcgen05.mma.cta_group::2 (each CTA of the pair holds half of B), mode 1 = cta_group::1 + multicast B
   const int pair = !want_pair ? 0 : (g_debug_flags & CALM_GEMM_PAIR_MULTICAST) ? 1 : 2;
   // TMA-staged epilogue unless the operand mix has no in-place form (addend of another dtype than C, GELU into fp32, ...)
