@@ -2,6 +2,7 @@
 checked against plain PyTorch fp32 math on the same (bf16-rounded) inputs. Tolerances are written at each assert.
 """
 import math
+import os
 
 import pytest
 import torch
@@ -342,6 +343,29 @@ def _attention_case(K, B, S, h, hd):
     assert rel(dq, tok(qr.grad)) < 1e-2
     assert rel(dk, tok(kr.grad)) < 1e-2
     assert rel(dbias, br.grad) < 1e-2
+
+
+@pytest.mark.parametrize("B,S,h,hd", [(64, 224, 12, 56), (64, 176, 12, 44), (96, 128, 12, 32), (128, 80, 12, 20), (16, 384, 12, 96), (8, 512, 12, 128)])
+def test_attention_bitwise_repeatable(K, B, S, h, hd):
+    """No atomics, fixed summation orders: repeated launches at trainer-like sizes (several items per persistent CTA, so the timing of
+    the producer / consumer warps differs from launch to launch) must give bit-identical results — a hand-over race between the
+    loader, MMA and worker warps would show up here as a flipped bit long before it shows up as a tolerance failure."""
+    D = h * hd
+    reps = int(os.environ.get("CALM_TEST_REPEATS", "4"))
+    qkv = rnd(B * S, 3 * D, seed=41)
+    q, k, v = qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:]
+    bias = rnd(B, S, S, seed=42)
+    d_o = rnd(B * S, D, seed=43)
+    first = None
+    for _ in range(reps):
+        o, lse = K.attention_fwd(q, k, v, bias, B, S, h, hd, 3 * D, 3 * D, 3 * D)
+        res = (o, lse) + tuple(K.attention_bwd(q, k, v, bias, o, d_o, lse, B, S, h, hd, 3 * D, 3 * D, 3 * D, D))
+        res = [t.clone() for t in res]
+        if first is None:
+            first = res
+        else:
+            for name, a, b in zip(("o", "lse", "dq", "dk", "dv", "dbias"), first, res):
+                assert torch.equal(a, b), "%s differs between two launches on the same inputs" % name
 
 
 # ------------------------------------------------------------------------------------------------------ latent
