@@ -648,8 +648,15 @@ class AttnCoreFn(Function):
         qc, ld_qc = role("qc"); qr, ld_qr = role("qr")
         kc, ld_kc = role("kc"); kr, ld_kr = role("kr")
         v, ld_v = role("v")
-        q = K.rope_fwd(qc, ld_qc, qr, ld_qr, inv_q, T, S, heads, dc, dr)
-        k = K.rope_fwd(kc, ld_kc, kr, ld_kr, inv_k, T, S, heads, dc, dr)
+        roped = {}
+
+        def _rope(name, c_, ldc_, r_, ldr_, inv):
+            def run():
+                roped[name] = K.rope_fwd(c_, ldc_, r_, ldr_, inv, T, S, heads, dc, dr)
+            return run
+        # the two rotations are independent 10 - 30 us kernels: side by side, each hides the other's launch / tail latency
+        fork_join(v.device, _rope("q", qc, ld_qc, qr, ld_qr, inv_q), _rope("k", kc, ld_kc, kr, ld_kr, inv_k))
+        q, k = roped["q"], roped["k"]
         logits = torch.empty(B, S, S, dtype=bf16, device=q.device)
         K.gemm(q, k, logits, S, S, D, batch=B, lda=D, ldb=D, ldc=S, stride_a=S * D, stride_b=S * D, stride_c=S * S)
         bias = torch.empty(B, S, S, dtype=bf16, device=q.device)
@@ -693,17 +700,22 @@ class AttnCoreFn(Function):
         need_w = ctx.needs_input_grad[0]
         dlog, db1, db2 = _mlp_backward(bank, ctx.g1, ctx.g2, dbias.view(T, S), T, S, logits.view(T, S), S, pre, hid, True, need_w, True)
         # logits = q k^T (all heads, unscaled): dq += dL k ; dk += dL^T q   (accumulated in place through the addend)
-        fork_join(q.device,
-                  lambda: K.gemm(dlog, k, dq, S, D, S, batch=B, lda=S, ldb=D, ldc=D, stride_a=S * S, stride_b=S * D, stride_c=S * D,
-                                 b_major=MAJOR_MN, addend=dq, ld_addend=D, stride_addend=S * D),
-                  lambda: K.gemm(dlog, q, dk, S, D, S, batch=B, lda=S, ldb=D, ldc=D, stride_a=S * S, stride_b=S * D, stride_c=S * D,
-                                 a_major=MAJOR_MN, b_major=MAJOR_MN, addend=dk, ld_addend=D, stride_addend=S * D))
         dqc, ld_dqc = role("qc", dsrc2); dqr, ld_dqr = role("qr", dsrc2)
         dkc, ld_dkc = role("kc", dsrc2); dkr, ld_dkr = role("kr", dsrc2)
-        _, _, dinv_q = K.rope_bwd(dq, D, q, inv_q, T, S, heads, dc, dr, dcontent=dqc, ld_dcontent=ld_dqc, dropein=dqr, ld_drope=ld_dqr)
-        _, _, dinv_k = K.rope_bwd(dk, D, k, inv_k, T, S, heads, dc, dr, dcontent=dkc, ld_dcontent=ld_dkc, dropein=dkr, ld_drope=ld_dkr)
+        dinv = {}
+
+        def _q_side():      # the q chain and the k chain are independent from here on: mask-logit dgrad, then the rotation's backward
+            K.gemm(dlog, k, dq, S, D, S, batch=B, lda=S, ldb=D, ldc=D, stride_a=S * S, stride_b=S * D, stride_c=S * D,
+                   b_major=MAJOR_MN, addend=dq, ld_addend=D, stride_addend=S * D)
+            dinv["q"] = K.rope_bwd(dq, D, q, inv_q, T, S, heads, dc, dr, dcontent=dqc, ld_dcontent=ld_dqc, dropein=dqr, ld_drope=ld_dqr)[2]
+
+        def _k_side():
+            K.gemm(dlog, q, dk, S, D, S, batch=B, lda=S, ldb=D, ldc=D, stride_a=S * S, stride_b=S * D, stride_c=S * D,
+                   a_major=MAJOR_MN, b_major=MAJOR_MN, addend=dk, ld_addend=D, stride_addend=S * D)
+            dinv["k"] = K.rope_bwd(dk, D, k, inv_k, T, S, heads, dc, dr, dcontent=dkc, ld_dcontent=ld_dkc, dropein=dkr, ld_drope=ld_dkr)[2]
+        fork_join(q.device, _q_side, _k_side)
         ctx.saved = None
-        return (None, dinv_q, dinv_k, db1, db2, None, None, None, None, None, *dsrc)
+        return (None, dinv["q"], dinv["k"], db1, db2, None, None, None, None, None, *dsrc)
 
 
 class LatentFn(Function):
