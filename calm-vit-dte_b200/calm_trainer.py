@@ -132,8 +132,8 @@ def huber_kl_loss(tokens, image, kl=None, kl_weight=0.1, delta=1.0):
 class GraphedStep:
     """One training step captured into a CUDA graph and replayed.
 
-    The reference loop launches ~1,260 kernels per step through Python; run eagerly the drop-in path is bound by that launch
-    path (~90 ms/step on the trainer config) rather than by the GPU (~59 ms). All shapes of the path are static, so the whole
+    The loop launches ~1,210 kernels per step through Python; run eagerly the drop-in path is bound by that launch
+    path (55 - 90 ms/step on the trainer config, by host CPU) rather than by the GPU (~47 ms). All shapes of the path are static, so the whole
     step — forward, loss head, backward, `TrainerStep.step()`, `zero_grad()` — can be captured once:
 
         x_dev, y_dev = torch.empty(...), torch.empty(...)            # static input buffers the step function reads
