@@ -222,6 +222,7 @@ attn_fwd_kernel(const bf16* __restrict__ q, const bf16* __restrict__ k, const bf
 // 2*hd-byte segments of the same token row, so the warp's accesses are contiguous)
 __global__ void attn_delta_kernel(const bf16* __restrict__ o, const bf16* __restrict__ d_o, float* __restrict__ delta, long long ld_o,
                                   long long ld_do, long long tokens, int S, int heads, int hd) {
+  pdl_wait(); pdl_launch_dependents();   // see common.cuh: launched with programmatic stream serialization
   const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (w >= tokens * heads) return;
   const long long t = w / heads;
@@ -591,8 +592,8 @@ extern "C" int32_t calm_attention_bwd(const void* q, const void* k, const void* 
                  "calm_attention_bwd: q/k/v/o/dO leading dims must be multiples of 4");
   const long long tokens = (long long)B * S;
   const long long nthr = tokens * heads;
-  attn_delta_kernel<<<(unsigned)((nthr + 255) / 256), 256, 0, stream>>>(
-      reinterpret_cast<const bf16*>(o), reinterpret_cast<const bf16*>(d_o), delta, ld_o, ld_do, tokens, S, heads, hd);
+  CALM_LAUNCH((attn_delta_kernel), (unsigned)((nthr + 255) / 256), 256, 0, stream,
+              reinterpret_cast<const bf16*>(o), reinterpret_cast<const bf16*>(d_o), delta, ld_o, ld_do, tokens, S, heads, hd);
   CALM_CHECK_LAUNCH("calm_attention_bwd(delta)");
   {
     const int64_t lds[4] = {ld_q, ld_k, ld_v, ld_do};

@@ -955,6 +955,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap mQ, const __grid_constant
 // dbias[b, q, k] = sum_h dS[b, h, q, k]  (bf16 in, fp32 sum in head order, bf16 out); 8 elements (16 bytes) per thread
 __global__ void dbias_reduce_kernel(const bf16* __restrict__ ds, bf16* __restrict__ dbias, int heads, long long ss8 /* S * S / 8 */,
                                     long long total8 /* B * S * S / 8 */) {
+  pdl_wait(); pdl_launch_dependents();   // see common.cuh: launched with programmatic stream serialization (after the backward kernel)
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total8) return;
   const long long b = i / ss8, r = i - b * ss8;
@@ -1098,8 +1099,8 @@ int calm_attention_bwd_tc(const void* q, const void* k, const void* v, const voi
 
 int calm_attention_dbias_reduce(const void* ds_scratch, void* dbias, int B, int S, int heads, cudaStream_t stream) {
   const long long ss8 = (long long)S * S / 8, total8 = ss8 * B;
-  dbias_reduce_kernel<<<(unsigned)((total8 + 255) / 256), 256, 0, stream>>>(reinterpret_cast<const bf16*>(ds_scratch),
-                                                                            reinterpret_cast<bf16*>(dbias), heads, ss8, total8);
+  CALM_LAUNCH((dbias_reduce_kernel), (unsigned)((total8 + 255) / 256), 256, 0, stream, reinterpret_cast<const bf16*>(ds_scratch),
+              reinterpret_cast<bf16*>(dbias), heads, ss8, total8);
   CALM_CHECK_LAUNCH("calm_attention_bwd(dbias reduce)");
   return CALM_OK;
 }

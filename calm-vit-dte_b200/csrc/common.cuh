@@ -68,15 +68,26 @@ struct CalmDeviceOnce {
 };
 
 // ---- programmatic dependent launch (PDL) ------------------------------------------------------------------------------------
-// A training step is ~1,200 short kernels in one stream; between two of them the GPU idles for the grid-completion -> next-launch
-// latency plus the next kernel's prologue (barrier init, TMEM allocation, descriptor prefetch). Kernels launched through
-// calm_launch_pdl carry cudaLaunchAttributeProgrammaticStreamSerialization: their CTAs may be scheduled while the predecessor
-// drains, run their prologue, and block in pdl_wait() until the predecessor has completed and its writes are visible.
-// RULE: a kernel launched this way executes pdl_wait() in every thread before its first global-memory access (read OR write).
+// A training step is ~1,500 short kernels in one stream; between two of them the GPU idles for the grid-completion -> flush ->
+// next-launch latency. Kernels launched through calm_launch_pdl / CALM_LAUNCH carry cudaLaunchAttributeProgrammaticStreamSerialization:
+// their CTAs may be scheduled as soon as the predecessor's CTAs have exited (or earlier, if the predecessor triggers), and block in
+// pdl_wait() until the predecessor has completed and its writes are visible.
+// RULE: a kernel launched this way executes pdl_wait() before its first global-memory access (read OR write).
 // Since every such kernel waits for its predecessor before finishing, completion stays transitive along the stream.
 // CALM_PDL=0 in the environment (read once at load) launches the same kernels without the attribute (A/B and fault isolation).
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+// Early trigger: lets the dependents' CTAs become resident while this grid still runs. Measured (r02f build, all small kernels converted):
+// -0.2 ms/step at 224^2 but +2.7 ms at 512^2 — CTAs of several future kernels pile up resident and waiting, and a 227 KB GEMM /
+// attention CTA of a forked stream no longer finds an empty SM. So the trigger is compiled out (-DCALM_PDL_EARLY brings it back):
+// dependents launch when this grid's CTAs have exited, which still hides the completion -> flush -> launch latency.
+// The exception: a kernel whose dependent is its own tiny reduction (LayerNorm backward -> dw partial sums, column sums -> their
+// reduction): ~20 CTAs that follow immediately and have no PDL dependents that could pile up behind them.
+__device__ __forceinline__ void pdl_launch_small_dependent() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() {
+#ifdef CALM_PDL_EARLY
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
 inline bool calm_pdl_enabled() {
   static const bool on = [] { const char* e = getenv("CALM_PDL"); return !(e && e[0] == '0'); }();
   return on;
@@ -99,6 +110,11 @@ inline cudaError_t calm_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 blo
   cfg.attrs = attr; cfg.numAttrs = (unsigned)n;
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
+
+// kernel<<<grid, block, smem, stream>>>(args...) with the PDL attribute; the kernel must start with pdl_wait() (see above). Errors
+// surface through the CALM_CHECK_LAUNCH that follows (cudaLaunchKernelEx records them as the last error).
+#define CALM_LAUNCH(KERNEL, GRID, BLOCK, SMEM, STREAM, ...) \
+  (void)calm_launch_pdl(KERNEL, dim3(GRID), dim3(BLOCK), (size_t)(SMEM), STREAM, nullptr, 0, __VA_ARGS__)
 
 typedef __nv_bfloat16 bf16;
 typedef __nv_bfloat162 bf162;

@@ -18,6 +18,7 @@ __device__ __forceinline__ float sigmoid_ref(float x) { return x > 20.f ? 1.f : 
 __global__ void __launch_bounds__(LAT_THREADS)
 latent_fwd_kernel(const bf16* __restrict__ mv, const float* __restrict__ eps, const float* __restrict__ zsum_prev,
                   float* __restrict__ zsum, bf16* __restrict__ zsum_bf16, float* __restrict__ kl_partial, long long rows, int Mh) {
+  pdl_wait(); pdl_launch_dependents();   // see common.cuh: launched with programmatic stream serialization
   __shared__ float red[32];
   const long long total = rows * Mh;
   float kl = 0.f;
@@ -42,6 +43,7 @@ __global__ void __launch_bounds__(LAT_THREADS)
 latent_bwd_kernel(const bf16* __restrict__ mv, const float* __restrict__ eps, const float* __restrict__ dz,
                   const bf16* __restrict__ dz2, float kl_scale, const float* __restrict__ dkl, bf16* __restrict__ dmv,
                   float* __restrict__ dz_total, long long rows, int Mh) {
+  pdl_wait(); pdl_launch_dependents();   // see common.cuh: launched with programmatic stream serialization
   const long long total = rows * Mh;
   // KL = kl_scale * sum(1 + 2 log sg - mu^2 - sg^2)  =>  dKL/dmu = -2 kl_scale mu ; dKL/dsg = -2 kl_scale (sg - 1/sg)
   const float gk = dkl ? -2.f * (*dkl) * kl_scale : 0.f;
@@ -77,6 +79,7 @@ __device__ __forceinline__ void st4_bf16(bf16* p, const float* f) {
 __global__ void __launch_bounds__(LAT_THREADS)
 latent_fwd4_kernel(const bf16* __restrict__ mv, const float* __restrict__ eps, const float* __restrict__ zsum_prev,
                    float* __restrict__ zsum, bf16* __restrict__ zsum_bf16, float* __restrict__ kl_partial, long long rows, int Mh) {
+  pdl_wait(); pdl_launch_dependents();   // see common.cuh: launched with programmatic stream serialization
   __shared__ float red[32];
   const int q = Mh >> 2;
   const long long total4 = rows * q;
@@ -112,6 +115,7 @@ __global__ void __launch_bounds__(LAT_THREADS)
 latent_bwd4_kernel(const bf16* __restrict__ mv, const float* __restrict__ eps, const float* __restrict__ dz,
                    const bf16* __restrict__ dz2, float kl_scale, const float* __restrict__ dkl, bf16* __restrict__ dmv,
                    float* __restrict__ dz_total, long long rows, int Mh) {
+  pdl_wait(); pdl_launch_dependents();   // see common.cuh: launched with programmatic stream serialization
   const int q = Mh >> 2;
   const long long total4 = rows * q;
   const float gk = dkl ? -2.f * (*dkl) * kl_scale : 0.f;
@@ -150,6 +154,7 @@ __host__ inline bool latent_vec_ok(int Mh, std::initializer_list<const void*> pt
 // kl_out = kl_prev + scale * (sum part_q + sum part_kv): running KL total of ResidualStateManager (Vi_Tools…:24-26)
 __global__ void latent_kl_kernel(const float* __restrict__ part_q, const float* __restrict__ part_kv, int nblocks,
                                  const float* __restrict__ kl_prev, float* __restrict__ kl_out, float scale) {
+  pdl_wait(); pdl_launch_dependents();   // see common.cuh: launched with programmatic stream serialization
   __shared__ float red[32];
   float s = 0.f;
   for (int i = threadIdx.x; i < nblocks; i += blockDim.x) s += part_q[i] + part_kv[i];
@@ -162,7 +167,7 @@ __global__ void latent_kl_kernel(const float* __restrict__ part_q, const float* 
 extern "C" int32_t calm_latent_kl(const float* part_q, const float* part_kv, int32_t nblocks, const float* kl_prev,
                                   float* kl_out, float scale, cudaStream_t stream) {
   CALM_CHECK_ARG(part_q && part_kv && kl_out && nblocks > 0, "calm_latent_kl: bad args");
-  latent_kl_kernel<<<1, 256, 0, stream>>>(part_q, part_kv, nblocks, kl_prev, kl_out, scale);
+  CALM_LAUNCH((latent_kl_kernel), 1, 256, 0, stream, part_q, part_kv, nblocks, kl_prev, kl_out, scale);
   CALM_CHECK_LAUNCH("calm_latent_kl");
   return CALM_OK;
 }
@@ -178,10 +183,10 @@ extern "C" int32_t calm_latent_fwd(const void* mv, const float* eps, const float
   CALM_CHECK_ARG(rows > 0 && Mh > 0, "calm_latent_fwd: rows=%lld Mh=%d", (long long)rows, Mh);
   CALM_CHECK_ARG(nblocks == calm_latent_blocks(rows, Mh), "calm_latent_fwd: nblocks=%d expected %d", nblocks, calm_latent_blocks(rows, Mh));
   if (latent_vec_ok(Mh, {mv, eps, zsum_prev, zsum, zsum_bf16}))
-    latent_fwd4_kernel<<<nblocks, LAT_THREADS, 0, stream>>>(reinterpret_cast<const bf16*>(mv), eps, zsum_prev, zsum,
+    CALM_LAUNCH((latent_fwd4_kernel), nblocks, LAT_THREADS, 0, stream, reinterpret_cast<const bf16*>(mv), eps, zsum_prev, zsum,
                                                             reinterpret_cast<bf16*>(zsum_bf16), kl_partial, rows, Mh);
   else
-    latent_fwd_kernel<<<nblocks, LAT_THREADS, 0, stream>>>(reinterpret_cast<const bf16*>(mv), eps, zsum_prev, zsum,
+    CALM_LAUNCH((latent_fwd_kernel), nblocks, LAT_THREADS, 0, stream, reinterpret_cast<const bf16*>(mv), eps, zsum_prev, zsum,
                                                            reinterpret_cast<bf16*>(zsum_bf16), kl_partial, rows, Mh);
   CALM_CHECK_LAUNCH("calm_latent_fwd");
   return CALM_OK;
@@ -191,11 +196,11 @@ extern "C" int32_t calm_latent_bwd(const void* mv, const float* eps, const float
                                    const float* dkl, void* dmv, float* dz_total, int64_t rows, int32_t Mh, cudaStream_t stream) {
   CALM_CHECK_ARG(rows > 0 && Mh > 0, "calm_latent_bwd: rows=%lld Mh=%d", (long long)rows, Mh);
   if (latent_vec_ok(Mh, {mv, eps, dz, dz_bf16, dmv, dz_total}))
-    latent_bwd4_kernel<<<calm_latent_blocks(rows, Mh), LAT_THREADS, 0, stream>>>(reinterpret_cast<const bf16*>(mv), eps, dz,
+    CALM_LAUNCH((latent_bwd4_kernel), calm_latent_blocks(rows, Mh), LAT_THREADS, 0, stream, reinterpret_cast<const bf16*>(mv), eps, dz,
                                                                                  reinterpret_cast<const bf16*>(dz_bf16), kl_scale, dkl,
                                                                                  reinterpret_cast<bf16*>(dmv), dz_total, rows, Mh);
   else
-    latent_bwd_kernel<<<calm_latent_blocks(rows, Mh), LAT_THREADS, 0, stream>>>(reinterpret_cast<const bf16*>(mv), eps, dz,
+    CALM_LAUNCH((latent_bwd_kernel), calm_latent_blocks(rows, Mh), LAT_THREADS, 0, stream, reinterpret_cast<const bf16*>(mv), eps, dz,
                                                                                 reinterpret_cast<const bf16*>(dz_bf16), kl_scale, dkl,
                                                                                 reinterpret_cast<bf16*>(dmv), dz_total, rows, Mh);
   CALM_CHECK_LAUNCH("calm_latent_bwd");

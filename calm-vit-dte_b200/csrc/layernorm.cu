@@ -17,6 +17,7 @@ template <bool OUT_F32, int VPL>
 __global__ void __launch_bounds__(LN_THREADS)
 ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, void* __restrict__ y, float* __restrict__ mean,
               float* __restrict__ rstd, long long rows, int D, float eps) {
+  pdl_wait(); pdl_launch_dependents();   // see common.cuh: launched with programmatic stream serialization
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const long long row = (long long)blockIdx.x * LN_WARPS + warp;
   if (row >= rows) return;
@@ -93,6 +94,7 @@ constexpr int LN_IMG_PPL = 16;     // pixels per lane: S <= 512
 __global__ void __launch_bounds__(LN_THREADS)
 ln_fwd_image_kernel(const float* __restrict__ img, const float* __restrict__ w, bf16* __restrict__ y, float* __restrict__ tokens,
                     float* __restrict__ mean, float* __restrict__ rstd, int B, int S, float eps) {
+  pdl_wait(); pdl_launch_dependents();   // see common.cuh: launched with programmatic stream serialization
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const long long row = (long long)blockIdx.x * LN_WARPS + warp;      // token index b * S + image row
   if (row >= (long long)B * S) return;
@@ -151,6 +153,7 @@ __global__ void __launch_bounds__(LN_THREADS)
 ln_bwd_kernel(const void* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ w,
               const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ dres,
               float* __restrict__ dx, bf16* __restrict__ dx16, float* __restrict__ dw_partial, long long rows, int D) {
+  pdl_wait(); pdl_launch_dependents();   // see common.cuh: launched with programmatic stream serialization
   extern __shared__ float acc_s[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float* my = acc_s + (size_t)warp * D;
@@ -211,6 +214,7 @@ ln_bwd_reg_kernel(const void* __restrict__ dy, const float* __restrict__ x, cons
                   float* __restrict__ dx, bf16* __restrict__ dx16, float* __restrict__ dw_partial, long long rows, int D) {
   extern __shared__ float acc_s[];  // (LN_WARPS / WPR) * D, then D floats of w
   __shared__ float pair_red[2][LN_WARPS];
+  pdl_wait(); pdl_launch_small_dependent();   // the dw reduction kernel may be scheduled as CTAs of this grid retire (it waits for the whole grid)
   constexpr int RPC = LN_WARPS / WPR;      // rows per CTA iteration
   constexpr int LANES = 32 * WPR;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -317,6 +321,7 @@ reduce_partials_kernel(const float* __restrict__ partial, float* __restrict__ ou
   __shared__ float red[RP_GROUPS][33];
   const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + cx;
+  pdl_wait();                                   // launched while the backward kernel drains: its partial rows are complete from here on
   float s0 = 0.f, s1 = 0.f;
   if (c < n) {
     int p = ry;
@@ -343,7 +348,7 @@ extern "C" int32_t calm_layernorm_fwd(const float* x, const float* w, void* y, i
   CALM_CHECK_ARG(rows > 0 && D > 0 && D % 4 == 0, "calm_layernorm_fwd: rows=%lld D=%d (D must be a multiple of 4)", (long long)rows, D);
   const unsigned grid = (unsigned)((rows + LN_WARPS - 1) / LN_WARPS);
   const int vpl = (D / 4 + 31) / 32;  // float4 per lane and row
-#define LN_FWD_LAUNCH(F32, VPL) ln_fwd_kernel<F32, VPL><<<grid, LN_THREADS, 0, stream>>>(x, w, y, mean, rstd, rows, D, eps)
+#define LN_FWD_LAUNCH(F32, VPL) CALM_LAUNCH((ln_fwd_kernel<F32, VPL>), grid, LN_THREADS, 0, stream, x, w, y, mean, rstd, rows, D, eps)
   if (y_dtype == CALM_F32) {
     if (vpl <= 2) LN_FWD_LAUNCH(true, 2); else if (vpl <= 4) LN_FWD_LAUNCH(true, 4); else if (vpl <= 6) LN_FWD_LAUNCH(true, 6);
     else if (vpl <= 12) LN_FWD_LAUNCH(true, 12); else LN_FWD_LAUNCH(true, 0);
@@ -360,7 +365,7 @@ extern "C" int32_t calm_layernorm_fwd_image(const float* img, const float* w, vo
                                             int32_t B, int32_t S, float eps, cudaStream_t stream) {
   CALM_CHECK_ARG(B > 0 && S > 0 && S <= 32 * LN_IMG_PPL, "calm_layernorm_fwd_image: B=%d S=%d (S <= %d)", B, S, 32 * LN_IMG_PPL);
   const long long rows = (long long)B * S;
-  ln_fwd_image_kernel<<<(unsigned)((rows + LN_WARPS - 1) / LN_WARPS), LN_THREADS, 0, stream>>>(img, w, reinterpret_cast<bf16*>(y_bf16), tokens, mean,
+  CALM_LAUNCH((ln_fwd_image_kernel), (unsigned)((rows + LN_WARPS - 1) / LN_WARPS), LN_THREADS, 0, stream, img, w, reinterpret_cast<bf16*>(y_bf16), tokens, mean,
                                                                                               rstd, B, S, eps);
   CALM_CHECK_LAUNCH("calm_layernorm_fwd_image");
   return CALM_OK;
@@ -387,7 +392,7 @@ extern "C" int32_t calm_layernorm_bwd(const void* dy, int32_t dy_dtype, const fl
       cudaError_t e = cudaFuncSetAttribute(KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);           \
       if (e != cudaSuccess) { calm_set_error("calm_layernorm_bwd: smem %zu: %s", smem, cudaGetErrorString(e)); return CALM_ERR_CUDA; } \
     }                                                                                                                 \
-    KERNEL<<<nparts, LN_THREADS, smem, stream>>>(dy, x, w, mean, rstd, dres, dx, reinterpret_cast<bf16*>(dx_bf16), dw_partial, rows, D);                  \
+    CALM_LAUNCH((KERNEL), nparts, LN_THREADS, smem, stream, dy, x, w, mean, rstd, dres, dx, reinterpret_cast<bf16*>(dx_bf16), dw_partial, rows, D);                  \
   } while (0)
   if (vpl <= 3) { if (f32) LN_BWD_LAUNCH((ln_bwd_reg_kernel<3, true, 1>)); else LN_BWD_LAUNCH((ln_bwd_reg_kernel<3, false, 1>)); }
   else if (vpl <= 6) { if (f32) LN_BWD_LAUNCH((ln_bwd_reg_kernel<6, true, 1>)); else LN_BWD_LAUNCH((ln_bwd_reg_kernel<6, false, 1>)); }
@@ -395,7 +400,10 @@ extern "C" int32_t calm_layernorm_bwd(const void* dy, int32_t dy_dtype, const fl
   else { if (f32) LN_BWD_LAUNCH((ln_bwd_kernel<true>)); else LN_BWD_LAUNCH((ln_bwd_kernel<false>)); }
 #undef LN_BWD_LAUNCH
   CALM_CHECK_LAUNCH("calm_layernorm_bwd");
-  reduce_partials_kernel<<<(D + 31) / 32, 32 * RP_GROUPS, 0, stream>>>(dw_partial, dw, nparts, D);
-  CALM_CHECK_LAUNCH("calm_layernorm_bwd(reduce)");
+  {
+    cudaError_t e = calm_launch_pdl(reduce_partials_kernel, dim3((D + 31) / 32), dim3(32 * RP_GROUPS), 0, stream, nullptr, 0,
+                                    (const float*)dw_partial, dw, nparts, D);
+    if (e != cudaSuccess) { calm_set_error("calm_layernorm_bwd(reduce): launch failed: %s", cudaGetErrorString(e)); return CALM_ERR_CUDA; }
+  }
   return CALM_OK;
 }

@@ -13,6 +13,7 @@ template <bool VEC>
 __global__ void __launch_bounds__(256)
 token_transpose_kernel(const float* __restrict__ in, const float* __restrict__ addend, float* __restrict__ out,
                        bf16* __restrict__ out16, int S) {
+  pdl_wait(); pdl_launch_dependents();   // see common.cuh: launched with programmatic stream serialization
   __shared__ float tile[32][32 * 3 + 1];
   const int b = blockIdx.z, i0 = blockIdx.y * 32, j0 = blockIdx.x * 32;
   const float* src = in + (long long)b * S * S * 3;
@@ -69,6 +70,7 @@ token_transpose_kernel(const float* __restrict__ in, const float* __restrict__ a
 
 // (B,3,S,S) NCHW -> (B,S,S,3) tokens  (x.permute(0,2,3,1).reshape(B,S,3S), Vi_Tools_CNN_less_V2.py:389-391)
 __global__ void nchw_to_tokens_kernel(const float* __restrict__ in, float* __restrict__ out, long long npix_total, long long plane) {
+  pdl_wait(); pdl_launch_dependents();   // see common.cuh: launched with programmatic stream serialization
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // over B*S*S*3 output elements
   if (i >= npix_total * 3) return;
   const long long pix = i / 3;
@@ -81,6 +83,7 @@ __global__ void nchw_to_tokens_kernel(const float* __restrict__ in, float* __res
 // strided over the CTAs and unrolled 4x for memory-level parallelism
 __global__ void __launch_bounds__(256)
 colsum_kernel(const bf16* __restrict__ x, long long ld, float* __restrict__ partial, long long rows, int N) {
+  pdl_wait(); pdl_launch_dependents();   // see common.cuh: launched with programmatic stream serialization
   for (int c = 2 * threadIdx.x; c < N; c += 512) {
     float s0 = 0.f, s1 = 0.f;
     long long r = blockIdx.x;
@@ -108,6 +111,7 @@ colsum_kernel(const bf16* __restrict__ x, long long ld, float* __restrict__ part
 __global__ void __launch_bounds__(256)
 colsum_vec_kernel(const bf16* __restrict__ x, long long ld, float* __restrict__ partial, long long rows, int N) {
   __shared__ float red[2048];
+  pdl_wait(); pdl_launch_small_dependent();
   const int chunks = N >> 3, R = 256 / chunks;
   const int r = threadIdx.x / chunks, k = threadIdx.x - r * chunks;
   float s[8];
@@ -151,6 +155,7 @@ reduce_cols_kernel(const float* __restrict__ partial, float* __restrict__ out, i
   __shared__ float red[RC_GROUPS][33];
   const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + cx;
+  pdl_wait();                                   // launched while the column-sum kernel drains
   float s0 = 0.f, s1 = 0.f;
   if (c < n) {
     int p = ry;
@@ -172,6 +177,7 @@ reduce_cols_kernel(const float* __restrict__ partial, float* __restrict__ out, i
 
 __global__ void add3_kernel(const float4* __restrict__ a, const float4* __restrict__ b, const float4* __restrict__ c,
                             float4* __restrict__ out, long long n4) {
+  pdl_wait(); pdl_launch_dependents();   // see common.cuh: launched with programmatic stream serialization
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
     float4 v = a[i];
     const float4 w = b[i];
@@ -182,6 +188,7 @@ __global__ void add3_kernel(const float4* __restrict__ a, const float4* __restri
 }
 
 __global__ void cast_bf16_kernel(const float4* __restrict__ in, uint2* __restrict__ out, long long n4) {
+  pdl_wait(); pdl_launch_dependents();   // see common.cuh: launched with programmatic stream serialization
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
     const float4 v = in[i];
     uint2 o; o.x = pack_bf16x2(v.x, v.y); o.y = pack_bf16x2(v.z, v.w);
@@ -190,6 +197,7 @@ __global__ void cast_bf16_kernel(const float4* __restrict__ in, uint2* __restric
 }
 
 __global__ void cast_f32_kernel(const uint2* __restrict__ in, float4* __restrict__ out, long long n4) {
+  pdl_wait(); pdl_launch_dependents();   // see common.cuh: launched with programmatic stream serialization
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
     const uint2 v = in[i];
     const float2 a = unpack_bf16x2(v.x), b = unpack_bf16x2(v.y);
@@ -199,6 +207,7 @@ __global__ void cast_f32_kernel(const uint2* __restrict__ in, float4* __restrict
 
 // out[b, d] = mean_s x[b, s, d]
 __global__ void seq_mean_fwd_kernel(const float* __restrict__ x, bf16* __restrict__ out, int S, int D) {
+  pdl_wait(); pdl_launch_dependents();   // see common.cuh: launched with programmatic stream serialization
   const int b = blockIdx.y, d = blockIdx.x * blockDim.x + threadIdx.x;
   if (d >= D) return;
   const float* p = x + (long long)b * S * D + d;
@@ -207,6 +216,7 @@ __global__ void seq_mean_fwd_kernel(const float* __restrict__ x, bf16* __restric
   out[(long long)b * D + d] = __float2bfloat16(s / S);
 }
 __global__ void seq_mean_bwd_kernel(const bf16* __restrict__ dout, float* __restrict__ dx, int S, int D) {
+  pdl_wait(); pdl_launch_dependents();   // see common.cuh: launched with programmatic stream serialization
   const int b = blockIdx.z, s = blockIdx.y, d = blockIdx.x * blockDim.x + threadIdx.x;
   if (d >= D) return;
   dx[((long long)b * S + s) * D + d] = __bfloat162float(dout[(long long)b * D + d]) / S;
@@ -217,6 +227,7 @@ __global__ void seq_mean_bwd_kernel(const bf16* __restrict__ dout, float* __rest
 constexpr int SMB_ROWS = 16;
 __global__ void __launch_bounds__(256)
 seq_mean_bwd4_kernel(const bf16* __restrict__ dout, float* __restrict__ dx, int S, int D) {
+  pdl_wait(); pdl_launch_dependents();   // see common.cuh: launched with programmatic stream serialization
   const int b = blockIdx.y, s0 = blockIdx.x * SMB_ROWS;
   for (int q = threadIdx.x; q < (D >> 2); q += 256) {
     const uint2 v = *reinterpret_cast<const uint2*>(dout + (long long)b * D + 4 * q);
@@ -235,8 +246,8 @@ extern "C" int32_t calm_token_transpose(const float* in, const float* addend, fl
   dim3 grid((S + 31) / 32, (S + 31) / 32, B);
   const bool vec = S % 4 == 0 && ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(addend) |
                                    reinterpret_cast<uintptr_t>(out_bf16)) & 15) == 0;
-  if (vec) token_transpose_kernel<true><<<grid, 256, 0, stream>>>(in, addend, out, reinterpret_cast<bf16*>(out_bf16), S);
-  else token_transpose_kernel<false><<<grid, 256, 0, stream>>>(in, addend, out, reinterpret_cast<bf16*>(out_bf16), S);
+  if (vec) CALM_LAUNCH((token_transpose_kernel<true>), grid, 256, 0, stream, in, addend, out, reinterpret_cast<bf16*>(out_bf16), S);
+  else CALM_LAUNCH((token_transpose_kernel<false>), grid, 256, 0, stream, in, addend, out, reinterpret_cast<bf16*>(out_bf16), S);
   CALM_CHECK_LAUNCH("calm_token_transpose");
   return CALM_OK;
 }
@@ -244,7 +255,7 @@ extern "C" int32_t calm_token_transpose(const float* in, const float* addend, fl
 extern "C" int32_t calm_nchw_to_tokens(const float* in, float* out, int32_t B, int32_t S, cudaStream_t stream) {
   CALM_CHECK_ARG(B > 0 && S > 0, "calm_nchw_to_tokens: B=%d S=%d", B, S);
   const long long plane = (long long)S * S, npix = plane * B;
-  nchw_to_tokens_kernel<<<(unsigned)((npix * 3 + 255) / 256), 256, 0, stream>>>(in, out, npix, plane);
+  CALM_LAUNCH((nchw_to_tokens_kernel), (unsigned)((npix * 3 + 255) / 256), 256, 0, stream, in, out, npix, plane);
   CALM_CHECK_LAUNCH("calm_nchw_to_tokens");
   return CALM_OK;
 }
@@ -260,12 +271,15 @@ extern "C" int32_t calm_colsum(const void* x, int64_t ld, float* partial, int32_
   CALM_CHECK_ARG(rows > 0 && N > 0 && N % 2 == 0 && ld % 2 == 0, "calm_colsum: rows=%lld N=%d ld=%lld (N, ld must be even)", (long long)rows, N, (long long)ld);
   CALM_CHECK_ARG(nparts == calm_colsum_parts(rows, N), "calm_colsum: nparts=%d expected %d", nparts, calm_colsum_parts(rows, N));
   if (N % 8 == 0 && ld % 8 == 0 && N <= 2048 && (reinterpret_cast<uintptr_t>(x) & 15) == 0)
-    colsum_vec_kernel<<<nparts, 256, 0, stream>>>(reinterpret_cast<const bf16*>(x), ld, partial, rows, N);
+    CALM_LAUNCH((colsum_vec_kernel), nparts, 256, 0, stream, reinterpret_cast<const bf16*>(x), ld, partial, rows, N);
   else
-    colsum_kernel<<<nparts, 256, 0, stream>>>(reinterpret_cast<const bf16*>(x), ld, partial, rows, N);
+    CALM_LAUNCH((colsum_kernel), nparts, 256, 0, stream, reinterpret_cast<const bf16*>(x), ld, partial, rows, N);
   CALM_CHECK_LAUNCH("calm_colsum");
-  reduce_cols_kernel<<<(N + 31) / 32, 32 * RC_GROUPS, 0, stream>>>(partial, out, nparts, N);
-  CALM_CHECK_LAUNCH("calm_colsum(reduce)");
+  {
+    cudaError_t e = calm_launch_pdl(reduce_cols_kernel, dim3((N + 31) / 32), dim3(32 * RC_GROUPS), 0, stream, nullptr, 0,
+                                    (const float*)partial, out, nparts, N);
+    if (e != cudaSuccess) { calm_set_error("calm_colsum(reduce): launch failed: %s", cudaGetErrorString(e)); return CALM_ERR_CUDA; }
+  }
   return CALM_OK;
 }
 
@@ -275,7 +289,7 @@ extern "C" int32_t calm_add3(const float* a, const float* b, const float* c, flo
   long long blocks = (n4 + 255) / 256;
   const long long cap = 16LL * calm_num_sms();
   if (blocks > cap) blocks = cap;
-  add3_kernel<<<(unsigned)blocks, 256, 0, stream>>>(reinterpret_cast<const float4*>(a), reinterpret_cast<const float4*>(b),
+  CALM_LAUNCH((add3_kernel), (unsigned)blocks, 256, 0, stream, reinterpret_cast<const float4*>(a), reinterpret_cast<const float4*>(b),
                                                     reinterpret_cast<const float4*>(c), reinterpret_cast<float4*>(out), n4);
   CALM_CHECK_LAUNCH("calm_add3");
   return CALM_OK;
@@ -287,7 +301,7 @@ extern "C" int32_t calm_cast_bf16(const float* in, void* out, int64_t n, cudaStr
   long long blocks = (n4 + 255) / 256;
   const long long cap = 16LL * calm_num_sms();
   if (blocks > cap) blocks = cap;
-  cast_bf16_kernel<<<(unsigned)blocks, 256, 0, stream>>>(reinterpret_cast<const float4*>(in), reinterpret_cast<uint2*>(out), n4);
+  CALM_LAUNCH((cast_bf16_kernel), (unsigned)blocks, 256, 0, stream, reinterpret_cast<const float4*>(in), reinterpret_cast<uint2*>(out), n4);
   CALM_CHECK_LAUNCH("calm_cast_bf16");
   return CALM_OK;
 }
@@ -298,7 +312,7 @@ extern "C" int32_t calm_cast_f32(const void* in, float* out, int64_t n, cudaStre
   long long blocks = (n4 + 255) / 256;
   const long long cap = 16LL * calm_num_sms();
   if (blocks > cap) blocks = cap;
-  cast_f32_kernel<<<(unsigned)blocks, 256, 0, stream>>>(reinterpret_cast<const uint2*>(in), reinterpret_cast<float4*>(out), n4);
+  CALM_LAUNCH((cast_f32_kernel), (unsigned)blocks, 256, 0, stream, reinterpret_cast<const uint2*>(in), reinterpret_cast<float4*>(out), n4);
   CALM_CHECK_LAUNCH("calm_cast_f32");
   return CALM_OK;
 }
@@ -306,7 +320,7 @@ extern "C" int32_t calm_cast_f32(const void* in, float* out, int64_t n, cudaStre
 extern "C" int32_t calm_seq_mean_fwd(const float* x, void* out_bf16, int32_t B, int32_t S, int32_t D, cudaStream_t stream) {
   CALM_CHECK_ARG(B > 0 && S > 0 && D > 0, "calm_seq_mean_fwd: bad dims");
   dim3 grid((D + 127) / 128, B);
-  seq_mean_fwd_kernel<<<grid, 128, 0, stream>>>(x, reinterpret_cast<bf16*>(out_bf16), S, D);
+  CALM_LAUNCH((seq_mean_fwd_kernel), grid, 128, 0, stream, x, reinterpret_cast<bf16*>(out_bf16), S, D);
   CALM_CHECK_LAUNCH("calm_seq_mean_fwd");
   return CALM_OK;
 }
@@ -315,10 +329,10 @@ extern "C" int32_t calm_seq_mean_bwd(const void* dout_bf16, float* dx, int32_t B
   CALM_CHECK_ARG(B > 0 && S > 0 && D > 0, "calm_seq_mean_bwd: bad dims");
   if (D % 4 == 0 && ((reinterpret_cast<uintptr_t>(dout_bf16) & 7) == 0) && ((reinterpret_cast<uintptr_t>(dx) & 15) == 0)) {
     dim3 grid4((S + SMB_ROWS - 1) / SMB_ROWS, B);
-    seq_mean_bwd4_kernel<<<grid4, 256, 0, stream>>>(reinterpret_cast<const bf16*>(dout_bf16), dx, S, D);
+    CALM_LAUNCH((seq_mean_bwd4_kernel), grid4, 256, 0, stream, reinterpret_cast<const bf16*>(dout_bf16), dx, S, D);
   } else {
     dim3 grid((D + 127) / 128, S, B);
-    seq_mean_bwd_kernel<<<grid, 128, 0, stream>>>(reinterpret_cast<const bf16*>(dout_bf16), dx, S, D);
+    CALM_LAUNCH((seq_mean_bwd_kernel), grid, 128, 0, stream, reinterpret_cast<const bf16*>(dout_bf16), dx, S, D);
   }
   CALM_CHECK_LAUNCH("calm_seq_mean_bwd");
   return CALM_OK;

@@ -55,6 +55,7 @@ template <int V>
 __global__ void __launch_bounds__(256)
 rope_fwd_kernel(const bf16* __restrict__ content, long long ld_content, const bf16* __restrict__ ropein, long long ld_rope,
                 bf16* __restrict__ out, long long ld_out, const float* __restrict__ cs, int B, int S, int heads, int dc, int dr) {
+  pdl_wait(); pdl_launch_dependents();   // see common.cuh: launched with programmatic stream serialization
   const int half = dr >> 1;
   const int per_head = (dc + half) / V;
   const int pos = blockIdx.x;
@@ -112,6 +113,7 @@ __global__ void __launch_bounds__(256)
 rope_bwd_kernel(const bf16* __restrict__ dout, long long ld_dout, const bf16* __restrict__ out, long long ld_out,
                 bf16* __restrict__ dcontent, long long ld_dcontent, bf16* __restrict__ dropein, long long ld_drope,
                 const float* __restrict__ cs, float* __restrict__ dtheta_part, int B, int S, int heads, int dc, int dr) {
+  pdl_wait(); pdl_launch_dependents();   // see common.cuh: launched with programmatic stream serialization
   extern __shared__ float dth_s[];  // heads * half floats (one slot per (head, j): deterministic reduce)
   const int half = dr >> 1;
   const int per_head = (dc + half) / V;
@@ -247,6 +249,7 @@ __global__ void __launch_bounds__(RS_NT, 4)
 rope_rows_fwd_kernel(const bf16* __restrict__ content, long long ld_content, const bf16* __restrict__ ropein, long long ld_rope,
                      bf16* __restrict__ out, long long ld_out, const float* __restrict__ cs, int B, int S, int heads, int dc, int dr,
                      int R, int chunks) {
+  pdl_wait(); pdl_launch_dependents();   // see common.cuh: launched with programmatic stream serialization
   extern __shared__ __align__(16) unsigned char rs_smem[];
   bf16* stage = reinterpret_cast<bf16*>(rs_smem);
   const int rowlen = heads * (dc + dr), HC = heads * dc, half = dr >> 1;
@@ -314,6 +317,7 @@ rope_rows_bwd_kernel(const bf16* __restrict__ dout, long long ld_dout, const bf1
                      bf16* __restrict__ dcontent, long long ld_dcontent, bf16* __restrict__ dropein, long long ld_drope,
                      const float* __restrict__ cs, float* __restrict__ dtheta_part, int B, int S, int heads, int dc, int dr,
                      int R, int chunks) {
+  pdl_wait(); pdl_launch_dependents();   // see common.cuh: launched with programmatic stream serialization
   extern __shared__ __align__(16) unsigned char rs_smem[];
   const int rowlen = heads * (dc + dr), HC = heads * dc, half = dr >> 1, hd = dc + dr;
   const int pitch = rope_pitch(rowlen), set = RS_UB * R * pitch;
@@ -443,6 +447,7 @@ int rope_threads(int heads, int dc, int dr, int v) {
 
 // d inv_freq[j] = sum_pos pos * sum_chunk dtheta_part[chunk,pos,j]
 __global__ void rope_dfreq_kernel(const float* __restrict__ dtheta_part, float* __restrict__ dinv, int S, int half) {
+  pdl_wait(); pdl_launch_dependents();   // see common.cuh: launched with programmatic stream serialization
   const int j = blockIdx.x;
   __shared__ float red[32];
   float acc = 0.f;
@@ -476,7 +481,7 @@ extern "C" int32_t calm_rope_fwd(const void* content, int64_t ld_content, const 
   do {                                                                                                                           \
     static CalmDeviceOnce carve;                                                                                                   \
     if (carve.pending()) { cudaFuncSetAttribute(rope_rows_fwd_kernel<DC0, PAIR>, cudaFuncAttributePreferredSharedMemoryCarveout, 100); carve.done(); } \
-    rope_rows_fwd_kernel<DC0, PAIR><<<grid, nthreads, smem, stream>>>(reinterpret_cast<const bf16*>(content), ld_content,        \
+    CALM_LAUNCH((rope_rows_fwd_kernel<DC0, PAIR>), grid, nthreads, smem, stream, reinterpret_cast<const bf16*>(content), ld_content,        \
         reinterpret_cast<const bf16*>(ropein), ld_rope, reinterpret_cast<bf16*>(out), ld_out, cos_sin, B, S, heads, dc, dr, R, chunks); \
   } while (0)
       if (dc == 0) { if (pair) CALM_ROPE_ROWS_FWD(true, true); else CALM_ROPE_ROWS_FWD(true, false); }
@@ -489,7 +494,7 @@ extern "C" int32_t calm_rope_fwd(const void* content, int64_t ld_content, const 
   const int v = rope_vec(dc, dr, {(long long)ld_content, (long long)ld_rope, (long long)ld_out}, {content, ropein, out});
   const int threads = rope_threads(heads, dc, dr, v);
 #define CALM_ROPE_FWD(V)                                                                                                          \
-  rope_fwd_kernel<V><<<grid, threads, 0, stream>>>(reinterpret_cast<const bf16*>(content), ld_content,                            \
+  CALM_LAUNCH((rope_fwd_kernel<V>), grid, threads, 0, stream, reinterpret_cast<const bf16*>(content), ld_content,                            \
                                                    reinterpret_cast<const bf16*>(ropein), ld_rope, reinterpret_cast<bf16*>(out), \
                                                    ld_out, cos_sin, B, S, heads, dc, dr)
   if (v == 8) CALM_ROPE_FWD(8); else if (v == 4) CALM_ROPE_FWD(4); else if (v == 2) CALM_ROPE_FWD(2); else CALM_ROPE_FWD(1);
@@ -520,7 +525,7 @@ extern "C" int32_t calm_rope_bwd(const void* dout, int64_t ld_dout, const void* 
   do {                                                                                                                           \
     static CalmDeviceOnce carve;                                                                                                   \
     if (carve.pending()) { cudaFuncSetAttribute(rope_rows_bwd_kernel<DC0, PAIR>, cudaFuncAttributePreferredSharedMemoryCarveout, 100); carve.done(); } \
-    rope_rows_bwd_kernel<DC0, PAIR><<<grid, nthreads, rs_smem, stream>>>(                                                        \
+    CALM_LAUNCH((rope_rows_bwd_kernel<DC0, PAIR>), grid, nthreads, rs_smem, stream,                                                         \
         reinterpret_cast<const bf16*>(dout), ld_dout, reinterpret_cast<const bf16*>(out), ld_out, reinterpret_cast<bf16*>(dcontent), \
         ld_dcontent, reinterpret_cast<bf16*>(dropein), ld_drope, cos_sin, dtheta_part, B, S, heads, dc, dr, R, chunks);          \
   } while (0)
@@ -528,7 +533,7 @@ extern "C" int32_t calm_rope_bwd(const void* dout, int64_t ld_dout, const void* 
       else { if (pair) CALM_ROPE_ROWS_BWD(false, true); else CALM_ROPE_ROWS_BWD(false, false); }
 #undef CALM_ROPE_ROWS_BWD
       CALM_CHECK_LAUNCH("calm_rope_bwd(rows)");
-      rope_dfreq_kernel<<<half, 128, 0, stream>>>(dtheta_part, dinv_freq, S, half);
+      CALM_LAUNCH((rope_dfreq_kernel), half, 128, 0, stream, dtheta_part, dinv_freq, S, half);
       CALM_CHECK_LAUNCH("calm_rope_bwd(dfreq)");
       return CALM_OK;
     }
@@ -538,14 +543,14 @@ extern "C" int32_t calm_rope_bwd(const void* dout, int64_t ld_dout, const void* 
   const int threads = rope_threads(heads, dc, dr, v);
   const size_t smem = (size_t)heads * half * sizeof(float);
 #define CALM_ROPE_BWD(V)                                                                                                       \
-  rope_bwd_kernel<V><<<grid, threads, smem, stream>>>(reinterpret_cast<const bf16*>(dout), ld_dout,                            \
+  CALM_LAUNCH((rope_bwd_kernel<V>), grid, threads, smem, stream, reinterpret_cast<const bf16*>(dout), ld_dout,                            \
                                                       reinterpret_cast<const bf16*>(out), ld_out, reinterpret_cast<bf16*>(dcontent), \
                                                       ld_dcontent, reinterpret_cast<bf16*>(dropein), ld_drope, cos_sin, dtheta_part, \
                                                       B, S, heads, dc, dr)
   if (v == 8) CALM_ROPE_BWD(8); else if (v == 4) CALM_ROPE_BWD(4); else if (v == 2) CALM_ROPE_BWD(2); else CALM_ROPE_BWD(1);
 #undef CALM_ROPE_BWD
   CALM_CHECK_LAUNCH("calm_rope_bwd");
-  rope_dfreq_kernel<<<half, 128, 0, stream>>>(dtheta_part, dinv_freq, S, half);
+  CALM_LAUNCH((rope_dfreq_kernel), half, 128, 0, stream, dtheta_part, dinv_freq, S, half);
   CALM_CHECK_LAUNCH("calm_rope_bwd(dfreq)");
   return CALM_OK;
 }

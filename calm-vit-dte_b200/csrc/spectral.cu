@@ -27,6 +27,7 @@ __device__ __forceinline__ float block_sum256(float v, float* red) { return bloc
 // ---- A: partial t[c] = sum_{r in chunk} u[r] W[r,c]
 __global__ void __launch_bounds__(SN_THREADS)
 sn_a_kernel(const calm_sn_layer* __restrict__ table, const calm_sn_item* __restrict__ items) {
+  pdl_wait(); pdl_launch_dependents();   // see common.cuh: launched with programmatic stream serialization
   const calm_sn_item it = items[blockIdx.x];
   const calm_sn_layer L = table[it.layer];
   const int cols = L.cols;
@@ -54,6 +55,7 @@ sn_a_kernel(const calm_sn_layer* __restrict__ table, const calm_sn_item* __restr
 // ---- B: v = normalize(sum of partials)
 __global__ void __launch_bounds__(SN_THREADS)
 sn_b_kernel(const calm_sn_layer* __restrict__ table, float eps) {
+  pdl_wait(); pdl_launch_dependents();   // see common.cuh: launched with programmatic stream serialization
   __shared__ float red[32];
   const calm_sn_layer L = table[blockIdx.x];
   const int cols = L.cols;
@@ -81,6 +83,7 @@ sn_b_kernel(const calm_sn_layer* __restrict__ table, float eps) {
 // ---- C: s[r] = W[r,:] . v   (warp per row)
 __global__ void __launch_bounds__(SN_THREADS)
 sn_c_kernel(const calm_sn_layer* __restrict__ table, const calm_sn_item* __restrict__ items) {
+  pdl_wait(); pdl_launch_dependents();   // see common.cuh: launched with programmatic stream serialization
   const calm_sn_item it = items[blockIdx.x];
   const calm_sn_layer L = table[it.layer];
   const int cols = L.cols, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -104,6 +107,7 @@ sn_c_kernel(const calm_sn_layer* __restrict__ table, const calm_sn_item* __restr
 // ---- D: u, sigma
 __global__ void __launch_bounds__(SN_THREADS)
 sn_d_kernel(const calm_sn_layer* __restrict__ table, int training, float eps) {
+  pdl_wait(); pdl_launch_dependents();   // see common.cuh: launched with programmatic stream serialization
   __shared__ float red[32];
   const calm_sn_layer L = table[blockIdx.x];
   const int rows = L.rows;
@@ -124,6 +128,7 @@ sn_d_kernel(const calm_sn_layer* __restrict__ table, int training, float eps) {
 // ---- E: W_eff = rowscale * W / sigma
 __global__ void __launch_bounds__(SN_THREADS)
 sn_e_kernel(const calm_sn_layer* __restrict__ table, const calm_sn_item* __restrict__ items) {
+  pdl_wait(); pdl_launch_dependents();   // see common.cuh: launched with programmatic stream serialization
   const calm_sn_item it = items[blockIdx.x];
   const calm_sn_layer L = table[it.layer];
   const int cols = L.cols;
@@ -159,6 +164,7 @@ sn_e_kernel(const calm_sn_layer* __restrict__ table, const calm_sn_item* __restr
 // ---- backward A: H = rowscale * sum_splits G -> grad_w ; per-item partial <H, W> ; d rowscale
 __global__ void __launch_bounds__(SN_THREADS)
 sn_bwd_a_kernel(const calm_sn_layer* __restrict__ table, const calm_sn_item* __restrict__ items) {
+  pdl_wait(); pdl_launch_dependents();   // see common.cuh: launched with programmatic stream serialization
   __shared__ float red[32];
   const calm_sn_item it = items[blockIdx.x];
   const calm_sn_layer L = table[it.layer];
@@ -211,6 +217,7 @@ sn_bwd_a_kernel(const calm_sn_layer* __restrict__ table, const calm_sn_item* __r
 // ---- backward B: grad_w = H / sigma - (<H,W> / sigma^2) u v^T
 __global__ void __launch_bounds__(SN_THREADS)
 sn_bwd_b_kernel(const calm_sn_layer* __restrict__ table, const calm_sn_item* __restrict__ items) {
+  pdl_wait(); pdl_launch_dependents();   // see common.cuh: launched with programmatic stream serialization
   const calm_sn_item it = items[blockIdx.x];
   const calm_sn_layer L = table[it.layer];
   const int cols = L.cols;
@@ -232,16 +239,16 @@ extern "C" int32_t calm_sn_forward(const calm_sn_layer* table_dev, int32_t n_lay
                                    int32_t training, float eps, cudaStream_t stream) {
   CALM_CHECK_ARG(table_dev != nullptr && n_layers > 0 && items_dev != nullptr && n_items >= n_layers, "calm_sn_forward: empty table");
   if (training) {
-    sn_a_kernel<<<n_items, SN_THREADS, 0, stream>>>(table_dev, items_dev);
+    CALM_LAUNCH((sn_a_kernel), n_items, SN_THREADS, 0, stream, table_dev, items_dev);
     CALM_CHECK_LAUNCH("calm_sn_forward(A)");
-    sn_b_kernel<<<n_layers, SN_THREADS, 0, stream>>>(table_dev, eps);
+    CALM_LAUNCH((sn_b_kernel), n_layers, SN_THREADS, 0, stream, table_dev, eps);
     CALM_CHECK_LAUNCH("calm_sn_forward(B)");
   }
-  sn_c_kernel<<<n_items, SN_THREADS, 0, stream>>>(table_dev, items_dev);
+  CALM_LAUNCH((sn_c_kernel), n_items, SN_THREADS, 0, stream, table_dev, items_dev);
   CALM_CHECK_LAUNCH("calm_sn_forward(C)");
-  sn_d_kernel<<<n_layers, SN_THREADS, 0, stream>>>(table_dev, training, eps);
+  CALM_LAUNCH((sn_d_kernel), n_layers, SN_THREADS, 0, stream, table_dev, training, eps);
   CALM_CHECK_LAUNCH("calm_sn_forward(D)");
-  sn_e_kernel<<<n_items, SN_THREADS, 0, stream>>>(table_dev, items_dev);
+  CALM_LAUNCH((sn_e_kernel), n_items, SN_THREADS, 0, stream, table_dev, items_dev);
   CALM_CHECK_LAUNCH("calm_sn_forward(E)");
   return CALM_OK;
 }
@@ -249,9 +256,9 @@ extern "C" int32_t calm_sn_forward(const calm_sn_layer* table_dev, int32_t n_lay
 extern "C" int32_t calm_sn_backward(const calm_sn_layer* table_dev, int32_t n_layers, const calm_sn_item* items_dev, int32_t n_items,
                                     cudaStream_t stream) {
   CALM_CHECK_ARG(table_dev != nullptr && n_layers > 0 && items_dev != nullptr && n_items >= n_layers, "calm_sn_backward: empty table");
-  sn_bwd_a_kernel<<<n_items, SN_THREADS, 0, stream>>>(table_dev, items_dev);
+  CALM_LAUNCH((sn_bwd_a_kernel), n_items, SN_THREADS, 0, stream, table_dev, items_dev);
   CALM_CHECK_LAUNCH("calm_sn_backward(a)");
-  sn_bwd_b_kernel<<<n_items, SN_THREADS, 0, stream>>>(table_dev, items_dev);
+  CALM_LAUNCH((sn_bwd_b_kernel), n_items, SN_THREADS, 0, stream, table_dev, items_dev);
   CALM_CHECK_LAUNCH("calm_sn_backward(b)");
   return CALM_OK;
 }

@@ -24,6 +24,7 @@ __device__ __forceinline__ float target_at(const float* __restrict__ trow, long 
 __global__ void __launch_bounds__(128)
 soft_ce_row_kernel(const float* __restrict__ logits, long long ld, const float* __restrict__ target, long long ld_t,
                    const long long* __restrict__ labels, float* __restrict__ row_stats, int C) {
+  pdl_wait(); pdl_launch_dependents();   // see common.cuh: launched with programmatic stream serialization
   __shared__ float red[32];
   __shared__ int redi[8];
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -77,6 +78,7 @@ soft_ce_row_kernel(const float* __restrict__ logits, long long ld, const float* 
 // loss_out[0] = mean_b loss_b ; loss_out[1] = mean_b correct_b  (fixed summation order)
 __global__ void __launch_bounds__(256)
 soft_ce_mean_kernel(const float* __restrict__ row_stats, float* __restrict__ loss_out, int B) {
+  pdl_wait(); pdl_launch_dependents();   // see common.cuh: launched with programmatic stream serialization
   __shared__ float red[32];
   float l = 0.f, a = 0.f;
   for (int b = threadIdx.x; b < B; b += 256) { l += row_stats[(long long)b * 4]; a += row_stats[(long long)b * 4 + 3]; }
@@ -90,6 +92,7 @@ __global__ void __launch_bounds__(128)
 soft_ce_bwd_kernel(const float* __restrict__ logits, long long ld, const float* __restrict__ target, long long ld_t,
                    const long long* __restrict__ labels, const float* __restrict__ row_stats, const float* __restrict__ dloss,
                    float* __restrict__ dlogits, long long ld_d, int B, int C) {
+  pdl_wait(); pdl_launch_dependents();   // see common.cuh: launched with programmatic stream serialization
   const int b = blockIdx.x;
   const float* xr = logits + (long long)b * ld;
   const float* tr = target ? target + (long long)b * ld_t : nullptr;
@@ -112,6 +115,7 @@ __device__ __forceinline__ float huber(float d, float delta) {
 __global__ void __launch_bounds__(256)
 huber_fwd_kernel(const float* __restrict__ tokens, const float* __restrict__ target, float delta, float* __restrict__ partial,
                  long long npix, int S) {
+  pdl_wait(); pdl_launch_dependents();   // see common.cuh: launched with programmatic stream serialization
   __shared__ float red[32];
   const long long plane = (long long)S * S;
   float acc = 0.f;
@@ -129,6 +133,7 @@ huber_fwd_kernel(const float* __restrict__ tokens, const float* __restrict__ tar
 __global__ void __launch_bounds__(256)
 huber_final_kernel(const float* __restrict__ partial, int nparts, const float* __restrict__ kl, float kl_weight, float inv_n,
                    float* __restrict__ loss_out) {
+  pdl_wait(); pdl_launch_dependents();   // see common.cuh: launched with programmatic stream serialization
   __shared__ float red[32];
   float acc = 0.f;
   for (int i = threadIdx.x; i < nparts; i += 256) acc += partial[i];
@@ -143,6 +148,7 @@ huber_final_kernel(const float* __restrict__ partial, int nparts, const float* _
 __global__ void __launch_bounds__(256)
 huber_bwd_kernel(const float* __restrict__ tokens, const float* __restrict__ target, const float* __restrict__ dloss, float delta,
                  float inv_n, float kl_weight, float* __restrict__ dtokens, float* __restrict__ dkl, long long npix, int S) {
+  pdl_wait(); pdl_launch_dependents();   // see common.cuh: launched with programmatic stream serialization
   const long long plane = (long long)S * S;
   const float gl = dloss ? dloss[0] : 1.0f;
   const float g = gl * inv_n;
@@ -179,6 +185,7 @@ struct OptArgs {
 
 __global__ void __launch_bounds__(OPT_NT)
 opt_gradsq_kernel(OptArgs a) {
+  pdl_wait(); pdl_launch_dependents();   // see common.cuh: launched with programmatic stream serialization
   __shared__ float red[32];
   const int c = blockIdx.x, t = a.chunk_tensor[c];
   const long long n = a.elem_off[t + 1] - a.elem_off[t];
@@ -205,6 +212,7 @@ opt_gradsq_kernel(OptArgs a) {
 // one CTA: total norm, non-finite check, clip coefficient, step / bias corrections, GradScaler.update
 __global__ void __launch_bounds__(1024)
 opt_finalize_kernel(OptArgs a) {
+  pdl_wait(); pdl_launch_dependents();   // see common.cuh: launched with programmatic stream serialization
   __shared__ float red[32];
   float acc = 0.f;
   for (int i = threadIdx.x; i < a.nchunks; i += 1024) acc += a.partial[i];
@@ -254,6 +262,7 @@ __device__ __forceinline__ void adamw_one(float& p, float g, float& m, float& v,
 
 __global__ void __launch_bounds__(OPT_NT)
 opt_adamw_kernel(OptArgs a) {
+  pdl_wait(); pdl_launch_dependents();   // see common.cuh: launched with programmatic stream serialization
   const float* st = a.state;
   if (st[CALM_OPT_FOUND_INF] != 0.f) return;      // GradScaler.step: skip the update when a gradient was inf / nan
   const int c = blockIdx.x, t = a.chunk_tensor[c];
@@ -299,6 +308,7 @@ template <bool VEC>
 __global__ void __launch_bounds__(256)
 mix_batch_kernel(const float* __restrict__ x, float* __restrict__ out, long long per_image, int H, int W, int B, int mode, float lam,
                  float m, int bx1, int by1, int bx2, int by2) {
+  pdl_wait(); pdl_launch_dependents();   // see common.cuh: launched with programmatic stream serialization
   constexpr int V = VEC ? 4 : 1;
   const long long n = (long long)B * per_image / V;
   for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
@@ -340,6 +350,7 @@ mix_batch_kernel(const float* __restrict__ x, float* __restrict__ out, long long
 // soft[b, c] = lam [c == label_b] + (1 - lam) [c == label_{b-1}]  (one-hot labels mixed like the images)
 __global__ void __launch_bounds__(256)
 mix_labels_kernel(const long long* __restrict__ labels, float* __restrict__ soft, int B, int num_classes, float lam, float m) {
+  pdl_wait(); pdl_launch_dependents();   // see common.cuh: launched with programmatic stream serialization
   const int b = blockIdx.x;
   const long long cur = labels[b], prev = labels[b == 0 ? B - 1 : b - 1];
   for (int c = threadIdx.x; c < num_classes; c += 256)
@@ -362,11 +373,11 @@ int32_t calm_mix_batch(const float* x, const int64_t* labels, float* out, float*
   long long blocks = (n + 255) / 256;
   const long long cap = 16LL * calm_num_sms();
   if (blocks > cap) blocks = cap;
-  if (vec) mix_batch_kernel<true><<<(unsigned)blocks, 256, 0, stream>>>(x, out, per_image, H, W, B, mode, lam, one_minus_lam, x1, y1, x2, y2);
-  else mix_batch_kernel<false><<<(unsigned)blocks, 256, 0, stream>>>(x, out, per_image, H, W, B, mode, lam, one_minus_lam, x1, y1, x2, y2);
+  if (vec) CALM_LAUNCH((mix_batch_kernel<true>), (unsigned)blocks, 256, 0, stream, x, out, per_image, H, W, B, mode, lam, one_minus_lam, x1, y1, x2, y2);
+  else CALM_LAUNCH((mix_batch_kernel<false>), (unsigned)blocks, 256, 0, stream, x, out, per_image, H, W, B, mode, lam, one_minus_lam, x1, y1, x2, y2);
   CALM_CHECK_LAUNCH("mix_batch_kernel");
   if (labels) {
-    mix_labels_kernel<<<B, 256, 0, stream>>>(reinterpret_cast<const long long*>(labels), soft, B, num_classes, lam_labels, one_minus_lam_labels);
+    CALM_LAUNCH((mix_labels_kernel), B, 256, 0, stream, reinterpret_cast<const long long*>(labels), soft, B, num_classes, lam_labels, one_minus_lam_labels);
     CALM_CHECK_LAUNCH("mix_labels_kernel");
   }
   return CALM_OK;
@@ -377,9 +388,9 @@ int32_t calm_soft_ce_fwd(const float* logits, int64_t ld, const float* target, i
   CALM_CHECK_ARG(logits && row_stats && loss_out && B > 0 && C > 0, "calm_soft_ce_fwd: bad arguments");
   CALM_CHECK_ARG((target != nullptr) != (labels != nullptr), "calm_soft_ce_fwd: exactly one of target / labels");
   CALM_CHECK_ARG(ld >= C && (!target || ld_t >= C), "calm_soft_ce_fwd: leading dimension < C");
-  soft_ce_row_kernel<<<B, 128, 0, stream>>>(logits, ld, target, ld_t, reinterpret_cast<const long long*>(labels), row_stats, C);
+  CALM_LAUNCH((soft_ce_row_kernel), B, 128, 0, stream, logits, ld, target, ld_t, reinterpret_cast<const long long*>(labels), row_stats, C);
   CALM_CHECK_LAUNCH("soft_ce_row_kernel");
-  soft_ce_mean_kernel<<<1, 256, 0, stream>>>(row_stats, loss_out, B);
+  CALM_LAUNCH((soft_ce_mean_kernel), 1, 256, 0, stream, row_stats, loss_out, B);
   CALM_CHECK_LAUNCH("soft_ce_mean_kernel");
   return CALM_OK;
 }
@@ -389,7 +400,7 @@ int32_t calm_soft_ce_bwd(const float* logits, int64_t ld, const float* target, i
                          cudaStream_t stream) {
   CALM_CHECK_ARG(logits && row_stats && dlogits && B > 0 && C > 0, "calm_soft_ce_bwd: bad arguments");
   CALM_CHECK_ARG((target != nullptr) != (labels != nullptr), "calm_soft_ce_bwd: exactly one of target / labels");
-  soft_ce_bwd_kernel<<<B, 128, 0, stream>>>(logits, ld, target, ld_t, reinterpret_cast<const long long*>(labels), row_stats, dloss,
+  CALM_LAUNCH((soft_ce_bwd_kernel), B, 128, 0, stream, logits, ld, target, ld_t, reinterpret_cast<const long long*>(labels), row_stats, dloss,
                                             dlogits, ld_d, B, C);
   CALM_CHECK_LAUNCH("soft_ce_bwd_kernel");
   return CALM_OK;
@@ -406,9 +417,9 @@ int32_t calm_huber_tokens_fwd(const float* tokens, const float* target_nchw, con
                               float* partial, int32_t nparts, float* loss_out, int32_t B, int32_t S, cudaStream_t stream) {
   CALM_CHECK_ARG(tokens && target_nchw && partial && loss_out && B > 0 && S > 0 && nparts > 0, "calm_huber_tokens_fwd: bad arguments");
   const long long npix = (long long)B * S * S;
-  huber_fwd_kernel<<<nparts, 256, 0, stream>>>(tokens, target_nchw, delta, partial, npix, S);
+  CALM_LAUNCH((huber_fwd_kernel), nparts, 256, 0, stream, tokens, target_nchw, delta, partial, npix, S);
   CALM_CHECK_LAUNCH("huber_fwd_kernel");
-  huber_final_kernel<<<1, 256, 0, stream>>>(partial, nparts, kl, kl_weight, 1.0f / (float)(npix * 3), loss_out);
+  CALM_LAUNCH((huber_final_kernel), 1, 256, 0, stream, partial, nparts, kl, kl_weight, 1.0f / (float)(npix * 3), loss_out);
   CALM_CHECK_LAUNCH("huber_final_kernel");
   return CALM_OK;
 }
@@ -417,7 +428,7 @@ int32_t calm_huber_tokens_bwd(const float* tokens, const float* target_nchw, con
                               float* dtokens, float* dkl, int32_t B, int32_t S, cudaStream_t stream) {
   CALM_CHECK_ARG(tokens && target_nchw && dtokens && B > 0 && S > 0, "calm_huber_tokens_bwd: bad arguments");
   const long long npix = (long long)B * S * S;
-  huber_bwd_kernel<<<calm_huber_parts(B, S), 256, 0, stream>>>(tokens, target_nchw, dloss, delta, 1.0f / (float)(npix * 3), kl_weight,
+  CALM_LAUNCH((huber_bwd_kernel), calm_huber_parts(B, S), 256, 0, stream, tokens, target_nchw, dloss, delta, 1.0f / (float)(npix * 3), kl_weight,
                                                              dtokens, dkl, npix, S);
   CALM_CHECK_LAUNCH("huber_bwd_kernel");
   return CALM_OK;
@@ -444,11 +455,11 @@ int32_t calm_trainer_step(const calm_trainer_step_args* s, cudaStream_t stream) 
   a.beta1 = s->beta1; a.beta2 = s->beta2; a.eps = s->eps; a.weight_decay = s->weight_decay; a.max_norm = s->max_norm;
   a.growth_factor = s->growth_factor; a.backoff_factor = s->backoff_factor;
   a.growth_interval = s->growth_interval; a.use_scaler = s->use_scaler;
-  opt_gradsq_kernel<<<s->n_chunks, OPT_NT, 0, stream>>>(a);
+  CALM_LAUNCH((opt_gradsq_kernel), s->n_chunks, OPT_NT, 0, stream, a);
   CALM_CHECK_LAUNCH("opt_gradsq_kernel");
-  opt_finalize_kernel<<<1, 1024, 0, stream>>>(a);
+  CALM_LAUNCH((opt_finalize_kernel), 1, 1024, 0, stream, a);
   CALM_CHECK_LAUNCH("opt_finalize_kernel");
-  opt_adamw_kernel<<<s->n_chunks, OPT_NT, 0, stream>>>(a);
+  CALM_LAUNCH((opt_adamw_kernel), s->n_chunks, OPT_NT, 0, stream, a);
   CALM_CHECK_LAUNCH("opt_adamw_kernel");
   return CALM_OK;
 }
