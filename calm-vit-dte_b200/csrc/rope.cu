@@ -113,7 +113,7 @@ __global__ void __launch_bounds__(256)
 rope_bwd_kernel(const bf16* __restrict__ dout, long long ld_dout, const bf16* __restrict__ out, long long ld_out,
                 bf16* __restrict__ dcontent, long long ld_dcontent, bf16* __restrict__ dropein, long long ld_drope,
                 const float* __restrict__ cs, float* __restrict__ dtheta_part, int B, int S, int heads, int dc, int dr) {
-  pdl_wait(); pdl_launch_dependents();   // see common.cuh: launched with programmatic stream serialization
+  pdl_wait(); pdl_launch_small_dependent();   // its dependent is the ~12-CTA d inv_freq reduction
   extern __shared__ float dth_s[];  // heads * half floats (one slot per (head, j): deterministic reduce)
   const int half = dr >> 1;
   const int per_head = (dc + half) / V;
@@ -317,7 +317,7 @@ rope_rows_bwd_kernel(const bf16* __restrict__ dout, long long ld_dout, const bf1
                      bf16* __restrict__ dcontent, long long ld_dcontent, bf16* __restrict__ dropein, long long ld_drope,
                      const float* __restrict__ cs, float* __restrict__ dtheta_part, int B, int S, int heads, int dc, int dr,
                      int R, int chunks) {
-  pdl_wait(); pdl_launch_dependents();   // see common.cuh: launched with programmatic stream serialization
+  pdl_wait(); pdl_launch_small_dependent();   // its dependent is the ~12-CTA d inv_freq reduction
   extern __shared__ __align__(16) unsigned char rs_smem[];
   const int rowlen = heads * (dc + dr), HC = heads * dc, half = dr >> 1, hd = dc + dr;
   const int pitch = rope_pitch(rowlen), set = RS_UB * R * pitch;
